@@ -1,0 +1,223 @@
+"""ctypes binding of libcatb200.so (the C ABI declared in include/catb200.h).
+
+This is the stub a reference maintainer would add: plain pointers and sizes,
+no torch types in any signature.  torch is used only to own device memory and to name the current
+CUDA stream.  There is deliberately no CPU or eager fallback: if the shared library is missing or a
+kernel is asked to run without a CUDA device, the call raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REPO_ROOT = os.path.dirname(_HERE)
+CSRC = os.path.join(_HERE, "csrc")
+LIB_DIR = os.path.join(_HERE, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libcatb200.so")
+INCLUDE_DIR = os.path.join(REPO_ROOT, "include")
+
+MAX_SOURCES, MAX_TERMS, MAX_IDS, MAX_COLS = 16, 32, 32, 256
+F32, U8 = 0, 1
+
+# catb200_op
+OP_GENERIC = 0
+OP_ABS_MINUS = 1
+OP_ABSDIFF_MINUS = 2
+OP_ABSDIFF_MINUS_GATE_Y = 3
+OP_ACTION_RATE = 4
+OP_COMPONENT_GT = 5
+OP_CONTACT_ANY = 6
+OP_NORM2_MINUS = 7
+OP_AIR_TIME = 8
+OP_N_CONTACT = 9
+OP_FORCE_PEAK_MINUS = 10
+OP_LIMIT_MINUS = 11
+OP_ABS_MINUS_GATE_STILL = 12
+
+NO_SOURCE = 0xFF
+
+
+class Source(C.Structure):
+    _fields_ = [
+        ("ptr", C.c_void_p),
+        ("row_len", C.c_int32),
+        ("row_stride", C.c_int32),
+        ("dtype", C.c_int32),
+        ("aux", C.c_int32),
+        ("smem_off", C.c_int32),
+        ("magic", C.c_uint32),
+    ]
+
+
+class Term(C.Structure):
+    _fields_ = [
+        ("op", C.c_uint8),
+        ("n_cols", C.c_uint8),
+        ("n_ids", C.c_uint8),
+        ("src0", C.c_uint8),
+        ("src1", C.c_uint8),
+        ("src2", C.c_uint8),
+        ("stat_slot", C.c_uint8),
+        ("reserved", C.c_uint8),
+        ("col_offset", C.c_uint16),
+        ("reserved2", C.c_uint16),
+        ("p0", C.c_float),
+        ("p1", C.c_float),
+        ("p2", C.c_float),
+        ("ids", C.c_uint8 * MAX_IDS),
+    ]
+
+
+class Plan(C.Structure):
+    _fields_ = [
+        ("n_sources", C.c_int32),
+        ("n_terms", C.c_int32),
+        ("n_cols", C.c_int32),
+        ("n_slots", C.c_int32),
+        ("smem_floats_per_env", C.c_int32),
+        ("reserved", C.c_int32 * 3),
+        ("sources", Source * MAX_SOURCES),
+        ("terms", Term * MAX_TERMS),
+        ("col_term", C.c_uint8 * MAX_COLS),
+        ("slot_col_begin", C.c_uint16 * (MAX_TERMS + 2)),
+    ]
+
+
+class CatParams(C.Structure):
+    _fields_ = [
+        ("tau", C.c_float),
+        ("one_minus_tau", C.c_float),
+        ("min_p", C.c_float),
+        ("floor_max", C.c_float),
+        ("span", C.c_float * MAX_TERMS),
+    ]
+
+
+NVCC_FLAGS = [
+    "-gencode",
+    "arch=compute_100a,code=sm_100a",
+    "-O3",
+    "-lineinfo",
+    "-std=c++17",
+    "-Xcompiler",
+    "-fPIC",
+    "-shared",
+]
+
+
+def sources() -> list[str]:
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _stale() -> bool:
+    if not os.path.isfile(LIB_PATH):
+        return True
+    built = os.path.getmtime(LIB_PATH)
+    deps = sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    deps.append(os.path.join(INCLUDE_DIR, "catb200.h"))
+    return any(os.path.getmtime(d) > built for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into lib/libcatb200.so (nvcc cross-compiles without a GPU)."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.isfile(nvcc):
+        raise RuntimeError("nvcc not found: cannot build libcatb200.so")
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = [nvcc, *NVCC_FLAGS, f"-I{INCLUDE_DIR}", f"-I{CSRC}", *sources(), "-o", LIB_PATH + ".tmp"]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError(f"nvcc failed:\n{' '.join(cmd)}\n{proc.stdout}\n{proc.stderr}")
+    os.replace(LIB_PATH + ".tmp", LIB_PATH)
+    if verbose:
+        print(proc.stderr)
+    return LIB_PATH
+
+
+_P = C.c_void_p
+_I32 = C.c_int32
+_I64 = C.c_int64
+_F = C.c_float
+_SZ = C.c_size_t
+
+# name -> (restype, argtypes); one entry per symbol declared in include/catb200.h
+SIGNATURES = {
+    "catb200_version": (C.c_int, []),
+    "catb200_error_string": (C.c_char_p, [C.c_int]),
+    "catb200_cat_plan_finalize": (C.c_int, [C.POINTER(Plan)]),
+    "catb200_cat_workspace_bytes": (_SZ, [_I32, _I32]),
+    "catb200_cat_step": (
+        C.c_int,
+        [C.POINTER(Plan), C.POINTER(CatParams), _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P],
+    ),
+    "catb200_cat_eval_terms": (C.c_int, [C.POINTER(Plan), _I32, _P, _P]),
+    "catb200_cat_probs": (C.c_int, [C.POINTER(Plan), C.POINTER(CatParams), _I32, _P, _P, _P, _P]),
+    "catb200_cat_reset_stats": (C.c_int, [_P, _I32, _P, _P, _I32, _I32, _P, _P, _P, _P]),
+    "catb200_rms_workspace_bytes": (_SZ, [_I32]),
+    "catb200_rms_forward": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _F, _I32, _P, _P, _SZ, _P]),
+    "catb200_rollout_append": (C.c_int, [_P, _P, _P, _I32, _P, _P, _P, _P]),
+    "catb200_gae_workspace_bytes": (_SZ, []),
+    "catb200_gae": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _F, _F, _P, _P, _P, _P, _P, _SZ, _P]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen libcatb200.so and type every entry point.  Raises if the library is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "There is no CPU fallback for the CaT hot path."
+            )
+        lib = C.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+    return _lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = load().catb200_error_string(status).decode()
+        raise RuntimeError(f"libcatb200 {what} failed: {msg} (status {status})")
+
+
+def require_cuda(t: torch.Tensor, what: str = "tensor") -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{what} lives on {t.device}: the CaT hot path runs only as CUDA kernels on a B200 "
+            "(no CPU fallback is provided)."
+        )
+
+
+def ptr(t: torch.Tensor | None):
+    return None if t is None else t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def f32(x: float) -> float:
+    """Round a python double to fp32 like torch does when a python scalar meets an fp32 tensor."""
+    return float(torch.tensor(x, dtype=torch.float64).to(torch.float32).item())
+
+
+def zeros_workspace(nbytes: int, device) -> torch.Tensor:
+    """Zero-initialised scratch the kernels keep clean between calls."""
+    return torch.zeros((int(nbytes) + 7) // 8, dtype=torch.int64, device=device)

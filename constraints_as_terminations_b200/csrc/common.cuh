@@ -1,0 +1,69 @@
+// Shared helpers for libcatb200 (sm_100a).  Internal header; the public ABI is include/catb200.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "catb200.h"
+
+namespace catb200 {
+
+extern thread_local cudaError_t g_last_cuda_error;
+
+inline int cuda_status(cudaError_t e) {
+  if (e == cudaSuccess) return CATB200_OK;
+  g_last_cuda_error = e;
+  return CATB200_ERR_CUDA;
+}
+
+#define CATB200_CUDA_TRY(expr)                         \
+  do {                                                 \
+    cudaError_t _e = (expr);                           \
+    if (_e != cudaSuccess) return ::catb200::cuda_status(_e); \
+  } while (0)
+
+#define CATB200_LAUNCH_CHECK() CATB200_CUDA_TRY(cudaPeekAtLastError())
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+constexpr int kNumSMs = 148;  // B200
+
+// Monotone map float -> uint32 (unsigned compare == float compare); 0 is below every real number,
+// so a zero-initialised scratch word is the identity of atomicMax.
+__device__ __forceinline__ uint32_t float_to_ordered(float f) {
+  uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(uint32_t u) {
+  uint32_t b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+  return __uint_as_float(b);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Last-block-done ticket: returns true in exactly one block (the last to arrive), for all its threads.
+// Callers must have made their global writes visible (__threadfence) before calling.
+__device__ __forceinline__ bool last_block_ticket(unsigned int* counter, unsigned int total_blocks) {
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = atomicAdd(counter, 1u);
+    s_last = (t == total_blocks - 1);
+    if (s_last) *counter = 0u;  // leave the workspace clean for the next launch
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last;
+}
+
+}  // namespace catb200

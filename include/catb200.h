@@ -1,0 +1,209 @@
+/*
+ * catb200.h - C ABI of libcatb200.so: the constraints-as-terminations PPO hot path on B200 (sm_100a).
+ *
+ * The reference (Gepetto/constraints-as-terminations) is pure Python/PyTorch: it has no FFI.  The
+ * boundary this library plugs into is therefore its Python manager / trainer API; each entry point
+ * below names the reference code it replaces (paths relative to the reference root, with
+ * U/ = exts/cat_envs/cat_envs/tasks/utils/).  INTEGRATION.md shows the ctypes binding a reference
+ * maintainer would add (it is the one `constraints_as_terminations_b200/_lib.py` ships).
+ *
+ * Conventions
+ *  - plain C types only: device pointers, sizes, small POD structs passed by pointer (host memory).
+ *  - every function returns CATB200_OK (0) or a negative catb200_status; nothing throws.
+ *  - no hidden allocation and no hidden synchronisation: persistent state (running max, episode
+ *    statistics, running moments, Adam moments) lives in caller-owned device buffers; scratch comes
+ *    from a caller-provided workspace whose size `*_workspace_bytes` reports.  The workspace must be
+ *    zero-initialised once (cudaMemset) before its first use; kernels leave it clean for the next call.
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*); calls are CUDA-graph capturable.
+ *  - fp32 arithmetic on the CaT / GAE / moments paths is IEEE round-to-nearest with the reference's
+ *    operation order (no FMA contraction where torch rounds twice), so results are bit-comparable.
+ */
+#ifndef CATB200_H_
+#define CATB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CATB200_VERSION 100
+
+typedef enum {
+  CATB200_OK = 0,
+  CATB200_ERR_INVALID_ARGUMENT = -1,
+  CATB200_ERR_UNSUPPORTED = -2,
+  CATB200_ERR_WORKSPACE_TOO_SMALL = -3,
+  CATB200_ERR_CUDA = -4
+} catb200_status;
+
+int catb200_version(void);
+/* Static description of a status code; for CATB200_ERR_CUDA also the last CUDA error string. */
+const char* catb200_error_string(int status);
+
+/* ------------------------------------------------------------------------------------------------
+ * Per-step path: constraint terms -> termination probabilities  (rows a1, a2, a3, a5 of SURVEY.md §8)
+ * ---------------------------------------------------------------------------------------------- */
+#define CATB200_MAX_SOURCES 16
+#define CATB200_MAX_TERMS 32
+#define CATB200_MAX_IDS 32
+#define CATB200_MAX_COLS 256
+
+typedef enum { CATB200_F32 = 0, CATB200_U8 = 1 } catb200_dtype;
+
+/* One fused operation per reference term function (U/cat/constraints.py, line of the def). */
+typedef enum {
+  CATB200_OP_GENERIC = 0,              /* x[id]                       user term already evaluated to [N,J]       */
+  CATB200_OP_ABS_MINUS = 1,            /* |x[id]| - p0                joint_position:23 joint_torque:57
+                                                                      joint_velocity:68 joint_acceleration:78   */
+  CATB200_OP_ABSDIFF_MINUS = 2,        /* |x[id]-y[id]| - p0          joint_range:171                            */
+  CATB200_OP_ABSDIFF_MINUS_GATE_Y = 3, /* (|x-y| - p0)*[|cmd.y|<p1]   joint_position_when_moving_forward:34      */
+  CATB200_OP_ACTION_RATE = 4,          /* |a-a_prev|/p1 - p0          action_rate:184  (p1 = step_dt, true div)  */
+  CATB200_OP_COMPONENT_GT = 5,         /* x[id] > p0  (bool)          upsidedown:88   (id = 2)                   */
+  CATB200_OP_CONTACT_ANY = 6,          /* any_b max_h|F[h,b]| > p0    contact:97      (p0 = 1.0; bool, 1 column) */
+  CATB200_OP_NORM2_MINUS = 7,          /* |x[0:2]| - p0               base_orientation:113                       */
+  CATB200_OP_AIR_TIME = 8,             /* (p0-air[b])*first[b]*[|cmd|>p1]  air_time:122                          */
+  CATB200_OP_N_CONTACT = 9,            /* |#b(max_h|F|>1) - p0|*[|cmd|>p1] n_foot_contact:144  (1 column)        */
+  CATB200_OP_FORCE_PEAK_MINUS = 10,    /* max_h|F[h,b]| - p0          foot_contact_force:201                     */
+  CATB200_OP_LIMIT_MINUS = 11,         /* p0 - x[id]                  min_base_height:214 (id = 2)               */
+  CATB200_OP_ABS_MINUS_GATE_STILL = 12 /* (|x[id]|-p0)*[|cmd|<p1]     no_move:223                                */
+} catb200_op;
+
+/* A device tensor the terms read: env-major rows, `row_len` elements used per env. */
+typedef struct {
+  const void* ptr;    /* device pointer to element [0,0]                                  */
+  int32_t row_len;    /* elements per env row (e.g. 12 joints, 3*17*3 contact history)   */
+  int32_t row_stride; /* elements between consecutive env rows (== row_len if contiguous) */
+  int32_t dtype;      /* catb200_dtype                                                    */
+  int32_t aux;        /* contact history: number of bodies B (row = [H, B, 3]); else 0    */
+  int32_t smem_off;   /* filled by catb200_cat_plan_finalize                              */
+  uint32_t magic;     /* filled by catb200_cat_plan_finalize (fast division by row_len)   */
+} catb200_source_t;
+
+typedef struct {
+  uint8_t op;        /* catb200_op                                                          */
+  uint8_t n_cols;    /* columns this term contributes to the [N,K] constraint matrix        */
+  uint8_t n_ids;     /* joint / body ids in `ids` (== n_cols for per-joint ops)             */
+  uint8_t src0;      /* main source index                                                   */
+  uint8_t src1;      /* second source (y, a_prev, first_contact) or 0xff                    */
+  uint8_t src2;      /* command source or 0xff                                              */
+  uint8_t stat_slot; /* row of episode_sums / mean_values this term accumulates into        */
+  uint8_t reserved;
+  uint16_t col_offset; /* first column of this term in the [N,K] layout                     */
+  uint16_t reserved2;
+  float p0, p1, p2;
+  uint8_t ids[CATB200_MAX_IDS];
+} catb200_term_t;
+
+typedef struct {
+  int32_t n_sources, n_terms, n_cols, n_slots;
+  int32_t smem_floats_per_env; /* filled by catb200_cat_plan_finalize */
+  int32_t reserved[3];
+  catb200_source_t sources[CATB200_MAX_SOURCES];
+  catb200_term_t terms[CATB200_MAX_TERMS];
+  uint8_t col_term[CATB200_MAX_COLS];               /* filled by finalize: term of each column        */
+  uint16_t slot_col_begin[CATB200_MAX_TERMS + 2];   /* filled by finalize: [begin,end) cols per slot  */
+} catb200_plan_t;
+
+/* Scalars of CaT.add (U/cat/constraint_manager.py:39-76), rounded on the host exactly like torch
+ * rounds python doubles that meet fp32 tensors. */
+typedef struct {
+  float tau;           /* fl32(tau)                                          :59 */
+  float one_minus_tau; /* fl32(1.0 - tau) evaluated in double first          :59 */
+  float min_p;         /* fl32(min_p)                                        :72 */
+  float floor_max;     /* fl32(1e-6) clamp of the column max                 :55 */
+  float span[CATB200_MAX_TERMS]; /* fl32(max_p - min_p) per term (double subtraction)  :72 */
+} catb200_cat_params_t;
+
+/* Validates a plan and fills the derived fields (shared-memory layout, division magics). */
+int catb200_cat_plan_finalize(catb200_plan_t* plan);
+
+/* Bytes of zero-initialised device scratch needed by catb200_cat_step for this problem size. */
+size_t catb200_cat_workspace_bytes(int32_t num_envs, int32_t n_cols);
+
+/*
+ * One env step of ConstraintManager.compute() (U/cat/constraint_manager.py:213-229), i.e. for every
+ * term: evaluate the constraint (constraints.py), CaT.add (:39-76: column max over envs, clamp,
+ * Polyak running max, violation -> probability), then CaT.get_probs (:78-82: max over all columns)
+ * and the per-term episode statistics (:223-227).  Optionally also the reward / dones lines of
+ * CaTEnv.step (U/cat/cat_env.py:102-107,118-121) when raw_reward != NULL.
+ *
+ *   running_max  [n_cols]          fp32, in/out     rm_init [n_cols] int32 in/out (0 = first call assigns)
+ *   episode_sums [n_slots,num_envs] fp32, in/out    mean_values [n_slots,num_envs] fp32, in/out
+ *   cstr_prob    [num_envs]        fp32, out
+ *   raw_reward   [num_envs] fp32 in (nullable)      reset_buf [num_envs] u8/bool in (nullable)
+ *   reward_out   [num_envs] fp32 out                dones_out [num_envs] fp32 out
+ */
+int catb200_cat_step(const catb200_plan_t* plan, const catb200_cat_params_t* params, int32_t num_envs,
+                     float* running_max, int32_t* rm_init, float* episode_sums, float* mean_values,
+                     float* cstr_prob, const float* raw_reward, const uint8_t* reset_buf,
+                     float* reward_out, float* dones_out, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* Raw constraint values of every term, row-major [num_envs, n_cols] (what CaT keeps as
+ * raw_constraints, constraint_manager.py:52; also backs the stand-alone term functions). */
+int catb200_cat_eval_terms(const catb200_plan_t* plan, int32_t num_envs, float* out, void* stream);
+
+/* Per-column probabilities [num_envs, n_cols] of the most recent catb200_cat_step, rebuilt from the
+ * constraint values kept in `workspace` (what CaT keeps as `probs`, constraint_manager.py:74). */
+int catb200_cat_probs(const catb200_plan_t* plan, const catb200_cat_params_t* params, int32_t num_envs,
+                      const float* running_max, float* probs_out, const void* workspace, void* stream);
+
+/*
+ * ConstraintManager.reset (U/cat/constraint_manager.py:190-211): for each statistics row s,
+ *   out[2*s]   = mean_i(episode_sums[s,i] / episode_length[i]) * 100
+ *   out[2*s+1] = mean_i(mean_values[s,i]  / episode_length[i])
+ * over the selected envs, then zero both rows at those envs.  Selection: `env_ids` (int64, n_ids
+ * entries) or, if env_ids == NULL, `mask` (u8 [num_envs], nonzero = selected) or, if both NULL, all.
+ */
+int catb200_cat_reset_stats(const int64_t* env_ids, int32_t n_ids, const uint8_t* mask,
+                            const int64_t* episode_length, int32_t num_envs, int32_t n_slots,
+                            float* episode_sums, float* mean_values, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Running moments + rollout append  (row a6: U/cleanrl/ppo.py:12-62,203-205,225)
+ * ---------------------------------------------------------------------------------------------- */
+size_t catb200_rms_workspace_bytes(int32_t dim);
+
+/*
+ * RunningMeanStd.forward(x, update=True) for x [rows, dim] (dim = 1 for scalars):
+ * batch mean / biased variance, Chan merge into (mean[dim], var[dim], count[1]) and
+ * out = (x - mean) / sqrt(var + eps) with the *updated* statistics.  `out` may alias x or be NULL
+ * (update only).  update == 0 skips the statistics and only normalises.
+ */
+int catb200_rms_forward(const float* x, int64_t rows, int32_t dim, float* mean, float* var, float* count,
+                        float eps, int32_t update, float* out, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+/*
+ * Post-step rollout append (U/cleanrl/ppo.py:203-205,215-216,225 for step t):
+ *   rewards[t] = reward; dones[t+1] = done; true_dones[t+1] = float(time_out)
+ * where dones / true_dones have T+1 time slots so that slot t+1 doubles as next_done / next_true_done.
+ */
+int catb200_rollout_append(const float* reward, const float* done, const uint8_t* time_out, int32_t num_envs,
+                           float* rewards_t, float* dones_t1, float* true_dones_t1, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GAE + value normalisation statistics  (rows a7, a8: U/cleanrl/ppo.py:251-277,287-288)
+ * ---------------------------------------------------------------------------------------------- */
+size_t catb200_gae_workspace_bytes(void);
+
+/*
+ * rewards, values: [T, N]; dones, true_dones: [T+1, N] (slot T = next_done / next_true_done);
+ * next_value: [N].  Writes advantages, returns: [T, N].  gamma_lambda = fl32(gamma * lambda) with the
+ * product taken in double, as python does before it meets the tensor (ppo.py:271-273).
+ * If value_rms != NULL (3 floats: mean, var, count), also performs the two consecutive
+ * RunningMeanStd updates of ppo.py:287-288 (first with all values, then with all returns) and writes
+ * norm_stats[4] = {mean_after_values, var_after_values, mean_after_returns, var_after_returns}, the
+ * statistics b_values resp. b_returns are normalised with.
+ */
+int catb200_gae(const float* rewards, const float* values, const float* dones, const float* true_dones,
+                const float* next_value, int32_t T, int32_t num_envs, float gamma, float gamma_lambda,
+                float* advantages, float* returns, float* value_rms, float* norm_stats, void* workspace,
+                size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CATB200_H_ */
