@@ -1,0 +1,47 @@
+"""One small invocation of the hot path on the GPU, checked against the CPU oracle (used by
+`__graft_entry__.smoke()`)."""
+
+from __future__ import annotations
+
+import torch
+
+from constraints_as_terminations_b200 import ConstraintManager, ops
+from constraints_as_terminations_b200 import synthetic_env as se
+from oracle import cat_oracle, ppo_oracle
+
+
+def run(device: str = "cuda:0") -> None:
+    n, T = 512, 24
+    # ---- per-step path: 13 Solo12 terms, 3 steps ----
+    cpu_env = se.SyntheticSolo12Env(n, device="cpu", seed=0, pool=1)
+    gpu_env = se.SyntheticSolo12Env(n, device=device, seed=0, pool=1)
+    cfg_cpu, cfg_gpu = se.solo12_constraints_cfg(), se.solo12_constraints_cfg()
+    oracle = cat_oracle.ManagerOracle(cpu_env, cat_oracle.terms_from_cfg(cfg_cpu, resolve_scene=cpu_env.scene))
+    mgr = ConstraintManager(cfg_gpu, gpu_env)
+    gen = torch.Generator().manual_seed(1)
+    for _ in range(3):
+        state = se.sample_state(n, gen)
+        cpu_env.load_state(state)
+        gpu_env.load_state({k: v.to(device) for k, v in state.items()})
+        want = oracle.compute()
+        reset = torch.zeros(n, dtype=torch.bool)
+        reset[::50] = True
+        want_reward, want_dones = cat_oracle.step_epilogue(state["raw_reward"], want, reset)
+        reward, dones = mgr.compute_step(gpu_env._raw_reward, reset.to(device))
+        assert torch.equal(mgr._cstr_prob_buf.cpu(), want), "cstr_prob mismatch"
+        assert torch.equal(reward.cpu(), want_reward) and torch.equal(dones.cpu(), want_dones)
+    # ---- per-update path: GAE + moments ----
+    g = torch.Generator().manual_seed(2)
+    rewards, values = torch.rand(T, n, generator=g), torch.randn(T, n, generator=g)
+    dones = torch.rand(T + 1, n, generator=g) * (torch.rand(T + 1, n, generator=g) < 0.3)
+    true_dones = (torch.rand(T + 1, n, generator=g) < 0.02).float()
+    next_value = torch.randn(n, generator=g)
+    want_adv, want_ret = ppo_oracle.gae(rewards, values, dones[:-1], true_dones[:-1], next_value, dones[-1], true_dones[-1])
+    adv, ret = ops.gae(*(t.to(device) for t in (rewards, values, dones, true_dones, next_value)), 0.99, 0.95)
+    assert torch.equal(adv.cpu(), want_adv) and torch.equal(ret.cpu(), want_ret), "GAE mismatch"
+    x = torch.randn(n, 45, generator=g) * 3 + 1
+    st = ppo_oracle.rms_update(ppo_oracle.rms_init((45,)), x)
+    mean, var, count = torch.zeros(45, device=device), torch.ones(45, device=device), torch.ones(1, device=device)
+    got = ops.rms_forward(x.to(device), mean, var, count)
+    torch.testing.assert_close(got.cpu(), ppo_oracle.rms_normalize(st, x), rtol=1e-5, atol=1e-5)
+    torch.cuda.synchronize()
