@@ -99,6 +99,39 @@ class CatParams(C.Structure):
     ]
 
 
+class MlpDims(C.Structure):
+    _fields_ = [
+        ("obs_dim", C.c_int32),
+        ("act_dim", C.c_int32),
+        ("h1", C.c_int32),
+        ("h2", C.c_int32),
+        ("h3", C.c_int32),
+        ("obs_pad", C.c_int32),
+    ]
+
+
+class MlpLayout(C.Structure):
+    _fields_ = [
+        ("n_params", C.c_int64),
+        ("w", (C.c_int64 * 4) * 2),
+        ("b", (C.c_int64 * 4) * 2),
+        ("logstd", C.c_int64),
+        ("n_w16", C.c_int64),
+        ("w16", (C.c_int64 * 3) * 2),
+        ("wt16", (C.c_int64 * 3) * 2),
+    ]
+
+
+class PpoHparams(C.Structure):
+    _fields_ = [
+        ("clip_coef", C.c_float),
+        ("ent_coef", C.c_float),
+        ("vf_coef", C.c_float),
+        ("norm_adv", C.c_int32),
+        ("clip_vloss", C.c_int32),
+    ]
+
+
 NVCC_FLAGS = [
     "-gencode",
     "arch=compute_100a,code=sm_100a",
@@ -168,6 +201,19 @@ SIGNATURES = {
     "catb200_rollout_append": (C.c_int, [_P, _P, _P, _I32, _P, _P, _P, _P]),
     "catb200_gae_workspace_bytes": (_SZ, []),
     "catb200_gae": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _F, _F, _P, _P, _P, _P, _P, _SZ, _P]),
+    "catb200_mlp_layout": (C.c_int, [C.POINTER(MlpDims), C.POINTER(MlpLayout)]),
+    "catb200_mlp_cast_weights": (C.c_int, [C.POINTER(MlpDims), _P, _P, _P]),
+    "catb200_obs_to_bf16": (C.c_int, [_P, _I64, _I32, _I32, _P, _P]),
+    "catb200_mlp_workspace_bytes": (_SZ, [C.POINTER(MlpDims), _I32, _I32]),
+    "catb200_mlp_act": (C.c_int, [C.POINTER(MlpDims), _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "catb200_ppo_minibatch_grad": (
+        C.c_int,
+        [C.POINTER(MlpDims), C.POINTER(PpoHparams), _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P],
+    ),
+    "catb200_adam_step": (
+        C.c_int,
+        [C.POINTER(MlpDims), _P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _P, _P, _P],
+    ),
 }
 
 _lib = None

@@ -149,3 +149,98 @@ def gae(
         "gae",
     )  # fmt: skip
     return advantages, returns
+
+
+# --------------------------------------------------------------------------------------------------
+# actor-critic MLP, PPO minibatch gradient, Adam  (reference cleanrl/ppo.py:71-123,294-354)
+# --------------------------------------------------------------------------------------------------
+def make_dims(obs_dim: int, act_dim: int, hidden=(512, 256, 128)) -> L.MlpDims:
+    d = L.MlpDims()
+    d.obs_dim, d.act_dim = int(obs_dim), int(act_dim)
+    d.h1, d.h2, d.h3 = (int(h) for h in hidden)
+    d.obs_pad = (int(obs_dim) + 63) // 64 * 64
+    return d
+
+
+def mlp_layout(dims: L.MlpDims) -> L.MlpLayout:
+    layout = L.MlpLayout()
+    L.check(L.load().catb200_mlp_layout(dims, layout), "mlp_layout")
+    return layout
+
+
+def cast_weights(dims, params: torch.Tensor, w16: torch.Tensor) -> None:
+    _f32c(params, "params")
+    L.require_cuda(w16, "w16")
+    L.check(L.load().catb200_mlp_cast_weights(dims, params.data_ptr(), w16.data_ptr(), L.stream()), "mlp_cast_weights")
+
+
+def obs_to_bf16(obs: torch.Tensor, obs_pad: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    _f32c(obs, "obs")
+    rows, dim = obs.numel() // obs.shape[-1], obs.shape[-1]
+    if out is None:
+        out = torch.empty((*obs.shape[:-1], obs_pad), dtype=torch.bfloat16, device=obs.device)
+    if out.dtype != torch.bfloat16 or not out.is_contiguous() or out.numel() != rows * obs_pad:
+        raise ValueError("obs16 output must be a contiguous bf16 tensor [rows, obs_pad]")
+    L.check(L.load().catb200_obs_to_bf16(obs.data_ptr(), rows, dim, obs_pad, out.data_ptr(), L.stream()), "obs_to_bf16")
+    return out
+
+
+def mlp_workspace(dims, rows: int, training: bool, device) -> torch.Tensor:
+    need = L.load().catb200_mlp_workspace_bytes(dims, rows, int(training))
+    if need == 0:
+        raise RuntimeError("unsupported MLP dimensions for the fused kernels (h1, h2 multiples of 128, h3 == 128)")
+    return L.zeros_workspace(need, device)
+
+
+def mlp_act(dims, obs16, params, w16, ws, noise=None, action_in=None, action=None, logprob=None, value=None, mean_out=None):
+    rows = obs16.numel() // dims.obs_pad
+    for t, name in ((noise, "noise"), (action_in, "action_in"), (action, "action"), (logprob, "logprob"), (value, "value"), (mean_out, "mean_out")):  # fmt: skip
+        if t is not None:
+            _f32c(t, name)
+    L.check(
+        L.load().catb200_mlp_act(
+            dims, obs16.data_ptr(), rows, params.data_ptr(), w16.data_ptr(), L.ptr(noise), L.ptr(action_in),
+            L.ptr(action), L.ptr(logprob), L.ptr(value), L.ptr(mean_out), ws.data_ptr(), ws.numel() * 8, L.stream(),
+        ),
+        "mlp_act",
+    )  # fmt: skip
+
+
+def make_hparams(clip_coef=0.2, ent_coef=0.001, vf_coef=2.0, norm_adv=True, clip_vloss=True) -> L.PpoHparams:
+    hp = L.PpoHparams()
+    hp.clip_coef, hp.ent_coef, hp.vf_coef = clip_coef, ent_coef, vf_coef
+    hp.norm_adv, hp.clip_vloss = int(norm_adv), int(clip_vloss)
+    return hp
+
+
+def ppo_minibatch_grad(dims, hp, mb_inds, obs16_all, actions_all, logprobs_all, advantages_all, returns_all, values_all,
+                       norm_stats, params, w16, grads, loss_acc, ws) -> None:  # fmt: skip
+    L.require_cuda(mb_inds, "mb_inds")
+    if mb_inds.dtype != torch.int64 or not mb_inds.is_contiguous():
+        raise TypeError("mb_inds must be a contiguous int64 tensor")
+    for t, name in ((actions_all, "actions"), (logprobs_all, "logprobs"), (advantages_all, "advantages"), (returns_all, "returns"),
+                    (values_all, "values"), (norm_stats, "norm_stats"), (params, "params"), (grads, "grads"), (loss_acc, "loss_acc")):  # fmt: skip
+        _f32c(t, name)
+    L.check(
+        L.load().catb200_ppo_minibatch_grad(
+            dims, hp, mb_inds.numel(), mb_inds.data_ptr(), obs16_all.data_ptr(), actions_all.data_ptr(),
+            logprobs_all.data_ptr(), advantages_all.data_ptr(), returns_all.data_ptr(), values_all.data_ptr(),
+            norm_stats.data_ptr(), params.data_ptr(), w16.data_ptr(), grads.data_ptr(), loss_acc.data_ptr(),
+            ws.data_ptr(), ws.numel() * 8, L.stream(),
+        ),
+        "ppo_minibatch_grad",
+    )  # fmt: skip
+
+
+def adam_step(dims, params, grads, exp_avg, exp_avg_sq, w16, lr_dev, step_dev, opt_ws, max_grad_norm=1.0,
+              betas=(0.9, 0.999), eps=1e-5, grad_scale=1.0, grad_norm_out=None) -> None:  # fmt: skip
+    for t, name in ((params, "params"), (grads, "grads"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq"), (lr_dev, "lr")):
+        _f32c(t, name)
+    L.check(
+        L.load().catb200_adam_step(
+            dims, params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), w16.data_ptr(),
+            lr_dev.data_ptr(), step_dev.data_ptr(), max_grad_norm, betas[0], betas[1], eps, grad_scale,
+            L.ptr(grad_norm_out), opt_ws.data_ptr(), L.stream(),
+        ),
+        "adam_step",
+    )  # fmt: skip

@@ -203,6 +203,92 @@ int catb200_gae(const float* rewards, const float* values, const float* dones, c
                 float* advantages, float* returns, float* value_rms, float* norm_stats, void* workspace,
                 size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Actor-critic MLP + PPO-clip minibatch update  (rows a9, a10: U/cleanrl/ppo.py:71-123,294-354)
+ *
+ * Two separate MLPs obs -> h1 -> h2 -> h3 -> {act_dim, 1} with ELU (ppo.py:78-96) and a state-independent
+ * log-std (ppo.py:97).  Master parameters, gradients and Adam moments are flat fp32 buffers laid out in
+ * the reference's `agent.parameters()` order (critic, actor_mean, actor_logstd) so that the python
+ * `Agent` exposes them as views with the reference's state_dict keys.  The hidden-layer GEMMs run on the
+ * tensor cores with bf16 operands / fp32 accumulation from bf16 copies of the weights that the Adam
+ * kernel refreshes; heads, loss and optimizer math are fp32.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t obs_dim; /* 45                                  */
+  int32_t act_dim; /* 12 (<= 16)                          */
+  int32_t h1, h2, h3; /* 512, 256, 128: multiples of 128  */
+  int32_t obs_pad; /* obs_dim rounded up to 64            */
+} catb200_mlp_dims_t;
+
+/* Offsets (in elements) into the flat fp32 parameter vector and into the bf16 weight-copy buffer.
+ * Index 0 = critic, 1 = actor for every [2] array. */
+typedef struct {
+  int64_t n_params;                 /* total fp32 parameters (377241 for Solo12)                 */
+  int64_t w[2][4], b[2][4];         /* weight / bias offset of layer 0..3 of net 0/1             */
+  int64_t logstd;                   /* offset of actor_logstd [act_dim]                          */
+  int64_t n_w16;                    /* total bf16 elements of the compute copies                 */
+  int64_t w16[2][3];                /* W_l   [out, in_pad] bf16, l = 0..2                        */
+  int64_t wt16[2][3];               /* W_l^T [in, out]     bf16, l = 1..2 (entry 0 unused = -1)  */
+} catb200_mlp_layout_t;
+
+int catb200_mlp_layout(const catb200_mlp_dims_t* dims, catb200_mlp_layout_t* layout);
+
+/* bf16 compute copies (W and W^T of the hidden layers) from the fp32 master parameters. */
+int catb200_mlp_cast_weights(const catb200_mlp_dims_t* dims, const float* params, void* w16, void* stream);
+
+/* fp32 [rows, obs_dim] -> bf16 [rows, obs_pad] (zero padded), the layout the first GEMM reads. */
+int catb200_obs_to_bf16(const float* obs, int64_t rows, int32_t obs_dim, int32_t obs_pad, void* obs16,
+                        void* stream);
+
+/* Bytes of activation scratch for a forward (training = 0) or forward + backward (training = 1) pass
+ * over `rows` samples. */
+size_t catb200_mlp_workspace_bytes(const catb200_mlp_dims_t* dims, int32_t rows, int32_t training);
+
+/*
+ * Agent.get_action_and_value(x) for the rollout (ppo.py:104-119,208-212): both MLPs forward, then
+ *   action = action_in                    if action_in != NULL (evaluate given actions), else
+ *   action = mean + exp(logstd) * noise   (noise ~ N(0,1) supplied by the caller; NULL -> action = mean)
+ *   logprob = sum_j Normal(mean_j, std_j).log_prob(action_j),  value = critic(x)
+ * obs16: bf16 [rows, obs_pad].  Any of action / logprob / value / mean_out may be NULL.
+ */
+int catb200_mlp_act(const catb200_mlp_dims_t* dims, const void* obs16, int32_t rows, const float* params,
+                    const void* w16, const float* noise, const float* action_in, float* action, float* logprob,
+                    float* value, float* mean_out, void* workspace, size_t workspace_bytes, void* stream);
+
+typedef struct {
+  float clip_coef, ent_coef, vf_coef;
+  int32_t norm_adv, clip_vloss;
+} catb200_ppo_hparams_t;
+
+/*
+ * Forward + backward of one PPO minibatch (ppo.py:298-352 up to loss.backward()):
+ * gathers rows mb_inds[0..mb_rows) of the flattened rollout (obs16_all bf16 [B, obs_pad], actions_all
+ * [B, act_dim], logprobs_all / advantages_all / returns_all / values_all [B]), normalises advantages per
+ * minibatch (unbiased std + 1e-8), normalises returns / old values / new values with norm_stats
+ * (see catb200_gae), evaluates the clipped policy loss, clipped value loss and entropy bonus and
+ * accumulates d loss / d params into `grads` (flat fp32, must be zero on entry; catb200_adam_step
+ * leaves it zeroed).  loss_acc[8] += {pg_loss, v_loss, entropy, approx_kl, clipfrac, old_approx_kl,
+ * loss, 1} for this minibatch (running sums the trainer reads once per iteration).
+ */
+int catb200_ppo_minibatch_grad(const catb200_mlp_dims_t* dims, const catb200_ppo_hparams_t* hp, int32_t mb_rows,
+                               const int64_t* mb_inds, const void* obs16_all, const float* actions_all,
+                               const float* logprobs_all, const float* advantages_all, const float* returns_all,
+                               const float* values_all, const float* norm_stats, const float* params,
+                               const void* w16, float* grads, float* loss_acc, void* workspace,
+                               size_t workspace_bytes, void* stream);
+
+/*
+ * clip_grad_norm_(all params, max_grad_norm) + Adam step (ppo.py:353-354; torch.optim.Adam with
+ * eps, betas, no weight decay), then zero `grads` and refresh the bf16 weight copies.
+ * grads are first multiplied by grad_scale (1 / world_size after a sum-allreduce).
+ * lr_dev: device float; step_dev: device int32 step counter (incremented here).
+ * opt_ws: 64 bytes of zero-initialised device scratch.
+ */
+int catb200_adam_step(const catb200_mlp_dims_t* dims, float* params, float* grads, float* exp_avg,
+                      float* exp_avg_sq, void* w16, const float* lr_dev, int32_t* step_dev, float max_grad_norm,
+                      float beta1, float beta2, float eps, float grad_scale, float* grad_norm_out, void* opt_ws,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,243 @@
+"""GPU parity of the actor-critic MLP kernels, the PPO minibatch gradient and the Adam step.
+
+The tensor-core path computes with bf16 operands / fp32 accumulation (the reference's own GPU numerics
+are TF32 matmuls, scripts/clean_rl/train.py:86-87), so it is compared
+  (a) tightly against the fp32 oracle with bf16 rounding emulated at the points the kernels round, and
+  (b) loosely against the plain fp32 oracle (tolerances stated at each assert)."""
+
+import math
+
+import pytest
+import torch
+
+from constraints_as_terminations_b200 import ops
+from oracle import ppo_oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+OBS, ACT = 45, 12
+
+
+def flat_params(agent: ppo_oracle.AgentOracle, layout) -> torch.Tensor:
+    """Oracle parameters -> the flat fp32 vector in libcatb200's layout (== reference parameter order)."""
+    flat = torch.zeros(layout.n_params)
+    for z, net in enumerate((agent.critic, agent.actor_mean)):
+        for l, idx in enumerate((0, 2, 4, 6)):
+            w, b = net[idx].weight.detach(), net[idx].bias.detach()
+            flat[layout.w[z][l] : layout.w[z][l] + w.numel()] = w.reshape(-1)
+            flat[layout.b[z][l] : layout.b[z][l] + b.numel()] = b
+    flat[layout.logstd : layout.logstd + ACT] = agent.actor_logstd.detach().reshape(-1)
+    return flat
+
+
+def flat_grads(agent, layout) -> torch.Tensor:
+    flat = torch.zeros(layout.n_params)
+    for z, net in enumerate((agent.critic, agent.actor_mean)):
+        for l, idx in enumerate((0, 2, 4, 6)):
+            w, b = net[idx].weight.grad, net[idx].bias.grad
+            flat[layout.w[z][l] : layout.w[z][l] + w.numel()] = w.reshape(-1)
+            flat[layout.b[z][l] : layout.b[z][l] + b.numel()] = b
+    flat[layout.logstd : layout.logstd + ACT] = agent.actor_logstd.grad.reshape(-1)
+    return flat
+
+
+def test_layout_follows_reference_parameter_order():
+    agent = ppo_oracle.AgentOracle(OBS, ACT)
+    layout = ops.mlp_layout(ops.make_dims(OBS, ACT))
+    # reference registration order: critic.*, actor_mean.*, actor_logstd (ppo.py:78-97) -> agent.parameters()
+    want = torch.cat([p.detach().reshape(-1) for p in list(agent.critic.parameters()) + list(agent.actor_mean.parameters()) + [agent.actor_logstd]])
+    assert layout.n_params == want.numel() == 377241
+    assert torch.equal(flat_params(agent, layout), want)
+
+
+def bf16r(x):  # round to bf16, keep fp32 storage, straight-through gradient
+    return x + (x.to(torch.bfloat16).float() - x).detach()
+
+
+def emulated_forward(agent, obs):
+    """fp32 oracle with bf16 rounding where the kernels round: inputs, hidden weights, hidden activations."""
+    outs = []
+    for net in (agent.critic, agent.actor_mean):
+        h = bf16r(obs)
+        for idx in (0, 2, 4):
+            h = bf16r(torch.nn.functional.elu(h @ bf16r(net[idx].weight).T + net[idx].bias))
+        outs.append(h @ net[6].weight.T + net[6].bias)
+    return outs[1], outs[0]  # action mean, value
+
+
+def make_agent(seed=0, scale_heads=True):
+    torch.manual_seed(seed)
+    agent = ppo_oracle.AgentOracle(OBS, ACT)
+    with torch.no_grad():
+        agent.actor_logstd.copy_(torch.linspace(-0.5, 0.3, ACT).reshape(1, ACT))
+        for net in (agent.critic, agent.actor_mean):
+            for idx in (0, 2, 4, 6):
+                net[idx].bias.normal_(0, 0.1)
+        if scale_heads:
+            agent.actor_mean[6].weight.mul_(30.0)  # std=0.01 init makes the mean ~0: give it some signal
+    return agent
+
+
+def device_agent(agent):
+    dims = ops.make_dims(OBS, ACT)
+    layout = ops.mlp_layout(dims)
+    params = flat_params(agent, layout).to(DEV)
+    w16 = torch.zeros(layout.n_w16, dtype=torch.bfloat16, device=DEV)
+    ops.cast_weights(dims, params, w16)
+    return dims, layout, params, w16
+
+
+@pytest.mark.parametrize("rows", [4096, 1000, 1, 129])
+def test_rollout_forward_matches_oracle(rows):
+    agent = make_agent()
+    dims, layout, params, w16 = device_agent(agent)
+    g = torch.Generator().manual_seed(rows)
+    obs = torch.randn(rows, OBS, generator=g)
+    noise = torch.randn(rows, ACT, generator=g)
+    obs16 = ops.obs_to_bf16(obs.to(DEV), dims.obs_pad)
+    assert torch.equal(obs16[:, :OBS].float().cpu(), obs.to(torch.bfloat16).float()) and float(obs16[:, OBS:].abs().sum()) == 0
+    ws = ops.mlp_workspace(dims, rows, False, DEV)
+    action, logprob, value, mean = (torch.empty(rows, ACT, device=DEV), torch.empty(rows, device=DEV), torch.empty(rows, device=DEV), torch.empty(rows, ACT, device=DEV))
+    ops.mlp_act(dims, obs16, params, w16, ws, noise=noise.to(DEV), action=action, logprob=logprob, value=value, mean_out=mean)
+    with torch.no_grad():
+        e_mean, e_value = emulated_forward(agent, obs)
+        f_action, f_logp, f_value = agent.act(obs, noise)
+    # (a) emulated-rounding oracle: the accumulation order differs, which now and then flips the bf16
+    # rounding of a hidden activation (one flip = 2^-8 relative on that activation) -> 1e-2 on O(1) outputs,
+    # and a far smaller error on average
+    torch.testing.assert_close(mean.cpu(), e_mean, rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(value.cpu(), e_value.flatten(), rtol=1e-2, atol=1e-2)
+    assert float((value.cpu() - e_value.flatten()).abs().mean()) < 5e-4
+    # action / log-prob are exact functions of (mean, noise): check them against the device mean in fp32
+    std = agent.actor_logstd.detach().exp()
+    want_action = mean.cpu() + std * noise
+    torch.testing.assert_close(action.cpu(), want_action, rtol=1e-6, atol=1e-6)
+    want_logp = (-((action.cpu() - mean.cpu()) ** 2) / (2 * std**2) - agent.actor_logstd.detach() - math.log(math.sqrt(2 * math.pi))).sum(1)
+    torch.testing.assert_close(logprob.cpu(), want_logp, rtol=1e-5, atol=1e-5)
+    # (b) plain fp32 oracle: bf16 operand rounding -> 3e-2 absolute on O(1) outputs
+    torch.testing.assert_close(value.cpu(), f_value.flatten(), rtol=3e-2, atol=3e-2)
+    torch.testing.assert_close(action.cpu(), f_action, rtol=3e-2, atol=3e-2)
+    # evaluating given actions (ppo.py:110) reproduces the log-prob
+    lp2 = torch.empty(rows, device=DEV)
+    ops.mlp_act(dims, obs16, params, w16, ws, action_in=action, logprob=lp2)
+    torch.testing.assert_close(lp2, logprob, rtol=1e-6, atol=1e-6)
+    # deterministic action == mean
+    det = torch.empty(rows, ACT, device=DEV)
+    ops.mlp_act(dims, obs16, params, w16, ws, action=det)
+    assert torch.equal(det, mean)
+
+
+def _minibatch(agent, B, M, seed):
+    g = torch.Generator().manual_seed(seed)
+    obs = torch.randn(B, OBS, generator=g)
+    noise = torch.randn(B, ACT, generator=g)
+    with torch.no_grad():
+        actions, logp, values = agent.act(obs.to(torch.bfloat16).float(), noise)
+        logp = logp + 0.3 * torch.randn(B, generator=g)  # old policy differs: exercises both clip branches
+    adv = torch.randn(B, generator=g) * 2.0 + 0.5
+    values = values.flatten() + 0.2 * torch.randn(B, generator=g)
+    returns = values + adv
+    norm_stats = torch.tensor([0.1, 1.3, 0.15, 1.7])
+    idx = torch.randperm(B, generator=g)[:M]
+    return obs, actions, logp, adv, returns, values, norm_stats, idx
+
+
+@pytest.mark.parametrize("B,M", [(24 * 1024, 16384), (3000, 1000), (512, 512)])
+def test_minibatch_gradient_matches_oracle(B, M):
+    agent = make_agent(seed=1)
+    dims, layout, params, w16 = device_agent(agent)
+    obs, actions, logp, adv, returns, values, norm_stats, idx = _minibatch(agent, B, M, seed=B + M)
+    obs16 = ops.obs_to_bf16(obs.to(DEV), dims.obs_pad)
+    grads = torch.zeros(layout.n_params, device=DEV)
+    loss_acc = torch.zeros(8, device=DEV)
+    ws = ops.mlp_workspace(dims, M, True, DEV)
+    hp = ops.make_hparams()
+    ops.ppo_minibatch_grad(dims, hp, idx.to(DEV), obs16, actions.to(DEV), logp.to(DEV), adv.to(DEV), returns.to(DEV),
+                           values.to(DEV), norm_stats.to(DEV), params, w16, grads, loss_acc, ws)  # fmt: skip
+    torch.cuda.synchronize()
+    # oracle: value-normalised returns / values as the reference feeds them (ppo.py:287-288)
+    val_n = (values - norm_stats[0]) / torch.sqrt(norm_stats[1] + 1e-8)
+    ret_n = (returns - norm_stats[2]) / torch.sqrt(norm_stats[3] + 1e-8)
+    value_rms = {"mean": norm_stats[2], "var": norm_stats[3]}
+
+    class Emulated(ppo_oracle.AgentOracle):
+        def evaluate(self, o, a):
+            mean, value = emulated_forward(self, o)
+            std = torch.exp(self.actor_logstd.expand_as(mean))
+            lp = -((a - mean) ** 2) / (2 * std**2) - std.log() - math.log(math.sqrt(2 * math.pi))
+            ent = 0.5 + 0.5 * math.log(2 * math.pi) + std.log()
+            return lp.sum(1), ent.sum(1), value
+
+    results = {}
+    for name, cls in (("fp32", ppo_oracle.AgentOracle), ("emulated", Emulated)):
+        a = cls(OBS, ACT)
+        a.load_state_dict(agent.state_dict())
+        loss, info = ppo_oracle.ppo_minibatch_loss(a, value_rms, obs[idx], actions[idx], logp[idx], adv[idx], ret_n[idx], val_n[idx])
+        loss.backward()
+        results[name] = (float(loss), info, flat_grads(a, layout))
+    got = grads.cpu()
+    acc = loss_acc.cpu()
+    for name, (loss, info, want) in results.items():
+        tol = 2e-3 if name == "emulated" else 2e-2
+        assert acc[7] == 1.0
+        assert float(acc[0]) == pytest.approx(float(info["pg_loss"]), rel=tol, abs=tol)
+        assert float(acc[1]) == pytest.approx(float(info["v_loss"]), rel=tol, abs=tol)
+        assert float(acc[2]) == pytest.approx(float(info["entropy"]), rel=1e-5)
+        assert float(acc[3]) == pytest.approx(float(info["approx_kl"]), rel=tol, abs=tol)
+        assert float(acc[4]) == pytest.approx(float(info["clipfrac"]), abs=5e-3)
+        assert float(acc[6]) == pytest.approx(loss, rel=tol, abs=tol)
+        # whole gradient and every parameter tensor: relative Frobenius error
+        gtol = 1.5e-2 if name == "emulated" else 6e-2
+        rel = float((got - want).norm() / want.norm())
+        assert rel < gtol, f"{name}: relative gradient error {rel:.3e}"
+        for z in range(2):
+            for l in range(4):
+                for kind, off in (("w", layout.w[z][l]), ("b", layout.b[z][l])):
+                    nxt = sorted(o for o in [*layout.w[0], *layout.b[0], *layout.w[1], *layout.b[1], layout.logstd, layout.n_params] if o > off)[0]
+                    a_, b_ = got[off:nxt], want[off:nxt]
+                    r = float((a_ - b_).norm() / (b_.norm() + 1e-12))
+                    assert r < 2.5 * gtol, f"{name}: net {z} layer {l} {kind}: relative error {r:.3e}"
+        ls = slice(layout.logstd, layout.logstd + ACT)
+        # log-std gradient: a sum of mixed-sign per-sample terms (cancellation) -> judged norm-wise
+        r = float((got[ls] - want[ls]).norm() / want[ls].norm())
+        assert r < 5 * gtol, f"{name}: log-std gradient relative error {r:.3e}"
+
+
+def test_adam_step_matches_torch():
+    agent = make_agent(seed=2)
+    dims, layout, params, w16 = device_agent(agent)
+    n = layout.n_params
+    g = torch.Generator().manual_seed(0)
+    ref_p = torch.nn.Parameter(params.cpu().clone())
+    opt = torch.optim.Adam([ref_p], lr=3e-4, eps=1e-5)
+    m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    lr = torch.tensor(3e-4, device=DEV)
+    step = torch.zeros(1, dtype=torch.int32, device=DEV)
+    opt_ws = torch.zeros(8, dtype=torch.int64, device=DEV)
+    norm_out = torch.zeros(1, device=DEV)
+    for it in range(4):
+        grad = torch.randn(n, generator=g) * (0.001 if it == 1 else 0.05)  # it==1: norm below the clip threshold
+        grads = grad.to(DEV).clone()
+        ops.adam_step(dims, params, grads, m, v, w16, lr, step, opt_ws, max_grad_norm=1.0, eps=1e-5, grad_norm_out=norm_out)
+        ref_p.grad = grad.clone()
+        total = torch.nn.utils.clip_grad_norm_([ref_p], 1.0)
+        opt.step()
+        assert float(norm_out) == pytest.approx(float(total), rel=1e-5)
+        assert float(grads.abs().sum()) == 0.0  # gradient buffer zeroed for the next minibatch
+        torch.testing.assert_close(params.cpu(), ref_p.detach(), rtol=1e-5, atol=1e-7)
+    assert int(step) == 4
+    # bf16 compute copies refreshed: W and W^T of a hidden layer
+    w2 = params[layout.w[1][1] : layout.w[1][1] + 256 * 512].view(256, 512)
+    got_w = w16[layout.w16[1][1] : layout.w16[1][1] + 256 * 512].view(256, 512)
+    got_wt = w16[layout.wt16[1][1] : layout.wt16[1][1] + 256 * 512].view(512, 256)
+    assert torch.equal(got_w, w2.to(torch.bfloat16)) and torch.equal(got_wt, w2.T.to(torch.bfloat16))
+    w1 = params[layout.w[0][0] : layout.w[0][0] + 512 * 45].view(512, 45)
+    got_w1 = w16[layout.w16[0][0] : layout.w16[0][0] + 512 * 64].view(512, 64)
+    assert torch.equal(got_w1[:, :45], w1.to(torch.bfloat16)) and float(got_w1[:, 45:].abs().sum()) == 0.0
+    # grad_scale (1/world after a sum-allreduce) is equivalent to scaling the gradient
+    p2, m2, v2 = params.clone(), m.clone(), v.clone()
+    step2 = step.clone()
+    grad = torch.randn(n, generator=g).to(DEV) * 0.05
+    ops.adam_step(dims, params, (grad * 4).clone(), m, v, w16, lr, step, opt_ws, grad_scale=0.25)
+    ops.adam_step(dims, p2, grad.clone(), m2, v2, w16, lr, step2, opt_ws, grad_scale=1.0)
+    torch.testing.assert_close(params, p2, rtol=1e-6, atol=1e-8)
