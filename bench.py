@@ -1,0 +1,441 @@
+#!/usr/bin/env python
+"""Benchmark of the CaT PPO hot path (BASELINE.json metric: env-steps/sec, Solo12 CaT-Flat @4096 envs/GPU).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5                     # this repo's CUDA path (1 GPU)
+    torchrun --nproc-per-node N ... bench.py --gpus N --steps K --warmup W   # one rank per GPU, NCCL
+    python bench.py --impl reference --steps K --warmup W              # reference arm: CPU oracle port
+
+A "step" is one full PPO iteration on the trainer side of Isaac-Velocity-CaT-Flat-Solo12-v0 with the
+reference's hyper-parameters: 24 env steps x num_envs (policy forward + sampling, the 13-term constraint
+manager with reward / dones epilogue, rollout append, running observation normalisation), then GAE, value
+normalisation and 5 epochs x 6 minibatches of PPO-clip update (forward, backward, clip, Adam) -- nothing
+skipped.  Isaac Sim is not installed here, so physics is replaced by a synthetic Solo12 state source with
+the same tensors (`constraints_as_terminations_b200/synthetic_env.py`); the number is trainer-side
+env-steps/s and says so in `data`.
+
+Prints ONE JSON line (rank 0).  `value` has the env state already resident in HBM; `e2e` feeds every env
+step's state from pinned host memory (H2D inside the timed region) and reads the losses back (D2H).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p.get("bf16_tflops_sustained"), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )  # fmt: skip
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for name, val in zip(names, r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        mx = next((float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()), None)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# this repo's arm
+# ----------------------------------------------------------------------------------------------------------
+def make_trainer(num_envs, device, seed, host_fed=False, pool=8, graphs=True):
+    from constraints_as_terminations_b200 import PPOTrainer, solo12_flat_ppo_cfg
+    from constraints_as_terminations_b200 import synthetic_env as se
+
+    cls = HostFedEnv if host_fed else se.SyntheticSolo12Env
+    env = cls(num_envs, device=device, seed=seed, pool=pool, constraints_cfg=se.solo12_constraints_cfg())
+    env.load_managers()
+    cfg = solo12_flat_ppo_cfg(logger=None)
+    torch.manual_seed(cfg.seed + seed)
+    trainer = PPOTrainer(env, cfg, device=device, use_graphs=graphs)
+    trainer.start()
+    return env, trainer
+
+
+def _host_fed_env_cls():
+    from constraints_as_terminations_b200 import synthetic_env as se
+
+    class HostFed(se.SyntheticSolo12Env):
+        """Same env, but every step's state arrives from pinned host memory (the e2e leg)."""
+
+        def __init__(self, num_envs, device, seed, pool, constraints_cfg):
+            super().__init__(num_envs, device=device, seed=seed, pool=pool, constraints_cfg=constraints_cfg)
+            self._host_pool = [{k: v.cpu().pin_memory() for k, v in s.items()} for s in self._pool]
+            self._staging = {k: torch.empty_like(v) for k, v in self._pool[0].items()}
+            self.h2d_bytes = sum(v.numel() * v.element_size() for v in self._host_pool[0].values())
+            self.load_state(self._staging)
+
+        def reset(self):
+            self._cursor = -1
+            self._advance()
+            return self.obs_buf, {}
+
+        def _advance(self):
+            self._cursor = (self._cursor + 1) % len(self._host_pool)
+            src = self._host_pool[self._cursor]
+            for k, dst in self._staging.items():
+                dst.copy_(src[k], non_blocking=True)
+
+    return HostFed
+
+
+HostFedEnv = None
+
+
+def timed_iterations(trainer, steps, warmup, world, device, read_losses):
+    for _ in range(warmup):
+        trainer.train_iteration()
+        if read_losses:
+            trainer.losses()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    launches0 = trainer.kernel_launches()
+    sampler = ClockSampler(device.index or 0)
+    sampler.start()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    start.record()
+    for _ in range(steps):
+        trainer.train_iteration()
+        if read_losses:
+            trainer.losses()  # device -> host read of the step's result
+    end.record()
+    torch.cuda.synchronize()
+    ms = start.elapsed_time(end)
+    if world > 1:
+        torch.distributed.barrier()
+        t = torch.tensor([ms], device=device)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t)
+    clocks = sampler.stop()
+    return ms, trainer.kernel_launches() - launches0, clocks
+
+
+def kernel_rooflines(device, num_envs, peaks):
+    """Per-kernel achieved bandwidth / throughput, timed alone with CUDA events on the launch stream,
+    L2 flushed between timed launches (a 256 MiB write)."""
+    from constraints_as_terminations_b200 import ops
+    from constraints_as_terminations_b200 import synthetic_env as se
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+    out = {}
+
+    def time_kernel(fn, reps=20):
+        for _ in range(3):
+            fn()
+        times = []
+        for _ in range(reps):
+            flush.fill_(1)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            torch.cuda.synchronize()
+            times.append(s.elapsed_time(e) * 1e-3)
+        times.sort()
+        return sum(times[: max(1, len(times) // 2)]) / max(1, len(times) // 2)  # mean of the faster half
+
+    T = 24
+    for n in sorted({num_envs, 65536, 1 << 20}):
+        # GAE: 24*T*N + 12*N algorithmic bytes
+        rewards, values = torch.rand(T, n, device=device), torch.randn(T, n, device=device)
+        dones, tdones = torch.rand(T + 1, n, device=device), torch.zeros(T + 1, n, device=device)
+        nv = torch.randn(n, device=device)
+        adv, ret = torch.empty_like(rewards), torch.empty_like(rewards)
+        sec = time_kernel(lambda: ops.gae(rewards, values, dones, tdones, nv, 0.99, 0.95, advantages=adv, returns=ret))
+        nbytes = 24 * T * n + 12 * n
+        out[f"gae@{n}"] = {"bound": "hbm", "achieved": nbytes / sec / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": nbytes / sec / 1e9 / peaks["hbm_gbs"], "us": sec * 1e6, "bytes": nbytes}
+        del rewards, values, dones, tdones, adv, ret
+        # fused constraint step (cat_eval + cat_apply): 940 B/env-step algorithmic
+        env = se.SyntheticSolo12Env(n, device=device, seed=1, pool=1, constraints_cfg=se.solo12_constraints_cfg())
+        mgr = env.load_managers()
+        reset = torch.zeros(n, dtype=torch.bool, device=device)
+        sec = time_kernel(lambda: mgr.compute_step(env._raw_reward, reset))
+        nbytes = 940 * n
+        out[f"cat_step@{n}"] = {"bound": "hbm", "achieved": nbytes / sec / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": nbytes / sec / 1e9 / peaks["hbm_gbs"], "us": sec * 1e6, "bytes": nbytes, "launches": 2}
+        del env, mgr
+    return out
+
+
+def run_ours(args):
+    global HostFedEnv
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=device)
+    import __graft_entry__
+
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        torch.distributed.barrier()
+    HostFedEnv = _host_fed_env_cls()
+    peaks = load_peaks()
+    N, T = args.envs, 24
+
+    env, trainer = make_trainer(N, device, seed=rank, graphs=not args.no_graphs)
+    ms, launches, clocks = timed_iterations(trainer, args.steps, args.warmup, world, device, read_losses=False)
+    value = N * T * world * args.steps / (ms * 1e-3)
+    losses = trainer.losses()
+    working_set = sum(t.numel() * t.element_size() for t in (trainer.obs, trainer.obs16, trainer.actions, trainer.rewards, trainer.dones, trainer.values, trainer.advantages, trainer.returns, trainer.train_ws))
+    del env, trainer
+    torch.cuda.empty_cache()
+
+    # ---- e2e: host-resident env state, H2D each env step, D2H of the losses each iteration
+    env, trainer = make_trainer(N, device, seed=rank, host_fed=True, graphs=not args.no_graphs)
+    e_steps = max(3, args.steps // 2)
+    e_ms, _, _ = timed_iterations(trainer, e_steps, max(3, args.warmup // 2), world, device, read_losses=True)
+    e2e = {
+        "value": N * T * world * e_steps / (e_ms * 1e-3),
+        "unit": UNIT,
+        "h2d_bytes_per_step": env.h2d_bytes * T,
+        "d2h_bytes_per_step": 32,
+        "ms_per_step": e_ms / e_steps,
+    }
+    del env, trainer
+    torch.cuda.empty_cache()
+
+    line = None
+    if rank == 0:
+        roof = kernel_rooflines(device, N, peaks)
+        cpu = cpu_baseline(N, sample_steps=4, sample_minibatches=2)
+        main = dict(roof[f"gae@{N}"])
+        main.update({"kernel": "gae_kernel", "traffic": None, "peak_source": peaks["source"],
+                     "note": f"timed alone, L2 flushed; {main['bytes']/1e6:.2f} MB per launch is launch-latency bound at {N} envs, see the 65536 / 1M-env entries in `rooflines`"})
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32 (CaT/GAE/moments/loss/Adam), bf16 operands + fp32 accumulate (hidden-layer GEMMs)",
+            "data": "synthetic Solo12 state (no Isaac Sim physics): trainer-side env-steps/s",
+            "config": {
+                "workload": "Isaac-Velocity-CaT-Flat-Solo12-v0 trainer side, 4096 envs/GPU, CleanRL PPO cfg (T=24, 5 epochs x 6 minibatches of 16384)",
+                "envs_per_gpu": N, "num_steps": T, "constraint_terms": 13, "constraint_columns": 78,
+                "minibatch": 16384, "epochs": 5, "parallelism": f"dp{world} (one env shard per GPU, 1 gradient allreduce per optimizer step)",
+                "l2": f"per-step working set {working_set/1e6:.0f} MB > 126 MB L2 (inputs larger than L2)",
+                "cuda_graphs": not args.no_graphs and world == 1,
+            },
+            "e2e": e2e,
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": main,
+            "rooflines": roof,
+            "cpu_baseline": cpu,
+            "losses": losses,
+        }  # fmt: skip
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path, timed on the host cores
+# ----------------------------------------------------------------------------------------------------------
+class CpuReferencePath:
+    """The reference's CPU code path restated by oracle/ (the reference itself is Python on Isaac Lab and
+    cannot travel to the GPU box): per env step the 13-term ConstraintManager + reward/dones, Agent
+    sampling, obs RunningMeanStd; per update GAE, value normalisation and PPO-clip minibatches with Adam."""
+
+    def __init__(self, num_envs, seed=0):
+        from constraints_as_terminations_b200 import synthetic_env as se
+        from oracle import cat_oracle, ppo_oracle
+
+        self.se, self.cat_oracle, self.po = se, cat_oracle, ppo_oracle
+        torch.manual_seed(seed)
+        self.N, self.T = num_envs, 24
+        self.env = se.SyntheticSolo12Env(num_envs, device="cpu", seed=seed, pool=4)
+        cfg = se.solo12_constraints_cfg()
+        self.mgr = cat_oracle.ManagerOracle(self.env, cat_oracle.terms_from_cfg(cfg, resolve_scene=self.env.scene))
+        self.agent = ppo_oracle.AgentOracle(se.OBS_DIM, se.ACT_DIM)
+        params = list(self.agent.critic.parameters()) + list(self.agent.actor_mean.parameters()) + [self.agent.actor_logstd]
+        self.params = params
+        self.opt = torch.optim.Adam(params, lr=3e-4, eps=1e-5)
+        self.obs_rms = ppo_oracle.rms_init((se.OBS_DIM,))
+        self.value_rms = ppo_oracle.rms_init(())
+        N, T = self.N, self.T
+        self.obs = torch.zeros(T, N, se.OBS_DIM)
+        self.actions = torch.zeros(T, N, se.ACT_DIM)
+        self.logprobs, self.rewards, self.values = torch.zeros(T, N), torch.zeros(T, N), torch.zeros(T, N)
+        self.dones, self.true_dones = torch.zeros(T + 1, N), torch.zeros(T + 1, N)
+        self.next_obs = self._norm(self.env.obs_buf["policy"])
+
+    def _norm(self, raw):
+        self.obs_rms = self.po.rms_update(self.obs_rms, raw)
+        return self.po.rms_normalize(self.obs_rms, raw)
+
+    def env_step(self, t):
+        env = self.env
+        self.obs[t] = self.next_obs
+        with torch.no_grad():
+            action, logp, value = self.agent.act(self.next_obs, torch.randn(self.N, self.se.ACT_DIM))
+        self.actions[t], self.logprobs[t], self.values[t] = action, logp, value.flatten()
+        env._advance()
+        env.episode_length_buf += 1
+        reset = env.episode_length_buf >= env.max_episode_length
+        cstr = self.mgr.compute()
+        reward, dones = self.cat_oracle.step_epilogue(env._raw_reward, cstr, reset)
+        env.episode_length_buf[reset] = 0
+        self.rewards[t], self.dones[t + 1], self.true_dones[t + 1] = reward, dones, reset.float()
+        self.next_obs = self._norm(env.obs_buf["policy"])
+
+    def gae(self):
+        with torch.no_grad():
+            nv = self.agent.critic(self.next_obs).reshape(1, -1)
+            adv, ret = self.po.gae(self.rewards, self.values, self.dones[:-1], self.true_dones[:-1], nv, self.dones[-1], self.true_dones[-1])
+            self.value_rms, self.b_values, self.b_returns = self.po.value_normalisation(self.value_rms, self.values.reshape(-1), ret.reshape(-1))
+        self.b_adv = adv.reshape(-1)
+
+    def minibatch(self, idx):
+        B = self.N * self.T
+        loss, _ = self.po.ppo_minibatch_loss(
+            self.agent, self.value_rms, self.obs.reshape(B, -1)[idx], self.actions.reshape(B, -1)[idx], self.logprobs.reshape(-1)[idx],
+            self.b_adv[idx], self.b_returns[idx], self.b_values[idx],
+        )  # fmt: skip
+        self.opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(self.params, 1.0)
+        self.opt.step()
+
+
+def cpu_baseline(num_envs, sample_steps=4, sample_minibatches=2):
+    """Bounded sample of the same workload on the host cores; extrapolated to a full iteration."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ref = CpuReferencePath(num_envs)
+    ref.env_step(0)  # warm-up
+    t0 = time.perf_counter()
+    for t in range(sample_steps):
+        ref.env_step(t)
+    t_step = (time.perf_counter() - t0) / sample_steps
+    t0 = time.perf_counter()
+    ref.gae()
+    t_gae = time.perf_counter() - t0
+    perm = torch.randperm(num_envs * 24)
+    mb = min(16384, num_envs * 24)
+    ref.minibatch(perm[:mb])  # warm-up
+    t0 = time.perf_counter()
+    for i in range(sample_minibatches):
+        ref.minibatch(perm[i * mb : (i + 1) * mb] if (i + 1) * mb <= perm.numel() else perm[:mb])
+    t_mb = (time.perf_counter() - t0) / sample_minibatches
+    n_mb = 5 * max(1, num_envs * 24 // mb)
+    t_iter = 24 * t_step + t_gae + n_mb * t_mb
+    return {
+        "value": num_envs * 24 / t_iter, "unit": UNIT, "cores": cores, "kind": "port",
+        "sample": f"{sample_steps} env steps ({t_step*1e3:.1f} ms each) + 1 GAE ({t_gae*1e3:.1f} ms) + {sample_minibatches} minibatches of {mb} ({t_mb*1e3:.1f} ms each), extrapolated to 24 steps + GAE + {n_mb} minibatches = {t_iter:.2f} s per iteration; torch CPU, {cores} threads",
+    }  # fmt: skip
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port) on this box's host cores.  Each step is a
+    bounded sample of one iteration: the full 24-step rollout + GAE + one of the five epochs (6 minibatches);
+    the other four epochs repeat identical work and are accounted for by scaling that epoch's time."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    N, T = args.envs, 24
+    ref = CpuReferencePath(N)
+    mb = min(16384, N * T)
+    n_mb_epoch = max(1, N * T // mb)
+
+    def one_step():
+        t0 = time.perf_counter()
+        for t in range(T):
+            ref.env_step(t)
+        ref.gae()
+        t1 = time.perf_counter()
+        perm = torch.randperm(N * T)
+        for i in range(n_mb_epoch):
+            ref.minibatch(perm[i * mb : (i + 1) * mb])
+        t2 = time.perf_counter()
+        return (t1 - t0) + 5 * (t2 - t1)
+
+    for _ in range(args.warmup):
+        one_step()
+    total = sum(one_step() for _ in range(args.steps))
+    value = N * T * args.steps / total
+    sample = f"per step: full 24-step rollout + GAE + 1 of 5 epochs ({n_mb_epoch} minibatches of {mb}) measured, epoch time x5; torch CPU oracle port, {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic Solo12 state (no Isaac Sim physics): trainer-side env-steps/s",
+        "config": {"workload": "Isaac-Velocity-CaT-Flat-Solo12-v0 trainer side, 4096 envs, CleanRL PPO cfg (T=24, 5 epochs x 6 minibatches of 16384)", "envs_per_gpu": N},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))  # fmt: skip
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
+    ap.add_argument("--no-graphs", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

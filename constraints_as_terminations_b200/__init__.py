@@ -15,6 +15,8 @@ The arithmetic runs in hand-written sm_100a CUDA kernels behind the C ABI of `in
 from . import constraints, curriculums
 from .constraint_manager import CaT, ConstraintManager, ConstraintsManager
 from .manager_constraint_cfg import ConstraintTerm, ConstraintTermCfg
+from .ppo import PPO, Agent, PPOTrainer, RunningMeanStd
+from .rl_cfg import CleanRlPpoActorCriticCfg, solo12_flat_ppo_cfg
 
 __all__ = [
     "CaT",
@@ -24,4 +26,10 @@ __all__ = [
     "ConstraintTermCfg",
     "constraints",
     "curriculums",
+    "PPO",
+    "Agent",
+    "PPOTrainer",
+    "RunningMeanStd",
+    "CleanRlPpoActorCriticCfg",
+    "solo12_flat_ppo_cfg",
 ]

@@ -186,6 +186,7 @@ _SZ = C.c_size_t
 # name -> (restype, argtypes); one entry per symbol declared in include/catb200.h
 SIGNATURES = {
     "catb200_version": (C.c_int, []),
+    "catb200_launch_count": (C.c_uint64, []),
     "catb200_error_string": (C.c_char_p, [C.c_int]),
     "catb200_cat_plan_finalize": (C.c_int, [C.POINTER(Plan)]),
     "catb200_cat_workspace_bytes": (_SZ, [_I32, _I32]),
@@ -235,6 +236,10 @@ def load():
             fn.argtypes = argtypes
         _lib = lib
     return _lib
+
+
+def launch_count() -> int:
+    return int(load().catb200_launch_count())
 
 
 def check(status: int, what: str = "") -> None:

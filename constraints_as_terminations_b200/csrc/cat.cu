@@ -24,6 +24,7 @@
 namespace catb200 {
 
 thread_local cudaError_t g_last_cuda_error = cudaSuccess;
+unsigned long long g_launch_count = 0;
 
 constexpr int kTile = 32;          // envs per CTA in the eval kernel (one per lane)
 constexpr int kEvalWarps = 4;      // warps per CTA; warp w owns columns w, w+4, ...
@@ -341,6 +342,8 @@ using namespace catb200;
 extern "C" {
 
 int catb200_version(void) { return CATB200_VERSION; }
+
+uint64_t catb200_launch_count(void) { return g_launch_count; }
 
 const char* catb200_error_string(int status) {
   switch (status) {

@@ -22,7 +22,13 @@ inline int cuda_status(cudaError_t e) {
     if (_e != cudaSuccess) return ::catb200::cuda_status(_e); \
   } while (0)
 
-#define CATB200_LAUNCH_CHECK() CATB200_CUDA_TRY(cudaPeekAtLastError())
+// every kernel launch of the library passes through here; the count backs bench.py's `gpu_launches`
+extern unsigned long long g_launch_count;
+#define CATB200_LAUNCH_CHECK()                     \
+  do {                                             \
+    ++::catb200::g_launch_count;                   \
+    CATB200_CUDA_TRY(cudaPeekAtLastError());       \
+  } while (0)
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

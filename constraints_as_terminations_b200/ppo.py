@@ -1,0 +1,474 @@
+"""CleanRL-style PPO trainer of the reference, re-built on the libcatb200 kernels.
+
+Public names and behaviour follow `exts/cat_envs/cat_envs/tasks/utils/cleanrl/ppo.py`:
+
+    RunningMeanStd(shape, epsilon)            :12-45   buffers running_mean / running_var / count
+    Agent(envs)                               :71-123  critic / actor_mean / actor_logstd / obs_rms / value_rms,
+                                                       get_value, get_action_and_value, forward; identical
+                                                       state_dict keys (checkpoints interchange with play.py)
+    PPO(envs, ppo_cfg, run_path)              :126-372 the training loop (float `dones`, time-out aware GAE)
+
+Execution model (one process per GPU):
+  rollout step  : pre  = [randn] -> 3 batched GEMM launches -> head kernel (sample, log-prob, value)
+                  env.step(action)   (Isaac Lab + the fused ConstraintManager kernels)
+                  post = append -> running moments -> normalise (+bf16 copy)
+  update        : 1 GAE(+value statistics) launch, then per minibatch `catb200_ppo_minibatch_grad`
+                  (gather, 3 fwd GEMMs, head/loss, 3 wgrad + 2 dgrad GEMMs, reduce) [-> NCCL allreduce of the
+                  flat 1.5 MB gradient] -> `catb200_adam_step` (norm, clip, Adam, bf16 weight refresh)
+No tensor math runs in python; there is no eager fallback (CPU tensors raise).
+"""
+
+from __future__ import annotations
+
+import os
+import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import ops
+
+
+class RunningMeanStd(nn.Module):
+    """Running mean / variance with the reference's semantics (count starts at 1, Chan merge, eps 1e-8)."""
+
+    def __init__(self, shape=(), epsilon=1e-08):
+        super().__init__()
+        self.register_buffer("running_mean", torch.zeros(shape))
+        self.register_buffer("running_var", torch.ones(shape))
+        self.register_buffer("count", torch.ones(()))
+        self.epsilon = epsilon
+        self._ws = None
+
+    def _workspace(self):
+        if self._ws is None or self._ws.device != self.running_mean.device:
+            self._ws = ops.Workspace(self.running_mean.device)
+        return self._ws
+
+    def forward(self, obs, update=True, out=None):
+        obs = obs if obs.is_contiguous() else obs.contiguous()
+        return ops.rms_forward(
+            obs, self.running_mean, self.running_var, self.count, self.epsilon, update=update, out=out,
+            workspace=self._workspace(),
+        )  # fmt: skip
+
+    def update(self, x):
+        x = x if x.is_contiguous() else x.contiguous()
+        ops.rms_forward(
+            x, self.running_mean, self.running_var, self.count, self.epsilon, update=True, normalize=False,
+            workspace=self._workspace(),
+        )  # fmt: skip
+
+
+def layer_init(layer, std=np.sqrt(2), bias_const=0.0):
+    torch.nn.init.orthogonal_(layer.weight, std)
+    torch.nn.init.constant_(layer.bias, bias_const)
+    return layer
+
+
+class Agent(nn.Module):
+    """Actor-critic with the reference's module tree; parameters are views into one flat fp32 vector."""
+
+    HIDDEN = (512, 256, 128)
+
+    def __init__(self, envs, device=None):
+        super().__init__()
+        obs_shape = envs.unwrapped.single_observation_space["policy"].shape
+        act_shape = envs.unwrapped.single_action_space.shape
+        self.obs_dim = int(np.array(obs_shape).prod())
+        self.act_dim = int(np.prod(act_shape))
+        h1, h2, h3 = self.HIDDEN
+
+        def mlp(out_dim, last_std):
+            return nn.Sequential(
+                layer_init(nn.Linear(self.obs_dim, h1)), nn.ELU(),
+                layer_init(nn.Linear(h1, h2)), nn.ELU(),
+                layer_init(nn.Linear(h2, h3)), nn.ELU(),
+                layer_init(nn.Linear(h3, out_dim), std=last_std),
+            )  # fmt: skip
+
+        self.critic = mlp(1, 1.0)
+        self.actor_mean = mlp(self.act_dim, 0.01)
+        self.actor_logstd = nn.Parameter(torch.zeros(1, self.act_dim))
+        self.obs_rms = RunningMeanStd(shape=obs_shape)
+        self.value_rms = RunningMeanStd(shape=())
+
+        self.dims = ops.make_dims(self.obs_dim, self.act_dim, self.HIDDEN)
+        self.layout = ops.mlp_layout(self.dims)
+        self._flat = None
+        self._w16 = None
+        self._act_ws = None
+        self._bind_flat(torch.device("cpu"))
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.sync_weights())
+        if device is not None:
+            self.to(device)
+
+    # -- flat parameter storage ----------------------------------------------------------------------
+    def _param_slots(self):
+        lay = self.layout
+        for z, net in enumerate((self.critic, self.actor_mean)):
+            for l, idx in enumerate((0, 2, 4, 6)):
+                yield net[idx].weight, lay.w[z][l]
+                yield net[idx].bias, lay.b[z][l]
+        yield self.actor_logstd, lay.logstd
+
+    def _bind_flat(self, device):
+        """(Re)create the flat vector on `device` from the current parameter values and re-point every
+        nn.Parameter at its slice, so optimiser kernels and the module tree share storage."""
+        flat = torch.zeros(self.layout.n_params, dtype=torch.float32, device=device)
+        for p, off in self._param_slots():
+            flat[off : off + p.numel()] = p.detach().reshape(-1).to(device)
+        for p, off in self._param_slots():
+            p.data = flat[off : off + p.numel()].view(p.shape)
+        self._flat = flat
+        self._w16 = torch.zeros(self.layout.n_w16, dtype=torch.bfloat16, device=device)
+        self._act_ws = None
+        if device.type == "cuda":
+            self.sync_weights()
+
+    def _apply(self, fn, recurse=True):
+        super()._apply(fn, recurse)
+        new_device = self.actor_logstd.device
+        if self._flat is None or new_device != self._flat.device or self.actor_logstd.data_ptr() != (
+            self._flat.data_ptr() + self.layout.logstd * 4
+        ):
+            self._bind_flat(new_device)
+        return self
+
+    def parameters_flat(self) -> torch.Tensor:
+        return self._flat
+
+    def sync_weights(self) -> None:
+        """Refresh the bf16 compute copies after the fp32 parameters were written from outside
+        (load_state_dict, manual edits).  The Adam kernel keeps them fresh during training."""
+        if self._flat is not None and self._flat.is_cuda:
+            ops.cast_weights(self.dims, self._flat, self._w16)
+
+    # -- inference ---------------------------------------------------------------------------------
+    def _workspace(self, rows):
+        need = L.load().catb200_mlp_workspace_bytes(self.dims, rows, 0)
+        if self._act_ws is None or self._act_ws.numel() * 8 < need:
+            self._act_ws = L.zeros_workspace(need, self._flat.device)
+        return self._act_ws
+
+    def _as_obs16(self, x):
+        if x.dtype == torch.bfloat16 and x.shape[-1] == self.dims.obs_pad:
+            return x
+        x = x.float() if x.dtype != torch.float32 else x
+        return ops.obs_to_bf16(x if x.is_contiguous() else x.contiguous(), self.dims.obs_pad)
+
+    def get_value(self, x):
+        obs16 = self._as_obs16(x)
+        rows = obs16.numel() // self.dims.obs_pad
+        value = torch.empty((rows, 1), dtype=torch.float32, device=obs16.device)
+        ops.mlp_act(self.dims, obs16, self._flat, self._w16, self._workspace(rows), value=value)
+        return value
+
+    def get_action_and_value(self, x, action=None, deterministic=False, out=None):
+        """-> (action, log-prob summed over action dims, entropy summed over action dims, value [N,1]).
+
+        `out=(action, logprob, value)` lets the trainer write straight into its rollout buffers."""
+        obs16 = self._as_obs16(x)
+        rows = obs16.numel() // self.dims.obs_pad
+        dev = obs16.device
+        if out is None:
+            act_out = torch.empty((rows, self.act_dim), dtype=torch.float32, device=dev)
+            logprob = torch.empty(rows, dtype=torch.float32, device=dev)
+            value = torch.empty((rows, 1), dtype=torch.float32, device=dev)
+        else:
+            act_out, logprob, value = out
+        noise = None
+        if action is None and not deterministic:
+            noise = torch.randn((rows, self.act_dim), dtype=torch.float32, device=dev)  # Normal.sample's eps
+        ops.mlp_act(
+            self.dims, obs16, self._flat, self._w16, self._workspace(rows), noise=noise,
+            action_in=None if action is None else action.contiguous(), action=act_out, logprob=logprob, value=value,
+        )  # fmt: skip
+        if out is not None:
+            return act_out, logprob, None, value  # trainer fast path: the rollout never uses the entropy
+        # entropy of a diagonal Gaussian does not depend on the state: sum_j (0.5 + 0.5 log 2pi + logstd_j)
+        entropy = (0.5 + 0.5 * np.log(2 * np.pi) + self.actor_logstd.detach()).sum().expand(rows)
+        return act_out, logprob, entropy, value
+
+    def forward(self, x, deterministic=True):
+        action, _, _, _ = self.get_action_and_value(self.obs_rms(x, update=False), deterministic=deterministic)
+        return action
+
+    def export_module(self) -> nn.Module:
+        """Plain torch module computing `forward(x)` (normalise -> actor mean) from the same weights, for the
+        ONNX / TorchScript export of the reference's play script (scripts/clean_rl/play.py:123-137)."""
+
+        class _Export(nn.Module):
+            def __init__(self, agent):
+                super().__init__()
+                self.actor_mean = agent.actor_mean
+                self.register_buffer("mean", agent.obs_rms.running_mean)
+                self.register_buffer("var", agent.obs_rms.running_var)
+                self.eps = agent.obs_rms.epsilon
+
+            def forward(self, x):
+                return self.actor_mean((x - self.mean) / torch.sqrt(self.var + self.eps))
+
+        return _Export(self)
+
+
+class PPOTrainer:
+    """State and steps of the training loop; `PPO()` below drives it exactly like the reference function."""
+
+    def __init__(self, envs, cfg, device=None, seed=None, use_graphs=True):
+        self.envs = envs
+        self.cfg = cfg
+        env = envs.unwrapped
+        self.num_envs = int(env.num_envs)
+        self.T = int(cfg.num_steps)
+        if device is None:
+            device = getattr(env, "device", None) or torch.device("cuda")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("PPOTrainer needs a CUDA device: the hot path exists only as sm_100a kernels")
+        self.world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
+        self.rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
+
+        self.agent = Agent(envs, device=self.device)
+        if self.world > 1:  # rank 0 seeds everybody (the reference's multi-process front-ends do the same)
+            torch.distributed.broadcast(self.agent.parameters_flat(), src=0)
+            self.agent.sync_weights()
+        dims, lay = self.agent.dims, self.agent.layout
+        N, T, O, A, dev = self.num_envs, self.T, self.agent.obs_dim, self.agent.act_dim, self.device
+        self.batch_size = N * T
+        self.minibatch_size = min(int(cfg.minibatch_size), self.batch_size)
+
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.obs = torch.zeros((T + 1, N, O), **f32)
+        self.obs16 = torch.zeros((T + 1, N, dims.obs_pad), dtype=torch.bfloat16, device=dev)
+        self.actions = torch.zeros((T, N, A), **f32)
+        self.logprobs = torch.zeros((T, N), **f32)
+        self.rewards = torch.zeros((T, N), **f32)
+        self.dones = torch.zeros((T + 1, N), **f32)
+        self.true_dones = torch.zeros((T + 1, N), **f32)
+        self.values = torch.zeros((T, N), **f32)
+        self.advantages = torch.zeros((T, N), **f32)
+        self.returns = torch.zeros((T, N), **f32)
+        self.next_value = torch.zeros(N, **f32)
+        self.norm_stats = torch.zeros(4, **f32)
+        self.value_rms_state = torch.tensor([0.0, 1.0, 1.0], **f32)  # mean, var, count of agent.value_rms
+
+        self.grads = torch.zeros(lay.n_params, **f32)
+        self.exp_avg = torch.zeros(lay.n_params, **f32)
+        self.exp_avg_sq = torch.zeros(lay.n_params, **f32)
+        self.lr_dev = torch.tensor(float(cfg.learning_rate), **f32)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.opt_ws = torch.zeros(8, dtype=torch.int64, device=dev)
+        self.loss_acc = torch.zeros(8, **f32)
+        self.grad_norm = torch.zeros(1, **f32)
+        self.train_ws = ops.mlp_workspace(dims, self.minibatch_size, True, dev)
+        self.gae_ws = ops.Workspace(dev)
+        self.perm = torch.zeros(self.batch_size, dtype=torch.int64, device=dev)
+        self.hp = ops.make_hparams(cfg.clip_coef, cfg.ent_coef, cfg.vf_coef, cfg.norm_adv, cfg.clip_vloss)
+        self.global_step = 0
+        self.iteration = 0
+        self.use_graphs = bool(use_graphs) and self.world == 1
+        self._epoch_graph = None
+        self._graph_launches = 0  # kernels recorded in the epoch graph
+        self._graph_replays = 0
+
+    # -- rollout -------------------------------------------------------------------------------------
+    def start(self):
+        """envs.reset() and the first observation normalisation (reference ppo.py:186-189)."""
+        first = self.envs.reset()[0]["policy"]
+        self._ingest_obs(first, 0)
+        self.dones[0].zero_()
+        self.true_dones[0].zero_()
+
+    def _ingest_obs(self, raw_obs, slot):
+        raw_obs = raw_obs.float() if raw_obs.dtype != torch.float32 else raw_obs
+        self.agent.obs_rms(raw_obs, update=True, out=self.obs[slot])  # update + normalise (ppo.py:187,225)
+        ops.obs_to_bf16(self.obs[slot], self.agent.dims.obs_pad, out=self.obs16[slot])
+
+    def rollout_step(self, t):
+        """One env step of the rollout (reference ppo.py:201-230)."""
+        self.global_step += self.num_envs * self.world
+        # obs[t], dones[t], true_dones[t] are already in place (slot t was filled by the previous post-step)
+        self.agent.get_action_and_value(self.obs16[t], out=(self.actions[t], self.logprobs[t], self.values[t]))
+        next_obs, reward, next_done, timeouts, info = self.envs.step(self.actions[t])
+        if next_done.dtype != torch.float32:
+            next_done = next_done.to(torch.float)
+        ops.rollout_append(
+            reward if reward.is_contiguous() else reward.contiguous(), next_done, timeouts,
+            self.rewards[t], self.dones[t + 1], self.true_dones[t + 1],
+        )  # fmt: skip
+        info["true_dones"] = timeouts
+        self._ingest_obs(next_obs["policy"], t + 1)
+        return info
+
+    def collect_rollout(self):
+        ep_infos = []
+        for t in range(self.T):
+            info = self.rollout_step(t)
+            if "episode" in info:
+                ep_infos.append(info["episode"])
+            elif "log" in info:
+                ep_infos.append(info["log"])
+        return ep_infos
+
+    # -- update --------------------------------------------------------------------------------------
+    def compute_gae(self, bootstrap=True):
+        """Bootstrap value, GAE with float dones, value-normalisation statistics (ppo.py:251-288).
+        `bootstrap=False` keeps whatever `self.next_value` holds (replaying a recorded rollout)."""
+        a = self.agent
+        if bootstrap:
+            ops.mlp_act(a.dims, self.obs16[self.T], a.parameters_flat(), a._w16, a._workspace(self.num_envs), value=self.next_value)
+        vr = a.value_rms
+        self.value_rms_state[0:1].copy_(vr.running_mean.reshape(1))
+        self.value_rms_state[1:2].copy_(vr.running_var.reshape(1))
+        self.value_rms_state[2:3].copy_(vr.count.reshape(1))
+        ops.gae(
+            self.rewards, self.values, self.dones, self.true_dones, self.next_value, self.cfg.gamma, self.cfg.gae_lambda,
+            advantages=self.advantages, returns=self.returns, value_rms=self.value_rms_state, norm_stats=self.norm_stats,
+            workspace=self.gae_ws,
+        )  # fmt: skip
+        vr.running_mean.copy_(self.value_rms_state[0])
+        vr.running_var.copy_(self.value_rms_state[1])
+        vr.count.copy_(self.value_rms_state[2])
+
+    def _minibatch(self, mb_inds):
+        a = self.agent
+        B = self.batch_size
+        ops.ppo_minibatch_grad(
+            a.dims, self.hp, mb_inds, self.obs16.view(-1, a.dims.obs_pad), self.actions.view(B, -1),
+            self.logprobs.view(B), self.advantages.view(B), self.returns.view(B), self.values.view(B), self.norm_stats,
+            a.parameters_flat(), a._w16, self.grads, self.loss_acc, self.train_ws,
+        )  # fmt: skip
+        if self.world > 1:  # the one exchange step: sum-allreduce of the flat 1.5 MB gradient over NVLink
+            torch.distributed.all_reduce(self.grads, op=torch.distributed.ReduceOp.SUM)
+        ops.adam_step(
+            a.dims, a.parameters_flat(), self.grads, self.exp_avg, self.exp_avg_sq, a._w16, self.lr_dev, self.step_dev,
+            self.opt_ws, max_grad_norm=self.cfg.max_grad_norm, eps=1e-5, grad_scale=1.0 / self.world,
+            grad_norm_out=self.grad_norm,
+        )  # fmt: skip
+
+    def _epoch(self):
+        for start in range(0, self.batch_size, self.minibatch_size):
+            self._minibatch(self.perm[start : start + self.minibatch_size])
+
+    def update(self, perms=None):
+        """All epochs x minibatches of one iteration (ppo.py:290-354).  `perms` (one index permutation per
+        epoch) replaces the `torch.randperm` draws, for replaying a recorded run."""
+        self.loss_acc.zero_()
+        for epoch in range(int(self.cfg.updates_epochs)):
+            if perms is not None:
+                self.perm.copy_(perms[epoch])
+            else:
+                self.perm.copy_(torch.randperm(self.batch_size, device=self.device))
+            if self.use_graphs:
+                if self._epoch_graph is None:
+                    self._epoch()  # warm-up run (sets kernel attributes), then capture the same launches
+                    self.perm.copy_(torch.randperm(self.batch_size, device=self.device))
+                    graph = torch.cuda.CUDAGraph()
+                    before = L.launch_count()
+                    with torch.cuda.graph(graph):
+                        self._epoch()
+                    self._graph_launches = L.launch_count() - before
+                    self._epoch_graph = graph
+                self._epoch_graph.replay()
+                self._graph_replays += 1
+            else:
+                self._epoch()
+
+    def kernel_launches(self) -> int:
+        """libcatb200 kernels executed so far by this process (graph replays included)."""
+        return L.launch_count() - self._graph_launches * (1 if self._epoch_graph is not None else 0) + (
+            self._graph_launches * self._graph_replays
+        )
+
+    def finish_iteration(self):
+        """Slot T (the bootstrap observation / dones) becomes slot 0 of the next rollout (ppo.py:203-205)."""
+        T = self.T
+        self.obs[0].copy_(self.obs[T])
+        self.obs16[0].copy_(self.obs16[T])
+        self.dones[0].copy_(self.dones[T])
+        self.true_dones[0].copy_(self.true_dones[T])
+
+    def set_lr(self, lr: float):
+        self.lr_dev.fill_(lr)
+
+    def train_iteration(self):
+        """rollout + GAE + update; returns the episode infos gathered during the rollout."""
+        self.iteration += 1
+        cfg = self.cfg
+        if cfg.anneal_lr:  # ppo.py:196-199
+            frac = 1.0 - (self.iteration - 1.0) / cfg.num_iterations
+            self.set_lr(frac * cfg.learning_rate)
+        ep_infos = self.collect_rollout()
+        self.compute_gae()
+        self.update()
+        self.finish_iteration()
+        return ep_infos
+
+    def losses(self) -> dict:
+        """Mean losses over the minibatches of the last update (one device->host read)."""
+        acc = self.loss_acc.cpu()
+        n = max(float(acc[7]), 1.0)
+        return {
+            "mean_pg_loss": float(acc[0]) / n,
+            "mean_v_loss": float(acc[1]) / n,
+            "mean_entropy_loss": float(acc[2]) / n,
+            "approx_kl": float(acc[3]) / n,
+            "clipfrac": float(acc[4]) / n,
+            "mean_surrogate_loss": float(acc[6]) / n,
+        }
+
+
+def _make_writer(ppo_cfg, run_path):
+    if ppo_cfg.logger == "wandb":
+        from rsl_rl.utils.wandb_utils import WandbSummaryWriter
+
+        return WandbSummaryWriter(log_dir=run_path, flush_secs=10, cfg=ppo_cfg.to_dict())
+    if ppo_cfg.logger == "tensorboard":
+        from torch.utils.tensorboard import SummaryWriter as TensorboardSummaryWriter
+
+        return TensorboardSummaryWriter(log_dir=run_path)
+    if ppo_cfg.logger is None:  # extension: no logging (benchmarks)
+        return None
+    raise AssertionError("logger type not found")
+
+
+def PPO(envs, ppo_cfg, run_path):
+    """Train; same signature, logging keys and checkpoint files as the reference (ppo.py:126-372)."""
+    writer = _make_writer(ppo_cfg, run_path)
+    if not os.path.exists(run_path):
+        os.makedirs(run_path)
+    trainer = PPOTrainer(envs, ppo_cfg)
+    device = trainer.device
+    trainer.start()
+    print(f"Starting training for {ppo_cfg.num_iterations} steps")
+    start_time = time.time()
+    for iteration in range(1, ppo_cfg.num_iterations + 1):
+        ep_infos = trainer.train_iteration()
+        if writer is not None and ep_infos:  # adapted from rsl_rl like the reference (ppo.py:232-248)
+            for key in ep_infos[0]:
+                infotensor = torch.tensor([], device=device)
+                for ep_info in ep_infos:
+                    if key not in ep_info:
+                        continue
+                    if not isinstance(ep_info[key], torch.Tensor):
+                        ep_info[key] = torch.Tensor([ep_info[key]])
+                    if len(ep_info[key].shape) == 0:
+                        ep_info[key] = ep_info[key].unsqueeze(0)
+                    infotensor = torch.cat((infotensor, ep_info[key].to(device)))
+                value = torch.mean(infotensor)
+                writer.add_scalar(key if "/" in key else "Episode/" + key, value, iteration)
+        if writer is not None:
+            losses = trainer.losses()
+            for name in ("mean_pg_loss", "mean_entropy_loss", "mean_v_loss", "mean_surrogate_loss"):
+                writer.add_scalar("Loss/" + name, losses[name], iteration)
+            writer.add_scalar("Loss/learning_rate", float(trainer.lr_dev), iteration)
+        if (iteration + 1) % ppo_cfg.save_interval == 0 and trainer.rank == 0:
+            torch.save(trainer.agent.state_dict(), f"{run_path}/model_{iteration}.pt")
+            print("Saved model")
+    torch.cuda.synchronize()
+    elapsed = time.time() - start_time
+    print(f"Trained {trainer.global_step} env steps in {elapsed:.1f} s")
+    return trainer

@@ -39,6 +39,9 @@ typedef enum {
 } catb200_status;
 
 int catb200_version(void);
+/* Number of kernels this library has launched in this process (host-side count; launches captured
+ * into a CUDA graph are counted once at capture, replays are the caller's to multiply). */
+uint64_t catb200_launch_count(void);
 /* Static description of a status code; for CATB200_ERR_CUDA also the last CUDA error string. */
 const char* catb200_error_string(int status);
 
