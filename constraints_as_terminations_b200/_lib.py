@@ -198,7 +198,7 @@ SIGNATURES = {
     "catb200_cat_probs": (C.c_int, [C.POINTER(Plan), C.POINTER(CatParams), _I32, _P, _P, _P, _P]),
     "catb200_cat_reset_stats": (C.c_int, [_P, _I32, _P, _P, _I32, _I32, _P, _P, _P, _P]),
     "catb200_rms_workspace_bytes": (_SZ, [_I32]),
-    "catb200_rms_forward": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _F, _I32, _P, _P, _SZ, _P]),
+    "catb200_rms_forward": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _F, _I32, _P, _P, _I32, _P, _SZ, _P]),
     "catb200_rollout_append": (C.c_int, [_P, _P, _P, _I32, _P, _P, _P, _P]),
     "catb200_gae_workspace_bytes": (_SZ, []),
     "catb200_gae": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _F, _F, _P, _P, _P, _P, _P, _SZ, _P]),

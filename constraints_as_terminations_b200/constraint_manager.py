@@ -387,9 +387,14 @@ class ConstraintManager(ManagerBase):
         self._built: _BuiltPlan | None = None
         self._param_snapshot = None
         self._generic: list = []
+        self._param_watch: list = []
 
         super().__init__(cfg, env)  # parses the terms through _prepare_terms()
 
+        self._term_index = {name: i for i, name in enumerate(self._term_names)}
+        self._stat_keys = [
+            k for name in self._term_names for k in (f"Episode_Constraint_violation/{name}", f"Episode_Constraint_probability/{name}")
+        ]
         n, s = self.num_envs, max(1, len(self._term_names))
         dev = self._device
         self._stats = torch.zeros((2, s, n), dtype=torch.float, device=dev)
@@ -452,17 +457,18 @@ class ConstraintManager(ManagerBase):
         return self._term_names
 
     def set_term_cfg(self, term_name: str, cfg: ConstraintTermCfg):
-        if term_name not in self._term_names:
+        i = self._term_index.get(term_name)
+        if i is None:
             raise ValueError(f"Constraint term '{term_name}' not found.")
-        i = self._term_names.index(term_name)
         if cfg is not self._term_cfgs[i]:
             self._built = None  # a swapped cfg may change func / params: re-plan on the next compute
         self._term_cfgs[i] = cfg
 
     def get_term_cfg(self, term_name: str) -> ConstraintTermCfg:
-        if term_name not in self._term_names:
+        i = self._term_index.get(term_name)
+        if i is None:
             raise ValueError(f"Constraint term '{term_name}' not found.")
-        return self._term_cfgs[self._term_names.index(term_name)]
+        return self._term_cfgs[i]
 
     def compute(self) -> torch.Tensor:
         """Termination probability of every env for this step -> Tensor[N] (reference :213-229)."""
@@ -493,10 +499,7 @@ class ConstraintManager(ManagerBase):
         """Episode statistics of the envs being reset, then clear them (reference :190-211)."""
         extras = {}
         if self._term_names:
-            out = self._reset_stats(env_ids=env_ids, mask=None)
-            for i, key in enumerate(self._term_names):
-                extras[f"Episode_Constraint_violation/{key}"] = out[2 * i]
-                extras[f"Episode_Constraint_probability/{key}"] = out[2 * i + 1]
+            extras = dict(zip(self._stat_keys, self._reset_stats(env_ids=env_ids, mask=None).unbind(0)))
         ids = slice(None) if env_ids is None else env_ids
         for term_cfg in self._class_term_cfgs:
             term_cfg.func.reset(env_ids=ids)
@@ -504,13 +507,9 @@ class ConstraintManager(ManagerBase):
 
     def reset_masked(self, mask: torch.Tensor) -> dict[str, torch.Tensor]:
         """Like `reset` but selects envs with a device-side bool mask: no `nonzero()`, no host sync."""
-        extras = {}
-        if self._term_names:
-            out = self._reset_stats(env_ids=None, mask=mask)
-            for i, key in enumerate(self._term_names):
-                extras[f"Episode_Constraint_violation/{key}"] = out[2 * i]
-                extras[f"Episode_Constraint_probability/{key}"] = out[2 * i + 1]
-        return extras
+        if not self._term_names:
+            return {}
+        return dict(zip(self._stat_keys, self._reset_stats(env_ids=None, mask=mask).unbind(0)))
 
     # -- internals ---------------------------------------------------------------------------------
     def _prepare_terms(self):
@@ -533,8 +532,12 @@ class ConstraintManager(ManagerBase):
                 self._class_term_cfgs.append(term_cfg)
 
     @staticmethod
-    def _scalar_params(term_cfg):
-        return tuple((k, v) for k, v in term_cfg.params.items() if isinstance(v, (int, float)))
+    def _scalar_keys(term_cfg):
+        return [k for k, v in term_cfg.params.items() if isinstance(v, (int, float))]
+
+    def _param_values(self):
+        """Current scalar params of every term (cheap per-step check that a cfg was not edited in place)."""
+        return [[d[k] for k in keys] for d, keys in self._param_watch]
 
     def _specs(self):
         specs, generic = [], []
@@ -556,8 +559,7 @@ class ConstraintManager(ManagerBase):
         return value
 
     def _ensure_plan(self):
-        snapshot = tuple(self._scalar_params(c) for c in self._term_cfgs)
-        if self._built is not None and snapshot == self._param_snapshot:
+        if self._built is not None and self._param_values() == self._param_snapshot:
             for _, term_cfg, holder in self._generic:
                 holder["value"] = self._call_python_term(term_cfg)
             self._built.refresh(self._env)
@@ -567,7 +569,8 @@ class ConstraintManager(ManagerBase):
         if self._running_max is not None and built.n_cols != self._running_max.numel():
             raise RuntimeError("the number of constraint columns changed; create a new ConstraintManager")
         self._built = built
-        self._param_snapshot = snapshot
+        self._param_watch = [(c.params, self._scalar_keys(c)) for c in self._term_cfgs]
+        self._param_snapshot = self._param_values()
         if self._running_max is None:
             k = built.n_cols
             self._running_max = torch.zeros(k, dtype=torch.float, device=self._device)

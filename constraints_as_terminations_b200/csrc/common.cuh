@@ -30,6 +30,9 @@ extern unsigned long long g_launch_count;
     CATB200_CUDA_TRY(cudaPeekAtLastError());       \
   } while (0)
 
+// mlp.cu: refresh the bf16 compute copies (W and W^T of the hidden layers) from the fp32 master parameters
+int launch_cast_weights(const catb200_mlp_dims_t* dims, const float* params, void* w16, cudaStream_t st);
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 constexpr int kNumSMs = 148;  // B200

@@ -27,6 +27,14 @@ constexpr int kSmemNT = kStages * kStageBytesNT;       // 96 KiB
 
 enum Epilogue { kEpiBiasElu = 0, kEpiMulDelu = 1 };
 
+constexpr int kHeadThreads = 256;
+constexpr int kMaxAct = 16;
+constexpr float kLogSqrt2Pi = 0.91893853320467274178f;
+// layout of one head-kernel CTA's partial row: [value][lane]; values 0..63 = gW4a[j][f] (j = v/4, f = v%4)
+constexpr int kHvW4c = 64, kHvB3c = 68, kHvB3a = 72, kHvB4a = 76, kHvLogstd = 77, kHvScalars = 78;
+constexpr int kHeadValues = 84;
+constexpr int kHeadSmem = (kHeadThreads / 32) * kHeadValues * 32 * 4;  // 84 KiB
+
 struct GemmNTArgs {
   const bf16* A[2];  // [M, K] row-major, lda
   const bf16* B[2];  // [N, K] row-major, ldb
@@ -268,27 +276,85 @@ wgrad_kernel(const __grid_constant__ WgradArgs g) {
   }
 }
 
-// grads[n, k] += sum_s part[s, n, k] for k < Ktrue (the padded input columns of layer 0 are dropped)
+// grads[n, k] += sum_s part[s, n, k] for k < Ktrue (the padded input columns of layer 0 are dropped).
+// blockIdx.y selects the segment; the last segment is the head kernel's per-CTA rows.
 struct ReduceArgs {
   const float* part[6];
   float* grad[6];
   int N[6], Kpad[6], Ktrue[6], splits[6];
   int n_segments;
+  // head segment
+  const float* head_part; int head_rows;
+  float* gW4c; float* gb4c; float* gW4a; float* gb4a; float* glogstd; float* gb3[2];
+  const float* logstd; float* loss_acc;
+  int A, h3, M;
+  float ent_coef, vf_coef;
 };
 
-__global__ void reduce_partials_kernel(const __grid_constant__ ReduceArgs r) {
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const __grid_constant__ ReduceArgs r) {
   const int seg = blockIdx.y;
-  if (seg >= r.n_segments) return;
-  const int N = r.N[seg], Kpad = r.Kpad[seg], Kt = r.Ktrue[seg], S = r.splits[seg];
-  const int total = N * Kpad;
-  const float* __restrict__ part = r.part[seg];
-  float* __restrict__ grad = r.grad[seg];
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (seg < r.n_segments) {
+    const int N = r.N[seg], Kpad = r.Kpad[seg], Kt = r.Ktrue[seg], S = r.splits[seg];
+    const int total = N * Kpad;
+    if (e >= total) return;
     const int n = e / Kpad, k = e - n * Kpad;
-    if (k >= Kt) continue;
-    float s = 0.0f;
-    for (int p = 0; p < S; ++p) s += part[(size_t)p * total + e];
-    grad[(size_t)n * Kt + k] += s;
+    if (k >= Kt) return;
+    const float* __restrict__ p = r.part[seg] + e;
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    int q = 0;
+    for (; q + 4 <= S; q += 4) {
+      s0 += __ldcs(p + (size_t)q * total);
+      s1 += __ldcs(p + (size_t)(q + 1) * total);
+      s2 += __ldcs(p + (size_t)(q + 2) * total);
+      s3 += __ldcs(p + (size_t)(q + 3) * total);
+    }
+    for (; q < S; ++q) s0 += __ldcs(p + (size_t)q * total);
+    r.grad[seg][(size_t)n * Kt + k] += (s0 + s1) + (s2 + s3);
+    return;
+  }
+  // ---- head segment: sum the per-CTA rows, route every value to its gradient slot / loss accumulator
+  if (e >= kHeadValues * 32) return;
+  float t = 0.0f;
+  for (int c = 0; c < r.head_rows; ++c) t += r.head_part[(size_t)c * kHeadValues * 32 + e];
+  const int v = e >> 5, lane = e & 31;
+  const float inv_M = 1.0f / (float)r.M;
+  if (v < kHvW4c) {
+    const int j = v >> 2, f = v & 3;
+    if (j < r.A) r.gW4a[j * r.h3 + lane * 4 + f] += t;
+  } else if (v < kHvB3c) {
+    r.gW4c[lane * 4 + (v - kHvW4c)] += t;
+  } else if (v < kHvB3a) {
+    r.gb3[0][lane * 4 + (v - kHvB3c)] += t;
+  } else if (v < kHvB4a) {
+    r.gb3[1][lane * 4 + (v - kHvB3a)] += t;
+  } else if (v == kHvB4a) {
+    if (lane < r.A) r.gb4a[lane] += t;
+  } else if (v == kHvLogstd) {
+    // policy part + d(-ent_coef * mean entropy)/d logstd_j = -ent_coef (entropy is sample independent)
+    if (lane < r.A) r.glogstd[lane] += t - r.ent_coef;
+  } else if (lane == 0) {
+    const int k = v - kHvScalars;  // g_b4c, pg, v, kl, clip, old_kl
+    if (k == 0) {
+      r.gb4c[0] += t;
+    } else if (k == 1) {
+      r.loss_acc[0] += t * inv_M;
+      // entropy = sum_j (0.5 + 0.5 log(2 pi) + logstd_j); also the per-minibatch counter and total loss
+      float ent = 0.0f;
+      for (int j = 0; j < r.A; ++j) ent += 0.5f + kLogSqrt2Pi + r.logstd[j];
+      r.loss_acc[2] += ent;
+      atomicAdd(r.loss_acc + 6, t * inv_M - r.ent_coef * ent);
+      r.loss_acc[7] += 1.0f;
+    } else if (k == 2) {
+      r.loss_acc[1] += t * inv_M;
+      atomicAdd(r.loss_acc + 6, r.vf_coef * t * inv_M);
+    } else if (k == 3) {
+      r.loss_acc[3] += t * inv_M;
+    } else if (k == 4) {
+      r.loss_acc[4] += t * inv_M;
+    } else if (k == 5) {
+      r.loss_acc[5] += t * inv_M;
+    }
   }
 }
 
@@ -345,9 +411,6 @@ gather_kernel(const int64_t* __restrict__ mb_inds, int M, const bf16* __restrict
 }
 
 // ---- heads, loss and their gradients -----------------------------------------------------------------
-constexpr int kHeadThreads = 256;
-constexpr int kMaxAct = 16;
-constexpr float kLogSqrt2Pi = 0.91893853320467274178f;
 
 struct HeadArgs {
   const bf16* H3[2];   // [M, h3] activations of the last hidden layer (0 critic, 1 actor)
@@ -364,14 +427,14 @@ struct HeadArgs {
   const float* val_all; const float* norm_stats; const MbStats* mb;
   catb200_ppo_hparams_t hp;
   // training outputs
-  float* gW4c; float* gb4c; float* gW4a; float* gb4a; float* glogstd; float* gb3[2];
-  float* loss_acc;
+  float* head_part;  // [gridDim.x][kHeadValues][32] per-CTA partial sums (training)
 };
 
 // One warp per sample; lane owns features lane*4 .. lane*4+3 of each 128-wide slice of h3.
 template <bool TRAIN>
 __global__ void __launch_bounds__(kHeadThreads)
 head_kernel(const __grid_constant__ HeadArgs a) {
+  constexpr int AP = kMaxAct;  // action dims carried through the unrolled loops (weights beyond A are zero)
   constexpr int F = 4;  // features per lane (h3 == 128)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int warps = kHeadThreads / 32;
@@ -432,15 +495,22 @@ head_kernel(const __grid_constant__ HeadArgs a) {
     for (int f = 0; f < F; ++f) v = fmaf(hc[f], w4c[f], v);
     v = warp_sum(v) + b4c;
     float mean_j = 0.0f;  // lane j keeps mean_j
+    {
+      float p[AP];
 #pragma unroll
-    for (int j = 0; j < kMaxAct; ++j) {
-      if (j < A) {
-        float p = 0.0f;
+      for (int j = 0; j < AP; ++j) {
+        p[j] = 0.0f;
 #pragma unroll
-        for (int f = 0; f < F; ++f) p = fmaf(ha[f], w4a[j][f], p);
-        p = warp_sum(p);
-        if (lane == j) mean_j = p + my_b4a;
+        for (int f = 0; f < F; ++f) p[j] = fmaf(ha[f], w4a[j][f], p[j]);
       }
+      // butterfly all action dims together: AP independent shuffles per stage hide the shuffle latency
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int j = 0; j < AP; ++j) p[j] += __shfl_xor_sync(0xffffffffu, p[j], o);
+#pragma unroll
+      for (int j = 0; j < AP; ++j)
+        if (lane == j) mean_j = p[j] + my_b4a;
     }
     if (!TRAIN) {
       // ---- rollout: sample, log-prob, store (ppo.py:104-119)
@@ -545,62 +615,34 @@ head_kernel(const __grid_constant__ HeadArgs a) {
   }
   if (!TRAIN) return;
 
-  // ---- CTA-level reduction of the accumulators, then one atomic per value per CTA
-  __shared__ float sacc[kHeadThreads / 32][32];
-  auto block_sum_lane = [&](float x) -> float {  // sums x over warps for each lane; result valid in warp 0
-    __syncthreads();
-    sacc[warp][lane] = x;
-    __syncthreads();
-    float t = 0.0f;
-    if (warp == 0)
-      for (int w = 0; w < kHeadThreads / 32; ++w) t += sacc[w][lane];
-    return t;
-  };
+  // ---- CTA-level reduction: every warp parks its accumulators in shared memory ([value][lane] rows),
+  // one barrier, then the CTA sums over its warps and writes ONE partial row per CTA (plain coalesced
+  // stores, no atomics).  head_reduce (inside reduce_partials_kernel) folds the rows into the gradient.
+  extern __shared__ float hsm[];  // [warps][kHeadValues][32]
+  float* mine = hsm + (size_t)warp * kHeadValues * 32;
+#pragma unroll
+  for (int j = 0; j < kMaxAct; ++j)
+#pragma unroll
+    for (int f = 0; f < F; ++f) mine[(j * F + f) * 32 + lane] = gw4a[j][f];
 #pragma unroll
   for (int f = 0; f < F; ++f) {
-    float t = block_sum_lane(gw4c[f]);
-    if (warp == 0) atomicAdd(a.gW4c + lane * F + f, t);
-    t = block_sum_lane(gb3c[f]);
-    if (warp == 0) atomicAdd(a.gb3[0] + lane * F + f, t);
-    t = block_sum_lane(gb3a[f]);
-    if (warp == 0) atomicAdd(a.gb3[1] + lane * F + f, t);
+    mine[(kHvW4c + f) * 32 + lane] = gw4c[f];
+    mine[(kHvB3c + f) * 32 + lane] = gb3c[f];
+    mine[(kHvB3a + f) * 32 + lane] = gb3a[f];
+  }
+  mine[kHvB4a * 32 + lane] = g_b4a;        // lane j: d/d b4a[j]
+  mine[kHvLogstd * 32 + lane] = g_logstd;  // lane j: d/d logstd[j] (policy part)
+  // warp-uniform scalars: keep lane 0's copy only
+  const float scal[6] = {g_b4c, l_pg, l_v, l_kl, l_clip, l_oldkl};
 #pragma unroll
-    for (int j = 0; j < kMaxAct; ++j) {
-      if (j < A) {
-        t = block_sum_lane(gw4a[j][f]);
-        if (warp == 0) atomicAdd(a.gW4a + j * a.h3 + lane * F + f, t);
-      }
-    }
-  }
-  {
-    float t = block_sum_lane(g_b4a);
-    if (warp == 0 && lane < A) atomicAdd(a.gb4a + lane, t);
-    t = block_sum_lane(g_logstd);
-    if (warp == 0 && lane < A) atomicAdd(a.glogstd + lane, t);
-    // scalars are identical across lanes of a warp: sum lane 0 of every warp
-    t = block_sum_lane(g_b4c);
-    if (warp == 0 && lane == 0) atomicAdd(a.gb4c, t);
-    float s_pg = block_sum_lane(l_pg), s_v = block_sum_lane(l_v), s_kl = block_sum_lane(l_kl);
-    float s_clip = block_sum_lane(l_clip), s_old = block_sum_lane(l_oldkl);
-    if (warp == 0 && lane == 0) {
-      atomicAdd(a.loss_acc + 0, s_pg * inv_M);
-      atomicAdd(a.loss_acc + 1, s_v * inv_M);
-      atomicAdd(a.loss_acc + 3, s_kl * inv_M);
-      atomicAdd(a.loss_acc + 4, s_clip * inv_M);
-      atomicAdd(a.loss_acc + 5, s_old * inv_M);
-      atomicAdd(a.loss_acc + 6, (s_pg + a.hp.vf_coef * s_v) * inv_M);  // entropy part added by block 0 below
-    }
-  }
-  if (blockIdx.x == 0 && warp == 0) {
-    // entropy bonus: mean over the batch of sum_j (0.5 + 0.5 log(2 pi) + logstd_j) is sample independent
-    float ent = lane < A ? 0.5f + kLogSqrt2Pi + my_logstd : 0.0f;
-    ent = warp_sum(ent);
-    if (lane < A) atomicAdd(a.glogstd + lane, -a.hp.ent_coef);  // d(-ent_coef * entropy)/d logstd_j
-    if (lane == 0) {
-      atomicAdd(a.loss_acc + 2, ent);
-      atomicAdd(a.loss_acc + 6, -a.hp.ent_coef * ent);
-      atomicAdd(a.loss_acc + 7, 1.0f);
-    }
+  for (int k = 0; k < 6; ++k) mine[(kHvScalars + k) * 32 + lane] = lane == 0 ? scal[k] : 0.0f;
+  __syncthreads();
+  float* __restrict__ row = a.head_part + (size_t)blockIdx.x * kHeadValues * 32;
+  for (int o = threadIdx.x; o < kHeadValues * 32; o += kHeadThreads) {
+    float t = 0.0f;
+#pragma unroll
+    for (int w = 0; w < kHeadThreads / 32; ++w) t += hsm[(size_t)w * kHeadValues * 32 + o];
+    row[o] = t;
   }
 }
 
@@ -620,14 +662,27 @@ struct CastSeg {
 };
 struct CastArgs { CastSeg seg[6]; };
 
-__global__ void cast_weights_kernel(const __grid_constant__ CastArgs c) {
+// 32x32 tiles: coalesced fp32 reads, coalesced bf16 writes of W, and a shared-memory transpose for W^T.
+// grid = (max tiles over segments, 6 segments), block = (32, 8).
+__global__ void __launch_bounds__(256) cast_weights_kernel(const __grid_constant__ CastArgs c) {
   const CastSeg& s = c.seg[blockIdx.y];
-  const int total = s.rows * s.cols_pad;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-    const int r = e / s.cols_pad, k = e - r * s.cols_pad;
-    const bf16 v = __float2bfloat16(k < s.cols ? s.src[(size_t)r * s.cols + k] : 0.0f);
-    s.dst[e] = v;
-    if (s.dst_t != nullptr && k < s.cols) s.dst_t[(size_t)k * s.rows + r] = v;
+  const int tiles_c = (s.cols_pad + 31) / 32, tiles_r = s.rows / 32;
+  if ((int)blockIdx.x >= tiles_c * tiles_r) return;
+  const int tr = blockIdx.x / tiles_c, tc = blockIdx.x % tiles_c;
+  __shared__ float tile[32][33];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = tr * 32 + threadIdx.y + i * 8, k = tc * 32 + threadIdx.x;
+    const float v = k < s.cols ? s.src[(size_t)r * s.cols + k] : 0.0f;
+    tile[threadIdx.y + i * 8][threadIdx.x] = v;
+    if (k < s.cols_pad) s.dst[(size_t)r * s.cols_pad + k] = __float2bfloat16(v);
+  }
+  if (s.dst_t == nullptr) return;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = tc * 32 + threadIdx.y + i * 8, r = tr * 32 + threadIdx.x;
+    if (k < s.cols) s.dst_t[(size_t)k * s.rows + r] = __float2bfloat16(tile[threadIdx.x][threadIdx.y + i * 8]);
   }
 }
 
@@ -654,8 +709,8 @@ static Dims make_dims(const catb200_mlp_dims_t* d) {
 }
 
 struct ActLayout {  // byte offsets into the activation workspace
-  size_t X, H[2][3], dZ[2][3], mb, part[2][3], total;
-  int splits[3], m_range[3];
+  size_t X, H[2][3], dZ[2][3], mb, part[2][3], head_part, total;
+  int splits[3], m_range[3], head_rows;
 };
 
 static ActLayout act_layout(const catb200_mlp_dims_t* d, int rows, bool training) {
@@ -668,12 +723,14 @@ static ActLayout act_layout(const catb200_mlp_dims_t* d, int rows, bool training
   for (int z = 0; z < 2; ++z)
     for (int l = 0; l < 3; ++l) L.H[z][l] = take((size_t)rows * x.out[l] * 2);
   if (training) {
+    L.head_rows = min((rows + 7) / 8, kNumSMs);
+    L.head_part = take((size_t)L.head_rows * kHeadValues * 32 * 4);
     for (int z = 0; z < 2; ++z)
       for (int l = 0; l < 3; ++l) L.dZ[z][l] = take((size_t)rows * x.out[l] * 2);
     for (int l = 0; l < 3; ++l) {
       const int kt = x.in_pad[l] >= 128 ? 128 : 64;
       const int tiles = (x.out[l] / 128) * (x.in_pad[l] / kt) * 2;
-      int want = max(1, (2 * kNumSMs) / tiles);
+      int want = max(1, kNumSMs / tiles);  // ~one CTA per SM per layer: fewer, fatter splits = fewer partial bytes
       int m_range = ((rows + want - 1) / want + kWgBM - 1) / kWgBM * kWgBM;
       m_range = max(m_range, kWgBM);
       L.m_range[l] = m_range;
@@ -736,6 +793,27 @@ static int launch_forward(const catb200_mlp_dims_t* d, const catb200_mlp_layout_
   return CATB200_OK;
 }
 
+int launch_cast_weights(const catb200_mlp_dims_t* dims, const float* params, void* w16v, cudaStream_t st) {
+  catb200_mlp_layout_t P;
+  fill_layout(dims, &P);
+  Dims x = make_dims(dims);
+  bf16* w16 = static_cast<bf16*>(w16v);
+  CastArgs c;
+  int max_tiles = 1;
+  for (int z = 0; z < 2; ++z)
+    for (int l = 0; l < 3; ++l) {
+      CastSeg& s = c.seg[z * 3 + l];
+      s.src = params + P.w[z][l];
+      s.dst = w16 + P.w16[z][l];
+      s.dst_t = l > 0 ? w16 + P.wt16[z][l] : nullptr;
+      s.rows = x.out[l]; s.cols = x.in[l]; s.cols_pad = x.in_pad[l];
+      max_tiles = max(max_tiles, (s.rows / 32) * ((s.cols_pad + 31) / 32));
+    }
+  cast_weights_kernel<<<dim3(max_tiles, 6), dim3(32, 8), 0, st>>>(c);
+  CATB200_LAUNCH_CHECK();
+  return CATB200_OK;
+}
+
 }  // namespace catb200
 
 using namespace catb200;
@@ -751,22 +829,7 @@ int catb200_mlp_layout(const catb200_mlp_dims_t* dims, catb200_mlp_layout_t* lay
 int catb200_mlp_cast_weights(const catb200_mlp_dims_t* dims, const float* params, void* w16v, void* stream) {
   if (!dims_ok(dims)) return CATB200_ERR_UNSUPPORTED;
   if (!params || !w16v) return CATB200_ERR_INVALID_ARGUMENT;
-  catb200_mlp_layout_t P;
-  fill_layout(dims, &P);
-  Dims x = make_dims(dims);
-  bf16* w16 = static_cast<bf16*>(w16v);
-  CastArgs c;
-  for (int z = 0; z < 2; ++z)
-    for (int l = 0; l < 3; ++l) {
-      CastSeg& s = c.seg[z * 3 + l];
-      s.src = params + P.w[z][l];
-      s.dst = w16 + P.w16[z][l];
-      s.dst_t = l > 0 ? w16 + P.wt16[z][l] : nullptr;
-      s.rows = x.out[l]; s.cols = x.in[l]; s.cols_pad = x.in_pad[l];
-    }
-  cast_weights_kernel<<<dim3(64, 6), 256, 0, as_stream(stream)>>>(c);
-  CATB200_LAUNCH_CHECK();
-  return CATB200_OK;
+  return launch_cast_weights(dims, params, w16v, as_stream(stream));
 }
 
 int catb200_obs_to_bf16(const float* obs, int64_t rows, int32_t obs_dim, int32_t obs_pad, void* obs16, void* stream) {
@@ -843,7 +906,6 @@ int catb200_ppo_minibatch_grad(const catb200_mlp_dims_t* dims, const catb200_ppo
     for (int z = 0; z < 2; ++z) {
       a.H3[z] = reinterpret_cast<const bf16*>(ws + L.H[z][2]);
       a.dZ3[z] = reinterpret_cast<bf16*>(ws + L.dZ[z][2]);
-      a.gb3[z] = grads + P.b[z][2];
     }
     a.W4c = params + P.w[0][3]; a.b4c = params + P.b[0][3];
     a.W4a = params + P.w[1][3]; a.b4a = params + P.b[1][3];
@@ -851,12 +913,13 @@ int catb200_ppo_minibatch_grad(const catb200_mlp_dims_t* dims, const catb200_ppo
     a.M = M; a.h3 = dims->h3; a.A = dims->act_dim;
     a.mb_inds = mb_inds; a.actions_all = actions_all; a.logprobs_all = logprobs_all; a.adv_all = advantages_all;
     a.ret_all = returns_all; a.val_all = values_all; a.norm_stats = norm_stats; a.mb = mb; a.hp = *hp;
-    a.gW4c = grads + P.w[0][3]; a.gb4c = grads + P.b[0][3];
-    a.gW4a = grads + P.w[1][3]; a.gb4a = grads + P.b[1][3];
-    a.glogstd = grads + P.logstd;
-    a.loss_acc = loss_acc;
-    const int grid = min((M + 7) / 8, kNumSMs * 2);
-    head_kernel<true><<<grid, kHeadThreads, 0, st>>>(a);
+    a.head_part = reinterpret_cast<float*>(ws + L.head_part);
+    static bool head_attr = false;
+    if (!head_attr) {
+      CATB200_CUDA_TRY(cudaFuncSetAttribute(head_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmem));
+      head_attr = true;
+    }
+    head_kernel<true><<<L.head_rows, kHeadThreads, kHeadSmem, st>>>(a);
     CATB200_LAUNCH_CHECK();
   }
   // 4. backward through the hidden layers
@@ -903,8 +966,19 @@ int catb200_ppo_minibatch_grad(const catb200_mlp_dims_t* dims, const catb200_ppo
       CATB200_LAUNCH_CHECK();
     }
   }
-  // 5. fold the split partial sums into the flat gradient
-  reduce_partials_kernel<<<dim3(96, red.n_segments), 256, 0, st>>>(red);
+  // 5. fold the split partial sums (hidden layers) and the head kernel's per-CTA rows into the flat gradient
+  red.head_part = reinterpret_cast<const float*>(ws + L.head_part);
+  red.head_rows = L.head_rows;
+  red.gW4c = grads + P.w[0][3]; red.gb4c = grads + P.b[0][3];
+  red.gW4a = grads + P.w[1][3]; red.gb4a = grads + P.b[1][3];
+  red.glogstd = grads + P.logstd;
+  for (int z = 0; z < 2; ++z) red.gb3[z] = grads + P.b[z][2];
+  red.logstd = params + P.logstd; red.loss_acc = loss_acc;
+  red.A = dims->act_dim; red.h3 = dims->h3; red.M = M;
+  red.ent_coef = hp->ent_coef; red.vf_coef = hp->vf_coef;
+  int max_elems = kHeadValues * 32;
+  for (int sgm = 0; sgm < red.n_segments; ++sgm) max_elems = max(max_elems, red.N[sgm] * red.Kpad[sgm]);
+  reduce_partials_kernel<<<dim3((max_elems + 255) / 256, red.n_segments + 1), 256, 0, st>>>(red);
   CATB200_LAUNCH_CHECK();
   return CATB200_OK;
 }

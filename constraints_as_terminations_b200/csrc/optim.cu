@@ -4,8 +4,8 @@
 // of the reference (U/cleanrl/ppo.py:351-354; torch.optim.Adam, eps=1e-5 set at ppo.py:168) with two
 // launches over the 377k-element flat buffers:
 //   grad_norm_kernel : sum of squares (double) -> total norm, clip coefficient, Adam bias corrections
-//   adam_kernel      : scaled gradient -> moments -> parameter update, zeroes the gradient for the next
-//                      minibatch and refreshes the bf16 compute copies (W and W^T) of the hidden layers.
+//   adam_kernel      : scaled gradient -> moments -> parameter update (float4), zeroes the gradient for the
+//                      next minibatch; then the tiled cast kernel refreshes the bf16 copies (W and W^T).
 #include "common.cuh"
 #include "mma.cuh"
 
@@ -53,44 +53,43 @@ grad_norm_kernel(const float* __restrict__ grads, long long n, float grad_scale,
   }
 }
 
-struct CastTarget {
-  long long off;  // offset of the fp32 weight in the flat vector
-  int rows, cols, cols_pad;
-  long long dst, dst_t;  // bf16 offsets (dst_t < 0: no transposed copy)
-};
 struct AdamArgs {
-  float* params; float* grads; float* m; float* v; bf16* w16;
+  float* params; float* grads; float* m; float* v;
   const float* lr; const OptScratch* sc;
   long long n;
   float beta1, beta2, eps, grad_scale;
-  CastTarget cast[6];
 };
+
+__device__ __forceinline__ void adam_one(float& p, float& g, float& m, float& v, float clip, float step_size,
+                                         float bc2_sqrt, float beta1, float beta2, float eps) {
+  const float gs = g * clip;
+  g = 0.0f;
+  m = m + (gs - m) * (1.0f - beta1);            // exp_avg.lerp_(grad, 1 - beta1)
+  v = v * beta2 + (1.0f - beta2) * gs * gs;     // mul_(beta2).addcmul_(g, g, value = 1 - beta2)
+  const float denom = sqrtf(v) / bc2_sqrt + eps;  // (exp_avg_sq.sqrt() / bias_correction2_sqrt).add_(eps)
+  p = p - step_size * (m / denom);                // addcdiv_(exp_avg, denom, value = -step_size)
+}
 
 __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamArgs a) {
   const float clip = a.sc->clip_coef * a.grad_scale;
   const float step_size = __ldg(a.lr) * a.sc->step_size_scale;
   const float bc2_sqrt = a.sc->bc2_sqrt;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < a.n; e += (long long)gridDim.x * blockDim.x) {
-    const float g = a.grads[e] * clip;
-    a.grads[e] = 0.0f;
-    const float m = a.m[e] + (g - a.m[e]) * (1.0f - a.beta1);          // exp_avg.lerp_(grad, 1 - beta1)
-    const float v = a.v[e] * a.beta2 + (1.0f - a.beta2) * g * g;        // mul_(beta2).addcmul_(g, g, 1 - beta2)
-    a.m[e] = m;
-    a.v[e] = v;
-    const float denom = sqrtf(v) / bc2_sqrt + a.eps;
-    const float p = a.params[e] - step_size * (m / denom);
-    a.params[e] = p;
-#pragma unroll
-    for (int s = 0; s < 6; ++s) {
-      const CastTarget& c = a.cast[s];
-      const long long local = e - c.off;
-      if (local >= 0 && local < (long long)c.rows * c.cols) {
-        const int r = (int)(local / c.cols), k = (int)(local - (long long)r * c.cols);
-        const bf16 pv = __float2bfloat16(p);
-        a.w16[c.dst + (long long)r * c.cols_pad + k] = pv;
-        if (c.dst_t >= 0) a.w16[c.dst_t + (long long)k * c.rows + r] = pv;
-      }
-    }
+  const long long n4 = a.n / 4;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n4) {
+    float4 p = reinterpret_cast<float4*>(a.params)[i], g = reinterpret_cast<float4*>(a.grads)[i];
+    float4 m = reinterpret_cast<float4*>(a.m)[i], v = reinterpret_cast<float4*>(a.v)[i];
+    adam_one(p.x, g.x, m.x, v.x, clip, step_size, bc2_sqrt, a.beta1, a.beta2, a.eps);
+    adam_one(p.y, g.y, m.y, v.y, clip, step_size, bc2_sqrt, a.beta1, a.beta2, a.eps);
+    adam_one(p.z, g.z, m.z, v.z, clip, step_size, bc2_sqrt, a.beta1, a.beta2, a.eps);
+    adam_one(p.w, g.w, m.w, v.w, clip, step_size, bc2_sqrt, a.beta1, a.beta2, a.eps);
+    reinterpret_cast<float4*>(a.params)[i] = p;
+    reinterpret_cast<float4*>(a.grads)[i] = g;
+    reinterpret_cast<float4*>(a.m)[i] = m;
+    reinterpret_cast<float4*>(a.v)[i] = v;
+  } else if (i < n4 + (a.n - n4 * 4)) {  // scalar tail
+    const long long e = n4 * 4 + (i - n4);
+    adam_one(a.params[e], a.grads[e], a.m[e], a.v[e], clip, step_size, bc2_sqrt, a.beta1, a.beta2, a.eps);
   }
 }
 
@@ -114,18 +113,13 @@ int catb200_adam_step(const catb200_mlp_dims_t* dims, float* params, float* grad
   grad_norm_kernel<<<kNumSMs, 256, 0, st>>>(grads, n, grad_scale, max_grad_norm, beta1, beta2, step_dev, grad_norm_out, sc);
   CATB200_LAUNCH_CHECK();
   AdamArgs a = {};
-  a.params = params; a.grads = grads; a.m = exp_avg; a.v = exp_avg_sq; a.w16 = static_cast<bf16*>(w16);
+  a.params = params; a.grads = grads; a.m = exp_avg; a.v = exp_avg_sq;
   a.lr = lr_dev; a.sc = sc; a.n = n; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.grad_scale = grad_scale;
-  const int in[3] = {dims->obs_dim, dims->h1, dims->h2}, in_pad[3] = {dims->obs_pad, dims->h1, dims->h2};
-  const int out[3] = {dims->h1, dims->h2, dims->h3};
-  for (int z = 0; z < 2; ++z)
-    for (int l = 0; l < 3; ++l) {
-      CastTarget& c = a.cast[z * 3 + l];
-      c.off = P.w[z][l]; c.rows = out[l]; c.cols = in[l]; c.cols_pad = in_pad[l];
-      c.dst = P.w16[z][l]; c.dst_t = P.wt16[z][l];
-    }
-  adam_kernel<<<kNumSMs * 4, 256, 0, st>>>(a);
+  const long long threads = n / 4 + 4;
+  adam_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a);
   CATB200_LAUNCH_CHECK();
+  rc = launch_cast_weights(dims, params, w16, st);  // refresh the bf16 copies the tensor-core GEMMs read
+  if (rc != CATB200_OK) return rc;
   return CATB200_OK;
 }
 

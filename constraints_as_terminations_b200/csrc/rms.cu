@@ -11,6 +11,7 @@
 // the CTA walks whole rows; consecutive threads touch consecutive addresses (coalesced), no modulo in
 // the loop.  HBM-bound streaming work.
 #include "common.cuh"
+#include "mma.cuh"
 
 namespace catb200 {
 
@@ -93,7 +94,8 @@ rms_moments_kernel(const float* __restrict__ x, long long rows, int dim, float* 
 
 __global__ void __launch_bounds__(kRmsThreads)
 rms_normalize_kernel(const float* __restrict__ x, long long rows, int dim, const float* __restrict__ mean,
-                     const float* __restrict__ var, float eps, float* __restrict__ out) {
+                     const float* __restrict__ var, float eps, float* __restrict__ out, bf16* __restrict__ out16,
+                     int pad16) {
   const int rows_per_pass = kRmsThreads / dim;
   const int active = rows_per_pass * dim;
   if (threadIdx.x >= active) return;
@@ -104,7 +106,12 @@ rms_normalize_kernel(const float* __restrict__ x, long long rows, int dim, const
   for (long long r = (long long)blockIdx.x * rows_per_pass + slot; r < rows;
        r += (long long)gridDim.x * rows_per_pass) {
     const long long k = r * dim + col;
-    out[k] = __fdiv_rn(__fsub_rn(x[k], m), d);
+    const float y = __fdiv_rn(__fsub_rn(x[k], m), d);
+    out[k] = y;
+    if (out16 != nullptr) {  // bf16 copy in the zero-padded row layout the first GEMM layer reads
+      out16[r * pad16 + col] = __float2bfloat16(y);
+      if (col + dim < pad16) out16[r * pad16 + dim + col] = __float2bfloat16(0.0f);  // pad16 - dim <= dim
+    }
   }
 }
 
@@ -127,8 +134,10 @@ extern "C" {
 size_t catb200_rms_workspace_bytes(int32_t dim) { return dim > 0 ? 256 + sizeof(double) * 2 * (size_t)dim : 0; }
 
 int catb200_rms_forward(const float* x, int64_t rows, int32_t dim, float* mean, float* var, float* count, float eps,
-                        int32_t update, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+                        int32_t update, float* out, void* out16, int32_t pad16, void* workspace,
+                        size_t workspace_bytes, void* stream) {
   if (!x || rows <= 0 || dim <= 0 || dim > kRmsThreads || !mean || !var || !count) return CATB200_ERR_INVALID_ARGUMENT;
+  if (out16 && (!out || pad16 < dim || pad16 - dim > dim)) return CATB200_ERR_INVALID_ARGUMENT;
   cudaStream_t st = as_stream(stream);
   const int rows_per_pass = kRmsThreads / dim;
   long long want = (rows + rows_per_pass - 1) / rows_per_pass;
@@ -142,7 +151,7 @@ int catb200_rms_forward(const float* x, int64_t rows, int32_t dim, float* mean, 
   }
   if (out) {
     const int grid = (int)min((long long)kNumSMs * 8, max(1ll, (want + 1) / 2));
-    rms_normalize_kernel<<<grid, kRmsThreads, 0, st>>>(x, rows, dim, mean, var, eps, out);
+    rms_normalize_kernel<<<grid, kRmsThreads, 0, st>>>(x, rows, dim, mean, var, eps, out, static_cast<bf16*>(out16), pad16);
     CATB200_LAUNCH_CHECK();
   }
   return CATB200_OK;

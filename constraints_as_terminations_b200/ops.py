@@ -47,22 +47,29 @@ def rms_forward(
     out: torch.Tensor | None = None,
     normalize: bool = True,
     workspace: Workspace | None = None,
+    out16: torch.Tensor | None = None,
+    validate: bool = True,
 ) -> torch.Tensor | None:
     """x: [rows, dim] or [rows] (dim = 1).  Updates (mean, var, count) in place when `update`, then
-    returns (x - mean) / sqrt(var + eps) with the updated statistics (written to `out` if given)."""
-    _f32c(x, "x")
+    returns (x - mean) / sqrt(var + eps) with the updated statistics (written to `out` if given).
+    `out16` (bf16 [rows, pad]) additionally receives the zero-padded bf16 copy the MLP reads."""
     dim = 1 if x.ndim == 1 else x.shape[-1]
     rows = x.numel() // dim
-    for t, name in ((mean, "mean"), (var, "var"), (count, "count")):
-        _f32c(t, name)
-    if mean.numel() != dim or var.numel() != dim or count.numel() != 1:
-        raise ValueError("running statistics do not match the feature dimension of x")
+    if validate:
+        _f32c(x, "x")
+        for t, name in ((mean, "mean"), (var, "var"), (count, "count")):
+            _f32c(t, name)
+        if mean.numel() != dim or var.numel() != dim or count.numel() != 1:
+            raise ValueError("running statistics do not match the feature dimension of x")
     if normalize:
         if out is None:
             out = torch.empty_like(x)
-        _f32c(out, "out")
-        if out.numel() != x.numel():
-            raise ValueError("out must have as many elements as x")
+        if validate:
+            _f32c(out, "out")
+            if out.numel() != x.numel():
+                raise ValueError("out must have as many elements as x")
+            if out16 is not None and (out16.dtype != torch.bfloat16 or not out16.is_contiguous() or out16.numel() % rows):
+                raise ValueError("out16 must be a contiguous bf16 tensor [rows, pad]")
     lib = L.load()
     ws_ptr, ws_bytes = None, 0
     if update:
@@ -72,7 +79,8 @@ def rms_forward(
     L.check(
         lib.catb200_rms_forward(
             x.data_ptr(), rows, dim, mean.data_ptr(), var.data_ptr(), count.data_ptr(), eps, int(update),
-            out.data_ptr() if normalize else None, ws_ptr, ws_bytes, L.stream(),
+            out.data_ptr() if normalize else None, L.ptr(out16), (out16.numel() // rows) if out16 is not None else 0,
+            ws_ptr, ws_bytes, L.stream(),
         ),
         "rms_forward",
     )  # fmt: skip
@@ -82,9 +90,20 @@ def rms_forward(
 # --------------------------------------------------------------------------------------------------
 # rollout append  (reference cleanrl/ppo.py:203-205,215-216)
 # --------------------------------------------------------------------------------------------------
-def rollout_append(reward, done, time_out, rewards_t, dones_t1, true_dones_t1) -> None:
+def rollout_append(reward, done, time_out, rewards_t, dones_t1, true_dones_t1, validate: bool = True) -> None:
     """rewards[t] = reward; dones[t+1] = done; true_dones[t+1] = float(time_out)."""
     n = reward.numel()
+    if time_out.dtype == torch.bool:
+        time_out = time_out.view(torch.uint8)
+    if not validate:
+        L.check(
+            L.load().catb200_rollout_append(
+                reward.data_ptr(), done.data_ptr(), time_out.data_ptr(), n, rewards_t.data_ptr(), dones_t1.data_ptr(),
+                true_dones_t1.data_ptr(), L.stream(),
+            ),
+            "rollout_append",
+        )  # fmt: skip
+        return
     for t, name in ((reward, "reward"), (done, "done"), (rewards_t, "rewards[t]"), (dones_t1, "dones[t+1]"), (true_dones_t1, "true_dones[t+1]")):  # fmt: skip
         _f32c(t, name)
         if t.numel() != n:
@@ -192,9 +211,10 @@ def mlp_workspace(dims, rows: int, training: bool, device) -> torch.Tensor:
     return L.zeros_workspace(need, device)
 
 
-def mlp_act(dims, obs16, params, w16, ws, noise=None, action_in=None, action=None, logprob=None, value=None, mean_out=None):
+def mlp_act(dims, obs16, params, w16, ws, noise=None, action_in=None, action=None, logprob=None, value=None, mean_out=None,
+            validate: bool = True):  # fmt: skip
     rows = obs16.numel() // dims.obs_pad
-    for t, name in ((noise, "noise"), (action_in, "action_in"), (action, "action"), (logprob, "logprob"), (value, "value"), (mean_out, "mean_out")):  # fmt: skip
+    for t, name in () if not validate else ((noise, "noise"), (action_in, "action_in"), (action, "action"), (logprob, "logprob"), (value, "value"), (mean_out, "mean_out")):  # fmt: skip
         if t is not None:
             _f32c(t, name)
     L.check(

@@ -47,11 +47,11 @@ class RunningMeanStd(nn.Module):
             self._ws = ops.Workspace(self.running_mean.device)
         return self._ws
 
-    def forward(self, obs, update=True, out=None):
+    def forward(self, obs, update=True, out=None, out16=None, validate=True):
         obs = obs if obs.is_contiguous() else obs.contiguous()
         return ops.rms_forward(
             obs, self.running_mean, self.running_var, self.count, self.epsilon, update=update, out=out,
-            workspace=self._workspace(),
+            workspace=self._workspace(), out16=out16, validate=validate,
         )  # fmt: skip
 
     def update(self, x):
@@ -100,6 +100,8 @@ class Agent(nn.Module):
         self._flat = None
         self._w16 = None
         self._act_ws = None
+        self._ws_need: dict = {}
+        self._noise = None
         self._bind_flat(torch.device("cpu"))
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.sync_weights())
         if device is not None:
@@ -148,7 +150,9 @@ class Agent(nn.Module):
 
     # -- inference ---------------------------------------------------------------------------------
     def _workspace(self, rows):
-        need = L.load().catb200_mlp_workspace_bytes(self.dims, rows, 0)
+        need = self._ws_need.get(rows)
+        if need is None:
+            need = self._ws_need[rows] = L.load().catb200_mlp_workspace_bytes(self.dims, rows, 0)
         if self._act_ws is None or self._act_ws.numel() * 8 < need:
             self._act_ws = L.zeros_workspace(need, self._flat.device)
         return self._act_ws
@@ -166,7 +170,7 @@ class Agent(nn.Module):
         ops.mlp_act(self.dims, obs16, self._flat, self._w16, self._workspace(rows), value=value)
         return value
 
-    def get_action_and_value(self, x, action=None, deterministic=False, out=None):
+    def get_action_and_value(self, x, action=None, deterministic=False, out=None, validate=True):
         """-> (action, log-prob summed over action dims, entropy summed over action dims, value [N,1]).
 
         `out=(action, logprob, value)` lets the trainer write straight into its rollout buffers."""
@@ -180,11 +184,14 @@ class Agent(nn.Module):
         else:
             act_out, logprob, value = out
         noise = None
-        if action is None and not deterministic:
-            noise = torch.randn((rows, self.act_dim), dtype=torch.float32, device=dev)  # Normal.sample's eps
+        if action is None and not deterministic:  # Normal.sample's eps, from torch's generator
+            if self._noise is None or self._noise.shape[0] != rows or self._noise.device != dev:
+                self._noise = torch.empty((rows, self.act_dim), dtype=torch.float32, device=dev)
+            noise = self._noise.normal_()
         ops.mlp_act(
             self.dims, obs16, self._flat, self._w16, self._workspace(rows), noise=noise,
             action_in=None if action is None else action.contiguous(), action=act_out, logprob=logprob, value=value,
+            validate=validate,
         )  # fmt: skip
         if out is not None:
             return act_out, logprob, None, value  # trainer fast path: the rollout never uses the entropy
@@ -273,6 +280,12 @@ class PPOTrainer:
         self._epoch_graph = None
         self._graph_launches = 0  # kernels recorded in the epoch graph
         self._graph_replays = 0
+        self._eager_epochs = 0
+        self._policy_graphs: dict = {}
+        self._policy_graph_launches = 0
+        self._policy_captures = 0
+        self._policy_replays = 0
+        self._validate = True  # argument checks of the ops wrappers; switched off after the first iteration
 
     # -- rollout -------------------------------------------------------------------------------------
     def start(self):
@@ -284,20 +297,40 @@ class PPOTrainer:
 
     def _ingest_obs(self, raw_obs, slot):
         raw_obs = raw_obs.float() if raw_obs.dtype != torch.float32 else raw_obs
-        self.agent.obs_rms(raw_obs, update=True, out=self.obs[slot])  # update + normalise (ppo.py:187,225)
-        ops.obs_to_bf16(self.obs[slot], self.agent.dims.obs_pad, out=self.obs16[slot])
+        # update + normalise (ppo.py:187,225); the same kernel also emits the bf16 rows the MLP reads
+        self.agent.obs_rms(raw_obs, update=True, out=self.obs[slot], out16=self.obs16[slot], validate=self._validate)
+
+    def _policy(self, t):
+        """Agent.get_action_and_value on slot t -> actions[t], logprobs[t], values[t] (ppo.py:208-212);
+        after the first iteration the 5 launches (noise + 3 GEMMs + head) replay as one CUDA graph per slot."""
+        if not self.use_graphs or self.iteration < 2:
+            self.agent.get_action_and_value(
+                self.obs16[t], out=(self.actions[t], self.logprobs[t], self.values[t]), validate=self._validate
+            )
+            return
+        graph = self._policy_graphs.get(t)
+        if graph is None:
+            graph = torch.cuda.CUDAGraph()
+            before = L.launch_count()
+            with torch.cuda.graph(graph):
+                self.agent.get_action_and_value(self.obs16[t], out=(self.actions[t], self.logprobs[t], self.values[t]), validate=False)
+            self._policy_graph_launches = L.launch_count() - before
+            self._policy_captures += 1
+            self._policy_graphs[t] = graph
+        graph.replay()
+        self._policy_replays += 1
 
     def rollout_step(self, t):
         """One env step of the rollout (reference ppo.py:201-230)."""
         self.global_step += self.num_envs * self.world
         # obs[t], dones[t], true_dones[t] are already in place (slot t was filled by the previous post-step)
-        self.agent.get_action_and_value(self.obs16[t], out=(self.actions[t], self.logprobs[t], self.values[t]))
+        self._policy(t)
         next_obs, reward, next_done, timeouts, info = self.envs.step(self.actions[t])
         if next_done.dtype != torch.float32:
             next_done = next_done.to(torch.float)
         ops.rollout_append(
             reward if reward.is_contiguous() else reward.contiguous(), next_done, timeouts,
-            self.rewards[t], self.dones[t + 1], self.true_dones[t + 1],
+            self.rewards[t], self.dones[t + 1], self.true_dones[t + 1], validate=self._validate,
         )  # fmt: skip
         info["true_dones"] = timeouts
         self._ingest_obs(next_obs["policy"], t + 1)
@@ -362,26 +395,29 @@ class PPOTrainer:
                 self.perm.copy_(perms[epoch])
             else:
                 self.perm.copy_(torch.randperm(self.batch_size, device=self.device))
-            if self.use_graphs:
-                if self._epoch_graph is None:
-                    self._epoch()  # warm-up run (sets kernel attributes), then capture the same launches
-                    self.perm.copy_(torch.randperm(self.batch_size, device=self.device))
-                    graph = torch.cuda.CUDAGraph()
-                    before = L.launch_count()
-                    with torch.cuda.graph(graph):
-                        self._epoch()
-                    self._graph_launches = L.launch_count() - before
-                    self._epoch_graph = graph
+            if self.use_graphs and self._epoch_graph is None and self._eager_epochs >= 1:
+                # the first epoch ever ran eagerly (it also set the kernel attributes); record the identical
+                # launch sequence once and replay it from now on
+                graph = torch.cuda.CUDAGraph()
+                before = L.launch_count()
+                with torch.cuda.graph(graph):
+                    self._epoch()
+                self._graph_launches = L.launch_count() - before
+                self._epoch_graph = graph
+            if self._epoch_graph is not None:
                 self._epoch_graph.replay()
                 self._graph_replays += 1
+                self._eager_epochs += 1
             else:
                 self._epoch()
+                self._eager_epochs += 1
 
     def kernel_launches(self) -> int:
         """libcatb200 kernels executed so far by this process (graph replays included)."""
-        return L.launch_count() - self._graph_launches * (1 if self._epoch_graph is not None else 0) + (
-            self._graph_launches * self._graph_replays
-        )
+        captured = self._graph_launches * (1 if self._epoch_graph is not None else 0)
+        captured += self._policy_graph_launches * self._policy_captures
+        replayed = self._graph_launches * self._graph_replays + self._policy_graph_launches * self._policy_replays
+        return L.launch_count() - captured + replayed
 
     def finish_iteration(self):
         """Slot T (the bootstrap observation / dones) becomes slot 0 of the next rollout (ppo.py:203-205)."""
@@ -405,6 +441,7 @@ class PPOTrainer:
         self.compute_gae()
         self.update()
         self.finish_iteration()
+        self._validate = False
         return ep_infos
 
     def losses(self) -> dict:

@@ -157,7 +157,7 @@ class SyntheticSolo12Env:
         self.common_step_counter = 0
         self.cfg = SimpleNamespace(constraints=constraints_cfg)
         self.extras: dict = {}
-        self._curriculum = curriculum
+        self._curriculum_on = curriculum
 
         self.scene = _Scene(robot=_Articulation(), contact_forces=_ContactSensor())
         self.command_manager = _CommandManager()
@@ -178,7 +178,7 @@ class SyntheticSolo12Env:
         )
         # staggered episode phases so that resets trickle in like in a real run, without a host sync
         phase = torch.randint(0, self.max_episode_length, (self.num_envs,), generator=gen)
-        self._phase_cpu = phase
+        self._phase_np = phase.numpy().copy()  # host mirror of episode_length_buf: reset schedule without a sync
         self.episode_length_buf = phase.to(self.device, dtype=torch.long)
         self.reset_buf = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
         self.reset_time_outs = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
@@ -229,9 +229,10 @@ class SyntheticSolo12Env:
         self._advance()
         self.episode_length_buf += 1
         self.common_step_counter += 1
-        # time-outs on a host-known staggered schedule (Isaac Lab's termination manager in the real env)
-        self._phase_cpu += 1
-        due = self._phase_cpu >= self.max_episode_length
+        # time-outs (Isaac Lab's termination manager in the real env); the host mirror of the episode
+        # lengths tells whether anything resets this step without reading the device
+        self._phase_np += 1
+        due = self._phase_np >= self.max_episode_length
         self.reset_time_outs = self.episode_length_buf >= self.max_episode_length
         self.reset_buf = self.reset_time_outs
         mgr = self.constraint_manager
@@ -240,22 +241,33 @@ class SyntheticSolo12Env:
         else:
             self.reward_buf = self._raw_reward
             dones = self.reset_buf.float()
-        if bool(due.any()):
-            env_ids_cpu = due.nonzero(as_tuple=False).squeeze(-1)
-            env_ids = env_ids_cpu.to(self.device)
-            self._reset_idx(env_ids)
-            self._phase_cpu[env_ids_cpu] = 0
+        if due.any():
+            self._reset_masked(self.reset_buf)
+            self._phase_np[due] = 0
         return self.obs_buf, self.reward_buf, dones, self.reset_time_outs, self.extras
 
-    def _reset_idx(self, env_ids: torch.Tensor):
-        """CaT-relevant part of `CaTEnv._reset_idx` (reference cat_env.py:149-200)."""
+    def _curriculum(self):
+        mgr = self.constraint_manager
+        if self._curriculum_on:
+            for name in mgr.active_terms:
+                if name in SOLO12_CURRICULUM_TERMS:
+                    modify_constraint_p(self, None, name, num_steps=24 * 1000, init_max_p=0.25)
+
+    def _reset_masked(self, mask: torch.Tensor):
+        """CaT-relevant part of `CaTEnv._reset_idx` (cat_env.py:149-200), envs selected by a device mask."""
         mgr = self.constraint_manager
         self.extras["log"] = dict()
         if mgr is not None:
-            if self._curriculum:
-                for name in mgr.active_terms:
-                    if name in SOLO12_CURRICULUM_TERMS:
-                        modify_constraint_p(self, env_ids, name, num_steps=24 * 1000, init_max_p=0.25)
+            self._curriculum()
+            self.extras["log"].update(mgr.reset_masked(mask))
+        self.episode_length_buf.masked_fill_(mask, 0)
+
+    def _reset_idx(self, env_ids: torch.Tensor):
+        """Same with explicit env ids, the way Isaac Lab calls it (cat_env.py:149-200)."""
+        mgr = self.constraint_manager
+        self.extras["log"] = dict()
+        if mgr is not None:
+            self._curriculum()
             self.extras["log"].update(mgr.reset(env_ids))
         self.episode_length_buf[env_ids] = 0
 

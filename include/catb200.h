@@ -173,11 +173,13 @@ size_t catb200_rms_workspace_bytes(int32_t dim);
  * RunningMeanStd.forward(x, update=True) for x [rows, dim] (dim = 1 for scalars):
  * batch mean / biased variance, Chan merge into (mean[dim], var[dim], count[1]) and
  * out = (x - mean) / sqrt(var + eps) with the *updated* statistics.  `out` may alias x or be NULL
- * (update only).  update == 0 skips the statistics and only normalises.
+ * (update only).  update == 0 skips the statistics and only normalises.  If out16 != NULL the normalised
+ * rows are also written as bf16 [rows, pad16] (zero padded; dim <= pad16 <= 2 * dim), the layout the
+ * first MLP layer reads, so the rollout needs no separate conversion pass.
  */
 int catb200_rms_forward(const float* x, int64_t rows, int32_t dim, float* mean, float* var, float* count,
-                        float eps, int32_t update, float* out, void* workspace, size_t workspace_bytes,
-                        void* stream);
+                        float eps, int32_t update, float* out, void* out16, int32_t pad16, void* workspace,
+                        size_t workspace_bytes, void* stream);
 
 /*
  * Post-step rollout append (U/cleanrl/ppo.py:203-205,215-216,225 for step t):
