@@ -14,10 +14,25 @@
 //   reduce_partials    : sums the split partials into the flat gradient (deterministic order)
 // Tensor-core work is bf16 x bf16 -> fp32 (mma.sync m16n8k16 fed by cp.async + ldmatrix from XOR-swizzled
 // shared memory, 3-stage pipeline); everything the reference does elementwise is fused into epilogues.
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 #include "mma.cuh"
+#include "tc_gemm.cuh"
 
 namespace catb200 {
+
+// GEMM backend: tcgen05/TMEM/TMA (default) or the mma.sync kernels below (CATB200_GEMM=mma), kept as the
+// on-device cross-check of the tensor-core path.
+static bool use_tc() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("CATB200_GEMM");
+    v = (e && std::strcmp(e, "mma") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
 
 constexpr int kGemmThreads = 256;
 constexpr int kBM = 128, kBN = 128, kBK = 64;
@@ -776,7 +791,21 @@ static int launch_forward(const catb200_mlp_dims_t* d, const catb200_mlp_layout_
     CATB200_CUDA_TRY(cudaFuncSetAttribute(gemm_nt_kernel<kEpiMulDelu>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemNT));
     attr_set = true;
   }
-  for (int l = 0; l < 3; ++l) {
+  for (int l = 0; l < 3 && use_tc(); ++l) {
+    TcGemmArgs t = {};
+    for (int z = 0; z < 2; ++z) {
+      const bf16* A = l == 0 ? X : reinterpret_cast<const bf16*>(ws + L.H[z][l - 1]);
+      int rc = make_tmap_bf16(&t.mapA[z], A, x.in_pad[l], rows, x.in_pad[l], 64, 128);
+      if (rc == CATB200_OK) rc = make_tmap_bf16(&t.mapB[z], w16 + P.w16[z][l], x.in_pad[l], x.out[l], x.in_pad[l], 64, 128);
+      if (rc != CATB200_OK) return rc;
+      t.C[z] = reinterpret_cast<bf16*>(ws + L.H[z][l]);
+      t.bias[z] = params + P.b[z][l];
+    }
+    t.ldc = x.out[l]; t.M = rows; t.N = x.out[l]; t.K = x.in_pad[l];
+    int rc = tc_gemm_launch(kTcFwd, t, 1, st);
+    if (rc != CATB200_OK) return rc;
+  }
+  for (int l = 0; l < 3 && !use_tc(); ++l) {
     GemmNTArgs g = {};
     for (int z = 0; z < 2; ++z) {
       g.A[z] = l == 0 ? X : reinterpret_cast<const bf16*>(ws + L.H[z][l - 1]);
@@ -942,15 +971,40 @@ int catb200_ppo_minibatch_grad(const catb200_mlp_dims_t* dims, const catb200_ppo
       red.N[seg] = x.out[l]; red.Kpad[seg] = x.in_pad[l]; red.Ktrue[seg] = x.in[l]; red.splits[seg] = L.splits[l];
     }
     wgt.M = M; wgt.N = x.out[l]; wgt.Kpad = x.in_pad[l]; wgt.m_range = L.m_range[l];
-    if (x.in_pad[l] >= 128) {
+    if (use_tc()) {
+      TcGemmArgs t = {};
+      for (int z = 0; z < 2; ++z) {
+        int rc = make_tmap_bf16(&t.mapA[z], wgt.dZ[z], x.out[l], M, x.out[l], 64, 64);
+        if (rc == CATB200_OK) rc = make_tmap_bf16(&t.mapB[z], wgt.Hin[z], x.in_pad[l], M, x.in_pad[l], 64, 64);
+        if (rc != CATB200_OK) return rc;
+        t.part[z] = wgt.part[z];
+      }
+      t.M = x.out[l]; t.N = x.in_pad[l]; t.K = M; t.m_range = L.m_range[l];
+      int rc = tc_gemm_launch(kTcWgrad, t, L.splits[l], st);
+      if (rc != CATB200_OK) return rc;
+    } else if (x.in_pad[l] >= 128) {
       dim3 grid((x.out[l] / 128) * (x.in_pad[l] / 128), L.splits[l], 2);
       wgrad_kernel<128><<<grid, kGemmThreads, kStages * kWgBM * (256 + 256), st>>>(wgt);
+      CATB200_LAUNCH_CHECK();
     } else {
       dim3 grid((x.out[l] / 128) * (x.in_pad[l] / 64), L.splits[l], 2);
       wgrad_kernel<64><<<grid, kGemmThreads, kStages * kWgBM * (256 + 128), st>>>(wgt);
+      CATB200_LAUNCH_CHECK();
     }
-    CATB200_LAUNCH_CHECK();
-    if (l > 0) {  // dZ_{l-1} = (dZ_l W_l) * ELU'(H_{l-1}); A = dZ_l [M, out_l], B = W_l^T [in_l, out_l]
+    if (l > 0 && use_tc()) {  // dZ_{l-1} = (dZ_l W_l) * ELU'(H_{l-1}); A = dZ_l [M, out_l], B = W_l^T [in_l, out_l]
+      TcGemmArgs t = {};
+      for (int z = 0; z < 2; ++z) {
+        int rc = make_tmap_bf16(&t.mapA[z], reinterpret_cast<const bf16*>(ws + L.dZ[z][l]), x.out[l], M, x.out[l], 64, 128);
+        if (rc == CATB200_OK) rc = make_tmap_bf16(&t.mapB[z], w16 + P.wt16[z][l], x.out[l], x.in[l], x.out[l], 64, 128);
+        if (rc != CATB200_OK) return rc;
+        t.C[z] = reinterpret_cast<bf16*>(ws + L.dZ[z][l - 1]);
+        t.H[z] = reinterpret_cast<const bf16*>(ws + L.H[z][l - 1]);
+        t.dbias[z] = grads + P.b[z][l - 1];
+      }
+      t.ldc = x.in[l]; t.M = M; t.N = x.in[l]; t.K = x.out[l];
+      int rc = tc_gemm_launch(kTcDgrad, t, 1, st);
+      if (rc != CATB200_OK) return rc;
+    } else if (l > 0) {
       GemmNTArgs g = {};
       for (int z = 0; z < 2; ++z) {
         g.A[z] = reinterpret_cast<const bf16*>(ws + L.dZ[z][l]);

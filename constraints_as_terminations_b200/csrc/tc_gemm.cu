@@ -1,0 +1,421 @@
+// 5th-generation tensor-core GEMMs for the actor-critic MLP (sm_100a: tcgen05.mma + TMEM + TMA).
+//
+// One warp-specialised kernel, three modes (both nets batched over blockIdx.z):
+//   kFwd   : C[M,N]  = ELU(A[M,K] B[N,K]^T + bias)            A, B K-major            (hidden layers, forward)
+//   kDgrad : C[M,N]  = (A[M,K] B[N,K]^T) * ELU'(H[M,N]), db += colsum      K-major    (dZ_{l-1} from dZ_l, W_l^T)
+//   kWgrad : P[s,N,K] = sum_{m in split s} dZ[m,N]^T Hin[m,K]  A, B MN-major          (weight-gradient partials)
+//
+// CTA = one 128 x BN accumulator tile living in TMEM (128 lanes x BN fp32 columns).
+//   warp 0      : TMA producer  - cp.async.bulk.tensor 2D boxes (64 elements = 128 B inner, SWIZZLE_128B)
+//                                 into a 4-stage shared-memory ring, completion on mbarriers
+//   warp 1      : TMEM allocator + MMA issuer - one elected lane issues tcgen05.mma.cta_group::1.kind::f16
+//                                 (M = 128, N = BN, K = 16) from shared-memory matrix descriptors;
+//                                 tcgen05.commit releases ring slots and finally signals the epilogue
+//   warps 2..5  : epilogue      - tcgen05.ld (32 lanes x 32 columns per instruction) -> registers ->
+//                                 bias/ELU or ELU'-scale (+ recursive-halving column sums) or fp32 partials
+// Several CTAs are resident per SM (<= 96 KiB of shared memory, BN <= 128 TMEM columns each), so one CTA's
+// epilogue overlaps another CTA's main loop without a persistent scheduler.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "mma.cuh"
+#include "tc_gemm.cuh"
+
+namespace catb200 {
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives row (lane_base + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address >> 4 in bits [0,14),
+// leading byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version 1 in [46,48),
+// layout type SWIZZLE_128B (= 2) in [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (1 << 4), A/B bf16 (1 << 7, 1 << 10),
+// a_major bit 15, b_major bit 16 (1 = MN-major), N >> 3 in [17,23), M >> 4 in [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn_major, bool b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+constexpr int kTcThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kTcStages = 4;
+constexpr int kTcBK = 64;  // reduction elements per stage (= 4 UMMA K-steps of 16)
+
+template <int MODE, int BN>
+struct TcSmem {
+  static constexpr int kABytes = 128 * kTcBK * 2;  // 16 KiB: 128 (M) x 64 (K) bf16, or 2 boxes of 64 x 64 (MN-major)
+  static constexpr int kBBytes = BN * kTcBK * 2;
+  static constexpr int kStage = kABytes + kBBytes;
+  static constexpr int kTotal = kTcStages * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+template <int MODE, int BN>
+__global__ void __launch_bounds__(kTcThreads)
+tc_gemm_kernel(const __grid_constant__ TcGemmArgs g) {
+  using S = TcSmem<MODE, BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t tiles = (raw + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
+  const uint32_t bars = tiles + kTcStages * S::kStage;
+  const uint32_t full_bar = bars, empty_bar = bars + 8 * kTcStages, tmem_full_bar = bars + 16 * kTcStages;
+  const uint32_t tmem_slot = bars + 16 * kTcStages + 8;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int z = blockIdx.z;
+  const CUtensorMap* mapA = &g.mapA[z];
+  const CUtensorMap* mapB = &g.mapB[z];
+
+  // tile coordinates and reduction range
+  int row_base, col_base, k_begin, k_blocks;
+  if (MODE == kTcWgrad) {
+    const int k_tiles = g.N / BN;  // output columns (input features) per BN tile
+    row_base = (blockIdx.x / k_tiles) * 128;  // dW rows (output features of the layer)
+    col_base = (blockIdx.x % k_tiles) * BN;
+    k_begin = blockIdx.y * g.m_range;
+    const int k_end = min(g.K, k_begin + g.m_range);
+    k_blocks = max(0, (k_end - k_begin + kTcBK - 1) / kTcBK);
+  } else {
+    row_base = blockIdx.x * 128;
+    col_base = blockIdx.y * BN;
+    k_begin = 0;
+    k_blocks = g.K / kTcBK;
+  }
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(mapA));
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(mapB));
+    for (int s = 0; s < kTcStages; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        const int s = kb % kTcStages;
+        mbar_wait(empty_bar + 8 * s, ((kb / kTcStages) & 1) ^ 1);
+        const uint32_t sa = tiles + s * S::kStage, sb = sa + S::kABytes;
+        mbar_expect_tx(full_bar + 8 * s, S::kStage);
+        const int k0 = k_begin + kb * kTcBK;
+        if (MODE == kTcWgrad) {
+          // MN-major operands: boxes of 64 (contiguous features) x 64 (reduction rows), 8 KiB each
+          for (int h = 0; h < 2; ++h) tma_load_2d(sa + h * 8192, mapA, full_bar + 8 * s, row_base + h * 64, k0);
+          for (int h = 0; h < BN / 64; ++h) tma_load_2d(sb + h * 8192, mapB, full_bar + 8 * s, col_base + h * 64, k0);
+        } else {
+          tma_load_2d(sa, mapA, full_bar + 8 * s, k0, row_base);  // 64 (K) x 128 rows
+          tma_load_2d(sb, mapB, full_bar + 8 * s, k0, col_base);  // 64 (K) x BN rows
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc(128, BN, MODE == kTcWgrad, MODE == kTcWgrad);
+    for (int kb = 0; kb < k_blocks; ++kb) {
+      const int s = kb % kTcStages;
+      mbar_wait(full_bar + 8 * s, (kb / kTcStages) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = tiles + s * S::kStage, sb = sa + S::kABytes;
+#pragma unroll
+        for (int k = 0; k < kTcBK / 16; ++k) {
+          uint64_t da, db;
+          if (MODE == kTcWgrad) {
+            // MN-major SW128: 64-feature chunks LBO = 8 KiB apart, 8-row reduction groups SBO = 1 KiB apart;
+            // one UMMA K-step (16 reduction rows) = 2 KiB further
+            da = make_smem_desc(sa + k * 2048, 8192, 1024);
+            db = make_smem_desc(sb + k * 2048, 8192, 1024);
+          } else {
+            // K-major SW128: rows are 128 B, 8-row groups SBO = 1 KiB apart; one K-step = 32 B further
+            da = make_smem_desc(sa + k * 32, 16, 1024);
+            db = make_smem_desc(sb + k * 32, 16, 1024);
+          }
+          umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+      }
+      __syncwarp();
+      if (elect_one()) {
+        umma_commit(empty_bar + 8 * s);                         // frees the ring slot once these MMAs retire
+        if (kb == k_blocks - 1) umma_commit(tmem_full_bar);    // accumulator complete -> epilogue
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;  // TMEM lanes 32*quarter .. +31 are the ones this warp may read
+    const int row = row_base + quarter * 32 + lane;
+    if (k_blocks > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+    }
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    if (MODE == kTcFwd) {
+      const float* __restrict__ bias = g.bias[z];
+      bf16* __restrict__ crow = g.C[z] + (size_t)row * g.ldc + col_base;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c, v);
+        if (row < g.M) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 o;
+            uint32_t* op = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int cc = q * 8 + e * 2;
+              const float x0 = __uint_as_float(v[cc]) + __ldg(bias + col_base + c + cc);
+              const float x1 = __uint_as_float(v[cc + 1]) + __ldg(bias + col_base + c + cc + 1);
+              op[e] = pack_bf16x2(elu(x0), elu(x1));
+            }
+            *reinterpret_cast<uint4*>(crow + c + q * 8) = o;
+          }
+        }
+      }
+    } else if (MODE == kTcDgrad) {
+      const bf16* __restrict__ hrow = g.H[z] + (size_t)row * g.ldc + col_base;
+      bf16* __restrict__ crow = g.C[z] + (size_t)row * g.ldc + col_base;
+      float* __restrict__ dbias = g.dbias[z] + col_base;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c, v);
+        float f[32];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 hv = make_uint4(0, 0, 0, 0);
+          if (row < g.M) hv = __ldg(reinterpret_cast<const uint4*>(hrow + c + q * 8));
+          const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&hv);
+          uint4 o;
+          uint32_t* op = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int cc = q * 8 + e * 2;
+            const float x0 = row < g.M ? __uint_as_float(v[cc]) * elu_grad_from_output(__low2float(hp[e])) : 0.0f;
+            const float x1 = row < g.M ? __uint_as_float(v[cc + 1]) * elu_grad_from_output(__high2float(hp[e])) : 0.0f;
+            f[cc] = x0;
+            f[cc + 1] = x1;
+            op[e] = pack_bf16x2(x0, x1);
+          }
+          if (row < g.M) *reinterpret_cast<uint4*>(crow + c + q * 8) = o;
+        }
+        // column sums over this warp's 32 rows by recursive halving: after the 5 rounds lane l holds the
+        // sum of column (c + l)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const bool upper = (lane & o) != 0;
+#pragma unroll
+          for (int i = 0; i < o; ++i) {
+            const float send = upper ? f[i] : f[i + o];
+            const float keep = upper ? f[i + o] : f[i];
+            f[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+          }
+        }
+        atomicAdd(dbias + c + lane, f[0]);
+      }
+    } else {
+      // weight-gradient partial: fp32 [128 rows (layer outputs) x BN (layer inputs)]
+      float* __restrict__ prow = g.part[z] + ((size_t)blockIdx.y * g.M + row) * g.N + col_base;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        if (k_blocks > 0) {
+          tmem_ld32(taddr + c, v);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(prow + c + q * 4) = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                     uint32_t box_outer);
+
+static EncodeTiledFn encoder() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+struct TmapKey {
+  const void* ptr;
+  uint64_t inner, outer, ld;
+  uint32_t bi, bo;
+};
+struct TmapEntry {
+  TmapKey key;
+  CUtensorMap map;
+};
+static TmapEntry g_tmap_cache[128];
+static int g_tmap_count = 0;
+
+// bf16 row-major [outer, inner] with leading dimension ld (elements); box = [box_outer, box_inner].
+// Encodings are memoised: the trainer reuses a handful of (pointer, shape) combinations every step.
+int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                   uint32_t box_outer) {
+  for (int i = 0; i < g_tmap_count; ++i) {
+    const TmapKey& k = g_tmap_cache[i].key;
+    if (k.ptr == ptr && k.inner == inner && k.outer == outer && k.ld == ld && k.bi == box_inner && k.bo == box_outer) {
+      *map = g_tmap_cache[i].map;
+      return CATB200_OK;
+    }
+  }
+  int rc = encode_tmap_bf16(map, ptr, inner, outer, ld, box_inner, box_outer);
+  if (rc == CATB200_OK) {
+    const int slot = g_tmap_count < 128 ? g_tmap_count++ : 127;
+    g_tmap_cache[slot].key = TmapKey{ptr, inner, outer, ld, box_inner, box_outer};
+    g_tmap_cache[slot].map = *map;
+  }
+  return rc;
+}
+
+int encode_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                     uint32_t box_outer) {
+  EncodeTiledFn fn = encoder();
+  if (!fn) return CATB200_ERR_UNSUPPORTED;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? CATB200_OK : CATB200_ERR_CUDA;
+}
+
+template <int MODE, int BN>
+static int launch_one(const TcGemmArgs& g, dim3 grid, cudaStream_t st) {
+  using S = TcSmem<MODE, BN>;
+  static bool attr = false;
+  if (!attr) {
+    CATB200_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    attr = true;
+  }
+  tc_gemm_kernel<MODE, BN><<<grid, kTcThreads, S::kTotal, st>>>(g);
+  CATB200_LAUNCH_CHECK();
+  return CATB200_OK;
+}
+
+int tc_gemm_launch(int mode, const TcGemmArgs& g, int splits, cudaStream_t st) {
+  if (mode == kTcFwd) {
+    if (g.N % 128) return CATB200_ERR_UNSUPPORTED;
+    return launch_one<kTcFwd, 128>(g, dim3((g.M + 127) / 128, g.N / 128, 2), st);
+  }
+  if (mode == kTcDgrad) {
+    if (g.N % 128) return CATB200_ERR_UNSUPPORTED;
+    return launch_one<kTcDgrad, 128>(g, dim3((g.M + 127) / 128, g.N / 128, 2), st);
+  }
+  // wgrad: g.M = layer outputs (dW rows), g.N = padded layer inputs (dW cols), g.K = minibatch rows
+  if (g.M % 128) return CATB200_ERR_UNSUPPORTED;
+  if (g.N % 128 == 0) return launch_one<kTcWgrad, 128>(g, dim3((g.M / 128) * (g.N / 128), splits, 2), st);
+  if (g.N % 64 == 0) return launch_one<kTcWgrad, 64>(g, dim3((g.M / 128) * (g.N / 64), splits, 2), st);
+  return CATB200_ERR_UNSUPPORTED;
+}
+
+}  // namespace catb200
