@@ -382,7 +382,9 @@ struct MbStats {
 
 __global__ void __launch_bounds__(256)
 gather_kernel(const int64_t* __restrict__ mb_inds, int M, const bf16* __restrict__ obs16_all, int obs_pad,
-              const float* __restrict__ adv_all, bf16* __restrict__ X, MbStats* __restrict__ st) {
+              const float* __restrict__ adv_all, const float* __restrict__ logp_all, const float* __restrict__ ret_all,
+              const float* __restrict__ val_all, const float* __restrict__ act_all, int A, bf16* __restrict__ X,
+              float4* __restrict__ scal_mb, float* __restrict__ act_mb, MbStats* __restrict__ st) {
   const int chunks = obs_pad / 8;  // 16-byte chunks per row
   const int total = M * chunks;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
@@ -390,9 +392,18 @@ gather_kernel(const int64_t* __restrict__ mb_inds, int M, const bf16* __restrict
     const int64_t src = mb_inds[m];
     reinterpret_cast<uint4*>(X)[e] = __ldg(reinterpret_cast<const uint4*>(obs16_all + (size_t)src * obs_pad) + c);
   }
+  // per-sample scalars {old log-prob, advantage, return, old value} and actions, packed contiguously in
+  // minibatch order so that the head kernel streams them instead of chasing mb_inds
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < M * A; e += gridDim.x * blockDim.x) {
+    const int m = e / A, j = e - m * A;
+    act_mb[e] = __ldg(act_all + (size_t)mb_inds[m] * A + j);
+  }
   double s = 0.0, q = 0.0;
   for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < M; m += gridDim.x * blockDim.x) {
-    const double a = (double)__ldg(adv_all + mb_inds[m]);
+    const int64_t src = mb_inds[m];
+    const float adv = __ldg(adv_all + src);
+    scal_mb[m] = make_float4(__ldg(logp_all + src), adv, __ldg(ret_all + src), __ldg(val_all + src));
+    const double a = (double)adv;
     s += a;
     q += a * a;
   }
@@ -436,10 +447,10 @@ struct HeadArgs {
   int M, h3, A;
   // rollout outputs / inputs
   const float* noise; const float* action_in; float* action; float* logprob; float* value; float* mean_out;
-  // training inputs (flattened rollout, gathered by mb_inds)
-  const int64_t* mb_inds;
-  const float* actions_all; const float* logprobs_all; const float* adv_all; const float* ret_all;
-  const float* val_all; const float* norm_stats; const MbStats* mb;
+  // training inputs, packed in minibatch order by gather_kernel
+  const float4* scal_mb;  // {old log-prob, advantage, return, old value}
+  const float* act_mb;    // [M, A]
+  const float* norm_stats; const MbStats* mb;
   catb200_ppo_hparams_t hp;
   // training outputs
   float* head_part;  // [gridDim.x][kHeadValues][32] per-CTA partial sums (training)
@@ -493,17 +504,34 @@ head_kernel(const __grid_constant__ HeadArgs a) {
   const float inv_sd1 = 1.0f / sqrtf(v1 + 1e-8f), inv_sd2 = 1.0f / sqrtf(v2 + 1e-8f);
   const float inv_M = 1.0f / (float)a.M;
 
-  for (int m = blockIdx.x * warps + warp; m < a.M; m += gridDim.x * warps) {
-    // ---- load the two 128-wide activation rows (8 bytes per lane each, coalesced)
+  // software pipeline: the inputs of the next sample are in flight while the current one is processed
+  const int m_stride = gridDim.x * warps;
+  int m = blockIdx.x * warps + warp;
+  uint2 n_rc = make_uint2(0, 0), n_ra = make_uint2(0, 0);
+  float4 n_sc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float n_act = 0.0f;
+  auto fetch = [&](int mm) {
+    n_rc = __ldg(reinterpret_cast<const uint2*>(a.H3[0] + (size_t)mm * a.h3) + lane);
+    n_ra = __ldg(reinterpret_cast<const uint2*>(a.H3[1] + (size_t)mm * a.h3) + lane);
+    if (TRAIN) {
+      n_sc = __ldg(a.scal_mb + mm);
+      if (lane < A) n_act = __ldg(a.act_mb + (size_t)mm * A + lane);
+    }
+  };
+  if (m < a.M) fetch(m);
+  for (; m < a.M; m += m_stride) {
+    // ---- the two 128-wide activation rows (8 bytes per lane each, coalesced) + scalars of this sample
     float hc[F], ha[F];
+    const float4 sc = n_sc;
+    const float act_in = n_act;
     {
-      const uint2 rc = __ldg(reinterpret_cast<const uint2*>(a.H3[0] + (size_t)m * a.h3) + lane);
-      const uint2 ra = __ldg(reinterpret_cast<const uint2*>(a.H3[1] + (size_t)m * a.h3) + lane);
+      const uint2 rc = n_rc, ra = n_ra;
       const __nv_bfloat162* pc = reinterpret_cast<const __nv_bfloat162*>(&rc);
       const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&ra);
       hc[0] = __low2float(pc[0]); hc[1] = __high2float(pc[0]); hc[2] = __low2float(pc[1]); hc[3] = __high2float(pc[1]);
       ha[0] = __low2float(pa[0]); ha[1] = __high2float(pa[0]); ha[2] = __low2float(pa[1]); ha[3] = __high2float(pa[1]);
     }
+    if (m + m_stride < a.M) fetch(m + m_stride);
     // ---- heads: value and action mean (fp32), warp all-reduce of the per-lane partial dot products
     float v = 0.0f;
 #pragma unroll
@@ -550,19 +578,17 @@ head_kernel(const __grid_constant__ HeadArgs a) {
       continue;
     }
     // ---- training: PPO-clip loss and its gradient for this sample (ppo.py:300-344)
-    const int64_t src = a.mb_inds[m];
     float lp = 0.0f, dmu = 0.0f, dls = 0.0f;  // lane j: d logp / d mean_j, d logp / d logstd_j
     if (lane < A) {
-      const float act = __ldg(a.actions_all + (size_t)src * A + lane);
-      const float d = act - mean_j;
+      const float d = act_in - mean_j;
       lp = -(d * d) * 0.5f * my_inv_var - my_logstd - kLogSqrt2Pi;
       dmu = d * my_inv_var;
       dls = d * d * my_inv_var - 1.0f;
     }
     const float newlogp = warp_sum(lp);
-    const float logratio = newlogp - __ldg(a.logprobs_all + src);
+    const float logratio = newlogp - sc.x;
     const float ratio = expf(logratio);
-    float adv = __ldg(a.adv_all + src);
+    float adv = sc.y;
     if (a.hp.norm_adv) adv = (adv - adv_mean) / (adv_std + 1e-8f);
     const float clipped = fminf(fmaxf(ratio, 1.0f - a.hp.clip_coef), 1.0f + a.hp.clip_coef);
     const float pg1 = -adv * ratio, pg2 = -adv * clipped;
@@ -575,8 +601,8 @@ head_kernel(const __grid_constant__ HeadArgs a) {
     const float dL_dlogp = dpg_dratio * ratio * inv_M;
     // value loss on normalised values (ppo.py:328-341)
     const float nv = (v - m2) * inv_sd2;  // value_rms(newvalue, update=False): statistics after both updates
-    const float ret_n = (__ldg(a.ret_all + src) - m2) * inv_sd2;
-    const float val_n = (__ldg(a.val_all + src) - m1) * inv_sd1;
+    const float ret_n = (sc.z - m2) * inv_sd2;
+    const float val_n = (sc.w - m1) * inv_sd1;
     float vl, dvl_dnv;
     const float e_u = nv - ret_n;
     if (a.hp.clip_vloss) {
@@ -724,7 +750,7 @@ static Dims make_dims(const catb200_mlp_dims_t* d) {
 }
 
 struct ActLayout {  // byte offsets into the activation workspace
-  size_t X, H[2][3], dZ[2][3], mb, part[2][3], head_part, total;
+  size_t X, H[2][3], dZ[2][3], mb, part[2][3], head_part, scal_mb, act_mb, total;
   int splits[3], m_range[3], head_rows;
 };
 
@@ -740,6 +766,8 @@ static ActLayout act_layout(const catb200_mlp_dims_t* d, int rows, bool training
   if (training) {
     L.head_rows = min((rows + 7) / 8, kNumSMs);
     L.head_part = take((size_t)L.head_rows * kHeadValues * 32 * 4);
+    L.scal_mb = take((size_t)rows * 16);
+    L.act_mb = take((size_t)rows * d->act_dim * 4);
     for (int z = 0; z < 2; ++z)
       for (int l = 0; l < 3; ++l) L.dZ[z][l] = take((size_t)rows * x.out[l] * 2);
     for (int l = 0; l < 3; ++l) {
@@ -924,7 +952,8 @@ int catb200_ppo_minibatch_grad(const catb200_mlp_dims_t* dims, const catb200_ppo
 
   // 1. gather + advantage statistics
   gather_kernel<<<min((M * (dims->obs_pad / 8) + 255) / 256, kNumSMs * 8), 256, 0, st>>>(
-      mb_inds, M, static_cast<const bf16*>(obs16_all), dims->obs_pad, advantages_all, X, mb);
+      mb_inds, M, static_cast<const bf16*>(obs16_all), dims->obs_pad, advantages_all, logprobs_all, returns_all, values_all,
+      actions_all, dims->act_dim, X, reinterpret_cast<float4*>(ws + L.scal_mb), reinterpret_cast<float*>(ws + L.act_mb), mb);
   CATB200_LAUNCH_CHECK();
   // 2. forward through the three hidden layers of both nets
   int rc = launch_forward(dims, P, L, X, M, params, w16, ws, st);
@@ -940,8 +969,9 @@ int catb200_ppo_minibatch_grad(const catb200_mlp_dims_t* dims, const catb200_ppo
     a.W4a = params + P.w[1][3]; a.b4a = params + P.b[1][3];
     a.logstd = params + P.logstd;
     a.M = M; a.h3 = dims->h3; a.A = dims->act_dim;
-    a.mb_inds = mb_inds; a.actions_all = actions_all; a.logprobs_all = logprobs_all; a.adv_all = advantages_all;
-    a.ret_all = returns_all; a.val_all = values_all; a.norm_stats = norm_stats; a.mb = mb; a.hp = *hp;
+    a.scal_mb = reinterpret_cast<const float4*>(ws + L.scal_mb);
+    a.act_mb = reinterpret_cast<const float*>(ws + L.act_mb);
+    a.norm_stats = norm_stats; a.mb = mb; a.hp = *hp;
     a.head_part = reinterpret_cast<float*>(ws + L.head_part);
     static bool head_attr = false;
     if (!head_attr) {

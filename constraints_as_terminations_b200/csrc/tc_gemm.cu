@@ -90,8 +90,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
+// wait for outstanding tcgen05.ld; the registers are listed as in/out operands so that no use of them can be
+// scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+// ELU for the epilogue: ex2.approx based exp (abs error ~1e-7, far below the bf16 rounding of the result)
+__device__ __forceinline__ float elu_fast(float v) { return v > 0.0f ? v : __expf(v) - 1.0f; }
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address >> 4 in bits [0,14),
 // leading byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version 1 in [46,48),
@@ -113,8 +125,8 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn_major,
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-constexpr int kTcThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
-constexpr int kTcStages = 4;
+constexpr int kTcThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (2 warps per TMEM lane quarter)
+constexpr int kTcStages = 3;     // ring slots at most (fewer when the reduction is short)
 constexpr int kTcBK = 64;  // reduction elements per stage (= 4 UMMA K-steps of 16)
 
 template <int MODE, int BN>
@@ -122,20 +134,23 @@ struct TcSmem {
   static constexpr int kABytes = 128 * kTcBK * 2;  // 16 KiB: 128 (M) x 64 (K) bf16, or 2 boxes of 64 x 64 (MN-major)
   static constexpr int kBBytes = BN * kTcBK * 2;
   static constexpr int kStage = kABytes + kBBytes;
-  static constexpr int kTotal = kTcStages * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int kAux = 256 /*barriers*/ + BN * 4 /*bias tile*/;
+  static constexpr int total(int stages) { return stages * kStage + 1024 /*alignment slack*/ + kAux; }
 };
 
 template <int MODE, int BN>
-__global__ void __launch_bounds__(kTcThreads)
+__global__ void __launch_bounds__(kTcThreads, 2)
 tc_gemm_kernel(const __grid_constant__ TcGemmArgs g) {
   using S = TcSmem<MODE, BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t tiles = (raw + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
-  const uint32_t bars = tiles + kTcStages * S::kStage;
+  const int stages = g.stages;
+  const uint32_t bars = tiles + stages * S::kStage;
   const uint32_t full_bar = bars, empty_bar = bars + 8 * kTcStages, tmem_full_bar = bars + 16 * kTcStages;
   const uint32_t tmem_slot = bars + 16 * kTcStages + 8;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+  float* bias_sm = reinterpret_cast<float*>(smem_raw + (bars + 256 - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int z = blockIdx.z;
@@ -161,7 +176,7 @@ tc_gemm_kernel(const __grid_constant__ TcGemmArgs g) {
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(mapA));
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(mapB));
-    for (int s = 0; s < kTcStages; ++s) {
+    for (int s = 0; s < stages; ++s) {
       mbar_init(full_bar + 8 * s, 1);
       mbar_init(empty_bar + 8 * s, 1);
     }
@@ -169,6 +184,9 @@ tc_gemm_kernel(const __grid_constant__ TcGemmArgs g) {
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, BN);
+  if (MODE == kTcFwd && warp >= 2) {
+    for (int c = threadIdx.x - 64; c < BN; c += kTcThreads - 64) bias_sm[c] = __ldg(g.bias[z] + col_base + c);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -178,8 +196,8 @@ tc_gemm_kernel(const __grid_constant__ TcGemmArgs g) {
     // ===================== TMA producer =====================
     if (elect_one()) {
       for (int kb = 0; kb < k_blocks; ++kb) {
-        const int s = kb % kTcStages;
-        mbar_wait(empty_bar + 8 * s, ((kb / kTcStages) & 1) ^ 1);
+        const int s = kb % stages;
+        mbar_wait(empty_bar + 8 * s, ((kb / stages) & 1) ^ 1);
         const uint32_t sa = tiles + s * S::kStage, sb = sa + S::kABytes;
         mbar_expect_tx(full_bar + 8 * s, S::kStage);
         const int k0 = k_begin + kb * kTcBK;
@@ -197,8 +215,8 @@ tc_gemm_kernel(const __grid_constant__ TcGemmArgs g) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = make_idesc(128, BN, MODE == kTcWgrad, MODE == kTcWgrad);
     for (int kb = 0; kb < k_blocks; ++kb) {
-      const int s = kb % kTcStages;
-      mbar_wait(full_bar + 8 * s, (kb / kTcStages) & 1);
+      const int s = kb % stages;
+      mbar_wait(full_bar + 8 * s, (kb / stages) & 1);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t sa = tiles + s * S::kStage, sb = sa + S::kABytes;
@@ -226,22 +244,37 @@ tc_gemm_kernel(const __grid_constant__ TcGemmArgs g) {
       __syncwarp();
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int quarter = warp & 3;  // TMEM lanes 32*quarter .. +31 are the ones this warp may read
+    // ===================== epilogue (warps 2..9) =====================
+    // TMEM lanes 32*quarter .. +31 are the ones a warp may read (quarter = warp % 4); the two warps of a
+    // quarter split the BN columns in halves.  Both 32-column chunks of a half are fetched before one wait.
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int HC = BN / 2;       // columns per warp
+    constexpr int NCH = HC / 32;     // 32-column chunks per warp (1 or 2)
     const int row = row_base + quarter * 32 + lane;
+    const int c_first = half * HC;
     if (k_blocks > 0) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
     }
-    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + c_first;
+    uint32_t v[NCH][32];
+    if (k_blocks > 0) {
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) tmem_ld32(taddr + i * 32, v[i]);
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) tmem_ld_wait(v[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NCH; ++i)
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[i][e] = 0u;
+    }
     if (MODE == kTcFwd) {
-      const float* __restrict__ bias = g.bias[z];
-      bf16* __restrict__ crow = g.C[z] + (size_t)row * g.ldc + col_base;
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + c, v);
-        if (row < g.M) {
+      bf16* __restrict__ crow = g.C[z] + (size_t)row * g.ldc + col_base + c_first;
+      if (row < g.M) {
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             uint4 o;
@@ -249,71 +282,66 @@ tc_gemm_kernel(const __grid_constant__ TcGemmArgs g) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int cc = q * 8 + e * 2;
-              const float x0 = __uint_as_float(v[cc]) + __ldg(bias + col_base + c + cc);
-              const float x1 = __uint_as_float(v[cc + 1]) + __ldg(bias + col_base + c + cc + 1);
-              op[e] = pack_bf16x2(elu(x0), elu(x1));
+              const float x0 = __uint_as_float(v[i][cc]) + bias_sm[c_first + i * 32 + cc];
+              const float x1 = __uint_as_float(v[i][cc + 1]) + bias_sm[c_first + i * 32 + cc + 1];
+              op[e] = pack_bf16x2(elu_fast(x0), elu_fast(x1));
             }
-            *reinterpret_cast<uint4*>(crow + c + q * 8) = o;
+            *reinterpret_cast<uint4*>(crow + i * 32 + q * 8) = o;
           }
         }
       }
     } else if (MODE == kTcDgrad) {
-      const bf16* __restrict__ hrow = g.H[z] + (size_t)row * g.ldc + col_base;
-      bf16* __restrict__ crow = g.C[z] + (size_t)row * g.ldc + col_base;
-      float* __restrict__ dbias = g.dbias[z] + col_base;
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + c, v);
+      const bf16* __restrict__ hrow = g.H[z] + (size_t)row * g.ldc + col_base + c_first;
+      bf16* __restrict__ crow = g.C[z] + (size_t)row * g.ldc + col_base + c_first;
+      float* __restrict__ dbias = g.dbias[z] + col_base + c_first;
+      const bool live = row < g.M;
+      uint4 hv[NCH][4];
+#pragma unroll
+      for (int i = 0; i < NCH; ++i)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          hv[i][q] = live ? __ldg(reinterpret_cast<const uint4*>(hrow + i * 32 + q * 8)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
         float f[32];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          uint4 hv = make_uint4(0, 0, 0, 0);
-          if (row < g.M) hv = __ldg(reinterpret_cast<const uint4*>(hrow + c + q * 8));
-          const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&hv);
+          const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&hv[i][q]);
           uint4 o;
           uint32_t* op = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int cc = q * 8 + e * 2;
-            const float x0 = row < g.M ? __uint_as_float(v[cc]) * elu_grad_from_output(__low2float(hp[e])) : 0.0f;
-            const float x1 = row < g.M ? __uint_as_float(v[cc + 1]) * elu_grad_from_output(__high2float(hp[e])) : 0.0f;
+            const float x0 = live ? __uint_as_float(v[i][cc]) * elu_grad_from_output(__low2float(hp[e])) : 0.0f;
+            const float x1 = live ? __uint_as_float(v[i][cc + 1]) * elu_grad_from_output(__high2float(hp[e])) : 0.0f;
             f[cc] = x0;
             f[cc + 1] = x1;
             op[e] = pack_bf16x2(x0, x1);
           }
-          if (row < g.M) *reinterpret_cast<uint4*>(crow + c + q * 8) = o;
+          if (live) *reinterpret_cast<uint4*>(crow + i * 32 + q * 8) = o;
         }
         // column sums over this warp's 32 rows by recursive halving: after the 5 rounds lane l holds the
-        // sum of column (c + l)
+        // sum of column (i*32 + l)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           const bool upper = (lane & o) != 0;
 #pragma unroll
-          for (int i = 0; i < o; ++i) {
-            const float send = upper ? f[i] : f[i + o];
-            const float keep = upper ? f[i + o] : f[i];
-            f[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+          for (int j = 0; j < o; ++j) {
+            const float send = upper ? f[j] : f[j + o];
+            const float keep = upper ? f[j + o] : f[j];
+            f[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
           }
         }
-        atomicAdd(dbias + c + lane, f[0]);
+        atomicAdd(dbias + i * 32 + lane, f[0]);
       }
     } else {
       // weight-gradient partial: fp32 [128 rows (layer outputs) x BN (layer inputs)]
-      float* __restrict__ prow = g.part[z] + ((size_t)blockIdx.y * g.M + row) * g.N + col_base;
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t v[32];
-        if (k_blocks > 0) {
-          tmem_ld32(taddr + c, v);
-        } else {
+      float* __restrict__ prow = g.part[z] + ((size_t)blockIdx.y * g.M + row) * g.N + col_base + c_first;
 #pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = 0u;
-        }
+      for (int i = 0; i < NCH; ++i)
 #pragma unroll
         for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<uint4*>(prow + c + q * 4) = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-      }
+          *reinterpret_cast<uint4*>(prow + i * 32 + q * 4) = make_uint4(v[i][q * 4], v[i][q * 4 + 1], v[i][q * 4 + 2], v[i][q * 4 + 3]);
     }
     tc_fence_before();
   }
@@ -390,14 +418,17 @@ int encode_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t
 }
 
 template <int MODE, int BN>
-static int launch_one(const TcGemmArgs& g, dim3 grid, cudaStream_t st) {
+static int launch_one(TcGemmArgs g, dim3 grid, cudaStream_t st) {
   using S = TcSmem<MODE, BN>;
   static bool attr = false;
   if (!attr) {
-    CATB200_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    CATB200_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::total(kTcStages)));
     attr = true;
   }
-  tc_gemm_kernel<MODE, BN><<<grid, kTcThreads, S::kTotal, st>>>(g);
+  // ring depth: no more slots than reduction blocks (a K = 64 layer needs one), which keeps several CTAs per SM
+  const int red = MODE == kTcWgrad ? g.m_range : g.K;
+  g.stages = max(1, min(kTcStages, (red + kTcBK - 1) / kTcBK));
+  tc_gemm_kernel<MODE, BN><<<grid, kTcThreads, S::total(g.stages), st>>>(g);
   CATB200_LAUNCH_CHECK();
   return CATB200_OK;
 }

@@ -21,6 +21,7 @@ struct TcGemmArgs {
   int ldc;
   int M, N, K;          // fwd/dgrad: rows, output features, reduction; wgrad: outs, ins_pad, minibatch rows
   int m_range;          // wgrad: minibatch rows per split (multiple of 64)
+  int stages;           // ring depth, filled by tc_gemm_launch
 };
 
 int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,

@@ -28,6 +28,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib as L
+from . import dist as cdist
 from . import ops
 
 
@@ -235,12 +236,11 @@ class PPOTrainer:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("PPOTrainer needs a CUDA device: the hot path exists only as sm_100a kernels")
-        self.world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
-        self.rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
+        self.world, self.rank = cdist.world_size(), cdist.rank()
 
         self.agent = Agent(envs, device=self.device)
         if self.world > 1:  # rank 0 seeds everybody (the reference's multi-process front-ends do the same)
-            torch.distributed.broadcast(self.agent.parameters_flat(), src=0)
+            cdist.broadcast_params(self.agent.parameters_flat(), src=0)
             self.agent.sync_weights()
         dims, lay = self.agent.dims, self.agent.layout
         N, T, O, A, dev = self.num_envs, self.T, self.agent.obs_dim, self.agent.act_dim, self.device
@@ -375,7 +375,7 @@ class PPOTrainer:
             a.parameters_flat(), a._w16, self.grads, self.loss_acc, self.train_ws,
         )  # fmt: skip
         if self.world > 1:  # the one exchange step: sum-allreduce of the flat 1.5 MB gradient over NVLink
-            torch.distributed.all_reduce(self.grads, op=torch.distributed.ReduceOp.SUM)
+            cdist.allreduce_grads(self.grads)
         ops.adam_step(
             a.dims, a.parameters_flat(), self.grads, self.exp_avg, self.exp_avg_sq, a._w16, self.lr_dev, self.step_dev,
             self.opt_ws, max_grad_norm=self.cfg.max_grad_norm, eps=1e-5, grad_scale=1.0 / self.world,
