@@ -240,19 +240,29 @@ cat_apply_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_const
   const int i = blockIdx.x * kApplyThreads + threadIdx.x;
   if (i >= num_envs) return;
 
+  // All loads of an env are independent (K constraint values, 2 statistics per slot): the statistics of a
+  // slot are requested before its columns and the columns four at a time, so several loads are in flight
+  // per thread instead of one round trip each.
   float overall = -INFINITY;
+#pragma unroll 1
   for (int slot = 0; slot < plan.n_slots; ++slot) {
     const int c0 = plan.slot_col_begin[slot], c1 = plan.slot_col_begin[slot + 1];
     const float span = prm.span[slot];
-    float tmax = -INFINITY;
-#pragma unroll 4
-    for (int col = c0; col < c1; ++col) {
-      const float c = __ldcs(c_t + (size_t)col * num_envs + i);
-      tmax = fmaxf(tmax, violation_prob(c, s_rm[col], prm.min_p, span));
-    }
     const size_t k = (size_t)slot * num_envs + i;
-    episode_sums[k] = __fadd_rn(episode_sums[k], tmax > 0.0f ? 1.0f : 0.0f);  // :226
-    mean_values[k] = __fadd_rn(mean_values[k], tmax);                          // :227
+    const float es = episode_sums[k], mv = mean_values[k];
+    float tmax = -INFINITY;
+    int col = c0;
+    for (; col + 4 <= c1; col += 4) {
+      const float v0 = __ldcs(c_t + (size_t)col * num_envs + i);
+      const float v1 = __ldcs(c_t + (size_t)(col + 1) * num_envs + i);
+      const float v2 = __ldcs(c_t + (size_t)(col + 2) * num_envs + i);
+      const float v3 = __ldcs(c_t + (size_t)(col + 3) * num_envs + i);
+      tmax = fmaxf(tmax, fmaxf(fmaxf(violation_prob(v0, s_rm[col], prm.min_p, span), violation_prob(v1, s_rm[col + 1], prm.min_p, span)),
+                               fmaxf(violation_prob(v2, s_rm[col + 2], prm.min_p, span), violation_prob(v3, s_rm[col + 3], prm.min_p, span))));
+    }
+    for (; col < c1; ++col) tmax = fmaxf(tmax, violation_prob(__ldcs(c_t + (size_t)col * num_envs + i), s_rm[col], prm.min_p, span));
+    episode_sums[k] = __fadd_rn(es, tmax > 0.0f ? 1.0f : 0.0f);  // :226
+    mean_values[k] = __fadd_rn(mv, tmax);                          // :227
     overall = fmaxf(overall, tmax);
   }
   cstr_prob[i] = overall;

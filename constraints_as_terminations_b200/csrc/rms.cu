@@ -53,8 +53,15 @@ rms_moments_kernel(const float* __restrict__ x, long long rows, int dim, float* 
   const int slot = threadIdx.x / dim;
   double s = 0.0, q = 0.0;
   if (threadIdx.x < active) {
-    for (long long r = (long long)blockIdx.x * rows_per_pass + slot; r < rows;
-         r += (long long)gridDim.x * rows_per_pass) {
+    const long long step = (long long)gridDim.x * rows_per_pass;
+    long long r = (long long)blockIdx.x * rows_per_pass + slot;
+    for (; r + 3 * step < rows; r += 4 * step) {  // 4 independent loads in flight per thread
+      const float v0 = __ldg(x + r * dim + col), v1 = __ldg(x + (r + step) * dim + col);
+      const float v2 = __ldg(x + (r + 2 * step) * dim + col), v3 = __ldg(x + (r + 3 * step) * dim + col);
+      s += ((double)v0 + (double)v1) + ((double)v2 + (double)v3);
+      q += ((double)v0 * v0 + (double)v1 * v1) + ((double)v2 * v2 + (double)v3 * v3);
+    }
+    for (; r < rows; r += step) {
       const double v = (double)__ldg(x + r * dim + col);
       s += v;
       q += v * v;

@@ -253,6 +253,16 @@ tc_gemm_kernel(const __grid_constant__ TcGemmArgs g) {
     constexpr int NCH = HC / 32;     // 32-column chunks per warp (1 or 2)
     const int row = row_base + quarter * 32 + lane;
     const int c_first = half * HC;
+    // dgrad: the forward activations whose ELU' scales the result are fetched while the MMAs still run
+    uint4 hv[NCH][4];
+    if (MODE == kTcDgrad) {
+      const bf16* __restrict__ hrow = g.H[z] + (size_t)row * g.ldc + col_base + c_first;
+#pragma unroll
+      for (int i = 0; i < NCH; ++i)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          hv[i][q] = row < g.M ? __ldg(reinterpret_cast<const uint4*>(hrow + i * 32 + q * 8)) : make_uint4(0, 0, 0, 0);
+    }
     if (k_blocks > 0) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
@@ -291,16 +301,9 @@ tc_gemm_kernel(const __grid_constant__ TcGemmArgs g) {
         }
       }
     } else if (MODE == kTcDgrad) {
-      const bf16* __restrict__ hrow = g.H[z] + (size_t)row * g.ldc + col_base + c_first;
       bf16* __restrict__ crow = g.C[z] + (size_t)row * g.ldc + col_base + c_first;
       float* __restrict__ dbias = g.dbias[z] + col_base + c_first;
       const bool live = row < g.M;
-      uint4 hv[NCH][4];
-#pragma unroll
-      for (int i = 0; i < NCH; ++i)
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          hv[i][q] = live ? __ldg(reinterpret_cast<const uint4*>(hrow + i * 32 + q * 8)) : make_uint4(0, 0, 0, 0);
 #pragma unroll
       for (int i = 0; i < NCH; ++i) {
         float f[32];
