@@ -80,12 +80,16 @@ class Plan(C.Structure):
         ("n_terms", C.c_int32),
         ("n_cols", C.c_int32),
         ("n_slots", C.c_int32),
-        ("smem_floats_per_env", C.c_int32),
-        ("reserved", C.c_int32 * 3),
+        ("smem_bytes", C.c_int32),
+        ("n_peaks", C.c_int32),
+        ("smem_peak_off", C.c_int32),
+        ("smem_bar_off", C.c_int32),
         ("sources", Source * MAX_SOURCES),
         ("terms", Term * MAX_TERMS),
         ("col_term", C.c_uint8 * MAX_COLS),
         ("slot_col_begin", C.c_uint16 * (MAX_TERMS + 2)),
+        ("peak_src", C.c_uint8 * 32),
+        ("peak_body", C.c_uint8 * 32),
     ]
 
 
@@ -196,7 +200,8 @@ SIGNATURES = {
     ),
     "catb200_cat_eval_terms": (C.c_int, [C.POINTER(Plan), _I32, _P, _P]),
     "catb200_cat_probs": (C.c_int, [C.POINTER(Plan), C.POINTER(CatParams), _I32, _P, _P, _P, _P]),
-    "catb200_cat_reset_stats": (C.c_int, [_P, _I32, _P, _P, _I32, _I32, _P, _P, _P, _P]),
+    "catb200_cat_reset_workspace_bytes": (_SZ, []),
+    "catb200_cat_reset_stats": (C.c_int, [_P, _I32, _P, _P, _I32, _I32, _P, _P, _P, _P, _SZ, _P]),
     "catb200_rms_workspace_bytes": (_SZ, [_I32]),
     "catb200_rms_forward": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _F, _I32, _P, _P, _I32, _P, _SZ, _P]),
     "catb200_rollout_append": (C.c_int, [_P, _P, _P, _I32, _P, _P, _P, _P]),

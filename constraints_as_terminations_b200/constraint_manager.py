@@ -410,6 +410,7 @@ class ConstraintManager(ManagerBase):
         self._max_p_cache: list[float | None] = [None] * len(self._term_names)
         self._probs_cache = None
         self._raw_cache = None
+        self._reset_ws = None
 
     # -- reference API -----------------------------------------------------------------------------
     def __str__(self) -> str:
@@ -623,6 +624,8 @@ class ConstraintManager(ManagerBase):
         elif mask is not None:
             mask_t = mask.view(torch.uint8) if mask.dtype == torch.bool else (mask != 0).view(torch.uint8)
             mask_t = mask_t.contiguous()
+        if self._reset_ws is None:
+            self._reset_ws = L.zeros_workspace(L.load().catb200_cat_reset_workspace_bytes(), dev)
         ep_len = self._env.episode_length_buf
         if ep_len.dtype != torch.int64 or not ep_len.is_contiguous():
             ep_len = ep_len.to(torch.int64).contiguous()
@@ -630,7 +633,8 @@ class ConstraintManager(ManagerBase):
         L.check(
             L.load().catb200_cat_reset_stats(
                 L.ptr(ids_t), n_ids, L.ptr(mask_t), ep_len.data_ptr(), self.num_envs, len(self._term_names),
-                self._stats[0].data_ptr(), self._stats[1].data_ptr(), out.data_ptr(), L.stream(),
+                self._stats[0].data_ptr(), self._stats[1].data_ptr(), out.data_ptr(),
+                self._reset_ws.data_ptr(), self._reset_ws.numel() * 8, L.stream(),
             ),
             "cat_reset_stats",
         )  # fmt: skip

@@ -31,18 +31,22 @@ constexpr int kEvalWarps = 4;      // warps per CTA; warp w owns columns w, w+4,
 constexpr int kEvalThreads = kEvalWarps * 32;
 constexpr int kApplyThreads = 64;
 
-__device__ __forceinline__ int pitch_of(const catb200_source_t& s) { return s.row_len | 1; }
-
 // ---- staged-source accessors ----------------------------------------------------------------------
-struct TileView {
-  const float* smem;
-  const catb200_plan_t* plan;
-  int row;  // env within the tile == lane
-  __device__ __forceinline__ float at(int src, int e) const {
-    const catb200_source_t& s = plan->sources[src];
-    return smem[s.smem_off * kTile + row * pitch_of(s) + e];
+// A tile's rows of every source are copied verbatim (row pitch = row_len) into shared memory by the bulk
+// async-copy engine (cp.async.bulk + mbarrier, i.e. TMA's 1-D path): zero per-element staging instructions.
+struct SrcView {
+  const uint8_t* base;  // shared-memory bytes of this source's tile
+  int row_len;
+  int is_u8;
+  __device__ __forceinline__ float at(int row, int e) const {
+    return is_u8 ? (base[row * row_len + e] ? 1.0f : 0.0f) : reinterpret_cast<const float*>(base)[row * row_len + e];
   }
 };
+
+__device__ __forceinline__ SrcView view_of(const catb200_plan_t& plan, const uint8_t* smem, int s) {
+  const catb200_source_t& src = plan.sources[s];
+  return SrcView{smem + src.smem_off, src.row_len, src.dtype == CATB200_U8};
+}
 
 // sqrt(x^2 + y^2 + z^2) the way torch.norm reduces a short contiguous dim on CPU and CUDA:
 // sequential fused multiply-adds from a zero accumulator, then a correctly rounded sqrt.
@@ -59,81 +63,25 @@ __device__ __forceinline__ float norm2(float x, float y) {
 }
 
 // max over the history axis of |F[h, body, :]| for one body (constraints.py:102-107,151-158,207-209)
-__device__ __forceinline__ float force_peak(const TileView& v, int src, int body) {
-  const catb200_source_t& s = v.plan->sources[src];
-  const int B = s.aux;
-  const int H = s.row_len / (3 * B);
+__device__ __forceinline__ float force_peak(const SrcView& v, int bodies, int row, int body) {
+  const int H = v.row_len / (3 * bodies);
   float peak = -INFINITY;
   for (int h = 0; h < H; ++h) {
-    const int e = (h * B + body) * 3;
-    peak = fmaxf(peak, norm3(v.at(src, e), v.at(src, e + 1), v.at(src, e + 2)));
+    const int e = (h * bodies + body) * 3;
+    peak = fmaxf(peak, norm3(v.at(row, e), v.at(row, e + 1), v.at(row, e + 2)));
   }
   return peak;
 }
 
-__device__ __forceinline__ float command_norm(const TileView& v, int src) {
-  return norm3(v.at(src, 0), v.at(src, 1), v.at(src, 2));
-}
-
-// Value of column `lc` of term `t` for the env of this lane.  Operation order follows the cited
-// reference lines; every intermediate is rounded to fp32 exactly where torch materialises a tensor.
-__device__ float eval_column(const TileView& v, const catb200_term_t& t, int lc) {
-  switch (t.op) {
-    case CATB200_OP_GENERIC:
-      return v.at(t.src0, t.ids[lc]);
-    case CATB200_OP_ABS_MINUS:  // constraints.py:30,64,75,85
-      return __fsub_rn(fabsf(v.at(t.src0, t.ids[lc])), t.p0);
-    case CATB200_OP_ABSDIFF_MINUS:  // constraints.py:176-181
-      return __fsub_rn(fabsf(__fsub_rn(v.at(t.src0, t.ids[lc]), v.at(t.src1, t.ids[lc]))), t.p0);
-    case CATB200_OP_ABSDIFF_MINUS_GATE_Y: {  // constraints.py:42-53
-      float c = __fsub_rn(fabsf(__fsub_rn(v.at(t.src0, t.ids[lc]), v.at(t.src1, t.ids[lc]))), t.p0);
-      float gate = fabsf(v.at(t.src2, 1)) < t.p1 ? 1.0f : 0.0f;
-      return __fmul_rn(c, gate);
-    }
-    case CATB200_OP_ACTION_RATE: {  // constraints.py:191-198 (true division by step_dt)
-      float d = fabsf(__fsub_rn(v.at(t.src0, t.ids[lc]), v.at(t.src1, t.ids[lc])));
-      return __fsub_rn(__fdiv_rn(d, t.p1), t.p0);
-    }
-    case CATB200_OP_COMPONENT_GT:  // constraints.py:94
-      return v.at(t.src0, t.ids[lc]) > t.p0 ? 1.0f : 0.0f;
-    case CATB200_OP_CONTACT_ANY: {  // constraints.py:103-110
-      bool any = false;
-      for (int b = 0; b < t.n_ids; ++b) any |= force_peak(v, t.src0, t.ids[b]) > t.p0;
-      return any ? 1.0f : 0.0f;
-    }
-    case CATB200_OP_NORM2_MINUS:  // constraints.py:119
-      return __fsub_rn(norm2(v.at(t.src0, 0), v.at(t.src0, 1)), t.p0);
-    case CATB200_OP_AIR_TIME: {  // constraints.py:129-141
-      float td = v.at(t.src1, t.ids[lc]) != 0.0f ? 1.0f : 0.0f;
-      float moving = command_norm(v, t.src2) > t.p1 ? 1.0f : 0.0f;
-      float c = __fsub_rn(t.p0, v.at(t.src0, t.ids[lc]));
-      return __fmul_rn(__fmul_rn(c, td), moving);
-    }
-    case CATB200_OP_N_CONTACT: {  // constraints.py:151-168
-      int n = 0;
-      for (int b = 0; b < t.n_ids; ++b) n += force_peak(v, t.src0, t.ids[b]) > t.p2 ? 1 : 0;
-      float miss = fabsf((float)n - t.p0);
-      float moving = command_norm(v, t.src2) > t.p1 ? 1.0f : 0.0f;
-      return __fmul_rn(miss, moving);
-    }
-    case CATB200_OP_FORCE_PEAK_MINUS:  // constraints.py:207-210
-      return __fsub_rn(force_peak(v, t.src0, t.ids[lc]), t.p0);
-    case CATB200_OP_LIMIT_MINUS:  // constraints.py:220
-      return __fsub_rn(t.p0, v.at(t.src0, t.ids[lc]));
-    case CATB200_OP_ABS_MINUS_GATE_STILL: {  // constraints.py:231-235
-      float c = __fsub_rn(fabsf(v.at(t.src0, t.ids[lc])), t.p0);
-      float still = command_norm(v, t.src2) < t.p1 ? 1.0f : 0.0f;
-      return __fmul_rn(c, still);
-    }
-    default:
-      return 0.0f;
-  }
-}
+// Same-address atomics serialise in L2 (tens of ns each): with one scratch word per column, 32 768 CTAs
+// (1 M envs) would queue 32 768 deep.  CTAs therefore fold their column maxima into one of kMaxGroups
+// scratch rows (blockIdx % groups) and the last CTA reduces the rows.
+constexpr int kMaxGroups = 64;
 
 struct CatWorkspace {
   // layout inside the caller's workspace (all 256-byte aligned)
   unsigned int* ticket;   // 1 word (padded)
-  uint32_t* colmax;       // [CATB200_MAX_COLS] ordered-float column maxima, 0 between launches
+  uint32_t* colmax;       // [kMaxGroups][CATB200_MAX_COLS] ordered-float column maxima, 0 between launches
   float* c_t;             // [K][N] raw constraints, column-major
 };
 
@@ -144,67 +92,195 @@ __host__ __device__ inline CatWorkspace carve(void* base, int num_envs) {
   char* p = static_cast<char*>(base);
   w.ticket = reinterpret_cast<unsigned int*>(p);
   w.colmax = reinterpret_cast<uint32_t*>(p + 256);
-  w.c_t = reinterpret_cast<float*>(p + 256 + align256(sizeof(uint32_t) * CATB200_MAX_COLS));
+  w.c_t = reinterpret_cast<float*>(p + 256 + align256(sizeof(uint32_t) * CATB200_MAX_COLS * kMaxGroups));
   (void)num_envs;
   return w;
 }
 
 enum EvalMode { kEvalStep = 0, kEvalRowMajor = 1 };
 
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kEvalThreads)
 cat_eval_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_constant__ catb200_cat_params_t prm,
                 int num_envs, float* __restrict__ running_max, int* __restrict__ rm_init,
                 CatWorkspace ws, float* __restrict__ out_rowmajor) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(128) uint8_t smem[];
   const int tile0 = blockIdx.x * kTile;
   const int rows = min(kTile, num_envs - tile0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* peaks = reinterpret_cast<float*>(smem + plan.smem_peak_off);  // [n_peaks][32]
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(smem + plan.smem_bar_off);
 
-  // ---- stage every source row block of this tile (coalesced: consecutive threads, consecutive elements)
+  // ---- stage the tile: one bulk async copy per source whose tile is contiguous and 16-byte aligned,
+  //      a cooperative copy otherwise (strided views, ragged last tile)
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t bulk_mask = 0;
   for (int s = 0; s < plan.n_sources; ++s) {
     const catb200_source_t& src = plan.sources[s];
-    const int pitch = pitch_of(src);
-    float* dst = smem + src.smem_off * kTile;
+    const int es = src.dtype == CATB200_U8 ? 1 : 4;
+    const uint8_t* g = static_cast<const uint8_t*>(src.ptr) + (size_t)tile0 * src.row_stride * es;
+    const bool bulk = rows == kTile && src.row_stride == src.row_len && ((reinterpret_cast<uintptr_t>(g) & 15) == 0);
+    if (bulk) bulk_mask |= 1u << s;
+  }
+  if (threadIdx.x == 0) {
+    uint32_t total = 0;
+    for (int s = 0; s < plan.n_sources; ++s)
+      if (bulk_mask >> s & 1) total += kTile * plan.sources[s].row_len * (plan.sources[s].dtype == CATB200_U8 ? 1 : 4);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(total) : "memory");
+    for (int s = 0; s < plan.n_sources; ++s) {
+      if (!(bulk_mask >> s & 1)) continue;
+      const catb200_source_t& src = plan.sources[s];
+      const int es = src.dtype == CATB200_U8 ? 1 : 4;
+      bulk_copy_g2s((uint32_t)__cvta_generic_to_shared(smem + src.smem_off),
+                    static_cast<const uint8_t*>(src.ptr) + (size_t)tile0 * src.row_len * es, kTile * src.row_len * es, bar);
+    }
+  }
+  for (int s = 0; s < plan.n_sources; ++s) {
+    if (bulk_mask >> s & 1) continue;
+    const catb200_source_t& src = plan.sources[s];
     const int total = rows * src.row_len;
     if (src.dtype == CATB200_F32) {
       const float* g = static_cast<const float*>(src.ptr);
+      float* dst = reinterpret_cast<float*>(smem + src.smem_off);
       for (int f = threadIdx.x; f < total; f += kEvalThreads) {
-        const int r = src.row_len == 1 ? f : (int)__umulhi((unsigned)f, src.magic);
-        const int e = f - r * src.row_len;
-        dst[r * pitch + e] = __ldg(g + (size_t)(tile0 + r) * src.row_stride + e);
+        const int r = f / src.row_len, e = f - r * src.row_len;
+        dst[f] = __ldg(g + (size_t)(tile0 + r) * src.row_stride + e);
       }
     } else {
       const uint8_t* g = static_cast<const uint8_t*>(src.ptr);
       for (int f = threadIdx.x; f < total; f += kEvalThreads) {
-        const int r = src.row_len == 1 ? f : (int)__umulhi((unsigned)f, src.magic);
-        const int e = f - r * src.row_len;
-        dst[r * pitch + e] = g[(size_t)(tile0 + r) * src.row_stride + e] ? 1.0f : 0.0f;
+        const int r = f / src.row_len, e = f - r * src.row_len;
+        smem[src.smem_off + f] = g[(size_t)(tile0 + r) * src.row_stride + e];
       }
     }
   }
   __syncthreads();
+  {  // wait for the bulk copies (phase 0 of the barrier)
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+          : "=r"(done)
+          : "r"(bar)
+          : "memory");
+    }
+  }
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool live = lane < rows;
-  TileView view{smem, &plan, live ? lane : 0};
-  for (int col = warp; col < plan.n_cols; col += kEvalWarps) {
-    const catb200_term_t& t = plan.terms[plan.col_term[col]];
-    const float c = eval_column(view, t, col - t.col_offset);
-    if (MODE == kEvalRowMajor) {
-      if (live) out_rowmajor[(size_t)(tile0 + lane) * plan.n_cols + col] = c;
-    } else {
-      if (live) ws.c_t[(size_t)col * num_envs + tile0 + lane] = c;
-      const uint32_t key = live ? float_to_ordered(c) : 0u;
-      const uint32_t m = __reduce_max_sync(0xffffffffu, key);
-      if (lane == 0) atomicMax(&ws.colmax[col], m);
+  const int row = live ? lane : 0;
+  const int n_groups = max(1, min((int)gridDim.x / 8, kMaxGroups));  // ~8+ CTAs share a scratch row
+
+  // ---- phase A: contact-force peaks, once per (history tensor, body) pair referenced by any term
+  for (int p = warp; p < plan.n_peaks; p += kEvalWarps) {
+    const int s = plan.peak_src[p];
+    peaks[p * kTile + lane] = force_peak(view_of(plan, smem, s), plan.sources[s].aux, row, plan.peak_body[p]);
+  }
+  __syncthreads();
+
+  // ---- phase B: terms.  Term-level scalars and gates are computed once per term; the term's columns are
+  //      dealt to the 4 warps by global column index (lane = env, so the op dispatch never diverges).
+  for (int ti = 0; ti < plan.n_terms; ++ti) {
+    const catb200_term_t& t = plan.terms[ti];
+    const int n_cols = t.n_cols, col0 = t.col_offset, op = t.op;
+    int first = (warp - (col0 & (kEvalWarps - 1))) & (kEvalWarps - 1);  // first local column owned by this warp
+    if (first >= n_cols) continue;
+    const float p0 = t.p0, p1 = t.p1, p2 = t.p2;
+    const SrcView v0 = view_of(plan, smem, t.src0);
+    SrcView v1 = v0;
+    if (t.src1 != 0xff) v1 = view_of(plan, smem, t.src1);
+    float gate = 1.0f;  // command-dependent factor shared by all columns of the term
+    if (t.src2 != 0xff) {
+      const SrcView vc = view_of(plan, smem, t.src2);
+      if (op == CATB200_OP_ABSDIFF_MINUS_GATE_Y) {
+        gate = fabsf(vc.at(row, 1)) < p1 ? 1.0f : 0.0f;  // constraints.py:46-53
+      } else {
+        const float cn = norm3(vc.at(row, 0), vc.at(row, 1), vc.at(row, 2));
+        gate = op == CATB200_OP_ABS_MINUS_GATE_STILL ? (cn < p1 ? 1.0f : 0.0f) : (cn > p1 ? 1.0f : 0.0f);
+      }
+    }
+    for (int lc = first; lc < n_cols; lc += kEvalWarps) {
+      const int id = t.ids[lc];
+      float c;
+      switch (op) {
+        case CATB200_OP_GENERIC:
+          c = v0.at(row, id);
+          break;
+        case CATB200_OP_ABS_MINUS:  // constraints.py:30,64,75,85
+          c = __fsub_rn(fabsf(v0.at(row, id)), p0);
+          break;
+        case CATB200_OP_ABSDIFF_MINUS:  // constraints.py:176-181
+          c = __fsub_rn(fabsf(__fsub_rn(v0.at(row, id), v1.at(row, id))), p0);
+          break;
+        case CATB200_OP_ABSDIFF_MINUS_GATE_Y:  // constraints.py:42-53
+          c = __fmul_rn(__fsub_rn(fabsf(__fsub_rn(v0.at(row, id), v1.at(row, id))), p0), gate);
+          break;
+        case CATB200_OP_ACTION_RATE:  // constraints.py:191-198 (true division by step_dt)
+          c = __fsub_rn(__fdiv_rn(fabsf(__fsub_rn(v0.at(row, id), v1.at(row, id))), p1), p0);
+          break;
+        case CATB200_OP_COMPONENT_GT:  // constraints.py:94
+          c = v0.at(row, id) > p0 ? 1.0f : 0.0f;
+          break;
+        case CATB200_OP_CONTACT_ANY: {  // constraints.py:103-110; ids index the peak table
+          bool any = false;
+          for (int b = 0; b < t.n_ids; ++b) any |= peaks[t.ids[b] * kTile + lane] > p0;
+          c = any ? 1.0f : 0.0f;
+          break;
+        }
+        case CATB200_OP_NORM2_MINUS:  // constraints.py:119
+          c = __fsub_rn(norm2(v0.at(row, 0), v0.at(row, 1)), p0);
+          break;
+        case CATB200_OP_AIR_TIME: {  // constraints.py:129-141
+          const float td = v1.at(row, id) != 0.0f ? 1.0f : 0.0f;
+          c = __fmul_rn(__fmul_rn(__fsub_rn(p0, v0.at(row, id)), td), gate);
+          break;
+        }
+        case CATB200_OP_N_CONTACT: {  // constraints.py:151-168
+          int n = 0;
+          for (int b = 0; b < t.n_ids; ++b) n += peaks[t.ids[b] * kTile + lane] > p2 ? 1 : 0;
+          c = __fmul_rn(fabsf((float)n - p0), gate);
+          break;
+        }
+        case CATB200_OP_FORCE_PEAK_MINUS:  // constraints.py:207-210
+          c = __fsub_rn(peaks[id * kTile + lane], p0);
+          break;
+        case CATB200_OP_LIMIT_MINUS:  // constraints.py:220
+          c = __fsub_rn(p0, v0.at(row, id));
+          break;
+        case CATB200_OP_ABS_MINUS_GATE_STILL:  // constraints.py:231-235
+          c = __fmul_rn(__fsub_rn(fabsf(v0.at(row, id)), p0), gate);
+          break;
+        default:
+          c = 0.0f;
+      }
+      const int col = col0 + lc;
+      if (MODE == kEvalRowMajor) {
+        if (live) out_rowmajor[(size_t)(tile0 + lane) * plan.n_cols + col] = c;
+      } else {
+        if (live) ws.c_t[(size_t)col * num_envs + tile0 + lane] = c;
+        const uint32_t key = live ? float_to_ordered(c) : 0u;
+        const uint32_t m = __reduce_max_sync(0xffffffffu, key);
+        if (lane == 0) atomicMax(&ws.colmax[(blockIdx.x % n_groups) * CATB200_MAX_COLS + col], m);
+      }
     }
   }
 
   if (MODE == kEvalStep) {
     // ---- the last CTA folds the column maxima into the Polyak running max (constraint_manager.py:55-61)
     if (last_block_ticket(ws.ticket, gridDim.x)) {
+      const int groups = n_groups;
       for (int col = threadIdx.x; col < plan.n_cols; col += kEvalThreads) {
-        const uint32_t key = atomicExch(&ws.colmax[col], 0u);
+        uint32_t key = 0u;
+        for (int gi = 0; gi < groups; ++gi) key = max(key, atomicExch(&ws.colmax[gi * CATB200_MAX_COLS + col], 0u));
         float cmax = fmaxf(ordered_to_float(key), prm.floor_max);
         float rm;
         if (rm_init[col]) {
@@ -227,7 +303,9 @@ __device__ __forceinline__ float violation_prob(float c, float rm, float min_p, 
   return __fadd_rn(min_p, __fmul_rn(x, span));
 }
 
-__global__ void __launch_bounds__(kApplyThreads)
+// One CTA per 32 envs (lane = env); the 4 warps split the statistics slots (terms) so that the dependent
+// load chains are 4x shorter and 4x more loads are in flight than with one thread per env.
+__global__ void __launch_bounds__(kEvalThreads)
 cat_apply_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_constant__ catb200_cat_params_t prm,
                  int num_envs, const float* __restrict__ running_max, const float* __restrict__ c_t,
                  float* __restrict__ episode_sums, float* __restrict__ mean_values,
@@ -235,36 +313,40 @@ cat_apply_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_const
                  const uint8_t* __restrict__ reset_buf, float* __restrict__ reward_out,
                  float* __restrict__ dones_out) {
   __shared__ float s_rm[CATB200_MAX_COLS];
-  for (int c = threadIdx.x; c < plan.n_cols; c += kApplyThreads) s_rm[c] = running_max[c];
+  __shared__ float s_part[kEvalWarps][kTile];
+  for (int c = threadIdx.x; c < plan.n_cols; c += kEvalThreads) s_rm[c] = running_max[c];
   __syncthreads();
-  const int i = blockIdx.x * kApplyThreads + threadIdx.x;
-  if (i >= num_envs) return;
-
-  // All loads of an env are independent (K constraint values, 2 statistics per slot): the statistics of a
-  // slot are requested before its columns and the columns four at a time, so several loads are in flight
-  // per thread instead of one round trip each.
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * kTile + lane;
+  const bool live = i < num_envs;
   float overall = -INFINITY;
-#pragma unroll 1
-  for (int slot = 0; slot < plan.n_slots; ++slot) {
-    const int c0 = plan.slot_col_begin[slot], c1 = plan.slot_col_begin[slot + 1];
-    const float span = prm.span[slot];
-    const size_t k = (size_t)slot * num_envs + i;
-    const float es = episode_sums[k], mv = mean_values[k];
-    float tmax = -INFINITY;
-    int col = c0;
-    for (; col + 4 <= c1; col += 4) {
-      const float v0 = __ldcs(c_t + (size_t)col * num_envs + i);
-      const float v1 = __ldcs(c_t + (size_t)(col + 1) * num_envs + i);
-      const float v2 = __ldcs(c_t + (size_t)(col + 2) * num_envs + i);
-      const float v3 = __ldcs(c_t + (size_t)(col + 3) * num_envs + i);
-      tmax = fmaxf(tmax, fmaxf(fmaxf(violation_prob(v0, s_rm[col], prm.min_p, span), violation_prob(v1, s_rm[col + 1], prm.min_p, span)),
-                               fmaxf(violation_prob(v2, s_rm[col + 2], prm.min_p, span), violation_prob(v3, s_rm[col + 3], prm.min_p, span))));
+  if (live) {
+    for (int slot = warp; slot < plan.n_slots; slot += kEvalWarps) {
+      const int c0 = plan.slot_col_begin[slot], c1 = plan.slot_col_begin[slot + 1];
+      const float span = prm.span[slot];
+      const size_t k = (size_t)slot * num_envs + i;
+      const float es = episode_sums[k], mv = mean_values[k];  // requested before the columns: all in flight together
+      float tmax = -INFINITY;
+      int col = c0;
+      for (; col + 4 <= c1; col += 4) {
+        const float v0 = __ldcs(c_t + (size_t)col * num_envs + i);
+        const float v1 = __ldcs(c_t + (size_t)(col + 1) * num_envs + i);
+        const float v2 = __ldcs(c_t + (size_t)(col + 2) * num_envs + i);
+        const float v3 = __ldcs(c_t + (size_t)(col + 3) * num_envs + i);
+        tmax = fmaxf(tmax, fmaxf(fmaxf(violation_prob(v0, s_rm[col], prm.min_p, span), violation_prob(v1, s_rm[col + 1], prm.min_p, span)),
+                                 fmaxf(violation_prob(v2, s_rm[col + 2], prm.min_p, span), violation_prob(v3, s_rm[col + 3], prm.min_p, span))));
+      }
+      for (; col < c1; ++col) tmax = fmaxf(tmax, violation_prob(__ldcs(c_t + (size_t)col * num_envs + i), s_rm[col], prm.min_p, span));
+      episode_sums[k] = __fadd_rn(es, tmax > 0.0f ? 1.0f : 0.0f);  // :226
+      mean_values[k] = __fadd_rn(mv, tmax);                          // :227
+      overall = fmaxf(overall, tmax);
     }
-    for (; col < c1; ++col) tmax = fmaxf(tmax, violation_prob(__ldcs(c_t + (size_t)col * num_envs + i), s_rm[col], prm.min_p, span));
-    episode_sums[k] = __fadd_rn(es, tmax > 0.0f ? 1.0f : 0.0f);  // :226
-    mean_values[k] = __fadd_rn(mv, tmax);                          // :227
-    overall = fmaxf(overall, tmax);
   }
+  s_part[warp][lane] = overall;
+  __syncthreads();
+  if (warp != 0 || !live) return;
+#pragma unroll
+  for (int w = 1; w < kEvalWarps; ++w) overall = fmaxf(overall, s_part[w][lane]);
   cstr_prob[i] = overall;
   if (raw_reward != nullptr) {
     // cat_env.py:102-107: reward = clip(reward * (1 - p), min=0); dones = p; :121 dones[reset] = 1
@@ -293,18 +375,30 @@ cat_probs_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_const
 // (torch's own fp32 reduction order is implementation defined; parity tolerance 1e-5 relative) and
 // then zeroes the selected entries.
 constexpr int kResetThreads = 256;
+constexpr int kResetChunk = 1024;  // selected envs (or mask entries) per CTA
 
+struct ResetScratch {  // per slot: double sums + count; zero between launches
+  double v[CATB200_MAX_TERMS], p[CATB200_MAX_TERMS];
+  unsigned long long cnt[CATB200_MAX_TERMS];
+  unsigned int ticket;
+};
+
+// grid = (n_slots, chunks): every CTA reduces one statistics row over one chunk of the selection in double
+// precision (torch's own fp32 reduction order is implementation defined; parity tolerance 1e-5 relative),
+// zeroes the selected entries and adds its partial sums to the slot's accumulators; the last CTA turns the
+// accumulators into the two means per slot.
 __global__ void __launch_bounds__(kResetThreads)
 cat_reset_kernel(const int64_t* __restrict__ env_ids, int n_ids, const uint8_t* __restrict__ mask,
-                 const int64_t* __restrict__ episode_length, int num_envs, float* __restrict__ episode_sums,
-                 float* __restrict__ mean_values, float* __restrict__ out) {
+                 const int64_t* __restrict__ episode_length, int num_envs, int n_slots, float* __restrict__ episode_sums,
+                 float* __restrict__ mean_values, float* __restrict__ out, ResetScratch* __restrict__ sc) {
   const int slot = blockIdx.x;
   float* sums = episode_sums + (size_t)slot * num_envs;
   float* means = mean_values + (size_t)slot * num_envs;
   double acc_v = 0.0, acc_p = 0.0;
-  long long cnt = 0;
+  unsigned long long cnt = 0;
   const int total = env_ids ? n_ids : num_envs;
-  for (int k = threadIdx.x; k < total; k += kResetThreads) {
+  const int begin = blockIdx.y * kResetChunk, end = min(total, begin + kResetChunk);
+  for (int k = begin + threadIdx.x; k < end; k += kResetThreads) {
     int i = k;
     if (env_ids) {
       i = (int)env_ids[k];
@@ -318,30 +412,25 @@ cat_reset_kernel(const int64_t* __restrict__ env_ids, int n_ids, const uint8_t* 
     sums[i] = 0.0f;
     means[i] = 0.0f;
   }
-  __shared__ double s_v[kResetThreads / 32], s_p[kResetThreads / 32];
-  __shared__ long long s_c[kResetThreads / 32];
   acc_v = warp_sum(acc_v);
   acc_p = warp_sum(acc_p);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  if ((threadIdx.x & 31) == 0) {
-    s_v[threadIdx.x >> 5] = acc_v;
-    s_p[threadIdx.x >> 5] = acc_p;
-    s_c[threadIdx.x >> 5] = cnt;
+  if ((threadIdx.x & 31) == 0 && cnt > 0) {
+    atomicAdd(&sc->v[slot], acc_v);
+    atomicAdd(&sc->p[slot], acc_p);
+    atomicAdd(&sc->cnt[slot], cnt);
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double v = 0.0, p = 0.0;
-    long long c = 0;
-    for (int w = 0; w < kResetThreads / 32; ++w) {
-      v += s_v[w];
-      p += s_p[w];
-      c += s_c[w];
+  if (last_block_ticket(&sc->ticket, gridDim.x * gridDim.y)) {
+    for (int s2 = threadIdx.x; s2 < n_slots; s2 += kResetThreads) {
+      const double v = __longlong_as_double(atomicExch((unsigned long long*)&sc->v[s2], 0ull));
+      const double p = __longlong_as_double(atomicExch((unsigned long long*)&sc->p[s2], 0ull));
+      const unsigned long long c = atomicExch(&sc->cnt[s2], 0ull);
+      // empty selection -> mean of nothing = NaN, like torch
+      const float mv = (float)(v / (double)c), mp = (float)(p / (double)c);
+      out[2 * s2] = __fmul_rn(mv, 100.0f);
+      out[2 * s2 + 1] = mp;
     }
-    // empty selection -> mean of nothing = NaN, like torch
-    const float mv = (float)(v / (double)c), mp = (float)(p / (double)c);
-    out[2 * slot] = __fmul_rn(mv, 100.0f);
-    out[2 * slot + 1] = mp;
   }
 }
 
@@ -370,19 +459,17 @@ int catb200_cat_plan_finalize(catb200_plan_t* plan) {
   if (!plan) return CATB200_ERR_INVALID_ARGUMENT;
   if (plan->n_sources < 0 || plan->n_sources > CATB200_MAX_SOURCES) return CATB200_ERR_INVALID_ARGUMENT;
   if (plan->n_terms < 0 || plan->n_terms > CATB200_MAX_TERMS) return CATB200_ERR_INVALID_ARGUMENT;
-  int off = 0;
+  int off = 0;  // bytes within a tile's shared-memory image
   for (int s = 0; s < plan->n_sources; ++s) {
     catb200_source_t& src = plan->sources[s];
     if (src.row_len <= 0 || src.row_len > 4096 || src.row_stride < src.row_len) return CATB200_ERR_INVALID_ARGUMENT;
     if (src.dtype != CATB200_F32 && src.dtype != CATB200_U8) return CATB200_ERR_UNSUPPORTED;
     if (src.aux < 0 || (src.aux > 0 && src.row_len % (3 * src.aux) != 0)) return CATB200_ERR_INVALID_ARGUMENT;
-    src.smem_off = off;
-    off += src.row_len | 1;
-    // exact floor(f / row_len) for f < 2^17 via umulhi (f * ceil(2^32 / d)) -- tile * row_len <= 131072
-    src.magic = (uint32_t)((0x100000000ull + (uint64_t)src.row_len - 1) / (uint64_t)src.row_len);
-    if (src.row_len == 1) src.magic = 0u;  // row_len 1 is special-cased in the kernel (2^32 does not fit)
+    src.smem_off = off;  // 16-byte aligned: destination of a bulk async copy
+    off += (kTile * src.row_len * (src.dtype == CATB200_U8 ? 1 : 4) + 15) & ~15;
+    src.magic = 0;
   }
-  plan->smem_floats_per_env = off;
+  plan->n_peaks = 0;
   int col = 0, slots = 0, last_slot = -1;
   for (int t = 0; t < plan->n_terms; ++t) {
     catb200_term_t& term = plan->terms[t];
@@ -400,6 +487,23 @@ int catb200_cat_plan_finalize(catb200_plan_t* plan) {
     for (int k = 0; k < term.n_ids; ++k) {
       const int bound = contact_op ? s0.aux : s0.row_len;
       if (term.ids[k] >= bound) return CATB200_ERR_INVALID_ARGUMENT;
+    }
+    if (contact_op) {
+      // body ids -> slots of the shared peak table (one entry per distinct (history tensor, body) pair)
+      if (term.reserved != 0) return CATB200_ERR_INVALID_ARGUMENT;  // plan was already finalized
+      for (int k = 0; k < term.n_ids; ++k) {
+        int slot = -1;
+        for (int p = 0; p < plan->n_peaks; ++p)
+          if (plan->peak_src[p] == term.src0 && plan->peak_body[p] == term.ids[k]) slot = p;
+        if (slot < 0) {
+          if (plan->n_peaks >= CATB200_MAX_PEAKS) return CATB200_ERR_UNSUPPORTED;
+          slot = plan->n_peaks++;
+          plan->peak_src[slot] = term.src0;
+          plan->peak_body[slot] = term.ids[k];
+        }
+        term.ids[k] = (uint8_t)slot;
+      }
+      term.reserved = 1;
     }
     const bool per_id = !(term.op == CATB200_OP_CONTACT_ANY || term.op == CATB200_OP_N_CONTACT ||
                           term.op == CATB200_OP_NORM2_MINUS);
@@ -424,18 +528,24 @@ int catb200_cat_plan_finalize(catb200_plan_t* plan) {
   plan->slot_col_begin[slots] = (uint16_t)col;
   plan->n_cols = col;
   plan->n_slots = slots;
-  if ((size_t)off * kTile * sizeof(float) > 200 * 1024) return CATB200_ERR_UNSUPPORTED;
+  plan->smem_peak_off = off;
+  off += plan->n_peaks * kTile * 4;
+  off = (off + 15) & ~15;
+  plan->smem_bar_off = off;
+  off += 16;
+  plan->smem_bytes = off;
+  if (off > 200 * 1024) return CATB200_ERR_UNSUPPORTED;
   return CATB200_OK;
 }
 
 size_t catb200_cat_workspace_bytes(int32_t num_envs, int32_t n_cols) {
   if (num_envs < 0 || n_cols < 0) return 0;
-  return 256 + align256(sizeof(uint32_t) * CATB200_MAX_COLS) + align256(sizeof(float) * (size_t)num_envs * n_cols);
+  return 256 + align256(sizeof(uint32_t) * CATB200_MAX_COLS * kMaxGroups) + align256(sizeof(float) * (size_t)num_envs * n_cols);
 }
 
 static int launch_eval(const catb200_plan_t* plan, const catb200_cat_params_t* prm, int num_envs, float* running_max,
                        int* rm_init, CatWorkspace ws, float* out_rowmajor, int mode, cudaStream_t stream) {
-  const size_t smem = (size_t)plan->smem_floats_per_env * kTile * sizeof(float);
+  const size_t smem = (size_t)plan->smem_bytes;
   const int grid = (num_envs + kTile - 1) / kTile;
   if (mode == kEvalStep) {
     if (smem > 48 * 1024)
@@ -457,15 +567,15 @@ int catb200_cat_step(const catb200_plan_t* plan, const catb200_cat_params_t* par
   if (!plan || !params || num_envs <= 0 || !running_max || !rm_init || !episode_sums || !mean_values || !cstr_prob ||
       !workspace)
     return CATB200_ERR_INVALID_ARGUMENT;
-  if (plan->n_cols <= 0 || plan->smem_floats_per_env <= 0) return CATB200_ERR_INVALID_ARGUMENT;
+  if (plan->n_cols <= 0 || plan->smem_bytes <= 0) return CATB200_ERR_INVALID_ARGUMENT;
   if (raw_reward && (!reward_out || !dones_out)) return CATB200_ERR_INVALID_ARGUMENT;
   if (workspace_bytes < catb200_cat_workspace_bytes(num_envs, plan->n_cols)) return CATB200_ERR_WORKSPACE_TOO_SMALL;
   cudaStream_t st = as_stream(stream);
   CatWorkspace ws = carve(workspace, num_envs);
   int rc = launch_eval(plan, params, num_envs, running_max, rm_init, ws, nullptr, kEvalStep, st);
   if (rc != CATB200_OK) return rc;
-  const int grid = (num_envs + kApplyThreads - 1) / kApplyThreads;
-  cat_apply_kernel<<<grid, kApplyThreads, 0, st>>>(*plan, *params, num_envs, running_max, ws.c_t, episode_sums,
+  const int grid = (num_envs + kTile - 1) / kTile;
+  cat_apply_kernel<<<grid, kEvalThreads, 0, st>>>(*plan, *params, num_envs, running_max, ws.c_t, episode_sums,
                                                    mean_values, cstr_prob, raw_reward, reset_buf, reward_out,
                                                    dones_out);
   CATB200_LAUNCH_CHECK();
@@ -489,14 +599,21 @@ int catb200_cat_probs(const catb200_plan_t* plan, const catb200_cat_params_t* pa
   return CATB200_OK;
 }
 
+size_t catb200_cat_reset_workspace_bytes(void) { return sizeof(ResetScratch); }
+
 int catb200_cat_reset_stats(const int64_t* env_ids, int32_t n_ids, const uint8_t* mask, const int64_t* episode_length,
                             int32_t num_envs, int32_t n_slots, float* episode_sums, float* mean_values, float* out,
-                            void* stream) {
-  if (!episode_length || num_envs <= 0 || n_slots <= 0 || !episode_sums || !mean_values || !out)
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  if (!episode_length || num_envs <= 0 || n_slots <= 0 || n_slots > CATB200_MAX_TERMS || !episode_sums || !mean_values ||
+      !out || !workspace)
     return CATB200_ERR_INVALID_ARGUMENT;
   if (env_ids && n_ids < 0) return CATB200_ERR_INVALID_ARGUMENT;
-  cat_reset_kernel<<<n_slots, kResetThreads, 0, as_stream(stream)>>>(env_ids, n_ids, mask, episode_length, num_envs,
-                                                                    episode_sums, mean_values, out);
+  if (workspace_bytes < sizeof(ResetScratch)) return CATB200_ERR_WORKSPACE_TOO_SMALL;
+  const int total = env_ids ? n_ids : num_envs;
+  const int chunks = max(1, (total + kResetChunk - 1) / kResetChunk);
+  cat_reset_kernel<<<dim3(n_slots, chunks), kResetThreads, 0, as_stream(stream)>>>(
+      env_ids, n_ids, mask, episode_length, num_envs, n_slots, episode_sums, mean_values, out,
+      static_cast<ResetScratch*>(workspace));
   CATB200_LAUNCH_CHECK();
   return CATB200_OK;
 }

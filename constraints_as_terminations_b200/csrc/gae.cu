@@ -16,9 +16,11 @@ namespace catb200 {
 constexpr int kGaeThreads = 64;
 constexpr int kGaeChunk = 8;  // time steps whose loads are issued together
 
+constexpr int kGaeGroups = 32;  // spread the 4 double accumulators: same-address atomics serialise in L2
+
 struct GaeWorkspace {
   unsigned int* ticket;
-  double* sums;  // sum v, sum v^2, sum ret, sum ret^2
+  double* sums;  // [kGaeGroups][4]: sum v, sum v^2, sum ret, sum ret^2
 };
 
 __device__ __forceinline__ void chan_merge_scalar(float& mean, float& var, float& count, float bmean, float bvar,
@@ -93,12 +95,13 @@ gae_kernel(const float* __restrict__ rewards, const float* __restrict__ values, 
   if (threadIdx.x < 4) {
     double a = 0.0;
     for (int w = 0; w < kGaeThreads / 32; ++w) a += sh[threadIdx.x][w];
-    atomicAdd(&ws.sums[threadIdx.x], a);
+    atomicAdd(&ws.sums[(blockIdx.x & (kGaeGroups - 1)) * 4 + threadIdx.x], a);
   }
   if (last_block_ticket(ws.ticket, gridDim.x)) {
     if (threadIdx.x == 0) {
-      double s[4];
-      for (int k = 0; k < 4; ++k) s[k] = __longlong_as_double(atomicExch((unsigned long long*)&ws.sums[k], 0ull));
+      double s[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int gi = 0; gi < kGaeGroups; ++gi)
+        for (int k = 0; k < 4; ++k) s[k] += __longlong_as_double(atomicExch((unsigned long long*)&ws.sums[gi * 4 + k], 0ull));
       const double cnt = (double)T * (double)N;
       const float n = (float)((long long)T * (long long)N);
       float mean = value_rms[0], var = value_rms[1], count = value_rms[2];
@@ -124,7 +127,7 @@ using namespace catb200;
 
 extern "C" {
 
-size_t catb200_gae_workspace_bytes(void) { return 256 + 4 * sizeof(double); }
+size_t catb200_gae_workspace_bytes(void) { return 256 + kGaeGroups * 4 * sizeof(double); }
 
 int catb200_gae(const float* rewards, const float* values, const float* dones, const float* true_dones,
                 const float* next_value, int32_t T, int32_t num_envs, float gamma, float gamma_lambda,

@@ -52,6 +52,7 @@ const char* catb200_error_string(int status);
 #define CATB200_MAX_TERMS 32
 #define CATB200_MAX_IDS 32
 #define CATB200_MAX_COLS 256
+#define CATB200_MAX_PEAKS 32
 
 typedef enum { CATB200_F32 = 0, CATB200_U8 = 1 } catb200_dtype;
 
@@ -80,8 +81,8 @@ typedef struct {
   int32_t row_stride; /* elements between consecutive env rows (== row_len if contiguous) */
   int32_t dtype;      /* catb200_dtype                                                    */
   int32_t aux;        /* contact history: number of bodies B (row = [H, B, 3]); else 0    */
-  int32_t smem_off;   /* filled by catb200_cat_plan_finalize                              */
-  uint32_t magic;     /* filled by catb200_cat_plan_finalize (fast division by row_len)   */
+  int32_t smem_off;   /* filled by catb200_cat_plan_finalize: byte offset in the tile's smem image */
+  uint32_t magic;     /* reserved                                                         */
 } catb200_source_t;
 
 typedef struct {
@@ -92,7 +93,7 @@ typedef struct {
   uint8_t src1;      /* second source (y, a_prev, first_contact) or 0xff                    */
   uint8_t src2;      /* command source or 0xff                                              */
   uint8_t stat_slot; /* row of episode_sums / mean_values this term accumulates into        */
-  uint8_t reserved;
+  uint8_t reserved;  /* must be 0 on entry to finalize (marks contact terms whose ids were remapped) */
   uint16_t col_offset; /* first column of this term in the [N,K] layout                     */
   uint16_t reserved2;
   float p0, p1, p2;
@@ -101,12 +102,16 @@ typedef struct {
 
 typedef struct {
   int32_t n_sources, n_terms, n_cols, n_slots;
-  int32_t smem_floats_per_env; /* filled by catb200_cat_plan_finalize */
-  int32_t reserved[3];
+  int32_t smem_bytes;    /* filled by finalize: shared memory per 32-env tile                */
+  int32_t n_peaks;       /* filled by finalize: distinct (contact history, body) pairs       */
+  int32_t smem_peak_off; /* filled by finalize                                               */
+  int32_t smem_bar_off;  /* filled by finalize                                               */
   catb200_source_t sources[CATB200_MAX_SOURCES];
   catb200_term_t terms[CATB200_MAX_TERMS];
   uint8_t col_term[CATB200_MAX_COLS];               /* filled by finalize: term of each column        */
   uint16_t slot_col_begin[CATB200_MAX_TERMS + 2];   /* filled by finalize: [begin,end) cols per slot  */
+  uint8_t peak_src[CATB200_MAX_PEAKS];              /* filled by finalize: source of each peak slot    */
+  uint8_t peak_body[CATB200_MAX_PEAKS];             /* filled by finalize: body of each peak slot      */
 } catb200_plan_t;
 
 /* Scalars of CaT.add (U/cat/constraint_manager.py:39-76), rounded on the host exactly like torch
@@ -159,10 +164,13 @@ int catb200_cat_probs(const catb200_plan_t* plan, const catb200_cat_params_t* pa
  *   out[2*s+1] = mean_i(mean_values[s,i]  / episode_length[i])
  * over the selected envs, then zero both rows at those envs.  Selection: `env_ids` (int64, n_ids
  * entries) or, if env_ids == NULL, `mask` (u8 [num_envs], nonzero = selected) or, if both NULL, all.
+ * workspace: catb200_cat_reset_workspace_bytes() of zero-initialised device scratch.
  */
+size_t catb200_cat_reset_workspace_bytes(void);
 int catb200_cat_reset_stats(const int64_t* env_ids, int32_t n_ids, const uint8_t* mask,
                             const int64_t* episode_length, int32_t num_envs, int32_t n_slots,
-                            float* episode_sums, float* mean_values, float* out, void* stream);
+                            float* episode_sums, float* mean_values, float* out, void* workspace,
+                            size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Running moments + rollout append  (row a6: U/cleanrl/ppo.py:12-62,203-205,225)

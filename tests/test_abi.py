@@ -36,7 +36,7 @@ def test_struct_sizes_match_header():
     # the kernels receive the plan by value as a launch parameter: must stay well below 4 KiB
     assert ctypes.sizeof(L.Source) == 32
     assert ctypes.sizeof(L.Term) == 56
-    assert ctypes.sizeof(L.Plan) < 3072
+    assert ctypes.sizeof(L.Plan) < 3072 + 64
     assert ctypes.sizeof(L.CatParams) == 16 + 4 * L.MAX_TERMS
 
 
@@ -49,7 +49,7 @@ def test_plan_finalize_validates(lib):
     for k, v in enumerate([0, 5, 11]):
         t.ids[k] = v
     assert lib.catb200_cat_plan_finalize(plan) == 0
-    assert plan.n_cols == 3 and plan.n_slots == 1 and plan.smem_floats_per_env == 13
+    assert plan.n_cols == 3 and plan.n_slots == 1 and plan.smem_bytes == 32 * 12 * 4 + 16 and plan.n_peaks == 0
     assert list(plan.slot_col_begin[:2]) == [0, 3]
     t.ids[2] = 12  # out of the 12-wide row
     assert lib.catb200_cat_plan_finalize(plan) == -1
