@@ -276,7 +276,7 @@ cat_eval_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_consta
 
   if (MODE == kEvalStep) {
     // ---- the last CTA folds the column maxima into the Polyak running max (constraint_manager.py:55-61)
-    if (last_block_ticket(ws.ticket, gridDim.x)) {
+    if (last_block_ticket_grouped(ws.ticket, gridDim.x)) {
       const int groups = n_groups;
       for (int col = threadIdx.x; col < plan.n_cols; col += kEvalThreads) {
         uint32_t key = 0u;

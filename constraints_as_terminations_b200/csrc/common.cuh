@@ -75,4 +75,34 @@ __device__ __forceinline__ bool last_block_ticket(unsigned int* counter, unsigne
   return s_last;
 }
 
+// Two-level variant for grids of tens of thousands of CTAs: one shared counter would queue every CTA's
+// atomic on a single L2 address (tens of ns each).  CTAs first count inside one of kTicketGroups groups;
+// only the last CTA of each group touches the global counter.  `counters` = 1 + kTicketGroups words, zero
+// between launches (left clean).  Returns true in exactly one block, for all its threads.
+constexpr unsigned int kTicketGroups = 32;
+
+__device__ __forceinline__ bool last_block_ticket_grouped(unsigned int* counters, unsigned int total_blocks) {
+  __shared__ bool s_last_g;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int groups = min(kTicketGroups, total_blocks);
+    const unsigned int g = blockIdx.x % groups;
+    const unsigned int members = total_blocks / groups + (g < total_blocks % groups ? 1u : 0u);
+    bool last = false;
+    if (atomicAdd(&counters[1 + g], 1u) == members - 1) {
+      counters[1 + g] = 0u;
+      __threadfence();
+      if (atomicAdd(&counters[0], 1u) == groups - 1) {
+        counters[0] = 0u;
+        last = true;
+      }
+    }
+    s_last_g = last;
+  }
+  __syncthreads();
+  if (s_last_g) __threadfence();
+  return s_last_g;
+}
+
 }  // namespace catb200

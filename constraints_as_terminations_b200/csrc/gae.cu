@@ -97,7 +97,7 @@ gae_kernel(const float* __restrict__ rewards, const float* __restrict__ values, 
     for (int w = 0; w < kGaeThreads / 32; ++w) a += sh[threadIdx.x][w];
     atomicAdd(&ws.sums[(blockIdx.x & (kGaeGroups - 1)) * 4 + threadIdx.x], a);
   }
-  if (last_block_ticket(ws.ticket, gridDim.x)) {
+  if (last_block_ticket_grouped(ws.ticket, gridDim.x)) {
     if (threadIdx.x == 0) {
       double s[4] = {0.0, 0.0, 0.0, 0.0};
       for (int gi = 0; gi < kGaeGroups; ++gi)
