@@ -164,16 +164,24 @@ cat_eval_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_consta
       }
     }
   }
-  __syncthreads();
-  {  // wait for the bulk copies (phase 0 of the barrier)
-    uint32_t done = 0;
-    while (!done) {
-      asm volatile(
-          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-          : "=r"(done)
-          : "r"(bar)
-          : "memory");
+  // wait for the bulk copies (phase 0 of the barrier): one lane sleeps on the mbarrier (try_wait with a
+  // suspend-time hint blocks in hardware instead of spinning), the CTA barrier releases everybody else, and
+  // each thread then performs one already-satisfied acquire of its own
+  auto try_wait0 = [&]() -> uint32_t {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0, 0x989680;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(bar)
+        : "memory");
+    return done;
+  };
+  if (threadIdx.x == 0) {
+    while (!try_wait0()) {
     }
+  }
+  __syncthreads();
+  while (!try_wait0()) {
   }
 
   const bool live = lane < rows;

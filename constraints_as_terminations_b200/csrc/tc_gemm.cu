@@ -41,7 +41,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"  // suspend-time hint: sleep, do not spin
       "selp.u32 %0, 1, 0, p;\n\t}\n"
       : "=r"(ok)
       : "r"(bar), "r"(parity)
@@ -264,7 +264,9 @@ tc_gemm_kernel(const __grid_constant__ TcGemmArgs g) {
           hv[i][q] = row < g.M ? __ldg(reinterpret_cast<const uint4*>(hrow + i * 32 + q * 8)) : make_uint4(0, 0, 0, 0);
     }
     if (k_blocks > 0) {
-      mbar_wait(tmem_full_bar, 0);
+      if (lane == 0) mbar_wait(tmem_full_bar, 0);  // one sleeping lane per warp instead of 256 pollers
+      __syncwarp();
+      mbar_wait(tmem_full_bar, 0);                 // already complete: a single acquire per thread
       tc_fence_after();
     }
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + c_first;

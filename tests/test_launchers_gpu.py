@@ -25,7 +25,7 @@ def test_train_then_play(tmp_path):
     assert [os.path.basename(c) for c in ckpts] == ["model_1.pt", "model_3.pt"]  # (iteration + 1) % save_interval == 0
     sd = torch.load(ckpts[-1], map_location="cpu")
     assert "critic.0.weight" in sd and "actor_mean.6.bias" in sd and "actor_logstd" in sd and "obs_rms.running_mean" in sd
-    assert float(sd["obs_rms.count"]) == 1 + 256 * (1 + 24 * 4)
+    assert float(sd["obs_rms.count"]) == 1 + 256 * (1 + 24 * 3)  # saved after iteration 3
     assert glob.glob(os.path.join(runs[0], "events.out.tfevents.*")), "tensorboard scalars missing"
     play = [sys.executable, os.path.join(ROOT, "scripts/clean_rl/play.py"), "--headless", "--num_envs", "32", "--video_length", "5",
             "--experiment_name", "launcher_test"]  # fmt: skip
