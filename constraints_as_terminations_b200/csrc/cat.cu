@@ -41,6 +41,8 @@ struct SrcView {
   __device__ __forceinline__ float at(int row, int e) const {
     return is_u8 ? (base[row * row_len + e] ? 1.0f : 0.0f) : reinterpret_cast<const float*>(base)[row * row_len + e];
   }
+  // sources the library ops read as fp32 by construction (state tensors); bool / u8 only reach `at`
+  __device__ __forceinline__ float f32(int row, int e) const { return reinterpret_cast<const float*>(base)[row * row_len + e]; }
 };
 
 __device__ __forceinline__ SrcView view_of(const catb200_plan_t& plan, const uint8_t* smem, int s) {
@@ -68,7 +70,7 @@ __device__ __forceinline__ float force_peak(const SrcView& v, int bodies, int ro
   float peak = -INFINITY;
   for (int h = 0; h < H; ++h) {
     const int e = (h * bodies + body) * 3;
-    peak = fmaxf(peak, norm3(v.at(row, e), v.at(row, e + 1), v.at(row, e + 2)));
+    peak = fmaxf(peak, norm3(v.f32(row, e), v.f32(row, e + 1), v.f32(row, e + 2)));
   }
   return peak;
 }
@@ -98,6 +100,84 @@ __host__ __device__ inline CatWorkspace carve(void* base, int num_envs) {
 }
 
 enum EvalMode { kEvalStep = 0, kEvalRowMajor = 1 };
+
+// ---- per-term column evaluation ----------------------------------------------------------------------
+struct TermCtx {
+  const uint8_t* ids;  // joint / body / peak-slot ids of the term (kernel-parameter memory)
+  int n_ids, first, n_cols, col0, row, lane;
+  float p0, p1, p2, gate;
+  const float* peaks;
+  SrcView v0, v1;
+};
+
+template <int MODE>
+struct ColumnSink {  // where a column value of this tile goes: C_T + column max, or the row-major debug matrix
+  bool live;
+  int lane, n_cols, num_envs;
+  float* ct;         // &C_T[0][tile0 + lane]
+  uint32_t* colmax;  // this CTA's scratch row
+  float* out_row;    // &out[tile0 + lane][0]
+  __device__ __forceinline__ void emit(int col, float c) const {
+    if (MODE == kEvalRowMajor) {
+      if (live) out_row[col] = c;
+    } else {
+      if (live) ct[(size_t)col * num_envs] = c;
+      const uint32_t m = __reduce_max_sync(0xffffffffu, live ? float_to_ordered(c) : 0u);
+      if (lane == 0) atomicMax(colmax + col, m);
+    }
+  }
+};
+
+// Operation order follows the cited reference lines; every intermediate is rounded to fp32 exactly where
+// torch materialises a tensor.
+template <int OP>
+__device__ __forceinline__ float column_value(const TermCtx& c, int lc) {
+  const int id = c.ids[lc];
+  const int row = c.row;
+  switch (OP) {
+    case CATB200_OP_GENERIC:
+      return c.v0.at(row, id);
+    case CATB200_OP_ABS_MINUS:  // constraints.py:30,64,75,85
+      return __fsub_rn(fabsf(c.v0.f32(row, id)), c.p0);
+    case CATB200_OP_ABSDIFF_MINUS:  // constraints.py:176-181
+      return __fsub_rn(fabsf(__fsub_rn(c.v0.f32(row, id), c.v1.f32(row, id))), c.p0);
+    case CATB200_OP_ABSDIFF_MINUS_GATE_Y:  // constraints.py:42-53
+      return __fmul_rn(__fsub_rn(fabsf(__fsub_rn(c.v0.f32(row, id), c.v1.f32(row, id))), c.p0), c.gate);
+    case CATB200_OP_ACTION_RATE:  // constraints.py:191-198 (true division by step_dt)
+      return __fsub_rn(__fdiv_rn(fabsf(__fsub_rn(c.v0.f32(row, id), c.v1.f32(row, id))), c.p1), c.p0);
+    case CATB200_OP_COMPONENT_GT:  // constraints.py:94
+      return c.v0.f32(row, id) > c.p0 ? 1.0f : 0.0f;
+    case CATB200_OP_CONTACT_ANY: {  // constraints.py:103-110; ids index the peak table
+      bool any = false;
+      for (int b = 0; b < c.n_ids; ++b) any |= c.peaks[c.ids[b] * kTile + c.lane] > c.p0;
+      return any ? 1.0f : 0.0f;
+    }
+    case CATB200_OP_NORM2_MINUS:  // constraints.py:119
+      return __fsub_rn(norm2(c.v0.f32(row, 0), c.v0.f32(row, 1)), c.p0);
+    case CATB200_OP_AIR_TIME: {  // constraints.py:129-141
+      const float td = c.v1.at(row, id) != 0.0f ? 1.0f : 0.0f;
+      return __fmul_rn(__fmul_rn(__fsub_rn(c.p0, c.v0.f32(row, id)), td), c.gate);
+    }
+    case CATB200_OP_N_CONTACT: {  // constraints.py:151-168
+      int n = 0;
+      for (int b = 0; b < c.n_ids; ++b) n += c.peaks[c.ids[b] * kTile + c.lane] > c.p2 ? 1 : 0;
+      return __fmul_rn(fabsf((float)n - c.p0), c.gate);
+    }
+    case CATB200_OP_FORCE_PEAK_MINUS:  // constraints.py:207-210
+      return __fsub_rn(c.peaks[id * kTile + c.lane], c.p0);
+    case CATB200_OP_LIMIT_MINUS:  // constraints.py:220
+      return __fsub_rn(c.p0, c.v0.f32(row, id));
+    case CATB200_OP_ABS_MINUS_GATE_STILL:  // constraints.py:231-235
+      return __fmul_rn(__fsub_rn(fabsf(c.v0.f32(row, id)), c.p0), c.gate);
+    default:
+      return 0.0f;
+  }
+}
+
+template <int OP, int MODE>
+__device__ __forceinline__ void term_columns(const TermCtx& c, const ColumnSink<MODE>& sink) {
+  for (int lc = c.first; lc < c.n_cols; lc += kEvalWarps) sink.emit(c.col0 + lc, column_value<OP>(c, lc));
+}
 
 __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
@@ -186,7 +266,8 @@ cat_eval_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_consta
 
   const bool live = lane < rows;
   const int row = live ? lane : 0;
-  const int n_groups = max(1, min((int)gridDim.x / 8, kMaxGroups));  // ~8+ CTAs share a scratch row
+  int n_groups = 1;  // power of two, ~8+ CTAs share a scratch row
+  while (n_groups < kMaxGroups && n_groups * 16 <= (int)gridDim.x) n_groups <<= 1;
 
   // ---- phase A: contact-force peaks, once per (history tensor, body) pair referenced by any term
   for (int p = warp; p < plan.n_peaks; p += kEvalWarps) {
@@ -196,89 +277,60 @@ cat_eval_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_consta
   __syncthreads();
 
   // ---- phase B: terms.  Term-level scalars and gates are computed once per term; the term's columns are
-  //      dealt to the 4 warps by global column index (lane = env, so the op dispatch never diverges).
+  //      dealt to the 4 warps by global column index (lane = env, so the op dispatch never diverges) and the
+  //      op switch sits outside the column loop.
+  ColumnSink<MODE> sink;
+  sink.live = live;
+  sink.lane = lane;
+  sink.n_cols = plan.n_cols;
+  sink.num_envs = num_envs;
+  sink.ct = MODE == kEvalStep ? ws.c_t + tile0 + lane : nullptr;
+  sink.colmax = MODE == kEvalStep ? ws.colmax + (blockIdx.x & (n_groups - 1)) * CATB200_MAX_COLS : nullptr;
+  sink.out_row = MODE == kEvalRowMajor ? out_rowmajor + (size_t)(tile0 + lane) * plan.n_cols : nullptr;
   for (int ti = 0; ti < plan.n_terms; ++ti) {
     const catb200_term_t& t = plan.terms[ti];
     const int n_cols = t.n_cols, col0 = t.col_offset, op = t.op;
-    int first = (warp - (col0 & (kEvalWarps - 1))) & (kEvalWarps - 1);  // first local column owned by this warp
+    const int first = (warp - (col0 & (kEvalWarps - 1))) & (kEvalWarps - 1);  // first local column of this warp
     if (first >= n_cols) continue;
-    const float p0 = t.p0, p1 = t.p1, p2 = t.p2;
-    const SrcView v0 = view_of(plan, smem, t.src0);
-    SrcView v1 = v0;
-    if (t.src1 != 0xff) v1 = view_of(plan, smem, t.src1);
-    float gate = 1.0f;  // command-dependent factor shared by all columns of the term
+    TermCtx c;
+    c.ids = t.ids;
+    c.n_ids = t.n_ids;
+    c.first = first;
+    c.n_cols = n_cols;
+    c.col0 = col0;
+    c.row = row;
+    c.lane = lane;
+    c.p0 = t.p0;
+    c.p1 = t.p1;
+    c.p2 = t.p2;
+    c.peaks = peaks;
+    c.v0 = view_of(plan, smem, t.src0);
+    c.v1 = t.src1 != 0xff ? view_of(plan, smem, t.src1) : c.v0;
+    c.gate = 1.0f;  // command-dependent factor shared by all columns of the term
     if (t.src2 != 0xff) {
       const SrcView vc = view_of(plan, smem, t.src2);
       if (op == CATB200_OP_ABSDIFF_MINUS_GATE_Y) {
-        gate = fabsf(vc.at(row, 1)) < p1 ? 1.0f : 0.0f;  // constraints.py:46-53
+        c.gate = fabsf(vc.f32(row, 1)) < c.p1 ? 1.0f : 0.0f;  // constraints.py:46-53
       } else {
-        const float cn = norm3(vc.at(row, 0), vc.at(row, 1), vc.at(row, 2));
-        gate = op == CATB200_OP_ABS_MINUS_GATE_STILL ? (cn < p1 ? 1.0f : 0.0f) : (cn > p1 ? 1.0f : 0.0f);
+        const float cn = norm3(vc.f32(row, 0), vc.f32(row, 1), vc.f32(row, 2));
+        c.gate = op == CATB200_OP_ABS_MINUS_GATE_STILL ? (cn < c.p1 ? 1.0f : 0.0f) : (cn > c.p1 ? 1.0f : 0.0f);
       }
     }
-    for (int lc = first; lc < n_cols; lc += kEvalWarps) {
-      const int id = t.ids[lc];
-      float c;
-      switch (op) {
-        case CATB200_OP_GENERIC:
-          c = v0.at(row, id);
-          break;
-        case CATB200_OP_ABS_MINUS:  // constraints.py:30,64,75,85
-          c = __fsub_rn(fabsf(v0.at(row, id)), p0);
-          break;
-        case CATB200_OP_ABSDIFF_MINUS:  // constraints.py:176-181
-          c = __fsub_rn(fabsf(__fsub_rn(v0.at(row, id), v1.at(row, id))), p0);
-          break;
-        case CATB200_OP_ABSDIFF_MINUS_GATE_Y:  // constraints.py:42-53
-          c = __fmul_rn(__fsub_rn(fabsf(__fsub_rn(v0.at(row, id), v1.at(row, id))), p0), gate);
-          break;
-        case CATB200_OP_ACTION_RATE:  // constraints.py:191-198 (true division by step_dt)
-          c = __fsub_rn(__fdiv_rn(fabsf(__fsub_rn(v0.at(row, id), v1.at(row, id))), p1), p0);
-          break;
-        case CATB200_OP_COMPONENT_GT:  // constraints.py:94
-          c = v0.at(row, id) > p0 ? 1.0f : 0.0f;
-          break;
-        case CATB200_OP_CONTACT_ANY: {  // constraints.py:103-110; ids index the peak table
-          bool any = false;
-          for (int b = 0; b < t.n_ids; ++b) any |= peaks[t.ids[b] * kTile + lane] > p0;
-          c = any ? 1.0f : 0.0f;
-          break;
-        }
-        case CATB200_OP_NORM2_MINUS:  // constraints.py:119
-          c = __fsub_rn(norm2(v0.at(row, 0), v0.at(row, 1)), p0);
-          break;
-        case CATB200_OP_AIR_TIME: {  // constraints.py:129-141
-          const float td = v1.at(row, id) != 0.0f ? 1.0f : 0.0f;
-          c = __fmul_rn(__fmul_rn(__fsub_rn(p0, v0.at(row, id)), td), gate);
-          break;
-        }
-        case CATB200_OP_N_CONTACT: {  // constraints.py:151-168
-          int n = 0;
-          for (int b = 0; b < t.n_ids; ++b) n += peaks[t.ids[b] * kTile + lane] > p2 ? 1 : 0;
-          c = __fmul_rn(fabsf((float)n - p0), gate);
-          break;
-        }
-        case CATB200_OP_FORCE_PEAK_MINUS:  // constraints.py:207-210
-          c = __fsub_rn(peaks[id * kTile + lane], p0);
-          break;
-        case CATB200_OP_LIMIT_MINUS:  // constraints.py:220
-          c = __fsub_rn(p0, v0.at(row, id));
-          break;
-        case CATB200_OP_ABS_MINUS_GATE_STILL:  // constraints.py:231-235
-          c = __fmul_rn(__fsub_rn(fabsf(v0.at(row, id)), p0), gate);
-          break;
-        default:
-          c = 0.0f;
-      }
-      const int col = col0 + lc;
-      if (MODE == kEvalRowMajor) {
-        if (live) out_rowmajor[(size_t)(tile0 + lane) * plan.n_cols + col] = c;
-      } else {
-        if (live) ws.c_t[(size_t)col * num_envs + tile0 + lane] = c;
-        const uint32_t key = live ? float_to_ordered(c) : 0u;
-        const uint32_t m = __reduce_max_sync(0xffffffffu, key);
-        if (lane == 0) atomicMax(&ws.colmax[(blockIdx.x % n_groups) * CATB200_MAX_COLS + col], m);
-      }
+    switch (op) {
+      case CATB200_OP_GENERIC: term_columns<CATB200_OP_GENERIC>(c, sink); break;
+      case CATB200_OP_ABS_MINUS: term_columns<CATB200_OP_ABS_MINUS>(c, sink); break;
+      case CATB200_OP_ABSDIFF_MINUS: term_columns<CATB200_OP_ABSDIFF_MINUS>(c, sink); break;
+      case CATB200_OP_ABSDIFF_MINUS_GATE_Y: term_columns<CATB200_OP_ABSDIFF_MINUS_GATE_Y>(c, sink); break;
+      case CATB200_OP_ACTION_RATE: term_columns<CATB200_OP_ACTION_RATE>(c, sink); break;
+      case CATB200_OP_COMPONENT_GT: term_columns<CATB200_OP_COMPONENT_GT>(c, sink); break;
+      case CATB200_OP_CONTACT_ANY: term_columns<CATB200_OP_CONTACT_ANY>(c, sink); break;
+      case CATB200_OP_NORM2_MINUS: term_columns<CATB200_OP_NORM2_MINUS>(c, sink); break;
+      case CATB200_OP_AIR_TIME: term_columns<CATB200_OP_AIR_TIME>(c, sink); break;
+      case CATB200_OP_N_CONTACT: term_columns<CATB200_OP_N_CONTACT>(c, sink); break;
+      case CATB200_OP_FORCE_PEAK_MINUS: term_columns<CATB200_OP_FORCE_PEAK_MINUS>(c, sink); break;
+      case CATB200_OP_LIMIT_MINUS: term_columns<CATB200_OP_LIMIT_MINUS>(c, sink); break;
+      case CATB200_OP_ABS_MINUS_GATE_STILL: term_columns<CATB200_OP_ABS_MINUS_GATE_STILL>(c, sink); break;
+      default: break;
     }
   }
 
