@@ -104,25 +104,52 @@ def _host_fed_env_cls():
     from constraints_as_terminations_b200 import synthetic_env as se
 
     class HostFed(se.SyntheticSolo12Env):
-        """Same env, but every step's state arrives from pinned host memory (the e2e leg)."""
+        """Same env, but every step's state arrives from pinned host memory (the e2e leg).  Two device staging
+        sets: while the kernels of step t read one, the H2D copy of step t+1 runs on a copy stream."""
 
         def __init__(self, num_envs, device, seed, pool, constraints_cfg):
             super().__init__(num_envs, device=device, seed=seed, pool=pool, constraints_cfg=constraints_cfg)
             self._host_pool = [{k: v.cpu().pin_memory() for k, v in s.items()} for s in self._pool]
-            self._staging = {k: torch.empty_like(v) for k, v in self._pool[0].items()}
+            self._staging = [{k: torch.empty_like(v) for k, v in self._pool[0].items()} for _ in range(2)]
+            self._pool = None  # nothing stays resident on the device except the two staging sets
             self.h2d_bytes = sum(v.numel() * v.element_size() for v in self._host_pool[0].values())
-            self.load_state(self._staging)
+            self._copy_stream = torch.cuda.Stream(device=device)
+            self._ready = [torch.cuda.Event(), torch.cuda.Event()]
+            self._consumed = [torch.cuda.Event(), torch.cuda.Event()]
+            self._slot = 0
+            self._cursor = 0
+            self._prefetch(0, self._cursor)
+            self._take(0)
+
+        def _prefetch(self, slot, cursor):
+            """Enqueue the H2D copy of host state `cursor` into staging set `slot` on the copy stream."""
+            main = torch.cuda.current_stream()
+            self._consumed[slot].record(main)  # the copy must not overwrite data kernels still read
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(self._consumed[slot])
+                src = self._host_pool[cursor]
+                for k, dst in self._staging[slot].items():
+                    dst.copy_(src[k], non_blocking=True)
+                self._ready[slot].record(self._copy_stream)
+
+        def _take(self, slot):
+            torch.cuda.current_stream().wait_event(self._ready[slot])
+            self.load_state(self._staging[slot])
 
         def reset(self):
-            self._cursor = -1
-            self._advance()
             return self.obs_buf, {}
 
         def _advance(self):
+            # state for this step was prefetched into the other set during the previous step
+            nxt = self._slot ^ 1
+            if not getattr(self, "_primed", False):
+                self._cursor = (self._cursor + 1) % len(self._host_pool)
+                self._prefetch(nxt, self._cursor)
+                self._primed = True
+            self._take(nxt)
+            self._slot = nxt
             self._cursor = (self._cursor + 1) % len(self._host_pool)
-            src = self._host_pool[self._cursor]
-            for k, dst in self._staging.items():
-                dst.copy_(src[k], non_blocking=True)
+            self._prefetch(nxt ^ 1, self._cursor)  # next step's state, overlapped with this step's kernels
 
     return HostFed
 
@@ -203,6 +230,22 @@ def kernel_rooflines(device, num_envs, peaks):
         nbytes = 940 * n
         out[f"cat_step@{n}"] = {"bound": "hbm", "achieved": nbytes / sec / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": nbytes / sec / 1e9 / peaks["hbm_gbs"], "us": sec * 1e6, "bytes": nbytes, "launches": 2}
         del env, mgr
+    # one PPO optimizer step on a 16384-row minibatch (gather, 3 fwd + 2 dgrad + 3 wgrad tcgen05 GEMMs, head/loss,
+    # reduce, clip + Adam + weight cast): 2.2525 MFLOP/sample of tensor work
+    env, tr = make_trainer(num_envs, device, seed=0, graphs=False)
+    tr.train_iteration()
+    mb = tr.minibatch_size
+    perm = torch.randperm(tr.batch_size, device=device)
+    sec = time_kernel(lambda: tr._minibatch(perm[:mb]), reps=10)
+    flops = 2.2525e6 * mb
+    out[f"ppo_minibatch_step@{mb}"] = {"bound": "tensor", "achieved": flops / sec / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": flops / sec / 1e12 / peaks["bf16_tflops"], "us": sec * 1e6, "flops": flops, "launches": 14}
+    del env, tr
+    # DRAM traffic per launch from the committed `ncu --set full` captures (profiles/), where available
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.isfile(tpath):
+        for k, v in json.load(open(tpath)).items():
+            if k in out:
+                out[k]["traffic"] = v
     return out
 
 
@@ -254,7 +297,7 @@ def run_ours(args):
         roof = kernel_rooflines(device, N, peaks)
         cpu = cpu_baseline(N, sample_steps=4, sample_minibatches=2)
         main = dict(roof[f"gae@{N}"])
-        main.update({"kernel": "gae_kernel", "traffic": None, "peak_source": peaks["source"],
+        main.update({"kernel": "gae_kernel", "traffic": main.get("traffic"), "peak_source": peaks["source"],
                      "note": f"timed alone, L2 flushed; {main['bytes']/1e6:.2f} MB per launch is launch-latency bound at {N} envs, see the 65536 / 1M-env entries in `rooflines`"})
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
