@@ -19,12 +19,23 @@
 //
 // The cross-env column max is a true global dependency (probability of env i depends on the max over
 // all envs of this step), hence two phases.  HBM-bound streaming work: no tensor cores involved.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace catb200 {
 
 thread_local cudaError_t g_last_cuda_error = cudaSuccess;
 unsigned long long g_launch_count = 0;
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("CATB200_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 constexpr int kTile = 32;          // envs per CTA in the eval kernel (one per lane)
 constexpr int kEvalWarps = 4;      // warps per CTA; warp w owns columns w, w+4, ...

@@ -33,6 +33,31 @@ extern unsigned long long g_launch_count;
 // mlp.cu: refresh the bf16 compute copies (W and W^T of the hidden layers) from the fp32 master parameters
 int launch_cast_weights(const catb200_mlp_dims_t* dims, const float* params, void* w16, cudaStream_t st);
 
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------
+// The update path is a chain of ~14 short dependent kernels per minibatch.  With PDL the next kernel's CTAs
+// are launched (and run their prologue: barrier init, TMEM allocation, descriptor prefetch) while the
+// previous kernel drains; `pdl_wait()` then blocks until the previous grid has completed and its writes are
+// visible, so every kernel still only reads finished data.  CATB200_PDL=0 disables it.
+bool pdl_enabled();
+
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 constexpr int kNumSMs = 148;  // B200

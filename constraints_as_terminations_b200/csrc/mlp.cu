@@ -65,6 +65,8 @@ struct GemmNTArgs {
 template <int EPI>
 __global__ void __launch_bounds__(kGemmThreads)
 gemm_nt_kernel(const __grid_constant__ GemmNTArgs g) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int z = blockIdx.z;
   const int m_base = blockIdx.x * kBM, n_base = blockIdx.y * kBN;
@@ -198,6 +200,8 @@ constexpr int kWgBM = 64;  // reduction rows per pipeline stage
 template <int KT>
 __global__ void __launch_bounds__(kGemmThreads)
 wgrad_kernel(const __grid_constant__ WgradArgs g) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(128) uint8_t smem_raw[];
   constexpr int kRowBytesZ = 128 * 2, kRowBytesH = KT * 2;
   constexpr int kStageBytes = kWgBM * (kRowBytesZ + kRowBytesH);
@@ -307,6 +311,8 @@ struct ReduceArgs {
 };
 
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const __grid_constant__ ReduceArgs r) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int seg = blockIdx.y;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (seg < r.n_segments) {
@@ -385,6 +391,8 @@ gather_kernel(const int64_t* __restrict__ mb_inds, int M, const bf16* __restrict
               const float* __restrict__ adv_all, const float* __restrict__ logp_all, const float* __restrict__ ret_all,
               const float* __restrict__ val_all, const float* __restrict__ act_all, int A, bf16* __restrict__ X,
               float4* __restrict__ scal_mb, float* __restrict__ act_mb, MbStats* __restrict__ st) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int chunks = obs_pad / 8;  // 16-byte chunks per row
   const int total = M * chunks;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
@@ -460,6 +468,8 @@ struct HeadArgs {
 template <bool TRAIN>
 __global__ void __launch_bounds__(kHeadThreads)
 head_kernel(const __grid_constant__ HeadArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int AP = kMaxAct;  // action dims carried through the unrolled loops (weights beyond A are zero)
   constexpr int F = 4;  // features per lane (h3 == 128)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -706,6 +716,8 @@ struct CastArgs { CastSeg seg[6]; };
 // 32x32 tiles: coalesced fp32 reads, coalesced bf16 writes of W, and a shared-memory transpose for W^T.
 // grid = (max tiles over segments, 6 segments), block = (32, 8).
 __global__ void __launch_bounds__(256) cast_weights_kernel(const __grid_constant__ CastArgs c) {
+  pdl_launch_dependents();
+  pdl_wait();
   const CastSeg& s = c.seg[blockIdx.y];
   const int tiles_c = (s.cols_pad + 31) / 32, tiles_r = s.rows / 32;
   if ((int)blockIdx.x >= tiles_c * tiles_r) return;
@@ -844,7 +856,7 @@ static int launch_forward(const catb200_mlp_dims_t* d, const catb200_mlp_layout_
     g.lda = x.in_pad[l]; g.ldb = x.in_pad[l]; g.ldc = x.out[l];
     g.M = rows; g.N = x.out[l]; g.K = x.in_pad[l];
     dim3 grid((rows + kBM - 1) / kBM, x.out[l] / kBN, 2);
-    gemm_nt_kernel<kEpiBiasElu><<<grid, kGemmThreads, kSmemNT, st>>>(g);
+    CATB200_CUDA_TRY(launch_pdl(gemm_nt_kernel<kEpiBiasElu>, grid, dim3(kGemmThreads), kSmemNT, st, g));
     CATB200_LAUNCH_CHECK();
   }
   return CATB200_OK;
@@ -866,7 +878,7 @@ int launch_cast_weights(const catb200_mlp_dims_t* dims, const float* params, voi
       s.rows = x.out[l]; s.cols = x.in[l]; s.cols_pad = x.in_pad[l];
       max_tiles = max(max_tiles, (s.rows / 32) * ((s.cols_pad + 31) / 32));
     }
-  cast_weights_kernel<<<dim3(max_tiles, 6), dim3(32, 8), 0, st>>>(c);
+  CATB200_CUDA_TRY(launch_pdl(cast_weights_kernel, dim3(max_tiles, 6), dim3(32, 8), 0, st, c));
   CATB200_LAUNCH_CHECK();
   return CATB200_OK;
 }
@@ -924,7 +936,7 @@ int catb200_mlp_act(const catb200_mlp_dims_t* dims, const void* obs16, int32_t r
   a.M = rows; a.h3 = dims->h3; a.A = dims->act_dim;
   a.noise = noise; a.action_in = action_in; a.action = action; a.logprob = logprob; a.value = value; a.mean_out = mean_out;
   const int grid = min((rows + 7) / 8, kNumSMs * 4);
-  head_kernel<false><<<grid, kHeadThreads, 0, st>>>(a);
+  CATB200_CUDA_TRY(launch_pdl(head_kernel<false>, dim3(grid), dim3(kHeadThreads), 0, st, a));
   CATB200_LAUNCH_CHECK();
   return CATB200_OK;
 }
@@ -951,9 +963,10 @@ int catb200_ppo_minibatch_grad(const catb200_mlp_dims_t* dims, const catb200_ppo
   MbStats* mb = reinterpret_cast<MbStats*>(ws + L.mb);
 
   // 1. gather + advantage statistics
-  gather_kernel<<<min((M * (dims->obs_pad / 8) + 255) / 256, kNumSMs * 8), 256, 0, st>>>(
-      mb_inds, M, static_cast<const bf16*>(obs16_all), dims->obs_pad, advantages_all, logprobs_all, returns_all, values_all,
-      actions_all, dims->act_dim, X, reinterpret_cast<float4*>(ws + L.scal_mb), reinterpret_cast<float*>(ws + L.act_mb), mb);
+  CATB200_CUDA_TRY(launch_pdl(gather_kernel, dim3(min((M * (dims->obs_pad / 8) + 255) / 256, kNumSMs * 8)), dim3(256), 0, st,
+                              mb_inds, M, static_cast<const bf16*>(obs16_all), (int)dims->obs_pad, advantages_all, logprobs_all,
+                              returns_all, values_all, actions_all, (int)dims->act_dim, X, reinterpret_cast<float4*>(ws + L.scal_mb),
+                              reinterpret_cast<float*>(ws + L.act_mb), mb));
   CATB200_LAUNCH_CHECK();
   // 2. forward through the three hidden layers of both nets
   int rc = launch_forward(dims, P, L, X, M, params, w16, ws, st);
@@ -978,7 +991,7 @@ int catb200_ppo_minibatch_grad(const catb200_mlp_dims_t* dims, const catb200_ppo
       CATB200_CUDA_TRY(cudaFuncSetAttribute(head_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadSmem));
       head_attr = true;
     }
-    head_kernel<true><<<L.head_rows, kHeadThreads, kHeadSmem, st>>>(a);
+    CATB200_CUDA_TRY(launch_pdl(head_kernel<true>, dim3(L.head_rows), dim3(kHeadThreads), kHeadSmem, st, a));
     CATB200_LAUNCH_CHECK();
   }
   // 4. backward through the hidden layers
@@ -1014,11 +1027,11 @@ int catb200_ppo_minibatch_grad(const catb200_mlp_dims_t* dims, const catb200_ppo
       if (rc != CATB200_OK) return rc;
     } else if (x.in_pad[l] >= 128) {
       dim3 grid((x.out[l] / 128) * (x.in_pad[l] / 128), L.splits[l], 2);
-      wgrad_kernel<128><<<grid, kGemmThreads, kStages * kWgBM * (256 + 256), st>>>(wgt);
+      CATB200_CUDA_TRY(launch_pdl(wgrad_kernel<128>, grid, dim3(kGemmThreads), kStages * kWgBM * (256 + 256), st, wgt));
       CATB200_LAUNCH_CHECK();
     } else {
       dim3 grid((x.out[l] / 128) * (x.in_pad[l] / 64), L.splits[l], 2);
-      wgrad_kernel<64><<<grid, kGemmThreads, kStages * kWgBM * (256 + 128), st>>>(wgt);
+      CATB200_CUDA_TRY(launch_pdl(wgrad_kernel<64>, grid, dim3(kGemmThreads), kStages * kWgBM * (256 + 128), st, wgt));
       CATB200_LAUNCH_CHECK();
     }
     if (l > 0 && use_tc()) {  // dZ_{l-1} = (dZ_l W_l) * ELU'(H_{l-1}); A = dZ_l [M, out_l], B = W_l^T [in_l, out_l]
@@ -1046,7 +1059,7 @@ int catb200_ppo_minibatch_grad(const catb200_mlp_dims_t* dims, const catb200_ppo
       g.lda = x.out[l]; g.ldb = x.out[l]; g.ldc = x.in[l];
       g.M = M; g.N = x.in[l]; g.K = x.out[l];
       dim3 grid((M + kBM - 1) / kBM, x.in[l] / kBN, 2);
-      gemm_nt_kernel<kEpiMulDelu><<<grid, kGemmThreads, kSmemNT, st>>>(g);
+      CATB200_CUDA_TRY(launch_pdl(gemm_nt_kernel<kEpiMulDelu>, grid, dim3(kGemmThreads), kSmemNT, st, g));
       CATB200_LAUNCH_CHECK();
     }
   }
@@ -1062,7 +1075,7 @@ int catb200_ppo_minibatch_grad(const catb200_mlp_dims_t* dims, const catb200_ppo
   red.ent_coef = hp->ent_coef; red.vf_coef = hp->vf_coef;
   int max_elems = kHeadValues * 32;
   for (int sgm = 0; sgm < red.n_segments; ++sgm) max_elems = max(max_elems, red.N[sgm] * red.Kpad[sgm]);
-  reduce_partials_kernel<<<dim3((max_elems + 255) / 256, red.n_segments + 1), 256, 0, st>>>(red);
+  CATB200_CUDA_TRY(launch_pdl(reduce_partials_kernel, dim3((max_elems + 255) / 256, red.n_segments + 1), dim3(256), 0, st, red));
   CATB200_LAUNCH_CHECK();
   return CATB200_OK;
 }

@@ -22,6 +22,8 @@ struct OptScratch {  // 64 bytes of caller-provided zero-initialised device memo
 __global__ void __launch_bounds__(256)
 grad_norm_kernel(const float* __restrict__ grads, long long n, float grad_scale, float max_norm, float beta1,
                  float beta2, int* __restrict__ step, float* __restrict__ grad_norm_out, OptScratch* __restrict__ sc) {
+  pdl_launch_dependents();
+  pdl_wait();
   double s = 0.0;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
     const double g = (double)(grads[e] * grad_scale);
@@ -71,6 +73,8 @@ __device__ __forceinline__ void adam_one(float& p, float& g, float& m, float& v,
 }
 
 __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const float clip = a.sc->clip_coef * a.grad_scale;
   const float step_size = __ldg(a.lr) * a.sc->step_size_scale;
   const float bc2_sqrt = a.sc->bc2_sqrt;
@@ -110,13 +114,14 @@ int catb200_adam_step(const catb200_mlp_dims_t* dims, float* params, float* grad
   cudaStream_t st = as_stream(stream);
   OptScratch* sc = static_cast<OptScratch*>(opt_ws);
   const long long n = P.n_params;
-  grad_norm_kernel<<<kNumSMs, 256, 0, st>>>(grads, n, grad_scale, max_grad_norm, beta1, beta2, step_dev, grad_norm_out, sc);
+  CATB200_CUDA_TRY(launch_pdl(grad_norm_kernel, dim3(kNumSMs), dim3(256), 0, st, (const float*)grads, n, grad_scale, max_grad_norm, beta1, beta2,
+                              (int*)step_dev, grad_norm_out, sc));
   CATB200_LAUNCH_CHECK();
   AdamArgs a = {};
   a.params = params; a.grads = grads; a.m = exp_avg; a.v = exp_avg_sq;
   a.lr = lr_dev; a.sc = sc; a.n = n; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.grad_scale = grad_scale;
   const long long threads = n / 4 + 4;
-  adam_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a);
+  CATB200_CUDA_TRY(launch_pdl(adam_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, st, a));
   CATB200_LAUNCH_CHECK();
   rc = launch_cast_weights(dims, params, w16, st);  // refresh the bf16 copies the tensor-core GEMMs read
   if (rc != CATB200_OK) return rc;

@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
 tc_gemm_kernel(const __grid_constant__ TcGemmArgs g) {
   using S = TcSmem<MODE, BN>;
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();  // let the next kernel of the chain get resident while this one runs
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t tiles = (raw + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
   const int stages = g.stages;
@@ -184,6 +185,9 @@ tc_gemm_kernel(const __grid_constant__ TcGemmArgs g) {
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, BN);
+  // everything above (barriers, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail;
+  // from here on global data produced by it is read
+  pdl_wait();
   if (MODE == kTcFwd && warp >= 2) {
     for (int c = threadIdx.x - 64; c < BN; c += kTcThreads - 64) bias_sm[c] = __ldg(g.bias[z] + col_base + c);
   }
@@ -433,7 +437,7 @@ static int launch_one(TcGemmArgs g, dim3 grid, cudaStream_t st) {
   // ring depth: no more slots than reduction blocks (a K = 64 layer needs one), which keeps several CTAs per SM
   const int red = MODE == kTcWgrad ? g.m_range : g.K;
   g.stages = max(1, min(kTcStages, (red + kTcBK - 1) / kTcBK));
-  tc_gemm_kernel<MODE, BN><<<grid, kTcThreads, S::total(g.stages), st>>>(g);
+  CATB200_CUDA_TRY(launch_pdl(tc_gemm_kernel<MODE, BN>, grid, dim3(kTcThreads), (size_t)S::total(g.stages), st, g));
   CATB200_LAUNCH_CHECK();
   return CATB200_OK;
 }
