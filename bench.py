@@ -109,10 +109,27 @@ def _host_fed_env_cls():
 
         def __init__(self, num_envs, device, seed, pool, constraints_cfg):
             super().__init__(num_envs, device=device, seed=seed, pool=pool, constraints_cfg=constraints_cfg)
-            self._host_pool = [{k: v.cpu().pin_memory() for k, v in s.items()} for s in self._pool]
-            self._staging = [{k: torch.empty_like(v) for k, v in self._pool[0].items()} for _ in range(2)]
+            # one packed pinned buffer per host state and one packed staging buffer per device set, so that a
+            # step's state moves with a single cudaMemcpyAsync; the state tensors are views into the buffers
+            layout, off = {}, 0
+            for k, v in self._pool[0].items():
+                layout[k] = (off, v.numel() * v.element_size(), v.dtype, tuple(v.shape))
+                off += (layout[k][1] + 255) // 256 * 256
+            self._packed_bytes = off
+
+            def views(buf):
+                return {k: buf[o : o + n].view(dt).view(shape) for k, (o, n, dt, shape) in layout.items()}
+
+            self._host_pool = []
+            for st in self._pool:
+                buf = torch.empty(off, dtype=torch.uint8).pin_memory()
+                for k, dst in views(buf).items():
+                    dst.copy_(st[k].cpu())
+                self._host_pool.append(buf)
+            self._staging_buf = [torch.empty(off, dtype=torch.uint8, device=device) for _ in range(2)]
+            self._staging = [views(b) for b in self._staging_buf]
             self._pool = None  # nothing stays resident on the device except the two staging sets
-            self.h2d_bytes = sum(v.numel() * v.element_size() for v in self._host_pool[0].values())
+            self.h2d_bytes = sum(n for _, n, _, _ in layout.values())
             self._copy_stream = torch.cuda.Stream(device=device)
             self._ready = [torch.cuda.Event(), torch.cuda.Event()]
             self._consumed = [torch.cuda.Event(), torch.cuda.Event()]
@@ -127,9 +144,7 @@ def _host_fed_env_cls():
             self._consumed[slot].record(main)  # the copy must not overwrite data kernels still read
             with torch.cuda.stream(self._copy_stream):
                 self._copy_stream.wait_event(self._consumed[slot])
-                src = self._host_pool[cursor]
-                for k, dst in self._staging[slot].items():
-                    dst.copy_(src[k], non_blocking=True)
+                self._staging_buf[slot].copy_(self._host_pool[cursor], non_blocking=True)
                 self._ready[slot].record(self._copy_stream)
 
         def _take(self, slot):

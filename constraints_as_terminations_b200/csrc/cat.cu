@@ -32,7 +32,7 @@ bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = std::getenv("CATB200_PDL");
-    v = (e && e[0] == '0') ? 0 : 1;
+    v = (e && e[0] == '1') ? 1 : 0;  // opt-in: measured neutral inside CUDA graphs on B200 (profiles/)
   }
   return v == 1;
 }

@@ -37,7 +37,8 @@ int launch_cast_weights(const catb200_mlp_dims_t* dims, const float* params, voi
 // The update path is a chain of ~14 short dependent kernels per minibatch.  With PDL the next kernel's CTAs
 // are launched (and run their prologue: barrier init, TMEM allocation, descriptor prefetch) while the
 // previous kernel drains; `pdl_wait()` then blocks until the previous grid has completed and its writes are
-// visible, so every kernel still only reads finished data.  CATB200_PDL=0 disables it.
+// visible, so every kernel still only reads finished data.  Opt-in with CATB200_PDL=1 (measured neutral
+// when the chain already replays from a CUDA graph).
 bool pdl_enabled();
 
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
