@@ -134,7 +134,7 @@ struct TcSmem {
   static constexpr int kABytes = 128 * kTcBK * 2;  // 16 KiB: 128 (M) x 64 (K) bf16, or 2 boxes of 64 x 64 (MN-major)
   static constexpr int kBBytes = BN * kTcBK * 2;
   static constexpr int kStage = kABytes + kBBytes;
-  static constexpr int kAux = 256 /*barriers*/ + BN * 4 /*bias tile*/;
+  static constexpr int kAux = 256 /*barriers*/ + 4 * BN * 4 /*bias tile (fwd) or 4 x BN column-sum scratch (dgrad)*/;
   static constexpr int total(int stages) { return stages * kStage + 1024 /*alignment slack*/ + kAux; }
 };
 
@@ -308,7 +308,6 @@ tc_gemm_kernel(const __grid_constant__ TcGemmArgs g) {
       }
     } else if (MODE == kTcDgrad) {
       bf16* __restrict__ crow = g.C[z] + (size_t)row * g.ldc + col_base + c_first;
-      float* __restrict__ dbias = g.dbias[z] + col_base + c_first;
       const bool live = row < g.M;
 #pragma unroll
       for (int i = 0; i < NCH; ++i) {
@@ -341,8 +340,14 @@ tc_gemm_kernel(const __grid_constant__ TcGemmArgs g) {
             f[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
           }
         }
-        atomicAdd(dbias + i * 32 + lane, f[0]);
+        bias_sm[quarter * BN + c_first + i * 32 + lane] = f[0];  // per-quarter column sums -> shared scratch
       }
+      // the four row quarters cover the same columns: combine them in shared memory and issue ONE atomic per
+      // column per CTA (same-address atomics from many CTAs serialise in L2, tens of ns each)
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");  // the 8 epilogue warps only
+      const int et = threadIdx.x - 64;
+      if (et < BN)
+        atomicAdd(g.dbias[z] + col_base + et, (bias_sm[et] + bias_sm[BN + et]) + (bias_sm[2 * BN + et] + bias_sm[3 * BN + et]));
     } else {
       // weight-gradient partial: fp32 [128 rows (layer outputs) x BN (layer inputs)]
       float* __restrict__ prow = g.part[z] + ((size_t)blockIdx.y * g.M + row) * g.N + col_base + c_first;
