@@ -276,7 +276,8 @@ class PPOTrainer:
         self.hp = ops.make_hparams(cfg.clip_coef, cfg.ent_coef, cfg.vf_coef, cfg.norm_adv, cfg.clip_vloss)
         self.global_step = 0
         self.iteration = 0
-        self.use_graphs = bool(use_graphs) and self.world == 1
+        self.use_graphs = bool(use_graphs)
+        self._split_graphs = None  # multi-GPU: (per-minibatch gradient graphs, optimizer graph)
         self._epoch_graph = None
         self._graph_launches = 0  # kernels recorded in the epoch graph
         self._graph_replays = 0
@@ -285,6 +286,9 @@ class PPOTrainer:
         self._policy_graph_launches = 0
         self._policy_captures = 0
         self._policy_replays = 0
+        self._split_launches = 0
+        self._split_captured = 0
+        self._split_replays = 0
         self._validate = True  # argument checks of the ops wrappers; switched off after the first iteration
 
     # -- rollout -------------------------------------------------------------------------------------
@@ -366,7 +370,7 @@ class PPOTrainer:
         vr.running_var.copy_(self.value_rms_state[1])
         vr.count.copy_(self.value_rms_state[2])
 
-    def _minibatch(self, mb_inds):
+    def _minibatch_grad(self, mb_inds):
         a = self.agent
         B = self.batch_size
         ops.ppo_minibatch_grad(
@@ -374,13 +378,48 @@ class PPOTrainer:
             self.logprobs.view(B), self.advantages.view(B), self.returns.view(B), self.values.view(B), self.norm_stats,
             a.parameters_flat(), a._w16, self.grads, self.loss_acc, self.train_ws,
         )  # fmt: skip
-        if self.world > 1:  # the one exchange step: sum-allreduce of the flat 1.5 MB gradient over NVLink
-            cdist.allreduce_grads(self.grads)
+
+    def _minibatch_opt(self):
+        a = self.agent
         ops.adam_step(
             a.dims, a.parameters_flat(), self.grads, self.exp_avg, self.exp_avg_sq, a._w16, self.lr_dev, self.step_dev,
             self.opt_ws, max_grad_norm=self.cfg.max_grad_norm, eps=1e-5, grad_scale=1.0 / self.world,
             grad_norm_out=self.grad_norm,
         )  # fmt: skip
+
+    def _minibatch(self, mb_inds):
+        self._minibatch_grad(mb_inds)
+        if self.world > 1:  # the one exchange step: sum-allreduce of the flat 1.5 MB gradient over NVLink
+            cdist.allreduce_grads(self.grads)
+        self._minibatch_opt()
+
+    def _capture(self, fn):
+        graph = torch.cuda.CUDAGraph()
+        before = L.launch_count()
+        # thread_local: the NCCL watchdog thread may query events while this thread captures
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+            fn()
+        return graph, L.launch_count() - before
+
+    def _epoch_split_graphs(self):
+        """Multi-GPU epoch: the gradient part of every minibatch and the optimizer part replay as CUDA graphs;
+        the NCCL all-reduce between them stays an ordinary stream operation."""
+        if self._split_graphs is None:
+            grads, n = [], 0
+            for start in range(0, self.batch_size, self.minibatch_size):
+                g, k = self._capture(lambda s=start: self._minibatch_grad(self.perm[s : s + self.minibatch_size]))
+                grads.append(g)
+                n += k
+            opt, k = self._capture(self._minibatch_opt)
+            self._split_graphs = (grads, opt)
+            self._split_launches = n + k * len(grads)
+            self._split_captured = n + k
+        grads, opt = self._split_graphs
+        for g in grads:
+            g.replay()
+            cdist.allreduce_grads(self.grads)
+            opt.replay()
+        self._split_replays += 1
 
     def _epoch(self):
         for start in range(0, self.batch_size, self.minibatch_size):
@@ -395,6 +434,10 @@ class PPOTrainer:
                 self.perm.copy_(perms[epoch])
             else:
                 self.perm.copy_(torch.randperm(self.batch_size, device=self.device))
+            if self.use_graphs and self.world > 1 and self._eager_epochs >= 1:
+                self._epoch_split_graphs()
+                self._eager_epochs += 1
+                continue
             if self.use_graphs and self._epoch_graph is None and self._eager_epochs >= 1:
                 # the first epoch ever ran eagerly (it also set the kernel attributes); record the identical
                 # launch sequence once and replay it from now on
@@ -416,7 +459,9 @@ class PPOTrainer:
         """libcatb200 kernels executed so far by this process (graph replays included)."""
         captured = self._graph_launches * (1 if self._epoch_graph is not None else 0)
         captured += self._policy_graph_launches * self._policy_captures
+        captured += self._split_captured
         replayed = self._graph_launches * self._graph_replays + self._policy_graph_launches * self._policy_replays
+        replayed += self._split_launches * self._split_replays
         return L.launch_count() - captured + replayed
 
     def finish_iteration(self):
