@@ -202,6 +202,53 @@ def timed_iterations(trainer, steps, warmup, world, device, read_losses):
     return ms, trainer.kernel_launches() - launches0, clocks
 
 
+def kernel_profile(trainer, iters=2):
+    """Device time of every kernel over `iters` full iterations of the timed workload (CUPTI timestamps via
+    torch.profiler, CUDA graphs included): name -> {us, launches, share}."""
+    from torch.profiler import ProfilerActivity, profile
+
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(iters):
+            trainer.train_iteration()
+        torch.cuda.synchronize()
+    rows = {}
+    for ev in prof.key_averages():
+        t = getattr(ev, "device_time_total", None) or getattr(ev, "cuda_time_total", 0.0)
+        if t <= 0:
+            continue
+        name = ev.key.split("(")[0].replace("void ", "").replace("catb200::", "")
+        rows[name] = {"us": t / iters, "launches": ev.count / iters}
+    total = sum(r["us"] for r in rows.values())
+    for r in rows.values():
+        r["share"] = r["us"] / total
+    return dict(sorted(rows.items(), key=lambda kv: -kv[1]["us"])), total
+
+
+# tensor-core flops per sample of the three tcgen05 GEMM modes (both nets, obs padded to 64): SURVEY.md §8d
+_MAC_FWD = 2 * (64 * 512 + 512 * 256 + 256 * 128)   # also the weight-gradient GEMMs
+_MAC_DGRAD = 2 * (256 * 128 + 512 * 256)
+
+
+def dominant_kernel_roofline(prof, total_us, trainer, peaks):
+    """Roofline entry of the kernel with the largest share of the iteration."""
+    n, T = trainer.num_envs, trainer.T
+    opt_rows = trainer.batch_size * int(trainer.cfg.updates_epochs)  # minibatch rows per iteration
+    flops = {
+        "tc_gemm_kernel<0, 128>": 2.0 * _MAC_FWD * (opt_rows + n * (T + 1)),  # update forward + rollout policy + bootstrap
+        "tc_gemm_kernel<1, 128>": 2.0 * _MAC_DGRAD * opt_rows,
+    }
+    name, row = next(iter(prof.items()))
+    out = {"kernel": name, "share_of_step": row["share"], "us_per_step": row["us"], "launches_per_step": row["launches"]}
+    if name in flops:
+        peak = peaks.get("bf16_tflops_sustained") or peaks["bf16_tflops"]
+        ach = flops[name] / (row["us"] * 1e-6) / 1e12
+        out.update({"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                    "flops_per_step": flops[name], "traffic": None,
+                    "peak_source": peaks["source"] + " (sustained bf16: the kernel runs inside a long step)"})
+    return out
+
+
 def kernel_rooflines(device, num_envs, peaks):
     """Per-kernel achieved bandwidth / throughput, timed alone with CUDA events on the launch stream,
     L2 flushed between timed launches (a 256 MiB write)."""
@@ -289,6 +336,8 @@ def run_ours(args):
     ms, launches, clocks = timed_iterations(trainer, args.steps, args.warmup, world, device, read_losses=False)
     value = N * T * world * args.steps / (ms * 1e-3)
     losses = trainer.losses()
+    prof, prof_total = kernel_profile(trainer) if rank == 0 else ({}, 0.0)
+    dominant = dominant_kernel_roofline(prof, prof_total, trainer, peaks) if rank == 0 else None
     working_set = sum(t.numel() * t.element_size() for t in (trainer.obs, trainer.obs16, trainer.actions, trainer.rewards, trainer.dones, trainer.values, trainer.advantages, trainer.returns, trainer.train_ws))
     del env, trainer
     torch.cuda.empty_cache()
@@ -311,9 +360,11 @@ def run_ours(args):
     if rank == 0:
         roof = kernel_rooflines(device, N, peaks)
         cpu = cpu_baseline(N, sample_steps=4, sample_minibatches=2)
-        main = dict(roof[f"gae@{N}"])
-        main.update({"kernel": "gae_kernel", "traffic": main.get("traffic"), "peak_source": peaks["source"],
-                     "note": f"timed alone, L2 flushed; {main['bytes']/1e6:.2f} MB per launch is launch-latency bound at {N} envs, see the 65536 / 1M-env entries in `rooflines`"})
+        main = dominant
+        main["note"] = ("dominant kernel of the step by device time (torch.profiler/CUPTI over 2 iterations of the timed workload); "
+                        "HBM-bound kernels (GAE, CaT) timed alone with CUDA events are in `rooflines`")
+        gae_main = roof[f"gae@{N}"]
+        gae_main["note"] = f"{gae_main['bytes']/1e6:.2f} MB per launch: launch-latency bound at {N} envs; see the 65536 / 1M-env entries"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -331,6 +382,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": main,
             "rooflines": roof,
+            "kernel_shares": {k: {"share": round(v["share"], 4), "us_per_step": round(v["us"], 1), "launches_per_step": v["launches"]} for k, v in list(prof.items())[:16]},
             "cpu_baseline": cpu,
             "losses": losses,
         }  # fmt: skip

@@ -621,7 +621,9 @@ class ConstraintManager(ManagerBase):
             else:
                 ids_t = torch.as_tensor(np.asarray(list(env_ids), dtype=np.int64), device=dev)
             n_ids = ids_t.numel()
-        elif mask is not None:
+            if n_ids == 0:  # empty selection (a NULL id pointer would mean "all envs" to the C ABI): all-false mask
+                ids_t, mask = None, torch.zeros(self.num_envs, dtype=torch.bool, device=dev)
+        if ids_t is None and mask is not None:
             mask_t = mask.view(torch.uint8) if mask.dtype == torch.bool else (mask != 0).view(torch.uint8)
             mask_t = mask_t.contiguous()
         if self._reset_ws is None:
