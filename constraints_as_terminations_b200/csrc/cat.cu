@@ -38,7 +38,7 @@ bool pdl_enabled() {
 }
 
 constexpr int kTile = 32;          // envs per CTA in the eval kernel (one per lane)
-constexpr int kEvalWarps = 4;      // warps per CTA; warp w owns columns w, w+4, ...
+constexpr int kEvalWarps = 8;      // warps per CTA; warp w owns columns w, w+8, ... (power of two)
 constexpr int kEvalThreads = kEvalWarps * 32;
 constexpr int kApplyThreads = 64;
 
@@ -277,8 +277,8 @@ cat_eval_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_consta
 
   const bool live = lane < rows;
   const int row = live ? lane : 0;
-  int n_groups = 1;  // power of two, ~8+ CTAs share a scratch row
-  while (n_groups < kMaxGroups && n_groups * 16 <= (int)gridDim.x) n_groups <<= 1;
+  int n_groups = 1;  // power of two; a few hundred CTAs per scratch row keep the atomic queues short
+  while (n_groups < kMaxGroups && n_groups * 512 <= (int)gridDim.x) n_groups <<= 1;
 
   // ---- phase A: contact-force peaks, once per (history tensor, body) pair referenced by any term
   for (int p = warp; p < plan.n_peaks; p += kEvalWarps) {
@@ -351,7 +351,15 @@ cat_eval_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_consta
       const int groups = n_groups;
       for (int col = threadIdx.x; col < plan.n_cols; col += kEvalThreads) {
         uint32_t key = 0u;
-        for (int gi = 0; gi < groups; ++gi) key = max(key, atomicExch(&ws.colmax[gi * CATB200_MAX_COLS + col], 0u));
+        int gi = 0;
+        for (; gi + 4 <= groups; gi += 4) {  // 4 independent exchanges in flight
+          const uint32_t k0 = atomicExch(&ws.colmax[gi * CATB200_MAX_COLS + col], 0u);
+          const uint32_t k1 = atomicExch(&ws.colmax[(gi + 1) * CATB200_MAX_COLS + col], 0u);
+          const uint32_t k2 = atomicExch(&ws.colmax[(gi + 2) * CATB200_MAX_COLS + col], 0u);
+          const uint32_t k3 = atomicExch(&ws.colmax[(gi + 3) * CATB200_MAX_COLS + col], 0u);
+          key = max(max(key, max(k0, k1)), max(k2, k3));
+        }
+        for (; gi < groups; ++gi) key = max(key, atomicExch(&ws.colmax[gi * CATB200_MAX_COLS + col], 0u));
         float cmax = fmaxf(ordered_to_float(key), prm.floor_max);
         float rm;
         if (rm_init[col]) {

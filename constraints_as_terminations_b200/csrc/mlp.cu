@@ -349,11 +349,11 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const __grid_const
     r.gb3[0][lane * 4 + (v - kHvB3c)] += t;
   } else if (v < kHvB4a) {
     r.gb3[1][lane * 4 + (v - kHvB3a)] += t;
-  } else if (v == kHvB4a) {
-    if (lane < r.A) r.gb4a[lane] += t;
+  } else if (v == kHvB4a) {  // per-action-dim scalars live in the even lane of pair (2j, 2j+1)
+    if ((lane & 1) == 0 && (lane >> 1) < r.A) r.gb4a[lane >> 1] += t;
   } else if (v == kHvLogstd) {
     // policy part + d(-ent_coef * mean entropy)/d logstd_j = -ent_coef (entropy is sample independent)
-    if (lane < r.A) r.glogstd[lane] += t - r.ent_coef;
+    if ((lane & 1) == 0 && (lane >> 1) < r.A) r.glogstd[lane >> 1] += t - r.ent_coef;
   } else if (lane == 0) {
     const int k = v - kHvScalars;  // g_b4c, pg, v, kl, clip, old_kl
     if (k == 0) {
@@ -483,10 +483,14 @@ head_kernel(const __grid_constant__ HeadArgs a) {
 #pragma unroll
     for (int f = 0; f < F; ++f) w4a[j][f] = j < A ? __ldg(a.W4a + j * a.h3 + lane * F + f) : 0.0f;
   const float b4c = __ldg(a.b4c);
-  float my_b4a = 0.0f, my_logstd = 0.0f;  // lane j < A holds the per-action-dim scalars
-  if (lane < A) {
-    my_b4a = __ldg(a.b4a + lane);
-    my_logstd = __ldg(a.logstd + lane);
+  // Action dim j lives in the lane pair (2j, 2j+1): that is where the recursive-halving reduction of the 16
+  // head dot products leaves its sums.  Only the even lane of a pair is "owner" (contributes to sums / stores).
+  const int aj = lane >> 1;
+  const bool owner = (lane & 1) == 0 && aj < A;
+  float my_b4a = 0.0f, my_logstd = 0.0f;
+  if (aj < A) {
+    my_b4a = __ldg(a.b4a + aj);
+    my_logstd = __ldg(a.logstd + aj);
   }
   const float my_std = expf(my_logstd);
   const float my_inv_var = 1.0f / (my_std * my_std);
@@ -525,7 +529,7 @@ head_kernel(const __grid_constant__ HeadArgs a) {
     n_ra = __ldg(reinterpret_cast<const uint2*>(a.H3[1] + (size_t)mm * a.h3) + lane);
     if (TRAIN) {
       n_sc = __ldg(a.scal_mb + mm);
-      if (lane < A) n_act = __ldg(a.act_mb + (size_t)mm * A + lane);
+      if (owner) n_act = __ldg(a.act_mb + (size_t)mm * A + aj);
     }
   };
   if (m < a.M) fetch(m);
@@ -556,29 +560,34 @@ head_kernel(const __grid_constant__ HeadArgs a) {
 #pragma unroll
         for (int f = 0; f < F; ++f) p[j] = fmaf(ha[f], w4a[j][f], p[j]);
       }
-      // butterfly all action dims together: AP independent shuffles per stage hide the shuffle latency
+      // recursive halving: 8 + 4 + 2 + 1 exchanges leave, in lane l, the 16-lane partial sum of dim (l >> 1);
+      // one more exchange with the pair partner completes the 32-lane sum (16 shuffles instead of 80)
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
+      for (int o = 16; o >= 2; o >>= 1) {
+        const bool upper = (lane & o) != 0;
 #pragma unroll
-        for (int j = 0; j < AP; ++j) p[j] += __shfl_xor_sync(0xffffffffu, p[j], o);
-#pragma unroll
-      for (int j = 0; j < AP; ++j)
-        if (lane == j) mean_j = p[j] + my_b4a;
+        for (int j = 0; j < o / 2; ++j) {
+          const float send = upper ? p[j] : p[j + o / 2];
+          const float keep = upper ? p[j + o / 2] : p[j];
+          p[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+      }
+      mean_j = p[0] + __shfl_xor_sync(0xffffffffu, p[0], 1) + my_b4a;
     }
     if (!TRAIN) {
       // ---- rollout: sample, log-prob, store (ppo.py:104-119)
       float act = 0.0f, lp = 0.0f;
-      if (lane < A) {
+      if (owner) {
         if (a.action_in) {
-          act = __ldg(a.action_in + (size_t)m * A + lane);  // evaluate a given action (ppo.py:110 `action is not None`)
+          act = __ldg(a.action_in + (size_t)m * A + aj);  // evaluate a given action (ppo.py:110 `action is not None`)
         } else {
-          const float eps = a.noise ? __ldg(a.noise + (size_t)m * A + lane) : 0.0f;
+          const float eps = a.noise ? __ldg(a.noise + (size_t)m * A + aj) : 0.0f;
           act = fmaf(my_std, eps, mean_j);
         }
         const float d = act - mean_j;
         lp = -(d * d) * 0.5f * my_inv_var - my_logstd - kLogSqrt2Pi;
-        if (a.action) a.action[(size_t)m * A + lane] = act;
-        if (a.mean_out) a.mean_out[(size_t)m * A + lane] = mean_j;
+        if (a.action) a.action[(size_t)m * A + aj] = act;
+        if (a.mean_out) a.mean_out[(size_t)m * A + aj] = mean_j;
       }
       lp = warp_sum(lp);
       if (lane == 0) {
@@ -588,8 +597,8 @@ head_kernel(const __grid_constant__ HeadArgs a) {
       continue;
     }
     // ---- training: PPO-clip loss and its gradient for this sample (ppo.py:300-344)
-    float lp = 0.0f, dmu = 0.0f, dls = 0.0f;  // lane j: d logp / d mean_j, d logp / d logstd_j
-    if (lane < A) {
+    float lp = 0.0f, dmu = 0.0f, dls = 0.0f;  // owner lane of dim j: d logp / d mean_j, d logp / d logstd_j
+    if (owner) {
       const float d = act_in - mean_j;
       lp = -(d * d) * 0.5f * my_inv_var - my_logstd - kLogSqrt2Pi;
       dmu = d * my_inv_var;
@@ -641,7 +650,7 @@ head_kernel(const __grid_constant__ HeadArgs a) {
 #pragma unroll
     for (int j = 0; j < kMaxAct; ++j) {
       if (j < A) {
-        const float dmj = __shfl_sync(0xffffffffu, dmean, j);
+        const float dmj = __shfl_sync(0xffffffffu, dmean, 2 * j);
 #pragma unroll
         for (int f = 0; f < F; ++f) {
           dha[f] = fmaf(dmj, w4a[j][f], dha[f]);
