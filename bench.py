@@ -55,7 +55,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "40", "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
             )  # fmt: skip
             self.thread = threading.Thread(target=self._read, daemon=True)
@@ -230,6 +230,12 @@ _MAC_FWD = 2 * (64 * 512 + 512 * 256 + 256 * 128)   # also the weight-gradient G
 _MAC_DGRAD = 2 * (256 * 128 + 512 * 256)
 
 
+def _traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    return json.load(open(path)) if os.path.isfile(path) else {}
+
+
 def dominant_kernel_roofline(prof, total_us, trainer, peaks):
     """Roofline entry of the kernel with the largest share of the iteration."""
     n, T = trainer.num_envs, trainer.T
@@ -244,7 +250,7 @@ def dominant_kernel_roofline(prof, total_us, trainer, peaks):
         peak = peaks.get("bf16_tflops_sustained") or peaks["bf16_tflops"]
         ach = flops[name] / (row["us"] * 1e-6) / 1e12
         out.update({"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                    "flops_per_step": flops[name], "traffic": None,
+                    "flops_per_step": flops[name], "traffic": _traffic().get(name),
                     "peak_source": peaks["source"] + " (sustained bf16: the kernel runs inside a long step)"})
     return out
 
