@@ -848,6 +848,8 @@ static int launch_forward(const catb200_mlp_dims_t* d, const catb200_mlp_layout_
       if (rc == CATB200_OK) rc = make_tmap_bf16(&t.mapB[z], w16 + P.w16[z][l], x.in_pad[l], x.out[l], x.in_pad[l], 64, 128);
       if (rc != CATB200_OK) return rc;
       t.C[z] = reinterpret_cast<bf16*>(ws + L.H[z][l]);
+      if (rc == CATB200_OK) rc = make_tmap_bf16(&t.mapC[z], t.C[z], x.out[l], rows, x.out[l], 64, 32);
+      if (rc != CATB200_OK) return rc;
       t.bias[z] = params + P.b[z][l];
     }
     t.ldc = x.out[l]; t.M = rows; t.N = x.out[l]; t.K = x.in_pad[l];
@@ -1050,6 +1052,8 @@ int catb200_ppo_minibatch_grad(const catb200_mlp_dims_t* dims, const catb200_ppo
         if (rc == CATB200_OK) rc = make_tmap_bf16(&t.mapB[z], w16 + P.wt16[z][l], x.out[l], x.in[l], x.out[l], 64, 128);
         if (rc != CATB200_OK) return rc;
         t.C[z] = reinterpret_cast<bf16*>(ws + L.dZ[z][l - 1]);
+        if (rc == CATB200_OK) rc = make_tmap_bf16(&t.mapC[z], t.C[z], x.in[l], M, x.in[l], 64, 32);
+        if (rc != CATB200_OK) return rc;
         t.H[z] = reinterpret_cast<const bf16*>(ws + L.H[z][l - 1]);
         t.dbias[z] = grads + P.b[z][l - 1];
       }

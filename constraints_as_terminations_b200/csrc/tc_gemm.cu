@@ -59,6 +59,20 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// shared -> global tensor store of one box (coordinates {c0 = column, c1 = row}); completion tracked by bulk groups
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(map), "r"(src), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_and_wait() {
+  asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(dst_smem), "r"(cols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
@@ -286,28 +300,37 @@ tc_gemm_kernel(const __grid_constant__ TcGemmArgs g) {
 #pragma unroll
         for (int e = 0; e < 32; ++e) v[i][e] = 0u;
     }
+    // Output path (fwd / dgrad): the warp's 32 rows x 64 columns (128 B per row) are written into the ring's
+    // first stage -- free by now, all MMAs have retired -- in the SWIZZLE_128B layout and leave with ONE TMA
+    // tensor store per warp: full 128-byte lines instead of 32 scattered 16-byte stores per instruction.
+    // box `half` = columns [half*64, half*64+64) of the tile: [128 rows][128 B], 16 KiB, rows of this warp at +quarter*4 KiB
+    const int trow = quarter * 32 + lane;  // row inside the 128-row tile
+    const uint32_t cbox = tiles + half * 16384;
     if (MODE == kTcFwd) {
-      bf16* __restrict__ crow = g.C[z] + (size_t)row * g.ldc + col_base + c_first;
-      if (row < g.M) {
 #pragma unroll
-        for (int i = 0; i < NCH; ++i) {
+      for (int i = 0; i < NCH; ++i) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 o;
-            uint32_t* op = reinterpret_cast<uint32_t*>(&o);
+        for (int q = 0; q < 4; ++q) {
+          uint4 o;
+          uint32_t* op = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int cc = q * 8 + e * 2;
-              const float x0 = __uint_as_float(v[i][cc]) + bias_sm[c_first + i * 32 + cc];
-              const float x1 = __uint_as_float(v[i][cc + 1]) + bias_sm[c_first + i * 32 + cc + 1];
-              op[e] = pack_bf16x2(elu_fast(x0), elu_fast(x1));
-            }
-            *reinterpret_cast<uint4*>(crow + i * 32 + q * 8) = o;
+          for (int e = 0; e < 4; ++e) {
+            const int cc = q * 8 + e * 2;
+            const float x0 = __uint_as_float(v[i][cc]) + bias_sm[c_first + i * 32 + cc];
+            const float x1 = __uint_as_float(v[i][cc + 1]) + bias_sm[c_first + i * 32 + cc + 1];
+            op[e] = pack_bf16x2(elu_fast(x0), elu_fast(x1));
           }
+          st_shared_v4(cbox + trow * 128 + (((i * 4 + q) ^ (trow & 7)) << 4), o);
         }
       }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&g.mapC[z], cbox + quarter * 4096, col_base + c_first, row_base + quarter * 32);
+        tma_store_commit_and_wait();
+      }
+      __syncwarp();
     } else if (MODE == kTcDgrad) {
-      bf16* __restrict__ crow = g.C[z] + (size_t)row * g.ldc + col_base + c_first;
       const bool live = row < g.M;
 #pragma unroll
       for (int i = 0; i < NCH; ++i) {
@@ -326,7 +349,7 @@ tc_gemm_kernel(const __grid_constant__ TcGemmArgs g) {
             f[cc + 1] = x1;
             op[e] = pack_bf16x2(x0, x1);
           }
-          if (live) *reinterpret_cast<uint4*>(crow + i * 32 + q * 8) = o;
+          st_shared_v4(cbox + trow * 128 + (((i * 4 + q) ^ (trow & 7)) << 4), o);
         }
         // column sums over this warp's 32 rows by recursive halving: after the 5 rounds lane l holds the
         // sum of column (i*32 + l)
@@ -341,6 +364,12 @@ tc_gemm_kernel(const __grid_constant__ TcGemmArgs g) {
           }
         }
         bias_sm[quarter * BN + c_first + i * 32 + lane] = f[0];  // per-quarter column sums -> shared scratch
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&g.mapC[z], cbox + quarter * 4096, col_base + c_first, row_base + quarter * 32);
+        tma_store_commit_and_wait();
       }
       // the four row quarters cover the same columns: combine them in shared memory and issue ONE atomic per
       // column per CTA (same-address atomics from many CTAs serialise in L2, tens of ns each)

@@ -13,6 +13,7 @@ enum TcMode { kTcFwd = 0, kTcDgrad = 1, kTcWgrad = 2 };
 struct TcGemmArgs {
   CUtensorMap mapA[2];  // per net; fwd/dgrad: A [M, K] boxes 64(K) x 128; wgrad: dZ [rows, outs] boxes 64 x 64
   CUtensorMap mapB[2];  // fwd/dgrad: B [N, K] boxes 64(K) x 128; wgrad: Hin [rows, ins_pad] boxes 64 x 64
+  CUtensorMap mapC[2];  // fwd/dgrad output C [M, N]: store boxes 64 (cols) x 32 (rows), SWIZZLE_128B
   bf16* C[2];           // fwd/dgrad output [M, N], ldc
   const float* bias[2]; // fwd
   const bf16* H[2];     // dgrad: forward activation whose ELU' scales the result (same layout as C)
