@@ -86,7 +86,7 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------
 # this repo's arm
 # ----------------------------------------------------------------------------------------------------------
-def make_trainer(num_envs, device, seed, host_fed=False, pool=8, graphs=True):
+def make_trainer(num_envs, device, seed, host_fed=False, pool=8, graphs=True, distributed=True):
     from constraints_as_terminations_b200 import PPOTrainer, solo12_flat_ppo_cfg
     from constraints_as_terminations_b200 import synthetic_env as se
 
@@ -95,7 +95,7 @@ def make_trainer(num_envs, device, seed, host_fed=False, pool=8, graphs=True):
     env.load_managers()
     cfg = solo12_flat_ppo_cfg(logger=None)
     torch.manual_seed(cfg.seed + seed)
-    trainer = PPOTrainer(env, cfg, device=device, use_graphs=graphs)
+    trainer = PPOTrainer(env, cfg, device=device, use_graphs=graphs, distributed=distributed)
     trainer.start()
     return env, trainer
 
@@ -202,12 +202,18 @@ def timed_iterations(trainer, steps, warmup, world, device, read_losses):
     return ms, trainer.kernel_launches() - launches0, clocks
 
 
-def kernel_profile(trainer, iters=2):
+def kernel_profile(trainer, iters=2, record=True):
     """Device time of every kernel over `iters` full iterations of the timed workload (CUPTI timestamps via
-    torch.profiler, CUDA graphs included): name -> {us, launches, share}."""
+    torch.profiler, CUDA graphs included): name -> {us, launches, share}.  Iterations contain the gradient
+    all-reduce, so under torchrun EVERY rank must call this; only ranks with record=True profile."""
     from torch.profiler import ProfilerActivity, profile
 
     torch.cuda.synchronize()
+    if not record:
+        for _ in range(iters):
+            trainer.train_iteration()
+        torch.cuda.synchronize()
+        return {}, 0.0
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         for _ in range(iters):
             trainer.train_iteration()
@@ -300,7 +306,7 @@ def kernel_rooflines(device, num_envs, peaks):
         del env, mgr
     # one PPO optimizer step on a 16384-row minibatch (gather, 3 fwd + 2 dgrad + 3 wgrad tcgen05 GEMMs, head/loss,
     # reduce, clip + Adam + weight cast): 2.2525 MFLOP/sample of tensor work
-    env, tr = make_trainer(num_envs, device, seed=0, graphs=False)
+    env, tr = make_trainer(num_envs, device, seed=0, graphs=False, distributed=False)  # rank-local probe
     tr.train_iteration()
     mb = tr.minibatch_size
     perm = torch.randperm(tr.batch_size, device=device)
@@ -342,7 +348,7 @@ def run_ours(args):
     ms, launches, clocks = timed_iterations(trainer, args.steps, args.warmup, world, device, read_losses=False)
     value = N * T * world * args.steps / (ms * 1e-3)
     losses = trainer.losses()
-    prof, prof_total = kernel_profile(trainer) if rank == 0 else ({}, 0.0)
+    prof, prof_total = kernel_profile(trainer, record=(rank == 0))
     dominant = dominant_kernel_roofline(prof, prof_total, trainer, peaks) if rank == 0 else None
     working_set = sum(t.numel() * t.element_size() for t in (trainer.obs, trainer.obs16, trainer.actions, trainer.rewards, trainer.dones, trainer.values, trainer.advantages, trainer.returns, trainer.train_ws))
     del env, trainer

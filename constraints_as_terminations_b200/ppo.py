@@ -225,7 +225,7 @@ class Agent(nn.Module):
 class PPOTrainer:
     """State and steps of the training loop; `PPO()` below drives it exactly like the reference function."""
 
-    def __init__(self, envs, cfg, device=None, seed=None, use_graphs=True):
+    def __init__(self, envs, cfg, device=None, seed=None, use_graphs=True, distributed=True):
         self.envs = envs
         self.cfg = cfg
         env = envs.unwrapped
@@ -236,7 +236,8 @@ class PPOTrainer:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("PPOTrainer needs a CUDA device: the hot path exists only as sm_100a kernels")
-        self.world, self.rank = cdist.world_size(), cdist.rank()
+        # distributed=False keeps this trainer rank-local even inside an initialised process group (bench probes)
+        self.world, self.rank = (cdist.world_size(), cdist.rank()) if distributed else (1, 0)
 
         self.agent = Agent(envs, device=self.device)
         if self.world > 1:  # rank 0 seeds everybody (the reference's multi-process front-ends do the same)
