@@ -387,7 +387,7 @@ def run_ours(args):
                 "envs_per_gpu": N, "num_steps": T, "constraint_terms": 13, "constraint_columns": 78,
                 "minibatch": 16384, "epochs": 5, "parallelism": f"dp{world} (one env shard per GPU, 1 gradient allreduce per optimizer step)",
                 "l2": f"per-step working set {working_set/1e6:.0f} MB > 126 MB L2 (inputs larger than L2)",
-                "cuda_graphs": not args.no_graphs and world == 1,
+                "cuda_graphs": not args.no_graphs,
             },
             "e2e": e2e,
             "gpu_launches": launches,

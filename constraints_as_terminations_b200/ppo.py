@@ -277,9 +277,9 @@ class PPOTrainer:
         self.hp = ops.make_hparams(cfg.clip_coef, cfg.ent_coef, cfg.vf_coef, cfg.norm_adv, cfg.clip_vloss)
         self.global_step = 0
         self.iteration = 0
-        # CUDA graphs: single-GPU by default.  With NCCL in the process the split-graph epoch below (graphs around
-        # the eager all-reduce) hung in a 2-GPU trial, so it stays opt-in (CATB200_MULTI_GPU_GRAPHS=1) until debugged.
-        self.use_graphs = bool(use_graphs) and (self.world == 1 or os.environ.get("CATB200_MULTI_GPU_GRAPHS") == "1")
+        # CUDA graphs: one whole-epoch graph on a single GPU; with several ranks the gradient and optimizer parts of
+        # every minibatch replay as graphs around the eager NCCL all-reduce (CATB200_MULTI_GPU_GRAPHS=0 -> all eager).
+        self.use_graphs = bool(use_graphs) and (self.world == 1 or os.environ.get("CATB200_MULTI_GPU_GRAPHS", "1") != "0")
         self._split_graphs = None  # multi-GPU: (per-minibatch gradient graphs, optimizer graph)
         self._epoch_graph = None
         self._graph_launches = 0  # kernels recorded in the epoch graph
