@@ -126,7 +126,7 @@ struct ColumnSink {  // where a column value of this tile goes: C_T + column max
   bool live;
   int lane, n_cols, num_envs;
   float* ct;         // &C_T[0][tile0 + lane]
-  uint32_t* colmax;  // this CTA's scratch row
+  uint32_t* colmax;  // this CTA's shared-memory column maxima (ordered-float keys), one writer warp per column
   float* out_row;    // &out[tile0 + lane][0]
   __device__ __forceinline__ void emit(int col, float c) const {
     if (MODE == kEvalRowMajor) {
@@ -134,7 +134,8 @@ struct ColumnSink {  // where a column value of this tile goes: C_T + column max
     } else {
       if (live) ct[(size_t)col * num_envs] = c;
       const uint32_t m = __reduce_max_sync(0xffffffffu, live ? float_to_ordered(c) : 0u);
-      if (lane == 0) atomicMax(colmax + col, m);
+      // column `col` is always handled by the same warp of this CTA: a plain read-modify-write suffices
+      if (lane == 0 && m > colmax[col]) colmax[col] = m;
     }
   }
 };
@@ -196,157 +197,185 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uin
                : "memory");
 }
 
+// Persistent, double-buffered: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; while tile i is
+// evaluated out of one shared-memory buffer the bulk async copies of tile i+1 land in the other.  Column
+// maxima are kept per CTA in shared memory and flushed with one atomicMax per column per CTA at the end.
 template <int MODE>
 __global__ void __launch_bounds__(kEvalThreads)
 cat_eval_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_constant__ catb200_cat_params_t prm,
                 int num_envs, float* __restrict__ running_max, int* __restrict__ rm_init,
                 CatWorkspace ws, float* __restrict__ out_rowmajor) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  const int tile0 = blockIdx.x * kTile;
-  const int rows = min(kTile, num_envs - tile0);
+  extern __shared__ __align__(128) uint8_t smem_all[];
+  __shared__ uint32_t s_colmax[CATB200_MAX_COLS];
+  __shared__ __align__(8) unsigned long long s_bar[2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* peaks = reinterpret_cast<float*>(smem + plan.smem_peak_off);  // [n_peaks][32]
-  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(smem + plan.smem_bar_off);
+  const int n_tiles = (num_envs + kTile - 1) / kTile;
+  const int buf_bytes = plan.smem_bar_off;  // sources + peak table of one buffer (16-byte multiple)
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&s_bar[0]);
 
-  // ---- stage the tile: one bulk async copy per source whose tile is contiguous and 16-byte aligned,
-  //      a cooperative copy otherwise (strided views, ragged last tile)
+  for (int c = threadIdx.x; c < plan.n_cols; c += kEvalThreads) s_colmax[c] = 0u;
   if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar0));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar0 + 8));
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
-  uint32_t bulk_mask = 0;
-  for (int s = 0; s < plan.n_sources; ++s) {
+
+  // a source tile can use the bulk copy engine if it is contiguous and 16-byte aligned (full tiles only)
+  auto bulk_ok = [&](int s, int tile0, int rows) -> bool {
     const catb200_source_t& src = plan.sources[s];
     const int es = src.dtype == CATB200_U8 ? 1 : 4;
     const uint8_t* g = static_cast<const uint8_t*>(src.ptr) + (size_t)tile0 * src.row_stride * es;
-    const bool bulk = rows == kTile && src.row_stride == src.row_len && ((reinterpret_cast<uintptr_t>(g) & 15) == 0);
-    if (bulk) bulk_mask |= 1u << s;
-  }
-  if (threadIdx.x == 0) {
+    return rows == kTile && src.row_stride == src.row_len && ((reinterpret_cast<uintptr_t>(g) & 15) == 0);
+  };
+  // thread 0: arm buffer `b`'s barrier and start the bulk copies of tile `t`
+  auto issue = [&](int t, int b) {
+    const int tile0 = t * kTile, rows = min(kTile, num_envs - tile0);
+    uint8_t* dst = smem_all + (size_t)b * buf_bytes;
     uint32_t total = 0;
     for (int s = 0; s < plan.n_sources; ++s)
-      if (bulk_mask >> s & 1) total += kTile * plan.sources[s].row_len * (plan.sources[s].dtype == CATB200_U8 ? 1 : 4);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(total) : "memory");
+      if (bulk_ok(s, tile0, rows)) total += kTile * plan.sources[s].row_len * (plan.sources[s].dtype == CATB200_U8 ? 1 : 4);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar0 + 8 * b), "r"(total) : "memory");
     for (int s = 0; s < plan.n_sources; ++s) {
-      if (!(bulk_mask >> s & 1)) continue;
+      if (!bulk_ok(s, tile0, rows)) continue;
       const catb200_source_t& src = plan.sources[s];
       const int es = src.dtype == CATB200_U8 ? 1 : 4;
-      bulk_copy_g2s((uint32_t)__cvta_generic_to_shared(smem + src.smem_off),
-                    static_cast<const uint8_t*>(src.ptr) + (size_t)tile0 * src.row_len * es, kTile * src.row_len * es, bar);
+      bulk_copy_g2s((uint32_t)__cvta_generic_to_shared(dst + src.smem_off),
+                    static_cast<const uint8_t*>(src.ptr) + (size_t)tile0 * src.row_len * es, kTile * src.row_len * es,
+                    bar0 + 8 * b);
     }
-  }
-  for (int s = 0; s < plan.n_sources; ++s) {
-    if (bulk_mask >> s & 1) continue;
-    const catb200_source_t& src = plan.sources[s];
-    const int total = rows * src.row_len;
-    if (src.dtype == CATB200_F32) {
-      const float* g = static_cast<const float*>(src.ptr);
-      float* dst = reinterpret_cast<float*>(smem + src.smem_off);
-      for (int f = threadIdx.x; f < total; f += kEvalThreads) {
-        const int r = f / src.row_len, e = f - r * src.row_len;
-        dst[f] = __ldg(g + (size_t)(tile0 + r) * src.row_stride + e);
-      }
-    } else {
-      const uint8_t* g = static_cast<const uint8_t*>(src.ptr);
-      for (int f = threadIdx.x; f < total; f += kEvalThreads) {
-        const int r = f / src.row_len, e = f - r * src.row_len;
-        smem[src.smem_off + f] = g[(size_t)(tile0 + r) * src.row_stride + e];
-      }
-    }
-  }
-  // wait for the bulk copies (phase 0 of the barrier): one lane sleeps on the mbarrier (try_wait with a
-  // suspend-time hint blocks in hardware instead of spinning), the CTA barrier releases everybody else, and
-  // each thread then performs one already-satisfied acquire of its own
-  auto try_wait0 = [&]() -> uint32_t {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0, 0x989680;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-        : "=r"(done)
-        : "r"(bar)
-        : "memory");
-    return done;
   };
-  if (threadIdx.x == 0) {
-    while (!try_wait0()) {
-    }
-  }
-  __syncthreads();
-  while (!try_wait0()) {
-  }
 
-  const bool live = lane < rows;
-  const int row = live ? lane : 0;
-  int n_groups = 1;  // power of two; a few hundred CTAs per scratch row keep the atomic queues short
-  while (n_groups < kMaxGroups && n_groups * 512 <= (int)gridDim.x) n_groups <<= 1;
-
-  // ---- phase A: contact-force peaks, once per (history tensor, body) pair referenced by any term
-  for (int p = warp; p < plan.n_peaks; p += kEvalWarps) {
-    const int s = plan.peak_src[p];
-    peaks[p * kTile + lane] = force_peak(view_of(plan, smem, s), plan.sources[s].aux, row, plan.peak_body[p]);
-  }
-  __syncthreads();
-
-  // ---- phase B: terms.  Term-level scalars and gates are computed once per term; the term's columns are
-  //      dealt to the 4 warps by global column index (lane = env, so the op dispatch never diverges) and the
-  //      op switch sits outside the column loop.
-  ColumnSink<MODE> sink;
-  sink.live = live;
-  sink.lane = lane;
-  sink.n_cols = plan.n_cols;
-  sink.num_envs = num_envs;
-  sink.ct = MODE == kEvalStep ? ws.c_t + tile0 + lane : nullptr;
-  sink.colmax = MODE == kEvalStep ? ws.colmax + (blockIdx.x & (n_groups - 1)) * CATB200_MAX_COLS : nullptr;
-  sink.out_row = MODE == kEvalRowMajor ? out_rowmajor + (size_t)(tile0 + lane) * plan.n_cols : nullptr;
-  for (int ti = 0; ti < plan.n_terms; ++ti) {
-    const catb200_term_t& t = plan.terms[ti];
-    const int n_cols = t.n_cols, col0 = t.col_offset, op = t.op;
-    const int first = (warp - (col0 & (kEvalWarps - 1))) & (kEvalWarps - 1);  // first local column of this warp
-    if (first >= n_cols) continue;
-    TermCtx c;
-    c.ids = t.ids;
-    c.n_ids = t.n_ids;
-    c.first = first;
-    c.n_cols = n_cols;
-    c.col0 = col0;
-    c.row = row;
-    c.lane = lane;
-    c.p0 = t.p0;
-    c.p1 = t.p1;
-    c.p2 = t.p2;
-    c.peaks = peaks;
-    c.v0 = view_of(plan, smem, t.src0);
-    c.v1 = t.src1 != 0xff ? view_of(plan, smem, t.src1) : c.v0;
-    c.gate = 1.0f;  // command-dependent factor shared by all columns of the term
-    if (t.src2 != 0xff) {
-      const SrcView vc = view_of(plan, smem, t.src2);
-      if (op == CATB200_OP_ABSDIFF_MINUS_GATE_Y) {
-        c.gate = fabsf(vc.f32(row, 1)) < c.p1 ? 1.0f : 0.0f;  // constraints.py:46-53
+  if (threadIdx.x == 0 && (int)blockIdx.x < n_tiles) issue(blockIdx.x, 0);
+  int it = 0;
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+    const int b = it & 1;
+    const uint8_t* smem = smem_all + (size_t)b * buf_bytes;
+    uint8_t* smem_w = smem_all + (size_t)b * buf_bytes;
+    float* peaks = reinterpret_cast<float*>(smem_w + plan.smem_peak_off);  // [n_peaks][32]
+    const int tile0 = t * kTile;
+    const int rows = min(kTile, num_envs - tile0);
+    // prefetch the next tile into the other buffer (its previous contents were consumed before the barrier that
+    // ended the previous iteration)
+    if (threadIdx.x == 0 && t + (int)gridDim.x < n_tiles) issue(t + gridDim.x, b ^ 1);
+    // sources that cannot use the bulk engine (strided views, unaligned bases, the ragged last tile): cooperative copy
+    for (int s = 0; s < plan.n_sources; ++s) {
+      if (bulk_ok(s, tile0, rows)) continue;
+      const catb200_source_t& src = plan.sources[s];
+      const int total = rows * src.row_len;
+      if (src.dtype == CATB200_F32) {
+        const float* g = static_cast<const float*>(src.ptr);
+        float* dst = reinterpret_cast<float*>(smem_w + src.smem_off);
+        for (int f = threadIdx.x; f < total; f += kEvalThreads) {
+          const int r = f / src.row_len, e = f - r * src.row_len;
+          dst[f] = __ldg(g + (size_t)(tile0 + r) * src.row_stride + e);
+        }
       } else {
-        const float cn = norm3(vc.f32(row, 0), vc.f32(row, 1), vc.f32(row, 2));
-        c.gate = op == CATB200_OP_ABS_MINUS_GATE_STILL ? (cn < c.p1 ? 1.0f : 0.0f) : (cn > c.p1 ? 1.0f : 0.0f);
+        const uint8_t* g = static_cast<const uint8_t*>(src.ptr);
+        for (int f = threadIdx.x; f < total; f += kEvalThreads) {
+          const int r = f / src.row_len, e = f - r * src.row_len;
+          smem_w[src.smem_off + f] = g[(size_t)(tile0 + r) * src.row_stride + e];
+        }
       }
     }
-    switch (op) {
-      case CATB200_OP_GENERIC: term_columns<CATB200_OP_GENERIC>(c, sink); break;
-      case CATB200_OP_ABS_MINUS: term_columns<CATB200_OP_ABS_MINUS>(c, sink); break;
-      case CATB200_OP_ABSDIFF_MINUS: term_columns<CATB200_OP_ABSDIFF_MINUS>(c, sink); break;
-      case CATB200_OP_ABSDIFF_MINUS_GATE_Y: term_columns<CATB200_OP_ABSDIFF_MINUS_GATE_Y>(c, sink); break;
-      case CATB200_OP_ACTION_RATE: term_columns<CATB200_OP_ACTION_RATE>(c, sink); break;
-      case CATB200_OP_COMPONENT_GT: term_columns<CATB200_OP_COMPONENT_GT>(c, sink); break;
-      case CATB200_OP_CONTACT_ANY: term_columns<CATB200_OP_CONTACT_ANY>(c, sink); break;
-      case CATB200_OP_NORM2_MINUS: term_columns<CATB200_OP_NORM2_MINUS>(c, sink); break;
-      case CATB200_OP_AIR_TIME: term_columns<CATB200_OP_AIR_TIME>(c, sink); break;
-      case CATB200_OP_N_CONTACT: term_columns<CATB200_OP_N_CONTACT>(c, sink); break;
-      case CATB200_OP_FORCE_PEAK_MINUS: term_columns<CATB200_OP_FORCE_PEAK_MINUS>(c, sink); break;
-      case CATB200_OP_LIMIT_MINUS: term_columns<CATB200_OP_LIMIT_MINUS>(c, sink); break;
-      case CATB200_OP_ABS_MINUS_GATE_STILL: term_columns<CATB200_OP_ABS_MINUS_GATE_STILL>(c, sink); break;
-      default: break;
+    // wait for this buffer's bulk copies: one lane sleeps on the mbarrier (suspend-time hint), the CTA barrier
+    // releases the rest, then every thread performs one already-satisfied acquire of its own
+    const uint32_t parity = (it >> 1) & 1;
+    auto try_wait = [&]() -> uint32_t {
+      uint32_t done;
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+          : "=r"(done)
+          : "r"(bar0 + 8 * b), "r"(parity)
+          : "memory");
+      return done;
+    };
+    if (threadIdx.x == 0) {
+      while (!try_wait()) {
+      }
     }
+    __syncthreads();
+    while (!try_wait()) {
+    }
+
+    const bool live = lane < rows;
+    const int row = live ? lane : 0;
+
+    // ---- phase A: contact-force peaks, once per (history tensor, body) pair referenced by any term
+    for (int p = warp; p < plan.n_peaks; p += kEvalWarps) {
+      const int s = plan.peak_src[p];
+      peaks[p * kTile + lane] = force_peak(view_of(plan, smem, s), plan.sources[s].aux, row, plan.peak_body[p]);
+    }
+    __syncthreads();
+
+    // ---- phase B: terms.  Term-level scalars and gates are computed once per term; the term's columns are
+    //      dealt to the warps by global column index (lane = env, so the op dispatch never diverges) and the
+    //      op switch sits outside the column loop.
+    ColumnSink<MODE> sink;
+    sink.live = live;
+    sink.lane = lane;
+    sink.n_cols = plan.n_cols;
+    sink.num_envs = num_envs;
+    sink.ct = MODE == kEvalStep ? ws.c_t + tile0 + lane : nullptr;
+    sink.colmax = s_colmax;
+    sink.out_row = MODE == kEvalRowMajor ? out_rowmajor + (size_t)(tile0 + lane) * plan.n_cols : nullptr;
+    for (int ti = 0; ti < plan.n_terms; ++ti) {
+      const catb200_term_t& t2 = plan.terms[ti];
+      const int n_cols = t2.n_cols, col0 = t2.col_offset, op = t2.op;
+      const int first = (warp - (col0 & (kEvalWarps - 1))) & (kEvalWarps - 1);  // first local column of this warp
+      if (first >= n_cols) continue;
+      TermCtx c;
+      c.ids = t2.ids;
+      c.n_ids = t2.n_ids;
+      c.first = first;
+      c.n_cols = n_cols;
+      c.col0 = col0;
+      c.row = row;
+      c.lane = lane;
+      c.p0 = t2.p0;
+      c.p1 = t2.p1;
+      c.p2 = t2.p2;
+      c.peaks = peaks;
+      c.v0 = view_of(plan, smem, t2.src0);
+      c.v1 = t2.src1 != 0xff ? view_of(plan, smem, t2.src1) : c.v0;
+      c.gate = 1.0f;  // command-dependent factor shared by all columns of the term
+      if (t2.src2 != 0xff) {
+        const SrcView vc = view_of(plan, smem, t2.src2);
+        if (op == CATB200_OP_ABSDIFF_MINUS_GATE_Y) {
+          c.gate = fabsf(vc.f32(row, 1)) < c.p1 ? 1.0f : 0.0f;  // constraints.py:46-53
+        } else {
+          const float cn = norm3(vc.f32(row, 0), vc.f32(row, 1), vc.f32(row, 2));
+          c.gate = op == CATB200_OP_ABS_MINUS_GATE_STILL ? (cn < c.p1 ? 1.0f : 0.0f) : (cn > c.p1 ? 1.0f : 0.0f);
+        }
+      }
+      switch (op) {
+        case CATB200_OP_GENERIC: term_columns<CATB200_OP_GENERIC>(c, sink); break;
+        case CATB200_OP_ABS_MINUS: term_columns<CATB200_OP_ABS_MINUS>(c, sink); break;
+        case CATB200_OP_ABSDIFF_MINUS: term_columns<CATB200_OP_ABSDIFF_MINUS>(c, sink); break;
+        case CATB200_OP_ABSDIFF_MINUS_GATE_Y: term_columns<CATB200_OP_ABSDIFF_MINUS_GATE_Y>(c, sink); break;
+        case CATB200_OP_ACTION_RATE: term_columns<CATB200_OP_ACTION_RATE>(c, sink); break;
+        case CATB200_OP_COMPONENT_GT: term_columns<CATB200_OP_COMPONENT_GT>(c, sink); break;
+        case CATB200_OP_CONTACT_ANY: term_columns<CATB200_OP_CONTACT_ANY>(c, sink); break;
+        case CATB200_OP_NORM2_MINUS: term_columns<CATB200_OP_NORM2_MINUS>(c, sink); break;
+        case CATB200_OP_AIR_TIME: term_columns<CATB200_OP_AIR_TIME>(c, sink); break;
+        case CATB200_OP_N_CONTACT: term_columns<CATB200_OP_N_CONTACT>(c, sink); break;
+        case CATB200_OP_FORCE_PEAK_MINUS: term_columns<CATB200_OP_FORCE_PEAK_MINUS>(c, sink); break;
+        case CATB200_OP_LIMIT_MINUS: term_columns<CATB200_OP_LIMIT_MINUS>(c, sink); break;
+        case CATB200_OP_ABS_MINUS_GATE_STILL: term_columns<CATB200_OP_ABS_MINUS_GATE_STILL>(c, sink); break;
+        default: break;
+      }
+    }
+    __syncthreads();  // every warp is done with this buffer before the next iteration's prefetch overwrites it
   }
 
   if (MODE == kEvalStep) {
-    // ---- the last CTA folds the column maxima into the Polyak running max (constraint_manager.py:55-61)
+    // ---- flush this CTA's column maxima (one atomic per column per CTA, spread over scratch rows), then the
+    //      last CTA folds everything into the Polyak running max (constraint_manager.py:55-61)
+    int n_groups = 1;  // power of two; a few hundred CTAs per scratch row keep the atomic queues short
+    while (n_groups < kMaxGroups && n_groups * 256 <= (int)gridDim.x) n_groups <<= 1;
+    uint32_t* grow = ws.colmax + (blockIdx.x & (n_groups - 1)) * CATB200_MAX_COLS;
+    for (int c = threadIdx.x; c < plan.n_cols; c += kEvalThreads)
+      if (s_colmax[c] != 0u) atomicMax(grow + c, s_colmax[c]);
     if (last_block_ticket_grouped(ws.ticket, gridDim.x)) {
       const int groups = n_groups;
       for (int col = threadIdx.x; col < plan.n_cols; col += kEvalThreads) {
@@ -613,7 +642,7 @@ int catb200_cat_plan_finalize(catb200_plan_t* plan) {
   plan->smem_bar_off = off;
   off += 16;
   plan->smem_bytes = off;
-  if (off > 200 * 1024) return CATB200_ERR_UNSUPPORTED;
+  if (2 * plan->smem_bar_off > 200 * 1024) return CATB200_ERR_UNSUPPORTED;  // two staging buffers must fit
   return CATB200_OK;
 }
 
@@ -624,8 +653,11 @@ size_t catb200_cat_workspace_bytes(int32_t num_envs, int32_t n_cols) {
 
 static int launch_eval(const catb200_plan_t* plan, const catb200_cat_params_t* prm, int num_envs, float* running_max,
                        int* rm_init, CatWorkspace ws, float* out_rowmajor, int mode, cudaStream_t stream) {
-  const size_t smem = (size_t)plan->smem_bytes;
-  const int grid = (num_envs + kTile - 1) / kTile;
+  const size_t smem = 2 * (size_t)plan->smem_bar_off;  // two staging buffers (sources + peak table each)
+  const int n_tiles = (num_envs + kTile - 1) / kTile;
+  // persistent grid: as many CTAs as fit (shared memory / 2048 threads per SM), never more than tiles
+  const int per_sm = (int)max((size_t)1, min((size_t)(2048 / kEvalThreads), (size_t)(220 * 1024) / max(smem + 2048, (size_t)1)));
+  const int grid = min(n_tiles, kNumSMs * per_sm);
   if (mode == kEvalStep) {
     if (smem > 48 * 1024)
       CATB200_CUDA_TRY(cudaFuncSetAttribute(cat_eval_kernel<kEvalStep>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
