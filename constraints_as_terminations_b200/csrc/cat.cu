@@ -38,8 +38,10 @@ bool pdl_enabled() {
 }
 
 constexpr int kTile = 32;          // envs per CTA in the eval kernel (one per lane)
-constexpr int kEvalWarps = 8;      // warps per CTA; warp w owns columns w, w+8, ... (power of two)
+constexpr int kEvalWarps = 8;      // warps per CTA of the apply kernel (and of the eval kernel at large N)
 constexpr int kEvalThreads = kEvalWarps * 32;
+constexpr int kEvalWarpsSmallN = 16;  // eval kernel at small N: shorter per-tile critical path (latency bound there)
+constexpr int kEvalThreadsMax = kEvalWarpsSmallN * 32;
 constexpr int kApplyThreads = 64;
 
 // ---- staged-source accessors ----------------------------------------------------------------------
@@ -115,7 +117,7 @@ enum EvalMode { kEvalStep = 0, kEvalRowMajor = 1 };
 // ---- per-term column evaluation ----------------------------------------------------------------------
 struct TermCtx {
   const uint8_t* ids;  // joint / body / peak-slot ids of the term (kernel-parameter memory)
-  int n_ids, first, n_cols, col0, row, lane;
+  int n_ids, first, n_cols, col0, row, lane, n_warps;
   float p0, p1, p2, gate;
   const float* peaks;
   SrcView v0, v1;
@@ -188,7 +190,7 @@ __device__ __forceinline__ float column_value(const TermCtx& c, int lc) {
 
 template <int OP, int MODE>
 __device__ __forceinline__ void term_columns(const TermCtx& c, const ColumnSink<MODE>& sink) {
-  for (int lc = c.first; lc < c.n_cols; lc += kEvalWarps) sink.emit(c.col0 + lc, column_value<OP>(c, lc));
+  for (int lc = c.first; lc < c.n_cols; lc += c.n_warps) sink.emit(c.col0 + lc, column_value<OP>(c, lc));
 }
 
 __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -201,7 +203,7 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uin
 // evaluated out of one shared-memory buffer the bulk async copies of tile i+1 land in the other.  Column
 // maxima are kept per CTA in shared memory and flushed with one atomicMax per column per CTA at the end.
 template <int MODE>
-__global__ void __launch_bounds__(kEvalThreads)
+__global__ void __launch_bounds__(kEvalThreadsMax)
 cat_eval_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_constant__ catb200_cat_params_t prm,
                 int num_envs, float* __restrict__ running_max, int* __restrict__ rm_init,
                 CatWorkspace ws, float* __restrict__ out_rowmajor) {
@@ -209,11 +211,12 @@ cat_eval_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_consta
   __shared__ uint32_t s_colmax[CATB200_MAX_COLS];
   __shared__ __align__(8) unsigned long long s_bar[2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_warps = blockDim.x >> 5, n_threads = blockDim.x;  // 8 or 16 warps (power of two)
   const int n_tiles = (num_envs + kTile - 1) / kTile;
   const int buf_bytes = plan.smem_bar_off;  // sources + peak table of one buffer (16-byte multiple)
   const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&s_bar[0]);
 
-  for (int c = threadIdx.x; c < plan.n_cols; c += kEvalThreads) s_colmax[c] = 0u;
+  for (int c = threadIdx.x; c < plan.n_cols; c += n_threads) s_colmax[c] = 0u;
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar0));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar0 + 8));
@@ -266,13 +269,13 @@ cat_eval_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_consta
       if (src.dtype == CATB200_F32) {
         const float* g = static_cast<const float*>(src.ptr);
         float* dst = reinterpret_cast<float*>(smem_w + src.smem_off);
-        for (int f = threadIdx.x; f < total; f += kEvalThreads) {
+        for (int f = threadIdx.x; f < total; f += n_threads) {
           const int r = f / src.row_len, e = f - r * src.row_len;
           dst[f] = __ldg(g + (size_t)(tile0 + r) * src.row_stride + e);
         }
       } else {
         const uint8_t* g = static_cast<const uint8_t*>(src.ptr);
-        for (int f = threadIdx.x; f < total; f += kEvalThreads) {
+        for (int f = threadIdx.x; f < total; f += n_threads) {
           const int r = f / src.row_len, e = f - r * src.row_len;
           smem_w[src.smem_off + f] = g[(size_t)(tile0 + r) * src.row_stride + e];
         }
@@ -302,7 +305,7 @@ cat_eval_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_consta
     const int row = live ? lane : 0;
 
     // ---- phase A: contact-force peaks, once per (history tensor, body) pair referenced by any term
-    for (int p = warp; p < plan.n_peaks; p += kEvalWarps) {
+    for (int p = warp; p < plan.n_peaks; p += n_warps) {
       const int s = plan.peak_src[p];
       peaks[p * kTile + lane] = force_peak(view_of(plan, smem, s), plan.sources[s].aux, row, plan.peak_body[p]);
     }
@@ -322,7 +325,7 @@ cat_eval_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_consta
     for (int ti = 0; ti < plan.n_terms; ++ti) {
       const catb200_term_t& t2 = plan.terms[ti];
       const int n_cols = t2.n_cols, col0 = t2.col_offset, op = t2.op;
-      const int first = (warp - (col0 & (kEvalWarps - 1))) & (kEvalWarps - 1);  // first local column of this warp
+      const int first = (warp - (col0 & (n_warps - 1))) & (n_warps - 1);  // first local column of this warp
       if (first >= n_cols) continue;
       TermCtx c;
       c.ids = t2.ids;
@@ -332,6 +335,7 @@ cat_eval_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_consta
       c.col0 = col0;
       c.row = row;
       c.lane = lane;
+      c.n_warps = n_warps;
       c.p0 = t2.p0;
       c.p1 = t2.p1;
       c.p2 = t2.p2;
@@ -374,11 +378,11 @@ cat_eval_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_consta
     int n_groups = 1;  // power of two; a few hundred CTAs per scratch row keep the atomic queues short
     while (n_groups < kMaxGroups && n_groups * 256 <= (int)gridDim.x) n_groups <<= 1;
     uint32_t* grow = ws.colmax + (blockIdx.x & (n_groups - 1)) * CATB200_MAX_COLS;
-    for (int c = threadIdx.x; c < plan.n_cols; c += kEvalThreads)
+    for (int c = threadIdx.x; c < plan.n_cols; c += n_threads)
       if (s_colmax[c] != 0u) atomicMax(grow + c, s_colmax[c]);
     if (last_block_ticket_grouped(ws.ticket, gridDim.x)) {
       const int groups = n_groups;
-      for (int col = threadIdx.x; col < plan.n_cols; col += kEvalThreads) {
+      for (int col = threadIdx.x; col < plan.n_cols; col += n_threads) {
         uint32_t key = 0u;
         int gi = 0;
         for (; gi + 4 <= groups; gi += 4) {  // 4 independent exchanges in flight
@@ -656,16 +660,19 @@ static int launch_eval(const catb200_plan_t* plan, const catb200_cat_params_t* p
   const size_t smem = 2 * (size_t)plan->smem_bar_off;  // two staging buffers (sources + peak table each)
   const int n_tiles = (num_envs + kTile - 1) / kTile;
   // persistent grid: as many CTAs as fit (shared memory / 2048 threads per SM), never more than tiles
-  const int per_sm = (int)max((size_t)1, min((size_t)(2048 / kEvalThreads), (size_t)(220 * 1024) / max(smem + 2048, (size_t)1)));
+  // small N (about one tile per SM-resident CTA): 16 warps shorten the per-tile critical path; large N: 8 warps
+  // spend fewer instructions on per-warp term prologues (throughput bound there)
+  const int threads = n_tiles <= 4 * kNumSMs ? kEvalThreadsMax : kEvalThreads;
+  const int per_sm = (int)max((size_t)1, min((size_t)(2048 / threads), (size_t)(220 * 1024) / max(smem + 2048, (size_t)1)));
   const int grid = min(n_tiles, kNumSMs * per_sm);
   if (mode == kEvalStep) {
     if (smem > 48 * 1024)
       CATB200_CUDA_TRY(cudaFuncSetAttribute(cat_eval_kernel<kEvalStep>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cat_eval_kernel<kEvalStep><<<grid, kEvalThreads, smem, stream>>>(*plan, *prm, num_envs, running_max, rm_init, ws, nullptr);
+    cat_eval_kernel<kEvalStep><<<grid, threads, smem, stream>>>(*plan, *prm, num_envs, running_max, rm_init, ws, nullptr);
   } else {
     if (smem > 48 * 1024)
       CATB200_CUDA_TRY(cudaFuncSetAttribute(cat_eval_kernel<kEvalRowMajor>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cat_eval_kernel<kEvalRowMajor><<<grid, kEvalThreads, smem, stream>>>(*plan, *prm, num_envs, nullptr, nullptr, ws, out_rowmajor);
+    cat_eval_kernel<kEvalRowMajor><<<grid, threads, smem, stream>>>(*plan, *prm, num_envs, nullptr, nullptr, ws, out_rowmajor);
   }
   CATB200_LAUNCH_CHECK();
   return CATB200_OK;
