@@ -5,17 +5,20 @@
 // CaT.add/get_probs :39-82) and the reward/dones lines of CaTEnv.step (U/cat/cat_env.py:102-121).
 //
 // Data flow (N envs, K constraint columns, S statistics slots):
-//   cat_eval_kernel : one CTA per 32-env tile.  Every source tensor row block of the tile is staged
-//                     into shared memory with coalesced loads (rows padded to an odd pitch -> lane r
-//                     reading row r is bank-conflict free).  Warp w evaluates columns w, w+4, ... for
-//                     the tile's 32 envs (one env per lane, warp-uniform op dispatch), stores the raw
-//                     constraint column-major into the workspace (C_T[K][N], coalesced) and folds the
-//                     column max over envs with redux.sync + one atomicMax per column per CTA.  The last
-//                     CTA to finish applies the clamp + Polyak update to running_max[K] (:55-61).
-//   cat_apply_kernel: one thread per env.  Reads its K constraint values back (coalesced, L2 hits),
-//                     maps violations to probabilities (:64-72), takes the per-term and overall row
-//                     max (:82,:225), updates the two per-term episode statistics (:226-227) and writes
-//                     cstr_prob plus, optionally, the scaled reward and float dones.
+//   cat_eval_kernel : persistent CTAs walk 32-env tiles.  The tile's rows of every source tensor are copied
+//                     verbatim into shared memory by the bulk async-copy engine (cp.async.bulk + mbarrier, one
+//                     copy per source, no per-element staging instructions), double buffered: tile i+1 lands
+//                     while tile i is evaluated.  Contact-force peaks are computed once per (history tensor,
+//                     body) pair into a shared table; then warp w evaluates columns w, w+W, ... of every term
+//                     (lane = env, warp-uniform op dispatch hoisted out of the column loop, term-level gates
+//                     computed once), stores the raw constraint column-major into the workspace (C_T[K][N],
+//                     coalesced) and keeps the column maxima in shared memory (redux.sync per column).  At the
+//                     end each CTA issues one atomicMax per column into one of up to 64 scratch rows and the
+//                     last CTA (two-level ticket) applies the clamp + Polyak update to running_max[K] (:55-61).
+//   cat_apply_kernel: one CTA per 32 envs (lane = env), 8 warps split the statistics slots.  Reads the K
+//                     constraint values back (coalesced, L2 hits), maps violations to probabilities (:64-72),
+//                     takes the per-term and overall row max (:82,:225), updates the two per-term episode
+//                     statistics (:226-227) and writes cstr_prob plus, optionally, the scaled reward / float dones.
 //
 // The cross-env column max is a true global dependency (probability of env i depends on the max over
 // all envs of this step), hence two phases.  HBM-bound streaming work: no tensor cores involved.
