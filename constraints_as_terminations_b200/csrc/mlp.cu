@@ -34,6 +34,16 @@ static bool use_tc() {
   return v == 1;
 }
 
+// fused three-layer forward kernel (tc_fwd3.cu) instead of three tc_gemm launches: CATB200_FUSED_FWD=1
+static bool use_fused_fwd() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("CATB200_FUSED_FWD");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 constexpr int kGemmThreads = 256;
 constexpr int kBM = 128, kBN = 128, kBK = 64;
 constexpr int kStages = 3;
@@ -839,6 +849,20 @@ static int launch_forward(const catb200_mlp_dims_t* d, const catb200_mlp_layout_
     CATB200_CUDA_TRY(cudaFuncSetAttribute(gemm_nt_kernel<kEpiBiasElu>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemNT));
     CATB200_CUDA_TRY(cudaFuncSetAttribute(gemm_nt_kernel<kEpiMulDelu>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemNT));
     attr_set = true;
+  }
+  if (use_tc() && use_fused_fwd() && d->obs_pad == 64 && d->h1 <= 512 && d->h2 <= 256 && d->h3 == 128) {
+    Fwd3Args f = {};
+    for (int z = 0; z < 2; ++z) {
+      int rc = make_tmap_bf16(&f.mapX[z], X, 64, rows, 64, 64, 128);
+      for (int l = 0; l < 3 && rc == CATB200_OK; ++l) {
+        rc = make_tmap_bf16(&f.mapW[z][l], w16 + P.w16[z][l], x.in_pad[l], x.out[l], x.in_pad[l], 64, 128);
+        if (rc == CATB200_OK) rc = make_tmap_bf16(&f.mapH[z][l], ws + L.H[z][l], x.out[l], rows, x.out[l], 64, 32);
+        f.bias[z][l] = params + P.b[z][l];
+      }
+      if (rc != CATB200_OK) return rc;
+    }
+    f.M = rows; f.h1 = d->h1; f.h2 = d->h2; f.h3 = d->h3;
+    return fwd3_launch(f, st);
   }
   for (int l = 0; l < 3 && use_tc(); ++l) {
     TcGemmArgs t = {};

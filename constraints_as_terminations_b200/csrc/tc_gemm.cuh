@@ -25,6 +25,16 @@ struct TcGemmArgs {
   int stages;           // ring depth, filled by tc_gemm_launch
 };
 
+// fused three-layer forward (tc_fwd3.cu)
+struct Fwd3Args {
+  CUtensorMap mapX[2];     // X [M, obs_pad = 64]: load box 64 x 128
+  CUtensorMap mapW[2][3];  // W_l [out_l, in_pad_l]: load boxes 64 (inputs) x 128 (outputs)
+  CUtensorMap mapH[2][3];  // H_l [M, out_l]: store boxes 64 (features) x 32 (rows)
+  const float* bias[2][3];
+  int M, h1, h2, h3;
+};
+int fwd3_launch(const Fwd3Args& g, cudaStream_t st);
+
 int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
                    uint32_t box_outer);
 int tc_gemm_launch(int mode, const TcGemmArgs& g, int splits, cudaStream_t st);
