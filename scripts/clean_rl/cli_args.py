@@ -1,42 +1,45 @@
-"""CLI arguments of the CleanRL launchers; same flags and override rules as the reference
-(`scripts/clean_rl/cli_args.py:11-73`)."""
+"""Command-line options shared by the CleanRL launchers.
+
+Same flag names and override semantics as the reference launcher helpers (`scripts/clean_rl/cli_args.py:11-73`),
+table-driven here."""
 
 from __future__ import annotations
 
 import argparse
 
+# flag, kwargs, cfg attribute the flag overrides (None = handled separately)
+_OPTIONS = [
+    ("--experiment_name", dict(type=str, help="log folder under logs/clean_rl/"), "experiment_name"),
+    ("--resume", dict(type=bool, help="resume from a checkpoint"), "resume"),
+    ("--load_run", dict(type=str, help="run folder (regex) to load from"), "load_run"),
+    ("--checkpoint", dict(type=str, help="checkpoint file (regex) to load"), "load_checkpoint"),
+    ("--logger", dict(type=str, choices=("wandb", "tensorboard"), help="scalar logger"), "logger"),
+    ("--log_project_name", dict(type=str, help="wandb project name"), None),
+]
 
-def add_clean_rl_args(parser: argparse.ArgumentParser):
-    group = parser.add_argument_group("clean_rl", description="Arguments for CleanRL agent.")
-    group.add_argument("--experiment_name", type=str, default=None, help="Name of the experiment folder where logs will be stored.")
-    group.add_argument("--resume", type=bool, default=None, help="Whether to resume from a checkpoint.")
-    group.add_argument("--load_run", type=str, default=None, help="Name of the run folder to resume from.")
-    group.add_argument("--checkpoint", type=str, default=None, help="Checkpoint file to resume from.")
-    group.add_argument("--logger", type=str, default=None, choices={"wandb", "tensorboard"}, help="Logger module to use.")
-    group.add_argument("--log_project_name", type=str, default=None, help="Name of the logging project when using wandb")
+
+def add_clean_rl_args(parser: argparse.ArgumentParser) -> None:
+    group = parser.add_argument_group("clean_rl", description="CleanRL agent options")
+    for flag, kwargs, _ in _OPTIONS:
+        group.add_argument(flag, default=None, **kwargs)
 
 
 def update_clean_rl_cfg(agent_cfg, args_cli: argparse.Namespace):
-    """Override the agent cfg with CLI arguments (reference cli_args.py:56-73)."""
-    if getattr(args_cli, "seed", None) is not None:
-        agent_cfg.seed = args_cli.seed
-    if args_cli.resume is not None:
-        agent_cfg.resume = args_cli.resume
-    if args_cli.load_run is not None:
-        agent_cfg.load_run = args_cli.load_run
-    if args_cli.checkpoint is not None:
-        agent_cfg.load_checkpoint = args_cli.checkpoint
-    if args_cli.logger is not None:
-        agent_cfg.logger = args_cli.logger
-    if agent_cfg.logger in {"wandb"} and args_cli.log_project_name:
+    """CLI values that were given win over the cfg defaults."""
+    seed = getattr(args_cli, "seed", None)
+    if seed is not None:
+        agent_cfg.seed = seed
+    for flag, _, attr in _OPTIONS:
+        value = getattr(args_cli, flag.lstrip("-"), None)
+        if attr is not None and value is not None:
+            setattr(agent_cfg, attr, value)
+    if agent_cfg.logger == "wandb" and getattr(args_cli, "log_project_name", None):
         agent_cfg.wandb_project = args_cli.log_project_name
-    if getattr(args_cli, "experiment_name", None) is not None:
-        agent_cfg.experiment_name = args_cli.experiment_name
     return agent_cfg
 
 
 def parse_clean_rl_cfg(task_name: str, args_cli: argparse.Namespace):
-    """Default agent cfg of the task: from the gym registry when Isaac Lab is present, else the Solo12 values."""
+    """Default agent cfg of the task (gym registry under Isaac Lab, Solo12 values otherwise) + CLI overrides."""
     try:
         from isaaclab_tasks.utils.parse_cfg import load_cfg_from_registry  # type: ignore
 
