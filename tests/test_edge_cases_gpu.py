@@ -93,3 +93,73 @@ def test_terms_that_nobody_violates_decay_to_the_clamp():
         assert float(p.abs().sum()) == 0.0
         assert torch.equal(mgr.cat.get_running_maxes().cpu(), orc.running_max["v"])
     assert float(mgr._episode_sums["v"].sum()) == 0.0
+
+
+def _random_cfg(rng, constraints_module=None):
+    """A random ConstraintsCfg: random subset / order of the 15 term functions with random ids and scalars."""
+    import random
+
+    c = constraints
+    J, B = se.JOINT_NAMES, se.BODY_NAMES
+
+    def joints():
+        k = rng.randint(1, 12)
+        return rng.sample(J, k)
+
+    def bodies():
+        k = rng.randint(1, 6)
+        return rng.sample(B, k)
+
+    makers = {
+        "joint_position": lambda: (c.joint_position, {"limit": rng.uniform(0.2, 1.5), "asset_cfg": SceneEntityCfg("robot", joint_names=joints())}),
+        "joint_position_when_moving_forward": lambda: (c.joint_position_when_moving_forward, {"limit": rng.uniform(0.05, 0.5), "velocity_deadzone": rng.uniform(0.05, 0.4), "asset_cfg": SceneEntityCfg("robot", joint_names=joints())}),
+        "joint_torque": lambda: (c.joint_torque, {"limit": rng.uniform(1.0, 4.0), "asset_cfg": SceneEntityCfg("robot", joint_names=joints())}),
+        "joint_velocity": lambda: (c.joint_velocity, {"limit": rng.uniform(4.0, 20.0), "asset_cfg": SceneEntityCfg("robot", joint_names=joints())}),
+        "joint_acceleration": lambda: (c.joint_acceleration, {"limit": rng.uniform(200.0, 900.0), "asset_cfg": SceneEntityCfg("robot", joint_names=joints())}),
+        "upsidedown": lambda: (c.upsidedown, {"limit": rng.uniform(-0.9, 0.2), "asset_cfg": SceneEntityCfg("robot")}),
+        "contact": lambda: (c.contact, {"asset_cfg": SceneEntityCfg("contact_forces", body_names=bodies())}),
+        "base_orientation": lambda: (c.base_orientation, {"limit": rng.uniform(0.05, 0.5), "asset_cfg": SceneEntityCfg("robot")}),
+        "air_time": lambda: (c.air_time, {"limit": rng.uniform(0.1, 0.4), "velocity_deadzone": rng.uniform(0.05, 0.5), "asset_cfg": SceneEntityCfg("contact_forces", body_names=bodies())}),
+        "n_foot_contact": lambda: (c.n_foot_contact, {"number_of_desired_feet": rng.randint(0, 4), "min_command_value": rng.uniform(0.1, 0.8), "asset_cfg": SceneEntityCfg("contact_forces", body_names=bodies())}),
+        "joint_range": lambda: (c.joint_range, {"limit": rng.uniform(0.2, 1.2), "asset_cfg": SceneEntityCfg("robot", joint_names=joints())}),
+        "action_rate": lambda: (c.action_rate, {"limit": rng.uniform(20.0, 100.0), "asset_cfg": SceneEntityCfg("robot", joint_names=joints())}),
+        "foot_contact_force": lambda: (c.foot_contact_force, {"limit": rng.uniform(5.0, 60.0), "asset_cfg": SceneEntityCfg("contact_forces", body_names=bodies())}),
+        "min_base_height": lambda: (c.min_base_height, {"limit": rng.uniform(0.1, 0.35), "asset_cfg": SceneEntityCfg("robot")}),
+        "no_move": lambda: (c.no_move, {"velocity_deadzone": rng.uniform(0.05, 0.6), "joint_vel_limit": rng.uniform(1.0, 8.0), "asset_cfg": SceneEntityCfg("robot", joint_names=joints())}),
+    }
+    names = rng.sample(sorted(makers), rng.randint(1, 15))
+    # the same function may appear twice under different names
+    names += [rng.choice(sorted(makers)) for _ in range(rng.randint(0, 3))]
+    cfg = {}
+    for i, name in enumerate(names):
+        func, params = makers[name]()
+        cfg[f"t{i}_{name}"] = ConstraintTermCfg(func=func, max_p=rng.choice([1.0, 0.25, 0.1, rng.uniform(0.01, 1.0)]), params=params)
+    return cfg
+
+
+@pytest.mark.parametrize("trial", range(12))
+def test_random_term_configurations_match_oracle_bit_exact(trial):
+    import copy
+    import random
+
+    rng = random.Random(1000 + trial)
+    n = rng.choice([1, 7, 32, 33, 100, 257, 1024, 2500])
+    tau, min_p = rng.choice([(0.95, 0.0), (0.9, 0.01), (0.5, 0.0)])
+    cfg = _random_cfg(rng)
+    cpu_env = se.SyntheticSolo12Env(n, device="cpu", pool=1)
+    gpu_env = se.SyntheticSolo12Env(n, device=DEV, pool=1)
+    cfg_cpu = copy.deepcopy(cfg)
+    oracle = cat_oracle.ManagerOracle(cpu_env, cat_oracle.terms_from_cfg(cfg_cpu, resolve_scene=cpu_env.scene), tau=tau, min_p=min_p)
+    mgr = ConstraintManager(cfg, gpu_env, tau=tau, min_p=min_p)
+    gen = torch.Generator().manual_seed(trial)
+    for step in range(3):
+        state = se.sample_state(n, gen, adversarial=(step == 1))
+        cpu_env.load_state(state)
+        gpu_env.load_state({k: v.to(DEV) for k, v in state.items()})
+        want = oracle.compute()
+        got = mgr.compute()
+        assert torch.equal(got.cpu(), want), f"trial {trial} step {step}: cstr_prob"
+        assert torch.equal(mgr.cat.get_running_maxes().cpu(), torch.cat(list(oracle.cat.running_max.values()), dim=1))
+    assert torch.equal(mgr.cat.get_raw_constraints().cpu(), torch.cat(list(oracle.cat.raw.values()), dim=1))
+    assert torch.equal(mgr._stats[0, : len(cfg)].cpu(), torch.stack(list(oracle.episode_sums.values())))
+    assert torch.equal(mgr._stats[1, : len(cfg)].cpu(), torch.stack(list(oracle.mean_values.values())))
