@@ -40,6 +40,36 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(L.CatParams) == 16 + 4 * L.MAX_TERMS
 
 
+def test_ctypes_layout_matches_header_compiled_as_c(tmp_path):
+    """include/catb200.h is plain C (gcc -std=c99 -pedantic) and every ctypes mirror has the header's size and field offsets."""
+    import subprocess
+
+    mirrors = {
+        "catb200_source_t": L.Source,
+        "catb200_term_t": L.Term,
+        "catb200_plan_t": L.Plan,
+        "catb200_cat_params_t": L.CatParams,
+        "catb200_mlp_dims_t": L.MlpDims,
+        "catb200_mlp_layout_t": L.MlpLayout,
+        "catb200_ppo_hparams_t": L.PpoHparams,
+    }
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "catb200.h"', "int main(void) {"]
+    for cname, cls in mirrors.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for field, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{field} %zu\\n", offsetof({cname}, {field}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", L.INCLUDE_DIR, str(src), "-o", str(exe)], check=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in mirrors.items():
+        assert int(out[cname]) == ctypes.sizeof(cls), cname
+        for field, _ in cls._fields_:
+            assert int(out[f"{cname}.{field}"]) == getattr(cls, field).offset, f"{cname}.{field}"
+
+
 def test_plan_finalize_validates(lib):
     plan = L.Plan()
     plan.n_sources, plan.n_terms = 1, 1
