@@ -42,6 +42,9 @@ OP_ABS_MINUS_GATE_STILL = 12
 
 NO_SOURCE = 0xFF
 
+# catb200_gae_variant
+GAE_RLGAMES, GAE_SKRL = 0, 1
+
 
 class Source(C.Structure):
     _fields_ = [
@@ -83,7 +86,7 @@ class Plan(C.Structure):
         ("smem_bytes", C.c_int32),
         ("n_peaks", C.c_int32),
         ("smem_peak_off", C.c_int32),
-        ("smem_bar_off", C.c_int32),
+        ("smem_ctile_off", C.c_int32),
         ("sources", Source * MAX_SOURCES),
         ("terms", Term * MAX_TERMS),
         ("col_term", C.c_uint8 * MAX_COLS),
@@ -207,6 +210,8 @@ SIGNATURES = {
     "catb200_rollout_append": (C.c_int, [_P, _P, _P, _I32, _P, _P, _P, _P]),
     "catb200_gae_workspace_bytes": (_SZ, []),
     "catb200_gae": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _F, _F, _P, _P, _P, _P, _P, _SZ, _P]),
+    "catb200_gae_float_dones_workspace_bytes": (_SZ, []),
+    "catb200_gae_float_dones": (C.c_int, [_I32, _P, _P, _P, _P, _P, _I32, _I32, _F, _F, _P, _P, _I32, _P, _SZ, _P]),
     "catb200_mlp_layout": (C.c_int, [C.POINTER(MlpDims), C.POINTER(MlpLayout)]),
     "catb200_mlp_cast_weights": (C.c_int, [C.POINTER(MlpDims), _P, _P, _P]),
     "catb200_obs_to_bf16": (C.c_int, [_P, _I64, _I32, _I32, _P, _P]),

@@ -4,18 +4,19 @@
 // ConstraintManager.compute() (U/cat/constraint_manager.py:213-229 driving constraints.py:23-235 and
 // CaT.add/get_probs :39-82) and the reward/dones lines of CaTEnv.step (U/cat/cat_env.py:102-121).
 //
-// Data flow (N envs, K constraint columns, S statistics slots):
-//   cat_eval_kernel : persistent CTAs walk 32-env tiles.  The tile's rows of every source tensor are copied
-//                     verbatim into shared memory by the bulk async-copy engine (cp.async.bulk + mbarrier, one
-//                     copy per source, no per-element staging instructions), double buffered: tile i+1 lands
-//                     while tile i is evaluated.  Contact-force peaks are computed once per (history tensor,
-//                     body) pair into a shared table; then warp w evaluates columns w, w+W, ... of every term
-//                     (lane = env, warp-uniform op dispatch hoisted out of the column loop, term-level gates
-//                     computed once), stores the raw constraint column-major into the workspace (C_T[K][N],
-//                     coalesced) and keeps the column maxima in shared memory (redux.sync per column).  At the
-//                     end each CTA issues one atomicMax per column into one of up to 64 scratch rows and the
-//                     last CTA (two-level ticket) applies the clamp + Polyak update to running_max[K] (:55-61).
-//   cat_apply_kernel: one CTA per 32 envs (lane = env), 8 warps split the statistics slots.  Reads the K
+// Data flow (N envs in tiles of 32, K constraint columns, S statistics slots):
+//   cat_eval_kernel : one CTA per 32-env tile, lane = env, G = 1..8 warps sharing the tile.  The tile's rows of
+//                     every source tensor are copied verbatim into shared memory by the bulk async-copy engine
+//                     (cp.async.bulk + mbarrier, one copy per source, no per-element staging instructions).
+//                     Contact-force peaks are computed once per (history tensor, body) pair into a shared table
+//                     and the command gates of all terms once per warp into a bit mask; then warp w evaluates
+//                     columns w, w+G, ... of every term (warp-uniform op dispatch hoisted out of the column
+//                     loop), writes the raw constraint into a shared [K][32] tile and the column maximum over
+//                     the 32 envs (one CREDUX.MAX.F32 per column) into a shared row.  The tile leaves as ONE
+//                     bulk async store into the workspace (C_T, tile-major [n_tiles][K][32]); each CTA issues at
+//                     most one atomicMax per column into one of up to 64 scratch rows and the last CTA
+//                     (two-level ticket) applies the clamp + Polyak update to running_max[K] (:55-61).
+//   cat_apply_kernel: one CTA per 32 envs (lane = env), 8 warps split the statistics slots.  Reads the tile's K
 //                     constraint values back (coalesced, L2 hits), maps violations to probabilities (:64-72),
 //                     takes the per-term and overall row max (:82,:225), updates the two per-term episode
 //                     statistics (:226-227) and writes cstr_prob plus, optionally, the scaled reward / float dones.
@@ -40,55 +41,24 @@ bool pdl_enabled() {
   return v == 1;
 }
 
-constexpr int kTile = 32;          // envs per CTA in the eval kernel (one per lane)
-constexpr int kEvalWarps = 8;      // warps per CTA of the apply kernel (and of the eval kernel at large N)
+constexpr int kTile = 32;          // envs per CTA in the eval and apply kernels (one per lane)
+constexpr int kEvalMaxWarps = 8;   // eval kernel: 1, 2, 4 or 8 warps share a tile (chosen per launch)
+constexpr int kEvalWarps = 8;      // warps per CTA of the apply kernel
 constexpr int kEvalThreads = kEvalWarps * 32;
-constexpr int kEvalWarpsSmallN = 16;  // eval kernel at small N: shorter per-tile critical path (latency bound there)
-constexpr int kEvalThreadsMax = kEvalWarpsSmallN * 32;
 constexpr int kApplyThreads = 64;
-
-// ---- staged-source accessors ----------------------------------------------------------------------
-// A tile's rows of every source are copied verbatim (row pitch = row_len) into shared memory by the bulk
-// async-copy engine (cp.async.bulk + mbarrier, i.e. TMA's 1-D path): zero per-element staging instructions.
-struct SrcView {
-  const uint8_t* base;  // shared-memory bytes of this source's tile
-  int row_len;
-  int is_u8;
-  __device__ __forceinline__ float at(int row, int e) const {
-    return is_u8 ? (base[row * row_len + e] ? 1.0f : 0.0f) : reinterpret_cast<const float*>(base)[row * row_len + e];
-  }
-  // sources the library ops read as fp32 by construction (state tensors); bool / u8 only reach `at`
-  __device__ __forceinline__ float f32(int row, int e) const { return reinterpret_cast<const float*>(base)[row * row_len + e]; }
-};
-
-__device__ __forceinline__ SrcView view_of(const catb200_plan_t& plan, const uint8_t* smem, int s) {
-  const catb200_source_t& src = plan.sources[s];
-  return SrcView{smem + src.smem_off, src.row_len, src.dtype == CATB200_U8};
-}
 
 // sqrt(x^2 + y^2 + z^2) the way torch.norm reduces a short contiguous dim on CPU and CUDA:
 // sequential fused multiply-adds from a zero accumulator, then a correctly rounded sqrt.
-__device__ __forceinline__ float norm3(float x, float y, float z) {
+__device__ __forceinline__ float sumsq3(float x, float y, float z) {
   float acc = __fmul_rn(x, x);
   acc = __fmaf_rn(y, y, acc);
-  acc = __fmaf_rn(z, z, acc);
-  return __fsqrt_rn(acc);
+  return __fmaf_rn(z, z, acc);
 }
+__device__ __forceinline__ float norm3(float x, float y, float z) { return __fsqrt_rn(sumsq3(x, y, z)); }
 __device__ __forceinline__ float norm2(float x, float y) {
   float acc = __fmul_rn(x, x);
   acc = __fmaf_rn(y, y, acc);
   return __fsqrt_rn(acc);
-}
-
-// max over the history axis of |F[h, body, :]| for one body (constraints.py:102-107,151-158,207-209)
-__device__ __forceinline__ float force_peak(const SrcView& v, int bodies, int row, int body) {
-  const int H = v.row_len / (3 * bodies);
-  float peak = -INFINITY;
-  for (int h = 0; h < H; ++h) {
-    const int e = (h * bodies + body) * 3;
-    peak = fmaxf(peak, norm3(v.f32(row, e), v.f32(row, e + 1), v.f32(row, e + 2)));
-  }
-  return peak;
 }
 
 // Same-address atomics serialise in L2 (tens of ns each): with one scratch word per column, 32 768 CTAs
@@ -98,9 +68,9 @@ constexpr int kMaxGroups = 64;
 
 struct CatWorkspace {
   // layout inside the caller's workspace (all 256-byte aligned)
-  unsigned int* ticket;   // 1 word (padded)
+  unsigned int* ticket;   // 1 + kTicketGroups words (padded)
   uint32_t* colmax;       // [kMaxGroups][CATB200_MAX_COLS] ordered-float column maxima, 0 between launches
-  float* c_t;             // [K][N] raw constraints, column-major
+  float* c_t;             // [n_tiles][K][32] raw constraints, tile-major
 };
 
 __host__ __device__ inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
@@ -117,83 +87,11 @@ __host__ __device__ inline CatWorkspace carve(void* base, int num_envs) {
 
 enum EvalMode { kEvalStep = 0, kEvalRowMajor = 1 };
 
-// ---- per-term column evaluation ----------------------------------------------------------------------
-struct TermCtx {
-  const uint8_t* ids;  // joint / body / peak-slot ids of the term (kernel-parameter memory)
-  int n_ids, first, n_cols, col0, row, lane, n_warps;
-  float p0, p1, p2, gate;
-  const float* peaks;
-  SrcView v0, v1;
-};
-
-template <int MODE>
-struct ColumnSink {  // where a column value of this tile goes: C_T + column max, or the row-major debug matrix
-  bool live;
-  int lane, n_cols, num_envs;
-  float* ct;         // &C_T[0][tile0 + lane]
-  uint32_t* colmax;  // this CTA's shared-memory column maxima (ordered-float keys), one writer warp per column
-  float* out_row;    // &out[tile0 + lane][0]
-  __device__ __forceinline__ void emit(int col, float c) const {
-    if (MODE == kEvalRowMajor) {
-      if (live) out_row[col] = c;
-    } else {
-      if (live) ct[(size_t)col * num_envs] = c;
-      const uint32_t m = __reduce_max_sync(0xffffffffu, live ? float_to_ordered(c) : 0u);
-      // column `col` is always handled by the same warp of this CTA: a plain read-modify-write suffices
-      if (lane == 0 && m > colmax[col]) colmax[col] = m;
-    }
-  }
-};
-
-// Operation order follows the cited reference lines; every intermediate is rounded to fp32 exactly where
-// torch materialises a tensor.
-template <int OP>
-__device__ __forceinline__ float column_value(const TermCtx& c, int lc) {
-  const int id = c.ids[lc];
-  const int row = c.row;
-  switch (OP) {
-    case CATB200_OP_GENERIC:
-      return c.v0.at(row, id);
-    case CATB200_OP_ABS_MINUS:  // constraints.py:30,64,75,85
-      return __fsub_rn(fabsf(c.v0.f32(row, id)), c.p0);
-    case CATB200_OP_ABSDIFF_MINUS:  // constraints.py:176-181
-      return __fsub_rn(fabsf(__fsub_rn(c.v0.f32(row, id), c.v1.f32(row, id))), c.p0);
-    case CATB200_OP_ABSDIFF_MINUS_GATE_Y:  // constraints.py:42-53
-      return __fmul_rn(__fsub_rn(fabsf(__fsub_rn(c.v0.f32(row, id), c.v1.f32(row, id))), c.p0), c.gate);
-    case CATB200_OP_ACTION_RATE:  // constraints.py:191-198 (true division by step_dt)
-      return __fsub_rn(__fdiv_rn(fabsf(__fsub_rn(c.v0.f32(row, id), c.v1.f32(row, id))), c.p1), c.p0);
-    case CATB200_OP_COMPONENT_GT:  // constraints.py:94
-      return c.v0.f32(row, id) > c.p0 ? 1.0f : 0.0f;
-    case CATB200_OP_CONTACT_ANY: {  // constraints.py:103-110; ids index the peak table
-      bool any = false;
-      for (int b = 0; b < c.n_ids; ++b) any |= c.peaks[c.ids[b] * kTile + c.lane] > c.p0;
-      return any ? 1.0f : 0.0f;
-    }
-    case CATB200_OP_NORM2_MINUS:  // constraints.py:119
-      return __fsub_rn(norm2(c.v0.f32(row, 0), c.v0.f32(row, 1)), c.p0);
-    case CATB200_OP_AIR_TIME: {  // constraints.py:129-141
-      const float td = c.v1.at(row, id) != 0.0f ? 1.0f : 0.0f;
-      return __fmul_rn(__fmul_rn(__fsub_rn(c.p0, c.v0.f32(row, id)), td), c.gate);
-    }
-    case CATB200_OP_N_CONTACT: {  // constraints.py:151-168
-      int n = 0;
-      for (int b = 0; b < c.n_ids; ++b) n += c.peaks[c.ids[b] * kTile + c.lane] > c.p2 ? 1 : 0;
-      return __fmul_rn(fabsf((float)n - c.p0), c.gate);
-    }
-    case CATB200_OP_FORCE_PEAK_MINUS:  // constraints.py:207-210
-      return __fsub_rn(c.peaks[id * kTile + c.lane], c.p0);
-    case CATB200_OP_LIMIT_MINUS:  // constraints.py:220
-      return __fsub_rn(c.p0, c.v0.f32(row, id));
-    case CATB200_OP_ABS_MINUS_GATE_STILL:  // constraints.py:231-235
-      return __fmul_rn(__fsub_rn(fabsf(c.v0.f32(row, id)), c.p0), c.gate);
-    default:
-      return 0.0f;
-  }
-}
-
-template <int OP, int MODE>
-__device__ __forceinline__ void term_columns(const TermCtx& c, const ColumnSink<MODE>& sink) {
-  for (int lc = c.first; lc < c.n_cols; lc += c.n_warps) sink.emit(c.col0 + lc, column_value<OP>(c, lc));
+// max over the warp of an fp32 value: one CREDUX.MAX.F32 on sm_100a
+__device__ __forceinline__ float warp_max_f32(float v) {
+  float m;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;\n" : "=f"(m) : "f"(v));
+  return m;
 }
 
 __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -202,210 +100,377 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uin
                : "memory");
 }
 
-// Persistent, double-buffered: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; while tile i is
-// evaluated out of one shared-memory buffer the bulk async copies of tile i+1 land in the other.  Column
-// maxima are kept per CTA in shared memory and flushed with one atomicMax per column per CTA at the end.
+// shared-state-space accesses at 32-bit addresses: no generic-address arithmetic in the column loops.  The loads
+// are deliberately NOT volatile so that the compiler may hoist the loads of the next columns above the stores /
+// warp reduction of the current one (the column chains are independent; with volatile loads each column was one
+// serial LDS -> FADD -> STS -> CREDUX chain).  They only ever read data that is constant while they can execute:
+// every address derives from an image base that is laundered through a volatile asm AFTER the barrier / mbarrier
+// wait that publishes the data, so the data dependence keeps them behind it.
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+  uint32_t v;
+  asm("ld.shared.u8 %0, [%1];\n" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t launder(uint32_t x) {
+  asm volatile("mov.u32 %0, %0;\n" : "+r"(x)::"memory");
+  return x;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(addr), "f"(v) : "memory"); }
+
+// ---- per-term column evaluation ----------------------------------------------------------------------
+// A term is evaluated by ONE warp (lane = env): its prologue (sources, scalars, command gate) runs once per tile
+// and the column loop is a handful of instructions per column.
+struct TermCtx {
+  const uint8_t* ids;  // joint / body / peak-slot ids of the term (kernel-parameter memory)
+  int n_ids, n_cols;
+  uint32_t x0, x1;     // shared addresses of this lane's row of source 0 / source 1
+  uint32_t u1;         // source 1 holds bytes (bool tensor)
+  uint32_t peaks;      // shared address of peak_table[0][lane]
+  uint32_t out;        // shared address of tile[col0][lane]
+  uint32_t colmax;     // shared address of tilemax[col0]
+  float p0, p1, p2, gate;
+  bool live, lane0;
+};
+
 template <int MODE>
-__global__ void __launch_bounds__(kEvalThreadsMax)
+__device__ __forceinline__ void emit(const TermCtx& c, int lc, float v) {
+  sts_f32(c.out + lc * (kTile * 4), v);
+  if (MODE == kEvalStep) {
+    const float m = warp_max_f32(c.live ? v : -INFINITY);
+    if (c.lane0) sts_f32(c.colmax + lc * 4, m);  // this tile's column maximum; folded into the CTA's in phase C
+  }
+}
+
+// Operation order follows the cited reference lines; every intermediate is rounded to fp32 exactly where
+// torch materialises a tensor.
+template <int OP>
+__device__ __forceinline__ float column_value(const TermCtx& c, int lc) {
+  const uint32_t id = c.ids[lc];
+  switch (OP) {
+    case CATB200_OP_ABS_MINUS:  // constraints.py:30,64,75,85
+      return __fsub_rn(fabsf(lds_f32(c.x0 + id * 4)), c.p0);
+    case CATB200_OP_ABSDIFF_MINUS:  // constraints.py:176-181
+      return __fsub_rn(fabsf(__fsub_rn(lds_f32(c.x0 + id * 4), lds_f32(c.x1 + id * 4))), c.p0);
+    case CATB200_OP_ABSDIFF_MINUS_GATE_Y:  // constraints.py:42-53
+      return __fmul_rn(__fsub_rn(fabsf(__fsub_rn(lds_f32(c.x0 + id * 4), lds_f32(c.x1 + id * 4))), c.p0), c.gate);
+    case CATB200_OP_ACTION_RATE:  // constraints.py:191-198 (true division by step_dt)
+      return __fsub_rn(__fdiv_rn(fabsf(__fsub_rn(lds_f32(c.x0 + id * 4), lds_f32(c.x1 + id * 4))), c.p1), c.p0);
+    case CATB200_OP_COMPONENT_GT:  // constraints.py:94
+      return lds_f32(c.x0 + id * 4) > c.p0 ? 1.0f : 0.0f;
+    case CATB200_OP_CONTACT_ANY: {  // constraints.py:103-110; ids index the peak table
+      bool any = false;
+      for (int b = 0; b < c.n_ids; ++b) any |= lds_f32(c.peaks + c.ids[b] * (kTile * 4)) > c.p0;
+      return any ? 1.0f : 0.0f;
+    }
+    case CATB200_OP_NORM2_MINUS:  // constraints.py:119
+      return __fsub_rn(norm2(lds_f32(c.x0), lds_f32(c.x0 + 4)), c.p0);
+    case CATB200_OP_AIR_TIME: {  // constraints.py:129-141
+      const bool touchdown = c.u1 ? lds_u8(c.x1 + id) != 0u : lds_f32(c.x1 + id * 4) != 0.0f;
+      return __fmul_rn(__fmul_rn(__fsub_rn(c.p0, lds_f32(c.x0 + id * 4)), touchdown ? 1.0f : 0.0f), c.gate);
+    }
+    case CATB200_OP_N_CONTACT: {  // constraints.py:151-168
+      int n = 0;
+      for (int b = 0; b < c.n_ids; ++b) n += lds_f32(c.peaks + c.ids[b] * (kTile * 4)) > c.p2 ? 1 : 0;
+      return __fmul_rn(fabsf((float)n - c.p0), c.gate);
+    }
+    case CATB200_OP_FORCE_PEAK_MINUS:  // constraints.py:207-210
+      return __fsub_rn(lds_f32(c.peaks + id * (kTile * 4)), c.p0);
+    case CATB200_OP_LIMIT_MINUS:  // constraints.py:220
+      return __fsub_rn(c.p0, lds_f32(c.x0 + id * 4));
+    case CATB200_OP_ABS_MINUS_GATE_STILL:  // constraints.py:231-235
+      return __fmul_rn(__fsub_rn(fabsf(lds_f32(c.x0 + id * 4)), c.p0), c.gate);
+    default:
+      return 0.0f;
+  }
+}
+
+// Columns are evaluated four at a time: all their loads are issued before the first store (ptxas cannot prove that the
+// constraint tile and the source rows do not alias, so a load never moves above an earlier store on its own).
+template <int OP, int MODE>
+__device__ __forceinline__ void term_columns(const TermCtx& c) {
+  int lc = 0;
+  for (; lc + 4 <= c.n_cols; lc += 4) {
+    const float v0 = column_value<OP>(c, lc), v1 = column_value<OP>(c, lc + 1);
+    const float v2 = column_value<OP>(c, lc + 2), v3 = column_value<OP>(c, lc + 3);
+    emit<MODE>(c, lc, v0);
+    emit<MODE>(c, lc + 1, v1);
+    emit<MODE>(c, lc + 2, v2);
+    emit<MODE>(c, lc + 3, v3);
+  }
+  for (; lc < c.n_cols; ++lc) emit<MODE>(c, lc, column_value<OP>(c, lc));
+}
+
+// user terms already evaluated to [N, J]: float or bool (CaT.add's cast, :45-47)
+template <int MODE>
+__device__ __forceinline__ void generic_columns(const TermCtx& c, bool is_u8) {
+  for (int lc = 0; lc < c.n_cols; ++lc) {
+    const uint32_t id = c.ids[lc];
+    emit<MODE>(c, lc, is_u8 ? (lds_u8(c.x0 + id) ? 1.0f : 0.0f) : lds_f32(c.x0 + id * 4));
+  }
+}
+
+// Persistent CTAs walk the 32-env tiles blockIdx.x, blockIdx.x + gridDim.x, ...; blockDim.x = 32 * G (G = 1, 2, 4
+// or 8 warps share a tile), lane = env.  Two shared-memory images: while tile i is evaluated out of one, the bulk
+// async copies of tile i+1 land in the other and the bulk async store of tile i-1's constraint tile drains.
+template <int MODE>
+__global__ void __launch_bounds__(kEvalMaxWarps * 32)
 cat_eval_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_constant__ catb200_cat_params_t prm,
-                int num_envs, float* __restrict__ running_max, int* __restrict__ rm_init,
+                int num_envs, int n_groups, float* __restrict__ running_max, int* __restrict__ rm_init,
                 CatWorkspace ws, float* __restrict__ out_rowmajor) {
-  extern __shared__ __align__(128) uint8_t smem_all[];
-  __shared__ uint32_t s_colmax[CATB200_MAX_COLS];
+  extern __shared__ __align__(128) uint8_t smem_all[];  // 2 x [source rows | peak table | constraint tile]
+  __shared__ float s_colmax[CATB200_MAX_COLS];   // column maxima over all tiles of this CTA
+  __shared__ float s_tilemax[CATB200_MAX_COLS];  // column maxima of the tile in flight (plain stores in the column loop)
   __shared__ __align__(8) unsigned long long s_bar[2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_warps = blockDim.x >> 5, n_threads = blockDim.x;  // 8 or 16 warps (power of two)
+  const int n_warps = blockDim.x >> 5, n_threads = blockDim.x;
+  const int K = plan.n_cols;
   const int n_tiles = (num_envs + kTile - 1) / kTile;
-  const int buf_bytes = plan.smem_bar_off;  // sources + peak table of one buffer (16-byte multiple)
   const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&s_bar[0]);
+  const uint32_t cm_base = launder((uint32_t)__cvta_generic_to_shared(s_tilemax));  // opaque: stays in a register
 
-  for (int c = threadIdx.x; c < plan.n_cols; c += n_threads) s_colmax[c] = 0u;
+  // lane s describes source s (n_sources <= 16): a source tile can use the bulk copy engine if it is a full tile,
+  // contiguous and 16-byte aligned
+  const uint8_t* my_ptr = nullptr;
+  int my_len = 0, my_stride = 0, my_es = 4, my_off = 0;
+  if (lane < plan.n_sources) {
+    const catb200_source_t& src = plan.sources[lane];
+    my_ptr = static_cast<const uint8_t*>(src.ptr);
+    my_len = src.row_len;
+    my_stride = src.row_stride;
+    my_es = src.dtype == CATB200_U8 ? 1 : 4;
+    my_off = src.smem_off;
+  }
+  auto bulk_ok = [&](int tile) -> bool {
+    const uintptr_t g = reinterpret_cast<uintptr_t>(my_ptr) + (size_t)tile * kTile * my_stride * my_es;
+    return lane < plan.n_sources && (tile + 1) * kTile <= num_envs && my_stride == my_len && (g & 15) == 0;
+  };
+  // warp 0: every source lane arrives on buffer b's barrier (with its byte count when it bulk-copies) and starts its copy
+  auto issue = [&](int tile, int b) {
+    if (lane < plan.n_sources) {
+      const uint32_t bar = bar0 + 8 * b;
+      if (bulk_ok(tile)) {
+        const uint32_t bytes = kTile * my_len * my_es;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+        bulk_copy_g2s((uint32_t)__cvta_generic_to_shared(smem_all) + b * plan.smem_bytes + my_off,
+                      my_ptr + (size_t)tile * kTile * my_len * my_es, bytes, bar);
+      } else {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+      }
+    }
+  };
+
+  for (int c = threadIdx.x; c < K; c += n_threads) s_colmax[c] = -INFINITY;
   if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar0));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar0 + 8));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar0), "r"(plan.n_sources));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar0 + 8), "r"(plan.n_sources));
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
+  if (warp == 0 && (int)blockIdx.x < n_tiles) issue(blockIdx.x, 0);
 
-  // a source tile can use the bulk copy engine if it is contiguous and 16-byte aligned (full tiles only)
-  auto bulk_ok = [&](int s, int tile0, int rows) -> bool {
-    const catb200_source_t& src = plan.sources[s];
-    const int es = src.dtype == CATB200_U8 ? 1 : 4;
-    const uint8_t* g = static_cast<const uint8_t*>(src.ptr) + (size_t)tile0 * src.row_stride * es;
-    return rows == kTile && src.row_stride == src.row_len && ((reinterpret_cast<uintptr_t>(g) & 15) == 0);
-  };
-  // thread 0: arm buffer `b`'s barrier and start the bulk copies of tile `t`
-  auto issue = [&](int t, int b) {
-    const int tile0 = t * kTile, rows = min(kTile, num_envs - tile0);
-    uint8_t* dst = smem_all + (size_t)b * buf_bytes;
-    uint32_t total = 0;
-    for (int s = 0; s < plan.n_sources; ++s)
-      if (bulk_ok(s, tile0, rows)) total += kTile * plan.sources[s].row_len * (plan.sources[s].dtype == CATB200_U8 ? 1 : 4);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar0 + 8 * b), "r"(total) : "memory");
-    for (int s = 0; s < plan.n_sources; ++s) {
-      if (!bulk_ok(s, tile0, rows)) continue;
-      const catb200_source_t& src = plan.sources[s];
-      const int es = src.dtype == CATB200_U8 ? 1 : 4;
-      bulk_copy_g2s((uint32_t)__cvta_generic_to_shared(dst + src.smem_off),
-                    static_cast<const uint8_t*>(src.ptr) + (size_t)tile0 * src.row_len * es, kTile * src.row_len * es,
-                    bar0 + 8 * b);
-    }
-  };
-
-  if (threadIdx.x == 0 && (int)blockIdx.x < n_tiles) issue(blockIdx.x, 0);
   int it = 0;
-  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-    const int b = it & 1;
-    const uint8_t* smem = smem_all + (size_t)b * buf_bytes;
-    uint8_t* smem_w = smem_all + (size_t)b * buf_bytes;
-    float* peaks = reinterpret_cast<float*>(smem_w + plan.smem_peak_off);  // [n_peaks][32]
-    const int tile0 = t * kTile;
-    const int rows = min(kTile, num_envs - tile0);
-    // prefetch the next tile into the other buffer (its previous contents were consumed before the barrier that
-    // ended the previous iteration)
-    if (threadIdx.x == 0 && t + (int)gridDim.x < n_tiles) issue(t + gridDim.x, b ^ 1);
-    // sources that cannot use the bulk engine (strided views, unaligned bases, the ragged last tile): cooperative copy
-    for (int s = 0; s < plan.n_sources; ++s) {
-      if (bulk_ok(s, tile0, rows)) continue;
-      const catb200_source_t& src = plan.sources[s];
-      const int total = rows * src.row_len;
-      if (src.dtype == CATB200_F32) {
-        const float* g = static_cast<const float*>(src.ptr);
-        float* dst = reinterpret_cast<float*>(smem_w + src.smem_off);
-        for (int f = threadIdx.x; f < total; f += n_threads) {
-          const int r = f / src.row_len, e = f - r * src.row_len;
-          dst[f] = __ldg(g + (size_t)(tile0 + r) * src.row_stride + e);
-        }
-      } else {
-        const uint8_t* g = static_cast<const uint8_t*>(src.ptr);
-        for (int f = threadIdx.x; f < total; f += n_threads) {
-          const int r = f / src.row_len, e = f - r * src.row_len;
-          smem_w[src.smem_off + f] = g[(size_t)(tile0 + r) * src.row_stride + e];
-        }
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+  const int b = it & 1;
+  uint8_t* smem = smem_all + (size_t)b * plan.smem_bytes;
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+  const float* s_c = reinterpret_cast<const float*>(smem + plan.smem_ctile_off);  // [K][32]
+  const int tile0 = tile * kTile;
+  const int rows = min(kTile, num_envs - tile0);
+  // prefetch the next tile into the other image: every warp left it behind at the barrier that ended the previous
+  // iteration; its constraint tile may still be draining (bulk store of iteration it-1), which only reads it
+  if (warp == 0 && tile + (int)gridDim.x < n_tiles) issue(tile + gridDim.x, b ^ 1);
+  // sources that cannot use the bulk engine (strided views, unaligned bases, the ragged last tile): cooperative copy
+  const uint32_t coop_mask = ~__ballot_sync(0xffffffffu, bulk_ok(tile)) & ((1u << plan.n_sources) - 1u);
+  for (uint32_t m = coop_mask; m; m &= m - 1) {
+    const catb200_source_t& src = plan.sources[__ffs(m) - 1];
+    const int total = rows * src.row_len;
+    if (src.dtype == CATB200_F32) {
+      const float* g = static_cast<const float*>(src.ptr);
+      float* dst = reinterpret_cast<float*>(smem + src.smem_off);
+      for (int f = threadIdx.x; f < total; f += n_threads) {
+        const int r = f / src.row_len, e = f - r * src.row_len;
+        dst[f] = __ldg(g + (size_t)(tile0 + r) * src.row_stride + e);
+      }
+    } else {
+      const uint8_t* g = static_cast<const uint8_t*>(src.ptr);
+      for (int f = threadIdx.x; f < total; f += n_threads) {
+        const int r = f / src.row_len, e = f - r * src.row_len;
+        smem[src.smem_off + f] = g[(size_t)(tile0 + r) * src.row_stride + e];
       }
     }
-    // wait for this buffer's bulk copies: one lane sleeps on the mbarrier (suspend-time hint), the CTA barrier
-    // releases the rest, then every thread performs one already-satisfied acquire of its own
-    const uint32_t parity = (it >> 1) & 1;
-    auto try_wait = [&]() -> uint32_t {
-      uint32_t done;
-      asm volatile(
-          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-          : "=r"(done)
-          : "r"(bar0 + 8 * b), "r"(parity)
-          : "memory");
-      return done;
-    };
-    if (threadIdx.x == 0) {
-      while (!try_wait()) {
-      }
-    }
-    __syncthreads();
+  }
+  if (coop_mask) __syncthreads();  // (CTA-uniform) cooperative copies visible
+  // wait for this image's bulk copies: one lane per warp sleeps on the mbarrier (suspend-time hint), then every
+  // lane performs one already-satisfied acquire of its own
+  const uint32_t parity = (it >> 1) & 1;
+  auto try_wait = [&]() -> uint32_t {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(bar0 + 8 * b), "r"(parity)
+        : "memory");
+    return done;
+  };
+  if (lane == 0) {
     while (!try_wait()) {
     }
-
-    const bool live = lane < rows;
-    const int row = live ? lane : 0;
-
-    // ---- phase A: contact-force peaks, once per (history tensor, body) pair referenced by any term
-    for (int p = warp; p < plan.n_peaks; p += n_warps) {
-      const int s = plan.peak_src[p];
-      peaks[p * kTile + lane] = force_peak(view_of(plan, smem, s), plan.sources[s].aux, row, plan.peak_body[p]);
-    }
-    __syncthreads();
-
-    // ---- phase B: terms.  Term-level scalars and gates are computed once per term; the term's columns are
-    //      dealt to the warps by global column index (lane = env, so the op dispatch never diverges) and the
-    //      op switch sits outside the column loop.
-    ColumnSink<MODE> sink;
-    sink.live = live;
-    sink.lane = lane;
-    sink.n_cols = plan.n_cols;
-    sink.num_envs = num_envs;
-    sink.ct = MODE == kEvalStep ? ws.c_t + tile0 + lane : nullptr;
-    sink.colmax = s_colmax;
-    sink.out_row = MODE == kEvalRowMajor ? out_rowmajor + (size_t)(tile0 + lane) * plan.n_cols : nullptr;
-    for (int ti = 0; ti < plan.n_terms; ++ti) {
-      const catb200_term_t& t2 = plan.terms[ti];
-      const int n_cols = t2.n_cols, col0 = t2.col_offset, op = t2.op;
-      const int first = (warp - (col0 & (n_warps - 1))) & (n_warps - 1);  // first local column of this warp
-      if (first >= n_cols) continue;
-      TermCtx c;
-      c.ids = t2.ids;
-      c.n_ids = t2.n_ids;
-      c.first = first;
-      c.n_cols = n_cols;
-      c.col0 = col0;
-      c.row = row;
-      c.lane = lane;
-      c.n_warps = n_warps;
-      c.p0 = t2.p0;
-      c.p1 = t2.p1;
-      c.p2 = t2.p2;
-      c.peaks = peaks;
-      c.v0 = view_of(plan, smem, t2.src0);
-      c.v1 = t2.src1 != 0xff ? view_of(plan, smem, t2.src1) : c.v0;
-      c.gate = 1.0f;  // command-dependent factor shared by all columns of the term
-      if (t2.src2 != 0xff) {
-        const SrcView vc = view_of(plan, smem, t2.src2);
-        if (op == CATB200_OP_ABSDIFF_MINUS_GATE_Y) {
-          c.gate = fabsf(vc.f32(row, 1)) < c.p1 ? 1.0f : 0.0f;  // constraints.py:46-53
-        } else {
-          const float cn = norm3(vc.f32(row, 0), vc.f32(row, 1), vc.f32(row, 2));
-          c.gate = op == CATB200_OP_ABS_MINUS_GATE_STILL ? (cn < c.p1 ? 1.0f : 0.0f) : (cn > c.p1 ? 1.0f : 0.0f);
-        }
-      }
-      switch (op) {
-        case CATB200_OP_GENERIC: term_columns<CATB200_OP_GENERIC>(c, sink); break;
-        case CATB200_OP_ABS_MINUS: term_columns<CATB200_OP_ABS_MINUS>(c, sink); break;
-        case CATB200_OP_ABSDIFF_MINUS: term_columns<CATB200_OP_ABSDIFF_MINUS>(c, sink); break;
-        case CATB200_OP_ABSDIFF_MINUS_GATE_Y: term_columns<CATB200_OP_ABSDIFF_MINUS_GATE_Y>(c, sink); break;
-        case CATB200_OP_ACTION_RATE: term_columns<CATB200_OP_ACTION_RATE>(c, sink); break;
-        case CATB200_OP_COMPONENT_GT: term_columns<CATB200_OP_COMPONENT_GT>(c, sink); break;
-        case CATB200_OP_CONTACT_ANY: term_columns<CATB200_OP_CONTACT_ANY>(c, sink); break;
-        case CATB200_OP_NORM2_MINUS: term_columns<CATB200_OP_NORM2_MINUS>(c, sink); break;
-        case CATB200_OP_AIR_TIME: term_columns<CATB200_OP_AIR_TIME>(c, sink); break;
-        case CATB200_OP_N_CONTACT: term_columns<CATB200_OP_N_CONTACT>(c, sink); break;
-        case CATB200_OP_FORCE_PEAK_MINUS: term_columns<CATB200_OP_FORCE_PEAK_MINUS>(c, sink); break;
-        case CATB200_OP_LIMIT_MINUS: term_columns<CATB200_OP_LIMIT_MINUS>(c, sink); break;
-        case CATB200_OP_ABS_MINUS_GATE_STILL: term_columns<CATB200_OP_ABS_MINUS_GATE_STILL>(c, sink); break;
-        default: break;
-      }
-    }
-    __syncthreads();  // every warp is done with this buffer before the next iteration's prefetch overwrites it
+  }
+  __syncwarp();
+  while (!try_wait()) {
   }
 
-  if (MODE == kEvalStep) {
-    // ---- flush this CTA's column maxima (one atomic per column per CTA, spread over scratch rows), then the
-    //      last CTA folds everything into the Polyak running max (constraint_manager.py:55-61)
-    int n_groups = 1;  // power of two; a few hundred CTAs per scratch row keep the atomic queues short
-    while (n_groups < kMaxGroups && n_groups * 256 <= (int)gridDim.x) n_groups <<= 1;
-    uint32_t* grow = ws.colmax + (blockIdx.x & (n_groups - 1)) * CATB200_MAX_COLS;
-    for (int c = threadIdx.x; c < plan.n_cols; c += n_threads)
-      if (s_colmax[c] != 0u) atomicMax(grow + c, s_colmax[c]);
-    if (last_block_ticket_grouped(ws.ticket, gridDim.x)) {
-      const int groups = n_groups;
-      for (int col = threadIdx.x; col < plan.n_cols; col += n_threads) {
-        uint32_t key = 0u;
-        int gi = 0;
-        for (; gi + 4 <= groups; gi += 4) {  // 4 independent exchanges in flight
-          const uint32_t k0 = atomicExch(&ws.colmax[gi * CATB200_MAX_COLS + col], 0u);
-          const uint32_t k1 = atomicExch(&ws.colmax[(gi + 1) * CATB200_MAX_COLS + col], 0u);
-          const uint32_t k2 = atomicExch(&ws.colmax[(gi + 2) * CATB200_MAX_COLS + col], 0u);
-          const uint32_t k3 = atomicExch(&ws.colmax[(gi + 3) * CATB200_MAX_COLS + col], 0u);
-          key = max(max(key, max(k0, k1)), max(k2, k3));
-        }
-        for (; gi < groups; ++gi) key = max(key, atomicExch(&ws.colmax[gi * CATB200_MAX_COLS + col], 0u));
-        float cmax = fmaxf(ordered_to_float(key), prm.floor_max);
-        float rm;
-        if (rm_init[col]) {
-          rm = __fadd_rn(__fmul_rn(running_max[col], prm.tau), __fmul_rn(prm.one_minus_tau, cmax));
-        } else {
-          rm = cmax;
-          rm_init[col] = 1;
-        }
-        running_max[col] = rm;
+  const bool live = lane < rows;
+  const uint32_t row = live ? lane : 0;
+  const uint32_t ibase = launder(sbase);  // loads of the staged rows must stay behind the wait above
+  const uint32_t peaks_w = sbase + plan.smem_peak_off + lane * 4;  // peak_table[0][lane]
+
+  // ---- phase A: contact-force peaks, once per (history tensor, body) pair referenced by any term (dealt to the
+  //      warps): max over the history axis of |F[h, body, :]| (constraints.py:102-107,151-158,207-209).  The
+  //      correctly rounded square root is monotone, so max_h sqrt(s_h) == sqrt(max_h s_h) bit for bit: one
+  //      square root per body.
+  for (int p = warp; p < plan.n_peaks; p += n_warps) {
+    const catb200_source_t& src = plan.sources[plan.peak_src[p]];
+    const uint32_t hstride = src.aux * 12;
+    const uint32_t end = ibase + src.smem_off + (row + 1) * (src.row_len * 4);
+    float peak = 0.0f;  // sums of squares are >= 0
+    for (uint32_t a = ibase + src.smem_off + row * (src.row_len * 4) + plan.peak_body[p] * 12; a < end; a += hstride)
+      peak = fmaxf(peak, sumsq3(lds_f32(a), lds_f32(a + 4), lds_f32(a + 8)));
+    sts_f32(peaks_w + p * (kTile * 4), __fsqrt_rn(peak));
+  }
+  __syncthreads();
+  const uint32_t peaks = launder(peaks_w);  // loads of the peak table stay behind this barrier
+
+  // ---- phase B: terms, dealt to the warps (term ti -> warp ti mod G).  lane = env, so the op dispatch never
+  //      diverges; the op switch sits outside the column loop.
+  //      Dealing order: finalize ranked the terms by descending cost; rank k goes to warp k mod G on even rounds
+  //      and to the mirrored warp on odd rounds (snake), which balances the warps for any G.
+  for (int k0 = 0; k0 < plan.n_terms; k0 += 2 * n_warps) {
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    const int k = half ? k0 + 2 * n_warps - 1 - warp : k0 + warp;
+    if (k >= plan.n_terms) continue;
+    const catb200_term_t& t2 = plan.terms[plan.terms[k].reserved2];
+    const int op = t2.op;
+    const catb200_source_t& s0 = plan.sources[t2.src0];
+    TermCtx c;
+    c.ids = t2.ids;
+    c.n_ids = t2.n_ids;
+    c.n_cols = t2.n_cols;
+    c.p0 = t2.p0;
+    c.p1 = t2.p1;
+    c.p2 = t2.p2;
+    c.live = live;
+    c.lane0 = lane == 0;
+    c.peaks = peaks;
+    c.out = sbase + plan.smem_ctile_off + (t2.col_offset * kTile + lane) * 4;
+    c.colmax = cm_base + t2.col_offset * 4;
+    const bool u0 = s0.dtype == CATB200_U8;
+    c.x0 = ibase + s0.smem_off + row * (s0.row_len * (u0 ? 1 : 4));
+    c.x1 = c.x0;
+    c.u1 = 0;
+    if (t2.src1 != 0xff) {
+      const catb200_source_t& s1 = plan.sources[t2.src1];
+      c.u1 = s1.dtype == CATB200_U8;
+      c.x1 = ibase + s1.smem_off + row * (s1.row_len * (c.u1 ? 1 : 4));
+    }
+    c.gate = 1.0f;  // command-dependent factor shared by all columns of the term
+    if (t2.src2 != 0xff) {
+      const catb200_source_t& sc = plan.sources[t2.src2];
+      const uint32_t a = ibase + sc.smem_off + row * (sc.row_len * 4);
+      if (op == CATB200_OP_ABSDIFF_MINUS_GATE_Y) {
+        c.gate = fabsf(lds_f32(a + 4)) < c.p1 ? 1.0f : 0.0f;  // constraints.py:46-53
+      } else {
+        const float cn = norm3(lds_f32(a), lds_f32(a + 4), lds_f32(a + 8));
+        c.gate = op == CATB200_OP_ABS_MINUS_GATE_STILL ? (cn < c.p1 ? 1.0f : 0.0f) : (cn > c.p1 ? 1.0f : 0.0f);
       }
+    }
+    switch (op) {
+      case CATB200_OP_GENERIC: generic_columns<MODE>(c, u0); break;
+      case CATB200_OP_ABS_MINUS: term_columns<CATB200_OP_ABS_MINUS, MODE>(c); break;
+      case CATB200_OP_ABSDIFF_MINUS: term_columns<CATB200_OP_ABSDIFF_MINUS, MODE>(c); break;
+      case CATB200_OP_ABSDIFF_MINUS_GATE_Y: term_columns<CATB200_OP_ABSDIFF_MINUS_GATE_Y, MODE>(c); break;
+      case CATB200_OP_ACTION_RATE: term_columns<CATB200_OP_ACTION_RATE, MODE>(c); break;
+      case CATB200_OP_COMPONENT_GT: term_columns<CATB200_OP_COMPONENT_GT, MODE>(c); break;
+      case CATB200_OP_CONTACT_ANY: term_columns<CATB200_OP_CONTACT_ANY, MODE>(c); break;
+      case CATB200_OP_NORM2_MINUS: term_columns<CATB200_OP_NORM2_MINUS, MODE>(c); break;
+      case CATB200_OP_AIR_TIME: term_columns<CATB200_OP_AIR_TIME, MODE>(c); break;
+      case CATB200_OP_N_CONTACT: term_columns<CATB200_OP_N_CONTACT, MODE>(c); break;
+      case CATB200_OP_FORCE_PEAK_MINUS: term_columns<CATB200_OP_FORCE_PEAK_MINUS, MODE>(c); break;
+      case CATB200_OP_LIMIT_MINUS: term_columns<CATB200_OP_LIMIT_MINUS, MODE>(c); break;
+      case CATB200_OP_ABS_MINUS_GATE_STILL: term_columns<CATB200_OP_ABS_MINUS_GATE_STILL, MODE>(c); break;
+      default: break;
+    }
+  }
+  }
+
+  if (MODE == kEvalRowMajor) {
+    // debug / stand-alone path: transpose the tile into the row-major [N][K] matrix (coalesced global writes)
+    __syncthreads();
+    for (int f = threadIdx.x; f < rows * K; f += n_threads) {
+      const int r = f / K, col = f - r * K;
+      out_rowmajor[(size_t)(tile0 + r) * K + col] = s_c[col * kTile + r];
+    }
+    __syncthreads();
+    continue;
+  }
+
+  // ---- phase C: the tile leaves as one bulk async store (generic-proxy writes fenced for the async proxy first).
+  //      Before that, the store issued two iterations ago out of this same image must have finished reading it --
+  //      thread 0 waited for that right after issuing the previous one (at most 1 group pending).
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  __syncthreads();  // also: every warp is done with this image's sources before the next iteration's prefetch
+  if (threadIdx.x == 0) {
+    float* dst = ws.c_t + (size_t)tile * K * kTile;
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst),
+                 "r"(sbase + plan.smem_ctile_off), "r"((uint32_t)(K * kTile * 4))
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");  // the other image's constraint tile is free again
+  }
+  // fold this tile's column maxima into the CTA's (the next tile overwrites s_tilemax only after its peak barrier)
+  for (int c = threadIdx.x; c < K; c += n_threads) s_colmax[c] = fmaxf(s_colmax[c], s_tilemax[c]);
+  }  // tiles
+  if (MODE == kEvalRowMajor) return;
+
+  // ---- the CTA folds its column maxima into the scratch rows, then the last CTA of the grid folds everything
+  //      into the Polyak running max (constraint_manager.py:55-61)
+  __syncthreads();
+  // n_groups scratch rows (power of two, chosen by the host: a few hundred CTAs per row keep the atomic queues short)
+  uint32_t* grow = ws.colmax + (blockIdx.x & (n_groups - 1)) * CATB200_MAX_COLS;
+  for (int c = threadIdx.x; c < K; c += n_threads) {
+    if ((int)blockIdx.x >= n_tiles) break;
+    const uint32_t key = float_to_ordered(s_colmax[c]);
+    // most CTAs cannot raise the maximum any more: a plain (L2) read first keeps the atomic units idle
+    if (key > __ldcg(grow + c)) atomicMax(grow + c, key);
+  }
+  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");  // smem read out before exit
+  if (last_block_ticket_grouped(ws.ticket, gridDim.x)) {
+    for (int col = threadIdx.x; col < K; col += n_threads) {
+      uint32_t key = 0u;
+      int gi = 0;
+      for (; gi + 4 <= n_groups; gi += 4) {  // 4 independent exchanges in flight
+        const uint32_t k0 = atomicExch(&ws.colmax[gi * CATB200_MAX_COLS + col], 0u);
+        const uint32_t k1 = atomicExch(&ws.colmax[(gi + 1) * CATB200_MAX_COLS + col], 0u);
+        const uint32_t k2 = atomicExch(&ws.colmax[(gi + 2) * CATB200_MAX_COLS + col], 0u);
+        const uint32_t k3 = atomicExch(&ws.colmax[(gi + 3) * CATB200_MAX_COLS + col], 0u);
+        key = max(max(key, max(k0, k1)), max(k2, k3));
+      }
+      for (; gi < n_groups; ++gi) key = max(key, atomicExch(&ws.colmax[gi * CATB200_MAX_COLS + col], 0u));
+      float cmax = fmaxf(ordered_to_float(key), prm.floor_max);
+      float rm;
+      if (rm_init[col]) {
+        rm = __fadd_rn(__fmul_rn(running_max[col], prm.tau), __fmul_rn(prm.one_minus_tau, cmax));
+      } else {
+        rm = cmax;
+        rm_init[col] = 1;
+      }
+      running_max[col] = rm;
     }
   }
 }
@@ -434,6 +499,7 @@ cat_apply_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = blockIdx.x * kTile + lane;
   const bool live = i < num_envs;
+  const float* ct = c_t + (size_t)blockIdx.x * plan.n_cols * kTile + lane;  // this env's column of the [K][32] tile
   float overall = -INFINITY;
   if (live) {
     for (int slot = warp; slot < plan.n_slots; slot += kEvalWarps) {
@@ -444,14 +510,14 @@ cat_apply_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_const
       float tmax = -INFINITY;
       int col = c0;
       for (; col + 4 <= c1; col += 4) {
-        const float v0 = __ldcs(c_t + (size_t)col * num_envs + i);
-        const float v1 = __ldcs(c_t + (size_t)(col + 1) * num_envs + i);
-        const float v2 = __ldcs(c_t + (size_t)(col + 2) * num_envs + i);
-        const float v3 = __ldcs(c_t + (size_t)(col + 3) * num_envs + i);
+        const float v0 = __ldcs(ct + col * kTile);
+        const float v1 = __ldcs(ct + (col + 1) * kTile);
+        const float v2 = __ldcs(ct + (col + 2) * kTile);
+        const float v3 = __ldcs(ct + (col + 3) * kTile);
         tmax = fmaxf(tmax, fmaxf(fmaxf(violation_prob(v0, s_rm[col], prm.min_p, span), violation_prob(v1, s_rm[col + 1], prm.min_p, span)),
                                  fmaxf(violation_prob(v2, s_rm[col + 2], prm.min_p, span), violation_prob(v3, s_rm[col + 3], prm.min_p, span))));
       }
-      for (; col < c1; ++col) tmax = fmaxf(tmax, violation_prob(__ldcs(c_t + (size_t)col * num_envs + i), s_rm[col], prm.min_p, span));
+      for (; col < c1; ++col) tmax = fmaxf(tmax, violation_prob(__ldcs(ct + col * kTile), s_rm[col], prm.min_p, span));
       episode_sums[k] = __fadd_rn(es, tmax > 0.0f ? 1.0f : 0.0f);  // :226
       mean_values[k] = __fadd_rn(mv, tmax);                          // :227
       overall = fmaxf(overall, tmax);
@@ -479,7 +545,7 @@ cat_probs_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_const
   for (int slot = 0; slot < plan.n_slots; ++slot) {
     const int c0 = plan.slot_col_begin[slot], c1 = plan.slot_col_begin[slot + 1];
     for (int col = c0; col < c1; ++col) {
-      const float c = c_t[(size_t)col * num_envs + i];
+      const float c = c_t[((size_t)(i / kTile) * plan.n_cols + col) * kTile + (i % kTile)];
       probs_out[(size_t)i * plan.n_cols + col] = violation_prob(c, running_max[col], prm.min_p, prm.span[slot]);
     }
   }
@@ -640,42 +706,67 @@ int catb200_cat_plan_finalize(catb200_plan_t* plan) {
     for (int k = 0; k < term.n_cols; ++k) plan->col_term[col + k] = (uint8_t)t;
     col += term.n_cols;
   }
+  // evaluation order: rank of every term by descending cost (prologue ~ 6 columns' worth; IEEE division doubles a
+  // column).  The kernel deals the ranks to its warps in snake order, which balances them for any warp count.
+  for (int t = 0; t < plan->n_terms; ++t) {
+    auto cost = [&](int i) {
+      const catb200_term_t& x = plan->terms[i];
+      return 6 + (int)x.n_cols * (x.op == CATB200_OP_ACTION_RATE ? 2 : 1);
+    };
+    int rank = 0;
+    for (int u = 0; u < plan->n_terms; ++u)
+      if (cost(u) > cost(t) || (cost(u) == cost(t) && u < t)) ++rank;
+    plan->terms[rank].reserved2 = (uint16_t)t;  // entry k holds the index of the term with rank k
+  }
   plan->slot_col_begin[slots] = (uint16_t)col;
   plan->n_cols = col;
   plan->n_slots = slots;
   plan->smem_peak_off = off;
   off += plan->n_peaks * kTile * 4;
-  off = (off + 15) & ~15;
-  plan->smem_bar_off = off;
-  off += 16;
+  off = (off + 127) & ~127;
+  plan->smem_ctile_off = off;  // [n_cols][32] fp32 constraint tile, source of the bulk async store
+  off += plan->n_cols * kTile * 4;
   plan->smem_bytes = off;
-  if (2 * plan->smem_bar_off > 200 * 1024) return CATB200_ERR_UNSUPPORTED;  // two staging buffers must fit
+  if (2 * plan->smem_bytes > 200 * 1024) return CATB200_ERR_UNSUPPORTED;  // two tile images must fit a CTA
   return CATB200_OK;
 }
 
 size_t catb200_cat_workspace_bytes(int32_t num_envs, int32_t n_cols) {
   if (num_envs < 0 || n_cols < 0) return 0;
-  return 256 + align256(sizeof(uint32_t) * CATB200_MAX_COLS * kMaxGroups) + align256(sizeof(float) * (size_t)num_envs * n_cols);
+  const size_t n_tiles = ((size_t)num_envs + kTile - 1) / kTile;  // C_T is tile-major: whole tiles
+  return 256 + align256(sizeof(uint32_t) * CATB200_MAX_COLS * kMaxGroups) + align256(sizeof(float) * n_tiles * kTile * n_cols);
+}
+
+// warps sharing one 32-env tile (terms are dealt to them).  CATB200_EVAL_WARPS overrides.
+static int eval_warps(int n_tiles) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = std::getenv("CATB200_EVAL_WARPS");
+    const int v = e ? std::atoi(e) : 0;
+    forced = (v == 1 || v == 2 || v == 4 || v == 8) ? v : 0;
+  }
+  (void)n_tiles;
+  return forced ? forced : 8;
 }
 
 static int launch_eval(const catb200_plan_t* plan, const catb200_cat_params_t* prm, int num_envs, float* running_max,
                        int* rm_init, CatWorkspace ws, float* out_rowmajor, int mode, cudaStream_t stream) {
-  const size_t smem = 2 * (size_t)plan->smem_bar_off;  // two staging buffers (sources + peak table each)
+  const size_t smem = 2 * (size_t)plan->smem_bytes;  // two images of [source rows | peak table | constraint tile]
   const int n_tiles = (num_envs + kTile - 1) / kTile;
-  // persistent grid: as many CTAs as fit (shared memory / 2048 threads per SM), never more than tiles
-  // small N (about one tile per SM-resident CTA): 16 warps shorten the per-tile critical path; large N: 8 warps
-  // spend fewer instructions on per-warp term prologues (throughput bound there)
-  const int threads = n_tiles <= 4 * kNumSMs ? kEvalThreadsMax : kEvalThreads;
-  const int per_sm = (int)max((size_t)1, min((size_t)(2048 / threads), (size_t)(220 * 1024) / max(smem + 2048, (size_t)1)));
+  const int threads = 32 * eval_warps(n_tiles);
+  // persistent grid: as many CTAs as stay resident (shared memory, 2048 threads per SM), never more than tiles
+  const int per_sm = (int)max((size_t)1, min((size_t)(2048 / threads), (size_t)(227 * 1024) / (smem + 3 * 1024)));
   const int grid = min(n_tiles, kNumSMs * per_sm);
+  int n_groups = 1;  // scratch rows for the cross-CTA column maxima (power of two, <= kMaxGroups)
+  while (n_groups < kMaxGroups && n_groups * 256 <= grid) n_groups <<= 1;
   if (mode == kEvalStep) {
     if (smem > 48 * 1024)
       CATB200_CUDA_TRY(cudaFuncSetAttribute(cat_eval_kernel<kEvalStep>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cat_eval_kernel<kEvalStep><<<grid, threads, smem, stream>>>(*plan, *prm, num_envs, running_max, rm_init, ws, nullptr);
+    cat_eval_kernel<kEvalStep><<<grid, threads, smem, stream>>>(*plan, *prm, num_envs, n_groups, running_max, rm_init, ws, nullptr);
   } else {
     if (smem > 48 * 1024)
       CATB200_CUDA_TRY(cudaFuncSetAttribute(cat_eval_kernel<kEvalRowMajor>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cat_eval_kernel<kEvalRowMajor><<<grid, threads, smem, stream>>>(*plan, *prm, num_envs, nullptr, nullptr, ws, out_rowmajor);
+    cat_eval_kernel<kEvalRowMajor><<<grid, threads, smem, stream>>>(*plan, *prm, num_envs, n_groups, nullptr, nullptr, ws, out_rowmajor);
   }
   CATB200_LAUNCH_CHECK();
   return CATB200_OK;

@@ -95,17 +95,17 @@ typedef struct {
   uint8_t stat_slot; /* row of episode_sums / mean_values this term accumulates into        */
   uint8_t reserved;  /* must be 0 on entry to finalize (marks contact terms whose ids were remapped) */
   uint16_t col_offset; /* first column of this term in the [N,K] layout                     */
-  uint16_t reserved2;
+  uint16_t reserved2;  /* filled by finalize: entry k = index of the term with the k-th largest evaluation cost */
   float p0, p1, p2;
   uint8_t ids[CATB200_MAX_IDS];
 } catb200_term_t;
 
 typedef struct {
   int32_t n_sources, n_terms, n_cols, n_slots;
-  int32_t smem_bytes;    /* filled by finalize: shared memory per 32-env tile                */
+  int32_t smem_bytes;    /* filled by finalize: dynamic shared memory of one 32-env tile     */
   int32_t n_peaks;       /* filled by finalize: distinct (contact history, body) pairs       */
   int32_t smem_peak_off; /* filled by finalize                                               */
-  int32_t smem_bar_off;  /* filled by finalize                                               */
+  int32_t smem_ctile_off; /* filled by finalize: [n_cols][32] constraint tile inside the image */
   catb200_source_t sources[CATB200_MAX_SOURCES];
   catb200_term_t terms[CATB200_MAX_TERMS];
   uint8_t col_term[CATB200_MAX_COLS];               /* filled by finalize: term of each column        */
@@ -215,6 +215,27 @@ int catb200_gae(const float* rewards, const float* values, const float* dones, c
                 const float* next_value, int32_t T, int32_t num_envs, float gamma, float gamma_lambda,
                 float* advantages, float* returns, float* value_rms, float* norm_stats, void* workspace,
                 size_t workspace_bytes, void* stream);
+
+/*
+ * GAE for the trainers that keep a single float `dones` buffer.  rewards, values: [T, N]
+ * time-major; last_values: [N]; writes advantages, returns: [T, N].
+ *   CATB200_GAE_RLGAMES  rl_games' A2CBase.discount_values as CaTA2CAgent.play_steps calls it
+ *                        (U/rl_games/cat_common.py:96-103) on the float32 dones of CaTExperienceBuffer
+ *                        (U/rl_games/cat_experience.py:27-33): dones [T, N] holds the flag observed BEFORE each
+ *                        step, last_dones [N] the one after the last step; coef = fl32(gamma * tau), the product
+ *                        taken in double.
+ *   CATB200_GAE_SKRL     compute_gae of the CaT skrl agent (U/skrl/ppo.py:397-442, `not_dones = 1 - dones`):
+ *                        dones [T, N] is the `terminated` memory tensor, last_dones unused (NULL);
+ *                        coef = fl32(lambda).  normalize != 0 also applies :440,
+ *                        advantages = (adv - mean) / (std + 1e-8) over all T*N entries (unbiased std).
+ * workspace (only read when normalize != 0): catb200_gae_float_dones_workspace_bytes() zero-initialised bytes.
+ */
+typedef enum { CATB200_GAE_RLGAMES = 0, CATB200_GAE_SKRL = 1 } catb200_gae_variant;
+size_t catb200_gae_float_dones_workspace_bytes(void);
+int catb200_gae_float_dones(int32_t variant, const float* rewards, const float* values, const float* dones,
+                            const float* last_dones, const float* last_values, int32_t T, int32_t num_envs,
+                            float gamma, float coef, float* advantages, float* returns, int32_t normalize,
+                            void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Actor-critic MLP + PPO-clip minibatch update  (rows a9, a10: U/cleanrl/ppo.py:71-123,294-354)

@@ -79,7 +79,7 @@ def test_plan_finalize_validates(lib):
     for k, v in enumerate([0, 5, 11]):
         t.ids[k] = v
     assert lib.catb200_cat_plan_finalize(plan) == 0
-    assert plan.n_cols == 3 and plan.n_slots == 1 and plan.smem_bytes == 32 * 12 * 4 + 16 and plan.n_peaks == 0
+    assert plan.n_cols == 3 and plan.n_slots == 1 and plan.smem_bytes == 32 * 12 * 4 + 3 * 32 * 4 and plan.n_peaks == 0
     assert list(plan.slot_col_begin[:2]) == [0, 3]
     t.ids[2] = 12  # out of the 12-wide row
     assert lib.catb200_cat_plan_finalize(plan) == -1
