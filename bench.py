@@ -104,8 +104,13 @@ def _host_fed_env_cls():
     from constraints_as_terminations_b200 import synthetic_env as se
 
     class HostFed(se.SyntheticSolo12Env):
-        """Same env, but every step's state arrives from pinned host memory (the e2e leg).  Two device staging
-        sets: while the kernels of step t read one, the H2D copy of step t+1 runs on a copy stream."""
+        """Same env, but every step's state arrives from pinned host memory (the e2e leg).  A ring of device staging
+        sets: the H2D copy of step t + depth - 1 runs on a copy stream while the kernels of step t read their set, so
+        the PCIe transfer (one packed cudaMemcpyAsync per env step) also proceeds during the update phase.  The
+        synthetic state does not depend on the actions, which is what makes reading ahead legitimate here; with a
+        real simulator the state is produced on the device and there is no such copy at all."""
+
+        DEPTH = 25  # staging sets: one rollout (24 env steps) of read-ahead, ~5 MB each at 4096 envs
 
         def __init__(self, num_envs, device, seed, pool, constraints_cfg):
             super().__init__(num_envs, device=device, seed=seed, pool=pool, constraints_cfg=constraints_cfg)
@@ -126,28 +131,31 @@ def _host_fed_env_cls():
                 for k, dst in views(buf).items():
                     dst.copy_(st[k].cpu())
                 self._host_pool.append(buf)
-            self._staging_buf = [torch.empty(off, dtype=torch.uint8, device=device) for _ in range(2)]
+            depth = self.DEPTH
+            self._staging_buf = [torch.empty(off, dtype=torch.uint8, device=device) for _ in range(depth)]
             self._staging = [views(b) for b in self._staging_buf]
-            self._pool = None  # nothing stays resident on the device except the two staging sets
+            self._pool = None  # nothing stays resident on the device except the staging ring
             self.h2d_bytes = sum(n for _, n, _, _ in layout.values())
             self._copy_stream = torch.cuda.Stream(device=device)
-            self._ready = [torch.cuda.Event(), torch.cuda.Event()]
-            self._consumed = [torch.cuda.Event(), torch.cuda.Event()]
-            self._slot = 0
-            self._cursor = 0
-            self._prefetch(0, self._cursor)
+            self._ready = [torch.cuda.Event() for _ in range(depth)]
+            self._consumed = [torch.cuda.Event() for _ in range(depth)]
+            self._step = 0  # env steps taken so far; step k reads staging set k % depth and host state k % pool
+            for k in range(depth - 1):  # fill the ring: steps 0 .. depth-2
+                self._prefetch(k)
             self._take(0)
 
-        def _prefetch(self, slot, cursor):
-            """Enqueue the H2D copy of host state `cursor` into staging set `slot` on the copy stream."""
+        def _prefetch(self, k):
+            """Enqueue the H2D copy of step k's host state into its staging set on the copy stream."""
+            slot = k % self.DEPTH
             main = torch.cuda.current_stream()
-            self._consumed[slot].record(main)  # the copy must not overwrite data kernels still read
+            self._consumed[slot].record(main)  # the copy must not overwrite data that enqueued kernels still read
             with torch.cuda.stream(self._copy_stream):
                 self._copy_stream.wait_event(self._consumed[slot])
-                self._staging_buf[slot].copy_(self._host_pool[cursor], non_blocking=True)
+                self._staging_buf[slot].copy_(self._host_pool[k % len(self._host_pool)], non_blocking=True)
                 self._ready[slot].record(self._copy_stream)
 
-        def _take(self, slot):
+        def _take(self, k):
+            slot = k % self.DEPTH
             torch.cuda.current_stream().wait_event(self._ready[slot])
             self.load_state(self._staging[slot])
 
@@ -155,16 +163,11 @@ def _host_fed_env_cls():
             return self.obs_buf, {}
 
         def _advance(self):
-            # state for this step was prefetched into the other set during the previous step
-            nxt = self._slot ^ 1
-            if not getattr(self, "_primed", False):
-                self._cursor = (self._cursor + 1) % len(self._host_pool)
-                self._prefetch(nxt, self._cursor)
-                self._primed = True
-            self._take(nxt)
-            self._slot = nxt
-            self._cursor = (self._cursor + 1) % len(self._host_pool)
-            self._prefetch(nxt ^ 1, self._cursor)  # next step's state, overlapped with this step's kernels
+            # the set read by the step before the one that just ended is certainly free once the kernels enqueued so
+            # far have run: refill it with the state of step k + depth - 1, then switch to this step's set
+            self._prefetch(self._step + self.DEPTH - 1)
+            self._step += 1
+            self._take(self._step)
 
     return HostFed
 
@@ -238,7 +241,7 @@ _MAC_DGRAD = 2 * (256 * 128 + 512 * 256)
 
 def _traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r1b_traffic.json")
     return json.load(open(path)) if os.path.isfile(path) else {}
 
 
@@ -250,6 +253,8 @@ def dominant_kernel_roofline(prof, total_us, trainer, peaks):
         "tc_gemm_kernel<0, 128>": 2.0 * _MAC_FWD * (opt_rows + n * (T + 1)),  # update forward + rollout policy + bootstrap
         "tc_gemm_kernel<1, 128>": 2.0 * _MAC_DGRAD * opt_rows,
     }
+    if not prof:  # no CUPTI records (e.g. the process itself runs under ncu, which owns the profiling interface)
+        return {"kernel": None, "note": "kernel shares unavailable: CUPTI produced no records in this process"}
     name, row = next(iter(prof.items()))
     out = {"kernel": name, "share_of_step": row["share"], "us_per_step": row["us"], "launches_per_step": row["launches"]}
     if name in flops:
@@ -315,7 +320,7 @@ def kernel_rooflines(device, num_envs, peaks):
     out[f"ppo_minibatch_step@{mb}"] = {"bound": "tensor", "achieved": flops / sec / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": flops / sec / 1e12 / peaks["bf16_tflops"], "us": sec * 1e6, "flops": flops, "launches": 14}
     del env, tr
     # DRAM traffic per launch from the committed `ncu --set full` captures (profiles/), where available
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r1b_traffic.json")
     if os.path.isfile(tpath):
         for k, v in json.load(open(tpath)).items():
             if k in out:
@@ -373,7 +378,7 @@ def run_ours(args):
         roof = kernel_rooflines(device, N, peaks)
         cpu = cpu_baseline(N, sample_steps=4, sample_minibatches=2)
         main = dominant
-        main["note"] = ("dominant kernel of the step by device time (torch.profiler/CUPTI over 2 iterations of the timed workload); "
+        main["note"] = main.get("note") or ("dominant kernel of the step by device time (torch.profiler/CUPTI over 2 iterations of the timed workload); "
                         "HBM-bound kernels (GAE, CaT) timed alone with CUDA events are in `rooflines`")
         gae_main = roof[f"gae@{N}"]
         gae_main["note"] = f"{gae_main['bytes']/1e6:.2f} MB per launch: launch-latency bound at {N} envs; see the 65536 / 1M-env entries"

@@ -42,9 +42,8 @@ bool pdl_enabled() {
 }
 
 constexpr int kTile = 32;          // envs per CTA in the eval and apply kernels (one per lane)
-constexpr int kEvalMaxWarps = 8;   // eval kernel: 1, 2, 4 or 8 warps share a tile (chosen per launch)
-constexpr int kEvalWarps = 8;      // warps per CTA of the apply kernel
-constexpr int kEvalThreads = kEvalWarps * 32;
+constexpr int kEvalMaxWarps = 16;  // eval kernel: 1, 2, 4, 8 or 16 warps share a tile (chosen per launch)
+constexpr int kApplyMaxWarps = 16; // apply kernel: one warp per statistics slot, at most 16 (chosen per launch)
 constexpr int kApplyThreads = 64;
 
 // sqrt(x^2 + y^2 + z^2) the way torch.norm reduces a short contiguous dim on CPU and CUDA:
@@ -483,9 +482,9 @@ __device__ __forceinline__ float violation_prob(float c, float rm, float min_p, 
   return __fadd_rn(min_p, __fmul_rn(x, span));
 }
 
-// One CTA per 32 envs (lane = env); the 4 warps split the statistics slots (terms) so that the dependent
+// One CTA per 32 envs (lane = env); the warps split the statistics slots (terms) so that the dependent
 // load chains are 4x shorter and 4x more loads are in flight than with one thread per env.
-__global__ void __launch_bounds__(kEvalThreads)
+__global__ void __launch_bounds__(kApplyMaxWarps * 32)
 cat_apply_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_constant__ catb200_cat_params_t prm,
                  int num_envs, const float* __restrict__ running_max, const float* __restrict__ c_t,
                  float* __restrict__ episode_sums, float* __restrict__ mean_values,
@@ -493,8 +492,9 @@ cat_apply_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_const
                  const uint8_t* __restrict__ reset_buf, float* __restrict__ reward_out,
                  float* __restrict__ dones_out) {
   __shared__ float s_rm[CATB200_MAX_COLS];
-  __shared__ float s_part[kEvalWarps][kTile];
-  for (int c = threadIdx.x; c < plan.n_cols; c += kEvalThreads) s_rm[c] = running_max[c];
+  __shared__ float s_part[kApplyMaxWarps][kTile];
+  const int n_warps = blockDim.x >> 5;
+  for (int c = threadIdx.x; c < plan.n_cols; c += blockDim.x) s_rm[c] = running_max[c];
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = blockIdx.x * kTile + lane;
@@ -502,7 +502,7 @@ cat_apply_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_const
   const float* ct = c_t + (size_t)blockIdx.x * plan.n_cols * kTile + lane;  // this env's column of the [K][32] tile
   float overall = -INFINITY;
   if (live) {
-    for (int slot = warp; slot < plan.n_slots; slot += kEvalWarps) {
+    for (int slot = warp; slot < plan.n_slots; slot += n_warps) {
       const int c0 = plan.slot_col_begin[slot], c1 = plan.slot_col_begin[slot + 1];
       const float span = prm.span[slot];
       const size_t k = (size_t)slot * num_envs + i;
@@ -526,8 +526,7 @@ cat_apply_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_const
   s_part[warp][lane] = overall;
   __syncthreads();
   if (warp != 0 || !live) return;
-#pragma unroll
-  for (int w = 1; w < kEvalWarps; ++w) overall = fmaxf(overall, s_part[w][lane]);
+  for (int w = 1; w < n_warps; ++w) overall = fmaxf(overall, s_part[w][lane]);
   cstr_prob[i] = overall;
   if (raw_reward != nullptr) {
     // cat_env.py:102-107: reward = clip(reward * (1 - p), min=0); dones = p; :121 dones[reset] = 1
@@ -738,22 +737,38 @@ size_t catb200_cat_workspace_bytes(int32_t num_envs, int32_t n_cols) {
 }
 
 // warps sharing one 32-env tile (terms are dealt to them).  CATB200_EVAL_WARPS overrides.
-static int eval_warps(int n_tiles) {
+static int eval_warps(int n_terms) {
   static int forced = -1;
   if (forced < 0) {
     const char* e = std::getenv("CATB200_EVAL_WARPS");
     const int v = e ? std::atoi(e) : 0;
-    forced = (v == 1 || v == 2 || v == 4 || v == 8) ? v : 0;
+    forced = (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) ? v : 0;
   }
-  (void)n_tiles;
-  return forced ? forced : 8;
+  if (forced) return forced;
+  int g = 1;  // a term is evaluated by one warp: no point in more warps than terms (measured: 16 >= 8 > 4 at every size)
+  while (g < kEvalMaxWarps && g < n_terms) g <<= 1;
+  return g;
+}
+
+// apply kernel: one warp per statistics slot up to 16 (CATB200_APPLY_WARPS overrides)
+static int apply_warps(int n_slots, int n_tiles) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = std::getenv("CATB200_APPLY_WARPS");
+    const int v = e ? std::atoi(e) : 0;
+    forced = (v >= 1 && v <= kApplyMaxWarps) ? v : 0;
+  }
+  if (forced) return forced;
+  // few tiles: the launch is one latency chain per CTA, a warp per slot shortens it (4.6 vs 6.4 us at 4096 envs);
+  // many tiles: 8 warps keep more CTAs resident and move more bytes (248 vs 314 us at 1 M envs)
+  return n_tiles <= 2 * kNumSMs ? max(1, min(kApplyMaxWarps, n_slots)) : max(1, min(8, n_slots));
 }
 
 static int launch_eval(const catb200_plan_t* plan, const catb200_cat_params_t* prm, int num_envs, float* running_max,
                        int* rm_init, CatWorkspace ws, float* out_rowmajor, int mode, cudaStream_t stream) {
   const size_t smem = 2 * (size_t)plan->smem_bytes;  // two images of [source rows | peak table | constraint tile]
   const int n_tiles = (num_envs + kTile - 1) / kTile;
-  const int threads = 32 * eval_warps(n_tiles);
+  const int threads = 32 * eval_warps(plan->n_terms);
   // persistent grid: as many CTAs as stay resident (shared memory, 2048 threads per SM), never more than tiles
   const int per_sm = (int)max((size_t)1, min((size_t)(2048 / threads), (size_t)(227 * 1024) / (smem + 3 * 1024)));
   const int grid = min(n_tiles, kNumSMs * per_sm);
@@ -787,7 +802,7 @@ int catb200_cat_step(const catb200_plan_t* plan, const catb200_cat_params_t* par
   int rc = launch_eval(plan, params, num_envs, running_max, rm_init, ws, nullptr, kEvalStep, st);
   if (rc != CATB200_OK) return rc;
   const int grid = (num_envs + kTile - 1) / kTile;
-  cat_apply_kernel<<<grid, kEvalThreads, 0, st>>>(*plan, *params, num_envs, running_max, ws.c_t, episode_sums,
+  cat_apply_kernel<<<grid, 32 * apply_warps(plan->n_slots, grid), 0, st>>>(*plan, *params, num_envs, running_max, ws.c_t, episode_sums,
                                                    mean_values, cstr_prob, raw_reward, reset_buf, reward_out,
                                                    dones_out);
   CATB200_LAUNCH_CHECK();

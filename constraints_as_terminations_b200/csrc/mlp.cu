@@ -35,13 +35,15 @@ static bool use_tc() {
 }
 
 // fused three-layer forward kernel (tc_fwd3.cu) instead of three tc_gemm launches: CATB200_FUSED_FWD=1
-static bool use_fused_fwd() {
-  static int v = -1;
+static bool use_fused_fwd(int rows) {
+  static int v = -1;  // row limit: 0 = never, INT_MAX = always ("1"), "r<N>" = only for at most N rows (rollout-sized launches)
   if (v < 0) {
     const char* e = std::getenv("CATB200_FUSED_FWD");
-    v = (e && e[0] == '1') ? 1 : 0;
+    v = 0;
+    if (e && e[0] == '1') v = 0x7fffffff;
+    if (e && e[0] == 'r') v = std::atoi(e + 1);
   }
-  return v == 1;
+  return rows <= v;
 }
 
 constexpr int kGemmThreads = 256;
@@ -850,7 +852,7 @@ static int launch_forward(const catb200_mlp_dims_t* d, const catb200_mlp_layout_
     CATB200_CUDA_TRY(cudaFuncSetAttribute(gemm_nt_kernel<kEpiMulDelu>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemNT));
     attr_set = true;
   }
-  if (use_tc() && use_fused_fwd() && d->obs_pad == 64 && d->h1 <= 512 && d->h2 <= 256 && d->h3 == 128) {
+  if (use_tc() && use_fused_fwd(rows) && d->obs_pad == 64 && d->h1 <= 512 && d->h2 <= 256 && d->h3 == 128) {
     Fwd3Args f = {};
     for (int z = 0; z < 2; ++z) {
       int rc = make_tmap_bf16(&f.mapX[z], X, 64, rows, 64, 64, 128);

@@ -264,3 +264,55 @@ def adam_step(dims, params, grads, exp_avg, exp_avg_sq, w16, lr_dev, step_dev, o
         ),
         "adam_step",
     )  # fmt: skip
+
+
+# --------------------------------------------------------------------------------------------------
+# single-`dones` GAE of the rl_games / skrl front-ends  (reference rl_games/cat_common.py:96-104,
+# skrl/ppo.py:397-442)
+# --------------------------------------------------------------------------------------------------
+def gae_float_dones(
+    variant: int,
+    rewards: torch.Tensor,
+    values: torch.Tensor,
+    dones: torch.Tensor,
+    last_values: torch.Tensor,
+    gamma: float,
+    coef: float,
+    last_dones: torch.Tensor | None = None,
+    normalize: bool = False,
+    advantages: torch.Tensor | None = None,
+    returns: torch.Tensor | None = None,
+    workspace: Workspace | None = None,
+):
+    """rewards / values / dones: [T, N] (trailing singleton dims allowed), last_values / last_dones: [N].
+    `variant` is L.GAE_RLGAMES (coef = gamma * tau, dones observed before each step, `last_dones` after the
+    last one) or L.GAE_SKRL (coef = lambda, dones = `terminated` of each step, optional global advantage
+    normalisation).  Returns (advantages, returns) shaped like `rewards`."""
+    shape = rewards.shape
+    T = shape[0]
+    N = rewards.numel() // max(T, 1)
+    for t, name in ((rewards, "rewards"), (values, "values"), (dones, "dones"), (last_values, "last_values")):
+        _f32c(t, name)
+    if values.numel() != T * N or dones.numel() != T * N or last_values.numel() != N:
+        raise ValueError("gae_float_dones: rewards / values / dones must hold T*N entries and last_values N")
+    if variant == L.GAE_RLGAMES:
+        if last_dones is None:
+            raise ValueError("gae_float_dones: the rl_games variant needs last_dones")
+        _f32c(last_dones, "last_dones")
+        if last_dones.numel() != N:
+            raise ValueError("gae_float_dones: last_dones must hold N entries")
+    advantages = torch.empty_like(rewards) if advantages is None else _f32c(advantages, "advantages")
+    returns = torch.empty_like(rewards) if returns is None else _f32c(returns, "returns")
+    lib = L.load()
+    ws_ptr, ws_bytes = None, 0
+    if normalize:
+        ws = (workspace or Workspace(rewards.device)).get(lib.catb200_gae_float_dones_workspace_bytes())
+        ws_ptr, ws_bytes = ws.data_ptr(), ws.numel() * 8
+    L.check(
+        lib.catb200_gae_float_dones(
+            variant, rewards.data_ptr(), values.data_ptr(), dones.data_ptr(), L.ptr(last_dones), last_values.data_ptr(),
+            T, N, gamma, coef, advantages.data_ptr(), returns.data_ptr(), 1 if normalize else 0, ws_ptr, ws_bytes, L.stream(),
+        ),
+        "gae_float_dones",
+    )  # fmt: skip
+    return advantages, returns

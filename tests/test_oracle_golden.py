@@ -142,3 +142,41 @@ def test_rollout_action_oracle_matches_reference(golden_dir):
         logp, _, value = agent.evaluate(g["obs"][0], g["actions"][0])
     torch.testing.assert_close(logp, g["logprobs"][0], rtol=1e-6, atol=1e-6)
     torch.testing.assert_close(value.flatten(), g["values"][0], rtol=1e-6, atol=1e-6)
+
+
+def test_gae_variant_oracles_match_golden(golden_dir):
+    """skrl compute_gae restatement vs outputs of the reference's own function (bit-exact raw, 1e-6 normalised);
+    rl_games discount_values restatement: regression vs the stored vectors and cross-check against the pinned
+    CleanRL GAE, to which it reduces when nothing times out."""
+    from oracle import gae_variants_oracle as go
+
+    golden = _load(golden_dir, "gae_variants.pt")
+    assert golden["skrl_pinned"] and not golden["rlgames_pinned"]
+    for case in golden["cases"]:
+        T, N, seed = case["T"], case["N"], case["seed"]
+        rewards, values, dones, last_values = go.sample_inputs(T, N, seed)
+        ret, adv = go.skrl_compute_gae(rewards, dones[:T], values, last_values)
+        assert torch.equal(ret, case["skrl_returns"])
+        if T * N > 1:
+            torch.testing.assert_close(adv, case["skrl_advantages"], rtol=1e-6, atol=1e-6)
+        rg = go.rlgames_discount_values(dones[T], last_values.unsqueeze(-1), dones[:T], values.unsqueeze(-1), rewards.unsqueeze(-1))
+        assert torch.equal(rg.squeeze(-1), case["rlgames_advs"])
+        zeros = torch.zeros(T, N)
+        adv_c, _ = ppo_oracle.gae(rewards, values, dones[:T], zeros, last_values, dones[T], torch.zeros(N))
+        assert torch.equal(rg.squeeze(-1), adv_c)
+
+
+def test_skrl_oracle_matches_reference_source():
+    """When /root/reference is present (build container), run the reference's own compute_gae next to the oracle."""
+    from oracle import gae_variants_oracle as go
+    from oracle import make_golden_gae, ref_loader
+
+    if not os.path.isfile(make_golden_gae.SKRL_PPO):
+        pytest.skip("reference tree absent (GPU box)")
+    assert ref_loader.reference_available()
+    ref_gae = make_golden_gae.load_reference_skrl_compute_gae()
+    rewards, values, dones, last_values = go.sample_inputs(24, 96, 11)
+    args = (rewards.unsqueeze(-1), dones[:24].unsqueeze(-1), values.unsqueeze(-1), last_values.unsqueeze(-1))
+    ret, adv = ref_gae(*args, 0.99, 0.95)
+    o_ret, o_adv = go.skrl_compute_gae(*args)
+    assert torch.equal(ret, o_ret) and torch.equal(adv, o_adv)
