@@ -104,18 +104,19 @@ def _host_fed_env_cls():
     from constraints_as_terminations_b200 import synthetic_env as se
 
     class HostFed(se.SyntheticSolo12Env):
-        """Same env, but every step's state arrives from pinned host memory (the e2e leg).  A ring of device staging
-        sets: the H2D copy of step t + depth - 1 runs on a copy stream while the kernels of step t read their set, so
-        the PCIe transfer (one packed cudaMemcpyAsync per env step) also proceeds during the update phase.  The
-        synthetic state does not depend on the actions, which is what makes reading ahead legitimate here; with a
-        real simulator the state is produced on the device and there is no such copy at all."""
+        """Same env, but every step's state arrives from pinned host memory (the e2e leg).  The states of one rollout
+        (24 env steps) sit back to back in one pinned buffer and move with ONE cudaMemcpyAsync per iteration on a copy
+        stream into one of two device staging sets: while the kernels of iteration i read set i & 1, the copy for
+        iteration i + 1 fills the other set.  Every step's inputs therefore cross PCIe inside the timed region, but the
+        per-step host cost is a pointer swap.  The synthetic state does not depend on the actions, which is what makes
+        reading ahead legitimate here; with a real simulator the state is produced on the device and there is no such
+        copy at all."""
 
-        DEPTH = 25  # staging sets: one rollout (24 env steps) of read-ahead, ~5 MB each at 4096 envs
+        STEPS = 24  # env steps per staging set = one rollout
 
         def __init__(self, num_envs, device, seed, pool, constraints_cfg):
             super().__init__(num_envs, device=device, seed=seed, pool=pool, constraints_cfg=constraints_cfg)
-            # one packed pinned buffer per host state and one packed staging buffer per device set, so that a
-            # step's state moves with a single cudaMemcpyAsync; the state tensors are views into the buffers
+            # packed layout of one state: the state tensors are views into the packed buffers
             layout, off = {}, 0
             for k, v in self._pool[0].items():
                 layout[k] = (off, v.numel() * v.element_size(), v.dtype, tuple(v.shape))
@@ -125,49 +126,44 @@ def _host_fed_env_cls():
             def views(buf):
                 return {k: buf[o : o + n].view(dt).view(shape) for k, (o, n, dt, shape) in layout.items()}
 
-            self._host_pool = []
-            for st in self._pool:
-                buf = torch.empty(off, dtype=torch.uint8).pin_memory()
-                for k, dst in views(buf).items():
-                    dst.copy_(st[k].cpu())
-                self._host_pool.append(buf)
-            depth = self.DEPTH
-            self._staging_buf = [torch.empty(off, dtype=torch.uint8, device=device) for _ in range(depth)]
-            self._staging = [views(b) for b in self._staging_buf]
-            self._pool = None  # nothing stays resident on the device except the staging ring
+            steps = self.STEPS
+            self._host = torch.empty((steps, off), dtype=torch.uint8).pin_memory()  # state of rollout step k at row k
+            for k in range(steps):
+                st = self._pool[(k + 1) % len(self._pool)]  # step k of a rollout follows the pool like the resident env
+                for name, dst in views(self._host[k]).items():
+                    dst.copy_(st[name].cpu())
+            first = {name: v.clone() for name, v in self._pool[0].items()}  # the state reset() exposes
+            self._staging_buf = [torch.empty((steps, off), dtype=torch.uint8, device=device) for _ in range(2)]
+            self._staging = [[views(b[k]) for k in range(steps)] for b in self._staging_buf]
+            self._pool = None  # nothing stays resident on the device except the two staging sets
             self.h2d_bytes = sum(n for _, n, _, _ in layout.values())
             self._copy_stream = torch.cuda.Stream(device=device)
-            self._ready = [torch.cuda.Event() for _ in range(depth)]
-            self._consumed = [torch.cuda.Event() for _ in range(depth)]
-            self._step = 0  # env steps taken so far; step k reads staging set k % depth and host state k % pool
-            for k in range(depth - 1):  # fill the ring: steps 0 .. depth-2
-                self._prefetch(k)
-            self._take(0)
+            self._ready = [torch.cuda.Event(), torch.cuda.Event()]
+            self._consumed = [torch.cuda.Event(), torch.cuda.Event()]
+            self._count = 0  # env steps taken so far
+            self.load_state(first)
+            self._prefetch(0)
 
-        def _prefetch(self, k):
-            """Enqueue the H2D copy of step k's host state into its staging set on the copy stream."""
-            slot = k % self.DEPTH
+        def _prefetch(self, buf):
+            """Enqueue the H2D copy of one rollout's states into staging set `buf` on the copy stream."""
             main = torch.cuda.current_stream()
-            self._consumed[slot].record(main)  # the copy must not overwrite data that enqueued kernels still read
+            self._consumed[buf].record(main)  # the copy must not overwrite data that enqueued kernels still read
             with torch.cuda.stream(self._copy_stream):
-                self._copy_stream.wait_event(self._consumed[slot])
-                self._staging_buf[slot].copy_(self._host_pool[k % len(self._host_pool)], non_blocking=True)
-                self._ready[slot].record(self._copy_stream)
-
-        def _take(self, k):
-            slot = k % self.DEPTH
-            torch.cuda.current_stream().wait_event(self._ready[slot])
-            self.load_state(self._staging[slot])
+                self._copy_stream.wait_event(self._consumed[buf])
+                self._staging_buf[buf].copy_(self._host, non_blocking=True)
+                self._ready[buf].record(self._copy_stream)
 
         def reset(self):
             return self.obs_buf, {}
 
         def _advance(self):
-            # the set read by the step before the one that just ended is certainly free once the kernels enqueued so
-            # far have run: refill it with the state of step k + depth - 1, then switch to this step's set
-            self._prefetch(self._step + self.DEPTH - 1)
-            self._step += 1
-            self._take(self._step)
+            it, k = divmod(self._count, self.STEPS)
+            buf = it & 1
+            if k == 0:  # first step of a rollout: its states were requested one iteration ago; request the next ones
+                torch.cuda.current_stream().wait_event(self._ready[buf])
+                self._prefetch(buf ^ 1)
+            self.load_state(self._staging[buf][k])
+            self._count += 1
 
     return HostFed
 

@@ -201,6 +201,10 @@ SIGNATURES = {
         C.c_int,
         [C.POINTER(Plan), C.POINTER(CatParams), _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P],
     ),
+    "catb200_cat_step_reset": (
+        C.c_int,
+        [C.POINTER(Plan), C.POINTER(CatParams), _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P, _P, _P, _SZ, _P],
+    ),
     "catb200_cat_eval_terms": (C.c_int, [C.POINTER(Plan), _I32, _P, _P]),
     "catb200_cat_probs": (C.c_int, [C.POINTER(Plan), C.POINTER(CatParams), _I32, _P, _P, _P, _P]),
     "catb200_cat_reset_workspace_bytes": (_SZ, []),

@@ -59,22 +59,36 @@ class _BuiltPlan:
         self.keys: list[str] = []
         self.live: list = []  # tensors currently referenced by plan.sources[i].ptr
         self.raw: list = []  # the objects the fetchers returned (identity check for the fast path)
+        self.cache: list = []  # per source: id(tensor) -> (tensor, data_ptr, row_stride) of tensors already checked
         self.n_cols = 0
         self.term_cols: list[tuple[int, int]] = []  # per slot: (col_begin, col_end)
 
     def refresh(self, env) -> None:
+        """Re-point the plan at the tensors the env exposes this step.  Simulators hand out the same buffer objects
+        every step (pointer compare only); envs that rotate between a few state sets (the synthetic one, a host-fed
+        staging ring) hit a small per-source cache of already normalised tensors, so the full layout check runs only
+        the first time a tensor object is seen."""
         srcs = self.plan.sources
         for i, fetch in enumerate(self.fetchers):
             t = fetch(env)
-            if t is self.raw[i] and t.data_ptr() == srcs[i].ptr:
+            ptr = t.data_ptr()
+            if t is self.raw[i] and ptr == srcs[i].ptr:
                 continue
+            hit = self.cache[i].get(id(t))
+            if hit is not None and hit[0] is t and hit[1] == ptr:
+                row_stride = hit[2]
+                nt = t
+            else:
+                nt, row_len, row_stride, dtype, _ = _as_source_tensor(t, self.keys[i])
+                if row_len != srcs[i].row_len or dtype != srcs[i].dtype:
+                    raise RuntimeError(
+                        f"source '{self.keys[i]}' changed layout (row_len {srcs[i].row_len}->{row_len}, "
+                        f"dtype {srcs[i].dtype}->{dtype}); rebuild the manager"
+                    )
+                # only tensors used in place are remembered: a converted copy would go stale
+                if nt.data_ptr() == ptr and len(self.cache[i]) < 64:
+                    self.cache[i][id(t)] = (t, ptr, row_stride)
             self.raw[i] = t
-            nt, row_len, row_stride, dtype, _ = _as_source_tensor(t, self.keys[i])
-            if row_len != srcs[i].row_len or dtype != srcs[i].dtype:
-                raise RuntimeError(
-                    f"source '{self.keys[i]}' changed layout (row_len {srcs[i].row_len}->{row_len}, "
-                    f"dtype {srcs[i].dtype}->{dtype}); rebuild the manager"
-                )
             self.live[i] = nt
             srcs[i].ptr = nt.data_ptr()
             srcs[i].row_stride = row_stride
@@ -111,6 +125,7 @@ def _build(env, term_specs) -> _BuiltPlan:
         built.keys.append(ref.key)
         built.live.append(t)
         built.raw.append(raw)
+        built.cache.append({})
         return i
 
     n_terms = 0
@@ -149,6 +164,61 @@ def _build(env, term_specs) -> _BuiltPlan:
     bounds = list(plan.slot_col_begin[: plan.n_slots + 1])
     built.term_cols = [(bounds[s], bounds[s + 1]) for s in range(plan.n_slots)]
     return built
+
+
+class _LazyStats(dict):
+    """dict of 0-d statistics tensors that splits the packed `[2 * n_terms]` device vector only when somebody looks
+    (a training loop that does not log this step never pays for 26 tensor views)."""
+
+    def __init__(self, keys, packed):
+        super().__init__()
+        self._pending = (keys, packed)
+
+    def _fill(self):
+        if self._pending is not None:
+            keys, packed = self._pending
+            self._pending = None
+            super().update(zip(keys, packed.unbind(0)))
+
+    def __getitem__(self, k):
+        self._fill()
+        return super().__getitem__(k)
+
+    def __iter__(self):
+        self._fill()
+        return super().__iter__()
+
+    def __len__(self):
+        self._fill()
+        return super().__len__()
+
+    def __contains__(self, k):
+        self._fill()
+        return super().__contains__(k)
+
+    def keys(self):
+        self._fill()
+        return super().keys()
+
+    def values(self):
+        self._fill()
+        return super().values()
+
+    def items(self):
+        self._fill()
+        return super().items()
+
+    def get(self, k, default=None):
+        self._fill()
+        return super().get(k, default)
+
+    def __eq__(self, other):
+        self._fill()
+        return super().__eq__(other)
+
+    def __repr__(self):
+        self._fill()
+        return super().__repr__()
 
 
 def _generic_spec(name: str, value: torch.Tensor) -> TermSpec:
@@ -411,6 +481,7 @@ class ConstraintManager(ManagerBase):
         self._probs_cache = None
         self._raw_cache = None
         self._reset_ws = None
+        self._fused_out = None
 
     # -- reference API -----------------------------------------------------------------------------
     def __str__(self) -> str:
@@ -476,12 +547,17 @@ class ConstraintManager(ManagerBase):
         self._launch(None, None)
         return self._cstr_prob_buf
 
-    def compute_step(self, raw_reward: torch.Tensor, reset_buf: torch.Tensor | None):
+    def compute_step(self, raw_reward: torch.Tensor, reset_buf: torch.Tensor | None, fuse_reset: bool = False):
         """`compute()` fused with the reward / dones lines of `CaTEnv.step` (reference cat_env.py:100-107,118-121).
 
         Returns `(reward_buf, dones)`: reward = clip(raw_reward * (1 - cstr_prob), min=0) and
         dones = cstr_prob with 1.0 where `reset_buf` is set.  Both are manager-owned buffers that the
         next call overwrites.
+
+        `fuse_reset=True` additionally performs `reset(ids of the envs flagged in reset_buf)` inside the same two
+        launches (the order of `CaTEnv.step`: compute at cat_env.py:100, `constraint_manager.reset` at :181 via
+        `_reset_idx`), reading `env.episode_length_buf` before anybody zeroes it; `fused_reset_stats()` then returns
+        what `reset()` would have.
         """
         L.require_cuda(raw_reward, "raw_reward")
         if raw_reward.dtype != torch.float32 or not raw_reward.is_contiguous():
@@ -493,8 +569,17 @@ class ConstraintManager(ManagerBase):
                 reset_buf = (reset_buf != 0).view(torch.uint8)
             if not reset_buf.is_contiguous():
                 reset_buf = reset_buf.contiguous()
-        self._launch(raw_reward, reset_buf)
+        if fuse_reset and reset_buf is None:
+            raise ValueError("compute_step(fuse_reset=True) needs reset_buf")
+        self._launch(raw_reward, reset_buf, fuse_reset=fuse_reset)
         return self._reward_buf, self._dones_buf
+
+    def fused_reset_stats(self) -> dict[str, torch.Tensor]:
+        """Episode statistics gathered by the last `compute_step(..., fuse_reset=True)`: same keys / values as
+        `reset(env_ids)` for the envs that were flagged in its `reset_buf` (NaN if none was)."""
+        if self._fused_out is None:
+            raise RuntimeError("no compute_step(fuse_reset=True) has run yet")
+        return _LazyStats(self._stat_keys, self._fused_out)
 
     def reset(self, env_ids: Sequence[int] | None = None) -> dict[str, torch.Tensor]:
         """Episode statistics of the envs being reset, then clear them (reference :190-211)."""
@@ -587,7 +672,14 @@ class ConstraintManager(ManagerBase):
                 self._max_p_cache[i] = mp
                 self._params.span[i] = mp - min_p
 
-    def _launch(self, raw_reward, reset_buf):
+    def _episode_lengths(self) -> torch.Tensor:
+        ep_len = self._env.episode_length_buf
+        if ep_len.dtype != torch.int64 or not ep_len.is_contiguous():
+            ep_len = ep_len.to(torch.int64).contiguous()
+        L.require_cuda(ep_len, "episode_length_buf")
+        return ep_len
+
+    def _launch(self, raw_reward, reset_buf, fuse_reset=False):
         if not self._term_names:
             self._cstr_prob_buf = torch.tensor([], device=self._device)
             self._computed = False
@@ -595,6 +687,28 @@ class ConstraintManager(ManagerBase):
         self._ensure_plan()
         self._refresh_max_p()
         ws = self._workspace
+        if fuse_reset:
+            dev = self._device
+            if self._reset_ws is None:
+                self._reset_ws = L.zeros_workspace(L.load().catb200_cat_reset_workspace_bytes(), dev)
+            # a fresh output per call: the dict handed out by fused_reset_stats() may be kept by the caller (extras["log"])
+            self._fused_out = torch.empty(2 * len(self._term_names), dtype=torch.float, device=dev)
+            ep_len = self._episode_lengths()
+            L.check(
+                L.load().catb200_cat_step_reset(
+                    self._built.plan, self._params, self.num_envs,
+                    self._running_max.data_ptr(), self._rm_init.data_ptr(),
+                    self._stats[0].data_ptr(), self._stats[1].data_ptr(), self._cstr_prob_buf.data_ptr(),
+                    L.ptr(raw_reward), L.ptr(reset_buf), self._reward_buf.data_ptr(), self._dones_buf.data_ptr(),
+                    ws.data_ptr(), ws.numel() * 8, ep_len.data_ptr(), self._fused_out.data_ptr(),
+                    self._reset_ws.data_ptr(), self._reset_ws.numel() * 8, L.stream(),
+                ),
+                "cat_step_reset",
+            )  # fmt: skip
+            self._computed = True
+            self._probs_cache = None
+            self._raw_cache = None
+            return
         L.check(
             L.load().catb200_cat_step(
                 self._built.plan, self._params, self.num_envs,
@@ -628,10 +742,7 @@ class ConstraintManager(ManagerBase):
             mask_t = mask_t.contiguous()
         if self._reset_ws is None:
             self._reset_ws = L.zeros_workspace(L.load().catb200_cat_reset_workspace_bytes(), dev)
-        ep_len = self._env.episode_length_buf
-        if ep_len.dtype != torch.int64 or not ep_len.is_contiguous():
-            ep_len = ep_len.to(torch.int64).contiguous()
-        L.require_cuda(ep_len, "episode_length_buf")
+        ep_len = self._episode_lengths()
         L.check(
             L.load().catb200_cat_reset_stats(
                 L.ptr(ids_t), n_ids, L.ptr(mask_t), ep_len.data_ptr(), self.num_envs, len(self._term_names),

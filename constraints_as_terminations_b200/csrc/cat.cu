@@ -482,15 +482,40 @@ __device__ __forceinline__ float violation_prob(float c, float rm, float min_p, 
   return __fadd_rn(min_p, __fmul_rn(x, span));
 }
 
+struct ResetScratch {  // per slot: double sums + count; zero between launches
+  double v[CATB200_MAX_TERMS], p[CATB200_MAX_TERMS];
+  unsigned long long cnt[CATB200_MAX_TERMS];
+  unsigned int ticket;                       // cat_reset_kernel (small grids)
+  unsigned int tickets[1 + kTicketGroups];   // fused reset inside cat_apply_kernel (grids of up to N / 32 CTAs)
+};
+
+// episode statistics of the envs being reset, from the per-slot accumulators (constraint_manager.py:197-209)
+__device__ __forceinline__ void reset_finalize(ResetScratch* sc, int n_slots, float* out) {
+  for (int s2 = threadIdx.x; s2 < n_slots; s2 += blockDim.x) {
+    const double v = __longlong_as_double(atomicExch((unsigned long long*)&sc->v[s2], 0ull));
+    const double p = __longlong_as_double(atomicExch((unsigned long long*)&sc->p[s2], 0ull));
+    const unsigned long long c = atomicExch(&sc->cnt[s2], 0ull);
+    // empty selection -> mean of nothing = NaN, like torch
+    const float mv = (float)(v / (double)c), mp = (float)(p / (double)c);
+    out[2 * s2] = __fmul_rn(mv, 100.0f);
+    out[2 * s2 + 1] = mp;
+  }
+}
+
 // One CTA per 32 envs (lane = env); the warps split the statistics slots (terms) so that the dependent
 // load chains are 4x shorter and 4x more loads are in flight than with one thread per env.
+// With `episode_length` (fused reset, the order of CaTEnv.step: compute() at cat_env.py:100, then
+// _reset_idx -> ConstraintManager.reset at :181): envs whose reset_buf is set contribute their just-updated
+// statistics / episode length to the per-term means (constraint_manager.py:197-209) and are zeroed, and the
+// last CTA writes the 2 * n_slots means -- ConstraintManager.reset(reset ids) without a second launch.
 __global__ void __launch_bounds__(kApplyMaxWarps * 32)
 cat_apply_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_constant__ catb200_cat_params_t prm,
                  int num_envs, const float* __restrict__ running_max, const float* __restrict__ c_t,
                  float* __restrict__ episode_sums, float* __restrict__ mean_values,
                  float* __restrict__ cstr_prob, const float* __restrict__ raw_reward,
                  const uint8_t* __restrict__ reset_buf, float* __restrict__ reward_out,
-                 float* __restrict__ dones_out) {
+                 float* __restrict__ dones_out, const int64_t* __restrict__ episode_length,
+                 float* __restrict__ reset_out, ResetScratch* __restrict__ rsc) {
   __shared__ float s_rm[CATB200_MAX_COLS];
   __shared__ float s_part[kApplyMaxWarps][kTile];
   const int n_warps = blockDim.x >> 5;
@@ -501,8 +526,13 @@ cat_apply_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_const
   const bool live = i < num_envs;
   const float* ct = c_t + (size_t)blockIdx.x * plan.n_cols * kTile + lane;  // this env's column of the [K][32] tile
   float overall = -INFINITY;
-  if (live) {
-    for (int slot = warp; slot < plan.n_slots; slot += n_warps) {
+  const bool fused_reset = episode_length != nullptr;
+  const bool resetting = fused_reset && live && reset_buf[i] != 0;
+  const unsigned reset_lanes = fused_reset ? __ballot_sync(0xffffffffu, resetting) : 0u;
+  const float ep_len = resetting ? (float)episode_length[i] : 1.0f;  // int64 -> float like torch's float / long promotion
+  for (int slot = warp; slot < plan.n_slots; slot += n_warps) {
+    float es2 = 0.0f, mv2 = 0.0f;
+    if (live) {
       const int c0 = plan.slot_col_begin[slot], c1 = plan.slot_col_begin[slot + 1];
       const float span = prm.span[slot];
       const size_t k = (size_t)slot * num_envs + i;
@@ -518,21 +548,34 @@ cat_apply_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_const
                                  fmaxf(violation_prob(v2, s_rm[col + 2], prm.min_p, span), violation_prob(v3, s_rm[col + 3], prm.min_p, span))));
       }
       for (; col < c1; ++col) tmax = fmaxf(tmax, violation_prob(__ldcs(ct + col * kTile), s_rm[col], prm.min_p, span));
-      episode_sums[k] = __fadd_rn(es, tmax > 0.0f ? 1.0f : 0.0f);  // :226
-      mean_values[k] = __fadd_rn(mv, tmax);                          // :227
+      es2 = __fadd_rn(es, tmax > 0.0f ? 1.0f : 0.0f);  // :226
+      mv2 = __fadd_rn(mv, tmax);                         // :227
+      episode_sums[k] = resetting ? 0.0f : es2;
+      mean_values[k] = resetting ? 0.0f : mv2;
       overall = fmaxf(overall, tmax);
+    }
+    if (reset_lanes) {  // warp-uniform: some env of this tile resets (every lane of the warp takes part in the sums)
+      const double av = warp_sum(resetting ? (double)__fdiv_rn(es2, ep_len) : 0.0);
+      const double ap = warp_sum(resetting ? (double)__fdiv_rn(mv2, ep_len) : 0.0);
+      if (lane == 0) {
+        atomicAdd(&rsc->v[slot], av);
+        atomicAdd(&rsc->p[slot], ap);
+        atomicAdd(&rsc->cnt[slot], (unsigned long long)__popc(reset_lanes));
+      }
     }
   }
   s_part[warp][lane] = overall;
   __syncthreads();
-  if (warp != 0 || !live) return;
-  for (int w = 1; w < n_warps; ++w) overall = fmaxf(overall, s_part[w][lane]);
-  cstr_prob[i] = overall;
-  if (raw_reward != nullptr) {
-    // cat_env.py:102-107: reward = clip(reward * (1 - p), min=0); dones = p; :121 dones[reset] = 1
-    reward_out[i] = fmaxf(__fmul_rn(raw_reward[i], __fsub_rn(1.0f, overall)), 0.0f);
-    dones_out[i] = (reset_buf != nullptr && reset_buf[i]) ? 1.0f : overall;
+  if (warp == 0 && live) {
+    for (int w = 1; w < n_warps; ++w) overall = fmaxf(overall, s_part[w][lane]);
+    cstr_prob[i] = overall;
+    if (raw_reward != nullptr) {
+      // cat_env.py:102-107: reward = clip(reward * (1 - p), min=0); dones = p; :121 dones[reset] = 1
+      reward_out[i] = fmaxf(__fmul_rn(raw_reward[i], __fsub_rn(1.0f, overall)), 0.0f);
+      dones_out[i] = (reset_buf != nullptr && reset_buf[i]) ? 1.0f : overall;
+    }
   }
+  if (fused_reset && last_block_ticket_grouped(rsc->tickets, gridDim.x)) reset_finalize(rsc, plan.n_slots, reset_out);
 }
 
 __global__ void __launch_bounds__(kApplyThreads)
@@ -557,11 +600,6 @@ cat_probs_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_const
 constexpr int kResetThreads = 256;
 constexpr int kResetChunk = 1024;  // selected envs (or mask entries) per CTA
 
-struct ResetScratch {  // per slot: double sums + count; zero between launches
-  double v[CATB200_MAX_TERMS], p[CATB200_MAX_TERMS];
-  unsigned long long cnt[CATB200_MAX_TERMS];
-  unsigned int ticket;
-};
 
 // grid = (n_slots, chunks): every CTA reduces one statistics row over one chunk of the selection in double
 // precision (torch's own fp32 reduction order is implementation defined; parity tolerance 1e-5 relative),
@@ -601,17 +639,7 @@ cat_reset_kernel(const int64_t* __restrict__ env_ids, int n_ids, const uint8_t* 
     atomicAdd(&sc->p[slot], acc_p);
     atomicAdd(&sc->cnt[slot], cnt);
   }
-  if (last_block_ticket(&sc->ticket, gridDim.x * gridDim.y)) {
-    for (int s2 = threadIdx.x; s2 < n_slots; s2 += kResetThreads) {
-      const double v = __longlong_as_double(atomicExch((unsigned long long*)&sc->v[s2], 0ull));
-      const double p = __longlong_as_double(atomicExch((unsigned long long*)&sc->p[s2], 0ull));
-      const unsigned long long c = atomicExch(&sc->cnt[s2], 0ull);
-      // empty selection -> mean of nothing = NaN, like torch
-      const float mv = (float)(v / (double)c), mp = (float)(p / (double)c);
-      out[2 * s2] = __fmul_rn(mv, 100.0f);
-      out[2 * s2 + 1] = mp;
-    }
-  }
+  if (last_block_ticket(&sc->ticket, gridDim.x * gridDim.y)) reset_finalize(sc, n_slots, out);
 }
 
 }  // namespace catb200
@@ -787,10 +815,11 @@ static int launch_eval(const catb200_plan_t* plan, const catb200_cat_params_t* p
   return CATB200_OK;
 }
 
-int catb200_cat_step(const catb200_plan_t* plan, const catb200_cat_params_t* params, int32_t num_envs,
-                     float* running_max, int32_t* rm_init, float* episode_sums, float* mean_values,
-                     float* cstr_prob, const float* raw_reward, const uint8_t* reset_buf, float* reward_out,
-                     float* dones_out, void* workspace, size_t workspace_bytes, void* stream) {
+static int cat_step_impl(const catb200_plan_t* plan, const catb200_cat_params_t* params, int32_t num_envs,
+                         float* running_max, int32_t* rm_init, float* episode_sums, float* mean_values,
+                         float* cstr_prob, const float* raw_reward, const uint8_t* reset_buf, float* reward_out,
+                         float* dones_out, void* workspace, size_t workspace_bytes, const int64_t* episode_length,
+                         float* reset_out, void* reset_workspace, void* stream) {
   if (!plan || !params || num_envs <= 0 || !running_max || !rm_init || !episode_sums || !mean_values || !cstr_prob ||
       !workspace)
     return CATB200_ERR_INVALID_ARGUMENT;
@@ -802,11 +831,31 @@ int catb200_cat_step(const catb200_plan_t* plan, const catb200_cat_params_t* par
   int rc = launch_eval(plan, params, num_envs, running_max, rm_init, ws, nullptr, kEvalStep, st);
   if (rc != CATB200_OK) return rc;
   const int grid = (num_envs + kTile - 1) / kTile;
-  cat_apply_kernel<<<grid, 32 * apply_warps(plan->n_slots, grid), 0, st>>>(*plan, *params, num_envs, running_max, ws.c_t, episode_sums,
-                                                   mean_values, cstr_prob, raw_reward, reset_buf, reward_out,
-                                                   dones_out);
+  cat_apply_kernel<<<grid, 32 * apply_warps(plan->n_slots, grid), 0, st>>>(
+      *plan, *params, num_envs, running_max, ws.c_t, episode_sums, mean_values, cstr_prob, raw_reward, reset_buf,
+      reward_out, dones_out, episode_length, reset_out, static_cast<ResetScratch*>(reset_workspace));
   CATB200_LAUNCH_CHECK();
   return CATB200_OK;
+}
+
+int catb200_cat_step(const catb200_plan_t* plan, const catb200_cat_params_t* params, int32_t num_envs,
+                     float* running_max, int32_t* rm_init, float* episode_sums, float* mean_values,
+                     float* cstr_prob, const float* raw_reward, const uint8_t* reset_buf, float* reward_out,
+                     float* dones_out, void* workspace, size_t workspace_bytes, void* stream) {
+  return cat_step_impl(plan, params, num_envs, running_max, rm_init, episode_sums, mean_values, cstr_prob, raw_reward,
+                       reset_buf, reward_out, dones_out, workspace, workspace_bytes, nullptr, nullptr, nullptr, stream);
+}
+
+int catb200_cat_step_reset(const catb200_plan_t* plan, const catb200_cat_params_t* params, int32_t num_envs,
+                           float* running_max, int32_t* rm_init, float* episode_sums, float* mean_values,
+                           float* cstr_prob, const float* raw_reward, const uint8_t* reset_buf, float* reward_out,
+                           float* dones_out, void* workspace, size_t workspace_bytes, const int64_t* episode_length,
+                           float* reset_out, void* reset_workspace, size_t reset_workspace_bytes, void* stream) {
+  if (!reset_buf || !episode_length || !reset_out || !reset_workspace) return CATB200_ERR_INVALID_ARGUMENT;
+  if (reset_workspace_bytes < sizeof(ResetScratch)) return CATB200_ERR_WORKSPACE_TOO_SMALL;
+  return cat_step_impl(plan, params, num_envs, running_max, rm_init, episode_sums, mean_values, cstr_prob, raw_reward,
+                       reset_buf, reward_out, dones_out, workspace, workspace_bytes, episode_length, reset_out,
+                       reset_workspace, stream);
 }
 
 int catb200_cat_eval_terms(const catb200_plan_t* plan, int32_t num_envs, float* out, void* stream) {

@@ -158,6 +158,7 @@ class SyntheticSolo12Env:
         self.cfg = SimpleNamespace(constraints=constraints_cfg)
         self.extras: dict = {}
         self._curriculum_on = curriculum
+        self.fuse_reset = True  # gather the reset statistics inside the constraint step (False: separate reset launch)
 
         self.scene = _Scene(robot=_Articulation(), contact_forces=_ContactSensor())
         self.command_manager = _CommandManager()
@@ -236,12 +237,14 @@ class SyntheticSolo12Env:
         self.reset_time_outs = self.episode_length_buf >= self.max_episode_length
         self.reset_buf = self.reset_time_outs
         mgr = self.constraint_manager
+        resetting = bool(due.any())
         if mgr is not None:
-            self.reward_buf, dones = mgr.compute_step(self._raw_reward, self.reset_buf)
+            # when some env resets this step, its episode statistics are gathered by the same two launches
+            self.reward_buf, dones = mgr.compute_step(self._raw_reward, self.reset_buf, fuse_reset=resetting and self.fuse_reset)
         else:
             self.reward_buf = self._raw_reward
             dones = self.reset_buf.float()
-        if due.any():
+        if resetting:
             self._reset_masked(self.reset_buf)
             self._phase_np[due] = 0
         return self.obs_buf, self.reward_buf, dones, self.reset_time_outs, self.extras
@@ -259,7 +262,8 @@ class SyntheticSolo12Env:
         self.extras["log"] = dict()
         if mgr is not None:
             self._curriculum()
-            self.extras["log"].update(mgr.reset_masked(mask))
+            # (assigned, not .update()d: the fused statistics stay one packed device vector until somebody reads them)
+            self.extras["log"] = mgr.fused_reset_stats() if self.fuse_reset else mgr.reset_masked(mask)
         self.episode_length_buf.masked_fill_(mask, 0)
 
     def _reset_idx(self, env_ids: torch.Tensor):

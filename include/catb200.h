@@ -149,6 +149,21 @@ int catb200_cat_step(const catb200_plan_t* plan, const catb200_cat_params_t* par
                      float* reward_out, float* dones_out, void* workspace, size_t workspace_bytes,
                      void* stream);
 
+/*
+ * catb200_cat_step followed by ConstraintManager.reset(ids of the envs whose reset_buf is set) in the same two
+ * launches -- the order of CaTEnv.step (U/cat/cat_env.py:100 compute, :181 constraint_manager.reset inside
+ * _reset_idx; U/cat/constraint_manager.py:190-211): the envs being reset contribute their just-updated statistics
+ * divided by episode_length[i] (int64) to the per-term means, are zeroed, and reset_out[2*s], reset_out[2*s+1]
+ * receive the same values catb200_cat_reset_stats would write (NaN when no env resets).  reset_buf is required.
+ * reset_workspace: catb200_cat_reset_workspace_bytes() of zero-initialised device scratch.
+ */
+int catb200_cat_step_reset(const catb200_plan_t* plan, const catb200_cat_params_t* params, int32_t num_envs,
+                           float* running_max, int32_t* rm_init, float* episode_sums, float* mean_values,
+                           float* cstr_prob, const float* raw_reward, const uint8_t* reset_buf,
+                           float* reward_out, float* dones_out, void* workspace, size_t workspace_bytes,
+                           const int64_t* episode_length, float* reset_out, void* reset_workspace,
+                           size_t reset_workspace_bytes, void* stream);
+
 /* Raw constraint values of every term, row-major [num_envs, n_cols] (what CaT keeps as
  * raw_constraints, constraint_manager.py:52; also backs the stand-alone term functions). */
 int catb200_cat_eval_terms(const catb200_plan_t* plan, int32_t num_envs, float* out, void* stream);

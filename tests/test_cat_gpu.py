@@ -205,3 +205,48 @@ def test_full_size_properties():
     colmax = raw.max(0).values.clamp(min=1e-6)
     assert torch.equal(mgr.cat.get_running_maxes().squeeze(0), rm0.squeeze(0) * 0.95 + (1.0 - 0.95) * colmax)
     assert torch.equal(mgr.cat.get_raw_constraints(), raw)
+
+
+@pytest.mark.parametrize("num_envs", [33, 1000, 4096])
+def test_fused_step_reset_equals_step_then_reset(num_envs):
+    """compute_step(fuse_reset=True) == compute_step() followed by reset(ids of reset_buf) (the order of CaTEnv.step,
+    reference cat_env.py:100 then :181) and == the oracle: cstr_prob / reward / dones / statistics bit-exact, the
+    episode means to 1e-5 (double-precision sums vs torch's fp32 reduction)."""
+    steps = 4
+    envs = [se.SyntheticSolo12Env(num_envs, device=DEV, seed=3, pool=1) for _ in range(2)]
+    cpu_env = se.SyntheticSolo12Env(num_envs, device="cpu", seed=3, pool=1)
+    mgrs = [ConstraintManager(se.solo12_constraints_cfg(), e) for e in envs]
+    cfg_cpu = se.solo12_constraints_cfg()
+    oracle = cat_oracle.ManagerOracle(cpu_env, cat_oracle.terms_from_cfg(cfg_cpu, resolve_scene=cpu_env.scene))
+    gen = torch.Generator().manual_seed(17)
+    for step in range(steps):
+        state = se.sample_state(num_envs, gen, adversarial=step == 1)
+        reset_cpu = torch.rand(num_envs, generator=gen) < (0.0 if step == 2 else 0.2)  # step 2: nobody resets
+        ep_len = torch.randint(1, 400, (num_envs,), generator=gen)
+        cpu_env.load_state(state)
+        cpu_env.episode_length_buf[:] = ep_len
+        for e in envs:
+            e.load_state({k: v.to(DEV) for k, v in state.items()})
+            e.episode_length_buf[:] = ep_len.to(DEV)
+        reset = reset_cpu.to(DEV)
+        raw_reward = envs[0]._raw_reward
+        # A: fused
+        rew_a, dones_a = mgrs[0].compute_step(raw_reward, reset, fuse_reset=True)
+        out_a = mgrs[0].fused_reset_stats()
+        # B: two calls
+        rew_b, dones_b = mgrs[1].compute_step(envs[1]._raw_reward, reset)
+        out_b = mgrs[1].reset(reset.nonzero().squeeze(-1))
+        # oracle
+        want_p = oracle.compute()
+        want_rew, want_dones = cat_oracle.step_epilogue(cpu_env._raw_reward, want_p, reset_cpu)
+        want_out = oracle.reset(reset_cpu.nonzero().squeeze(-1))
+        assert torch.equal(rew_a, rew_b) and torch.equal(dones_a, dones_b)
+        assert torch.equal(rew_a.cpu(), want_rew) and torch.equal(dones_a.cpu(), want_dones)
+        assert torch.equal(mgrs[0]._stats, mgrs[1]._stats), f"step {step}: statistics after reset differ"
+        assert torch.equal(mgrs[0]._stats[0].cpu(), torch.stack(list(oracle.episode_sums.values())))
+        assert list(out_a.keys()) == list(out_b.keys()) == list(want_out.keys())
+        for k in want_out:
+            torch.testing.assert_close(out_a[k].cpu(), want_out[k], rtol=1e-5, atol=1e-7, equal_nan=True)
+            torch.testing.assert_close(out_a[k], out_b[k], rtol=1e-6, atol=1e-8, equal_nan=True)
+    with pytest.raises(ValueError):
+        mgrs[0].compute_step(raw_reward, None, fuse_reset=True)
