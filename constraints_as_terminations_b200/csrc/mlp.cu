@@ -46,6 +46,37 @@ static bool use_fused_fwd(int rows) {
   return rows <= v;
 }
 
+// Backward-pass overlap: the weight-gradient GEMM of layer l and the data-gradient GEMM that produces dZ_{l-1} both
+// only read dZ_l, so they run concurrently -- wgrad on a library-owned side stream forked from / joined back into
+// the caller's stream with events (inside a CUDA graph capture these become plain graph edges).  All work is still
+// complete when the caller's stream reaches the end of the call.  Opt-in (CATB200_BWD_OVERLAP=1): measured +0.5 % at
+// 4096 envs and +1.1 % at 16384 -- every GEMM of the chain already fills the machine for at least one wave, so only
+// the tails overlap -- which does not pay for a hidden stream behind the C ABI.
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t dz_ready[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t done = nullptr;
+};
+static SideStream* side_stream() {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = std::getenv("CATB200_BWD_OVERLAP");
+    enabled = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (!enabled) return nullptr;
+  static SideStream per_device[16];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  SideStream& s = per_device[dev];
+  if (!s.stream) {
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    bool ok = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 3; ++i) ok = ok && cudaEventCreateWithFlags(&s.dz_ready[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) return nullptr;
+  }
+  return &s;
+}
+
 constexpr int kGemmThreads = 256;
 constexpr int kBM = 128, kBN = 128, kBK = 64;
 constexpr int kStages = 3;
@@ -1039,7 +1070,15 @@ int catb200_ppo_minibatch_grad(const catb200_mlp_dims_t* dims, const catb200_ppo
     wg_attr = true;
   }
   ReduceArgs red = {};
+  SideStream* side = use_tc() ? side_stream() : nullptr;
   for (int l = 2; l >= 0; --l) {
+    // dZ_l is complete on `st` here (head kernel or the previous dgrad): the weight gradient may start beside dgrad
+    cudaStream_t wst = st;
+    if (side && l > 0) {
+      CATB200_CUDA_TRY(cudaEventRecord(side->dz_ready[l], st));
+      CATB200_CUDA_TRY(cudaStreamWaitEvent(side->stream, side->dz_ready[l], 0));
+      wst = side->stream;
+    }
     WgradArgs wgt = {};
     for (int z = 0; z < 2; ++z) {
       wgt.dZ[z] = reinterpret_cast<const bf16*>(ws + L.dZ[z][l]);
@@ -1060,7 +1099,7 @@ int catb200_ppo_minibatch_grad(const catb200_mlp_dims_t* dims, const catb200_ppo
         t.part[z] = wgt.part[z];
       }
       t.M = x.out[l]; t.N = x.in_pad[l]; t.K = M; t.m_range = L.m_range[l];
-      int rc = tc_gemm_launch(kTcWgrad, t, L.splits[l], st);
+      int rc = tc_gemm_launch(kTcWgrad, t, L.splits[l], wst);
       if (rc != CATB200_OK) return rc;
     } else if (x.in_pad[l] >= 128) {
       dim3 grid((x.out[l] / 128) * (x.in_pad[l] / 128), L.splits[l], 2);
@@ -1101,6 +1140,10 @@ int catb200_ppo_minibatch_grad(const catb200_mlp_dims_t* dims, const catb200_ppo
       CATB200_CUDA_TRY(launch_pdl(gemm_nt_kernel<kEpiMulDelu>, grid, dim3(kGemmThreads), kSmemNT, st, g));
       CATB200_LAUNCH_CHECK();
     }
+  }
+  if (side) {  // join: the partial sums written on the side stream are reduced next
+    CATB200_CUDA_TRY(cudaEventRecord(side->done, side->stream));
+    CATB200_CUDA_TRY(cudaStreamWaitEvent(st, side->done, 0));
   }
   // 5. fold the split partial sums (hidden layers) and the head kernel's per-CTA rows into the flat gradient
   red.head_part = reinterpret_cast<const float*>(ws + L.head_part);
