@@ -17,6 +17,8 @@
 // epilogue overlaps another CTA's main loop without a persistent scheduler.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "mma.cuh"
 #include "tc_gemm.cuh"
@@ -280,6 +282,252 @@ tc_gemm_kernel(const __grid_constant__ TcGemmArgs g) {
   }
 }
 
+// ---- persistent variant (forward / dgrad) ----------------------------------------------------------------------
+// ncu on the one-tile-per-CTA kernel above: a 128 x 128 x 256 tile needs 0.5 us of tensor-pipe time but its CTA lives
+// ~15 us (prologue: barrier init, TMEM allocation, descriptor fetch; then load -> MMA -> TMEM read -> epilogue -> store
+// strictly one after the other), so the tensor pipe is 5-10 % busy even with two CTAs per SM.  Here ONE CTA per SM
+// walks the tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (n fastest, so CTAs that run side by side share the A
+// tile in L2) with the three roles decoupled across tiles:
+//   warp 0   TMA producer: keeps the 4-stage ring full across tile boundaries (running k-block counter)
+//   warp 1   MMA issuer  : accumulates tile j into TMEM stage j & 1 (2 x BN columns allocated once)
+//   warps 2-9 epilogue   : drain stage j & 1 (tcgen05.ld), hand it back (tmem_empty barrier, one arrival per warp)
+//                          and do the bias/ELU or ELU'-scale math + TMA store while the MMAs of tile j + 1 run.
+// The output staging area is separate from the ring (the ring is never idle any more).
+constexpr int kPStages = 4;
+
+template <int MODE, int BN>
+struct PSmem {
+  static constexpr int kABytes = 128 * kTcBK * 2, kBBytes = BN * kTcBK * 2, kStage = kABytes + kBBytes;
+  static constexpr int kOut = 2 * 2 * 16384;                    // 2 tiles x two [128 rows][64 cols] bf16 boxes, SWIZZLE_128B
+  static constexpr int kAux = 256 + 2 * 4 * BN * 4;             // barriers + double-buffered 4 x BN column-sum scratch
+  static constexpr int kTotal = kPStages * kStage + kOut + 1024 /*alignment slack*/ + kAux;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+
+template <int MODE, int BN>
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_gemm_persist_kernel(const __grid_constant__ TcGemmArgs g) {
+  using S = PSmem<MODE, BN>;
+  static_assert(MODE == kTcFwd || MODE == kTcDgrad, "persistent kernel: forward / dgrad only");
+  extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t tiles = (raw + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
+  const uint32_t out_sm = tiles + kPStages * S::kStage;
+  const uint32_t bars = out_sm + S::kOut;
+  const uint32_t full_bar = bars, empty_bar = bars + 8 * kPStages;
+  const uint32_t tfull_bar = bars + 16 * kPStages, tempty_bar = tfull_bar + 16;
+  const uint32_t tmem_slot = tempty_bar + 16;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+  float* colsum_sm = reinterpret_cast<float*>(smem_raw + (bars + 256 - raw));  // [2][4][BN]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_n = g.N / BN, tiles_m = (g.M + 127) / 128;
+  const int per_net = tiles_m * tiles_n, total = 2 * per_net;
+  const int k_blocks = g.K / kTcBK;
+
+  if (warp == 0 && lane == 0) {
+    for (int z = 0; z < 2; ++z) {
+      asm volatile("prefetch.tensormap [%0];\n" ::"l"(&g.mapA[z]));
+      asm volatile("prefetch.tensormap [%0];\n" ::"l"(&g.mapB[z]));
+      asm volatile("prefetch.tensormap [%0];\n" ::"l"(&g.mapC[z]));
+    }
+    for (int s = 0; s < kPStages; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar + 8 * a, 1);
+      mbar_init(tempty_bar + 8 * a, kTcThreads / 32 - 2);  // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+  pdl_wait();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int z = t / per_net, r = t - z * per_net;
+        const int row_base = (r / tiles_n) * 128, col_base = (r % tiles_n) * BN;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const uint32_t s = it % kPStages;
+          mbar_wait(empty_bar + 8 * s, ((it / kPStages) & 1) ^ 1);
+          const uint32_t sa = tiles + s * S::kStage, sb = sa + S::kABytes;
+          mbar_expect_tx(full_bar + 8 * s, S::kStage);
+          tma_load_2d(sa, &g.mapA[z], full_bar + 8 * s, kb * kTcBK, row_base);  // 64 (K) x 128 rows
+          tma_load_2d(sb, &g.mapB[z], full_bar + 8 * s, kb * kTcBK, col_base);  // 64 (K) x BN rows
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc(128, BN, false, false);
+    uint32_t it = 0, j = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
+      const uint32_t a = j & 1;
+      mbar_wait(tempty_bar + 8 * a, ((j >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator stage
+      tc_fence_after();
+      for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+        const uint32_t s = it % kPStages;
+        mbar_wait(full_bar + 8 * s, (it / kPStages) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = tiles + s * S::kStage, sb = sa + S::kABytes;
+#pragma unroll
+          for (int k = 0; k < kTcBK / 16; ++k) {
+            // K-major SW128: rows are 128 B, 8-row groups SBO = 1 KiB apart; one K-step = 32 B further
+            const uint64_t da = make_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t db = make_smem_desc(sb + k * 32, 16, 1024);
+            umma_bf16(tmem_base + a * BN, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+        }
+        __syncwarp();
+        if (elect_one()) {
+          umma_commit(empty_bar + 8 * s);                            // frees the ring slot once these MMAs retire
+          if (kb == k_blocks - 1) umma_commit(tfull_bar + 8 * a);   // accumulator complete -> epilogue
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9) =====================
+    const int quarter = warp & 3;      // TMEM lanes 32 * quarter .. + 31 are the ones this warp may read
+    const int half = (warp - 2) >> 2;  // the two warps of a quarter split the BN columns in halves
+    constexpr int HC = BN / 2, NCH = HC / 32;
+    const int c_first = half * HC;
+    const int trow = quarter * 32 + lane;  // row inside the 128-row tile
+    uint32_t j = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
+      const int z = t / per_net, r = t - z * per_net;
+      const int row_base = (r / tiles_n) * 128, col_base = (r % tiles_n) * BN;
+      const int row = row_base + trow;
+      const uint32_t a = j & 1;
+      const uint32_t cbox = out_sm + a * 32768 + half * 16384;  // output staging alternates with the tile parity
+      // dgrad: the forward activations whose ELU' scales the result are fetched while the MMAs still run
+      uint4 hv[NCH][4];
+      if (MODE == kTcDgrad) {
+        const bf16* __restrict__ hrow = g.H[z] + (size_t)row * g.ldc + col_base + c_first;
+#pragma unroll
+        for (int i = 0; i < NCH; ++i)
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            hv[i][q] = row < g.M ? __ldg(reinterpret_cast<const uint4*>(hrow + i * 32 + q * 8)) : make_uint4(0, 0, 0, 0);
+      }
+      if (lane == 0) mbar_wait(tfull_bar + 8 * a, (j >> 1) & 1);  // one sleeping lane per warp
+      __syncwarp();
+      mbar_wait(tfull_bar + 8 * a, (j >> 1) & 1);                 // already complete: a single acquire per thread
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * BN + c_first;
+      uint32_t v[NCH][32];
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) tmem_ld32(taddr + i * 32, v[i]);
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) tmem_ld_wait(v[i]);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + 8 * a);  // the MMA warp may overwrite this stage (tile j + 2)
+
+      if (MODE == kTcFwd) {
+        // bias straight from global memory (warp-uniform addresses: one broadcast transaction each, L1 hits); the
+        // flat parameter vector gives no 16-byte alignment, hence scalar loads
+        const float* __restrict__ bp = g.bias[z] + col_base + c_first;
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float bb[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) bb[e] = __ldg(bp + i * 32 + q * 8 + e);
+            uint4 o;
+            uint32_t* op = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int cc = q * 8 + e * 2;
+              const float x0 = __uint_as_float(v[i][cc]) + bb[e * 2];
+              const float x1 = __uint_as_float(v[i][cc + 1]) + bb[e * 2 + 1];
+              op[e] = pack_bf16x2(elu_fast(x0), elu_fast(x1));
+            }
+            st_shared_v4(cbox + trow * 128 + (((i * 4 + q) ^ (trow & 7)) << 4), o);
+          }
+        }
+      } else {
+        const bool live = row < g.M;
+        float* colsum = colsum_sm + (j & 1) * 4 * BN;
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+          float f[32];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&hv[i][q]);
+            uint4 o;
+            uint32_t* op = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int cc = q * 8 + e * 2;
+              const float x0 = live ? __uint_as_float(v[i][cc]) * elu_grad_from_output(__low2float(hp[e])) : 0.0f;
+              const float x1 = live ? __uint_as_float(v[i][cc + 1]) * elu_grad_from_output(__high2float(hp[e])) : 0.0f;
+              f[cc] = x0;
+              f[cc + 1] = x1;
+              op[e] = pack_bf16x2(x0, x1);
+            }
+            st_shared_v4(cbox + trow * 128 + (((i * 4 + q) ^ (trow & 7)) << 4), o);
+          }
+          // column sums over this warp's 32 rows by recursive halving: lane l ends with the sum of column i*32 + l
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const bool upper = (lane & o) != 0;
+#pragma unroll
+            for (int jj = 0; jj < o; ++jj) {
+              const float send = upper ? f[jj] : f[jj + o];
+              const float keep = upper ? f[jj + o] : f[jj];
+              f[jj] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+          }
+          colsum[quarter * BN + c_first + i * 32 + lane] = f[0];
+        }
+      }
+      // this warp's 32 rows x 64 columns leave with ONE TMA tensor store.  The slab is this warp's own and there are
+      // two of them: only the store issued one tile ago (which read the slab the next tile will overwrite) has to be
+      // done before going on, the one just issued drains behind the next tile's math; no CTA-wide barrier involved
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&g.mapC[z], cbox + quarter * 4096, col_base + c_first, row_base + quarter * 32);
+        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
+      }
+      __syncwarp();
+      if (MODE == kTcDgrad) {
+        // the four row quarters cover the same columns: combine them in shared memory and issue ONE atomic per
+        // column per tile.  The scratch alternates between two buffers: a warp that races ahead writes tile j + 1's
+        // sums into the other one, and reaches tile j + 2 only through tile j + 1's barrier.
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");  // the 8 epilogue warps only
+        const float* colsum = colsum_sm + (j & 1) * 4 * BN;
+        const int et = threadIdx.x - 64;
+        if (et < BN)
+          atomicAdd(g.dbias[z] + col_base + et, (colsum[et] + colsum[BN + et]) + (colsum[2 * BN + et] + colsum[3 * BN + et]));
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");  // staging read out before exit
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -361,13 +609,42 @@ static int launch_one(TcGemmArgs g, dim3 grid, cudaStream_t st) {
   return CATB200_OK;
 }
 
+// persistent kernel for launches whose tiles do not all fit on the machine at once (two one-tile CTAs per SM);
+// CATB200_TC_PERSIST=0: always one tile per CTA
+static bool use_persistent(int total_tiles) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("CATB200_TC_PERSIST");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1 && total_tiles > 2 * kNumSMs;
+}
+
+template <int MODE, int BN>
+static int launch_persist(TcGemmArgs g, int total_tiles, cudaStream_t st) {
+  using S = PSmem<MODE, BN>;
+  static bool attr = false;
+  if (!attr) {
+    CATB200_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_persist_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    attr = true;
+  }
+  g.stages = kPStages;
+  CATB200_CUDA_TRY(launch_pdl(tc_gemm_persist_kernel<MODE, BN>, dim3(min(total_tiles, kNumSMs)), dim3(kTcThreads), (size_t)S::kTotal, st, g));
+  CATB200_LAUNCH_CHECK();
+  return CATB200_OK;
+}
+
 int tc_gemm_launch(int mode, const TcGemmArgs& g, int splits, cudaStream_t st) {
   if (mode == kTcFwd) {
     if (g.N % 128) return CATB200_ERR_UNSUPPORTED;
+    const int total = 2 * ((g.M + 127) / 128) * (g.N / 128);
+    if (use_persistent(total)) return launch_persist<kTcFwd, 128>(g, total, st);
     return launch_one<kTcFwd, 128>(g, dim3((g.M + 127) / 128, g.N / 128, 2), st);
   }
   if (mode == kTcDgrad) {
     if (g.N % 128) return CATB200_ERR_UNSUPPORTED;
+    const int total = 2 * ((g.M + 127) / 128) * (g.N / 128);
+    if (use_persistent(total)) return launch_persist<kTcDgrad, 128>(g, total, st);
     return launch_one<kTcDgrad, 128>(g, dim3((g.M + 127) / 128, g.N / 128, 2), st);
   }
   // wgrad: g.M = layer outputs (dW rows), g.N = padded layer inputs (dW cols), g.K = minibatch rows
