@@ -241,14 +241,32 @@ def _traffic():
     return json.load(open(path)) if os.path.isfile(path) else {}
 
 
-def dominant_kernel_roofline(prof, total_us, trainer, peaks):
-    """Roofline entry of the kernel with the largest share of the iteration."""
+def _gemm_flops_by_kernel(trainer):
+    """Tensor-core flops per iteration attributed to each tcgen05 kernel name.  Forward / dgrad launches with more
+    than 2 x 148 output tiles run the persistent kernel, the others (rollout-sized launches, the 256 -> 128 layer)
+    the one-tile-per-CTA kernel (tc_gemm.cu: use_persistent)."""
     n, T = trainer.num_envs, trainer.T
     opt_rows = trainer.batch_size * int(trainer.cfg.updates_epochs)  # minibatch rows per iteration
-    flops = {
-        "tc_gemm_kernel<0, 128>": 2.0 * _MAC_FWD * (opt_rows + n * (T + 1)),  # update forward + rollout policy + bootstrap
-        "tc_gemm_kernel<1, 128>": 2.0 * _MAC_DGRAD * opt_rows,
-    }
+    mb = trainer.minibatch_size
+    layers = [(64, 512), (512, 256), (256, 128)]  # (K, N) of the hidden layers, both nets batched per launch
+    flops = {}
+
+    def add(kind, rows_per_launch, total_rows, k, n_out):
+        tiles = 2 * ((rows_per_launch + 127) // 128) * (n_out // 128)
+        name = f"tc_gemm_persist_kernel<{kind}, 128>" if tiles > 2 * 148 else f"tc_gemm_kernel<{kind}, 128>"
+        flops[name] = flops.get(name, 0.0) + 2.0 * 2 * k * n_out * total_rows
+
+    for k, n_out in layers:
+        add(0, mb, opt_rows, k, n_out)          # update forward
+        add(0, n, n * (T + 1), k, n_out)        # rollout policy + bootstrap value
+    for k, n_out in layers[1:]:
+        add(1, mb, opt_rows, n_out, k)          # dgrad: dZ_l [M, N_l] x W_l -> [M, K_l]
+    return flops
+
+
+def dominant_kernel_roofline(prof, total_us, trainer, peaks):
+    """Roofline entry of the kernel with the largest share of the iteration."""
+    flops = _gemm_flops_by_kernel(trainer)
     if not prof:  # no CUPTI records (e.g. the process itself runs under ncu, which owns the profiling interface)
         return {"kernel": None, "note": "kernel shares unavailable: CUPTI produced no records in this process"}
     name, row = next(iter(prof.items()))
