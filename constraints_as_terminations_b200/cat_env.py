@@ -7,8 +7,9 @@ fused constraint kernels:
 
 * `load_managers()` adds `self.constraint_manager = ConstraintManager(cfg.constraints, self)` (reference :34-40);
 * `step()` follows Isaac Lab's `ManagerBasedRLEnv.step` order and inserts ONE fused call,
-  `constraint_manager.compute_step(raw_reward, reset_buf)`, for the reference's lines :100-107,:118-121
-  (constraint probability, `clip(reward * (1 - p), 0)`, `dones = p`, `dones[reset] = 1`);
+  `constraint_manager.compute_step(raw_reward, reset_buf, fuse_reset=True)`, for the reference's lines :100-107,:118-121
+  (constraint probability, `clip(reward * (1 - p), 0)`, `dones = p`, `dones[reset] = 1`) and for the
+  `constraint_manager.reset(reset ids)` of :181;
 * `_reset_idx()` gathers the per-term episode statistics of the envs being reset *before* Isaac Lab zeroes their
   episode lengths and merges them into `extras["log"]` (reference :178-182), delegating everything else to
   `ManagerBasedRLEnv._reset_idx` instead of re-implementing it.
@@ -79,10 +80,12 @@ class CaTEnv(ManagerBasedRLEnv):  # pragma: no cover - needs Isaac Lab / Isaac S
 
         raw_reward = self.reward_manager.compute(dt=self.step_dt)
         if hasattr(self, "constraint_manager"):
-            # constraint probability, constrained reward and float dones (incl. dones[reset] = 1) in one fused call;
-            # clones because the manager owns and reuses its output buffers
-            reward, dones = self.constraint_manager.compute_step(raw_reward, self.reset_buf)
+            # constraint probability, constrained reward, float dones (incl. dones[reset] = 1) and the episode
+            # statistics of the envs flagged in reset_buf (which _reset_idx below would otherwise gather with a
+            # second call) in one fused call; clones because the manager owns and reuses its output buffers
+            reward, dones = self.constraint_manager.compute_step(raw_reward, self.reset_buf, fuse_reset=True)
             self.reward_buf, dones = reward.clone(), dones.clone()
+            self._fused_reset_pending = True
         else:
             self.reward_buf = raw_reward
             dones = self.reset_buf.to(torch.float32)
@@ -92,6 +95,8 @@ class CaTEnv(ManagerBasedRLEnv):  # pragma: no cover - needs Isaac Lab / Isaac S
             self.recorder_manager.record_post_step()
 
         reset_env_ids = self.reset_buf.nonzero(as_tuple=False).squeeze(-1)
+        if len(reset_env_ids) == 0:
+            self._fused_reset_pending = False
         if len(reset_env_ids) > 0:
             self.recorder_manager.record_pre_reset(reset_env_ids)
             self._reset_idx(reset_env_ids)
@@ -109,7 +114,15 @@ class CaTEnv(ManagerBasedRLEnv):  # pragma: no cover - needs Isaac Lab / Isaac S
     def _reset_idx(self, env_ids: Sequence[int]):
         info = None
         if hasattr(self, "constraint_manager"):
-            info = self.constraint_manager.reset(env_ids)  # needs the episode lengths Isaac Lab is about to zero
+            if getattr(self, "_fused_reset_pending", False):
+                # called from step() for exactly the envs flagged in reset_buf: their statistics were gathered (and
+                # cleared) by compute_step(..., fuse_reset=True), with the episode lengths as they were then
+                self._fused_reset_pending = False
+                info = self.constraint_manager.fused_reset_stats()
+                for term_cfg in self.constraint_manager._class_term_cfgs:
+                    term_cfg.func.reset(env_ids=env_ids)
+            else:  # reset() of the whole env, or any other caller
+                info = self.constraint_manager.reset(env_ids)  # needs the episode lengths Isaac Lab is about to zero
         super()._reset_idx(env_ids)
         if info is not None:
             self.extras["log"].update(info)
