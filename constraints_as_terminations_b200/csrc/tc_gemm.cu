@@ -423,6 +423,15 @@ tc_gemm_persist_kernel(const __grid_constant__ TcGemmArgs g) {
           for (int q = 0; q < 4; ++q)
             hv[i][q] = row < g.M ? __ldg(reinterpret_cast<const uint4*>(hrow + i * 32 + q * 8)) : make_uint4(0, 0, 0, 0);
       }
+      // forward: this warp's 64 bias values, fetched coalesced (2 loads per lane) into the warp's own scratch row while
+      // the MMAs still run; the epilogue then reads them back as 16-byte broadcasts.  (Per-element warp-uniform global
+      // loads cost a descriptor setup each: ncu counted 17 thread instructions per output element with them.)
+      float* bsm = colsum_sm + (((j & 1) * 8 + (warp - 2)) * 64);
+      if (MODE == kTcFwd) {
+        const float* __restrict__ bp = g.bias[z] + col_base + c_first;
+        bsm[lane] = __ldg(bp + lane);
+        bsm[32 + lane] = __ldg(bp + 32 + lane);
+      }
       if (lane == 0) mbar_wait(tfull_bar + 8 * a, (j >> 1) & 1);  // one sleeping lane per warp
       __syncwarp();
       mbar_wait(tfull_bar + 8 * a, (j >> 1) & 1);                 // already complete: a single acquire per thread
@@ -438,16 +447,13 @@ tc_gemm_persist_kernel(const __grid_constant__ TcGemmArgs g) {
       if (lane == 0) mbar_arrive(tempty_bar + 8 * a);  // the MMA warp may overwrite this stage (tile j + 2)
 
       if (MODE == kTcFwd) {
-        // bias straight from global memory (warp-uniform addresses: one broadcast transaction each, L1 hits); the
-        // flat parameter vector gives no 16-byte alignment, hence scalar loads
-        const float* __restrict__ bp = g.bias[z] + col_base + c_first;
 #pragma unroll
         for (int i = 0; i < NCH; ++i) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            float bb[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) bb[e] = __ldg(bp + i * 32 + q * 8 + e);
+            const float4 b0 = *reinterpret_cast<const float4*>(bsm + i * 32 + q * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(bsm + i * 32 + q * 8 + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
             uint4 o;
             uint32_t* op = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll

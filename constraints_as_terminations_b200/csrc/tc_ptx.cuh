@@ -103,8 +103,14 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
                :
                : "memory");
 }
-// ELU for the epilogue: ex2.approx based exp (abs error ~1e-7, far below the bf16 rounding of the result)
-__device__ __forceinline__ float elu_fast(float v) { return v > 0.0f ? v : __expf(v) - 1.0f; }
+// ELU for the epilogue: exp through one MUFU (ex2.approx.ftz of v * log2 e; abs error ~1e-7, far below the bf16
+// rounding of the result).  __expf adds a range fix-up for results below 2^-126 (4 more instructions and two
+// predicates per element); flushed to zero they give ELU = -1 exactly, which is what the fix-up would round to.
+__device__ __forceinline__ float elu_fast(float v) {
+  float t;
+  asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(t) : "f"(v * 1.4426950408889634f));
+  return v > 0.0f ? v : t - 1.0f;
+}
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address >> 4 in bits [0,14),
 // leading byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version 1 in [46,48),
