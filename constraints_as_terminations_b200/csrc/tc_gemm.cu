@@ -467,7 +467,8 @@ tc_gemm_persist_kernel(const __grid_constant__ TcGemmArgs g) {
           }
         }
       } else {
-        const bool live = row < g.M;
+        // rows beyond M need no masking: TMA zero-fills them in the A tile, so their accumulators are exactly 0 (and
+        // their ELU' factor is 1: hv was set to 0), i.e. they add nothing to the column sums; the TMA store clips them
         float* colsum = colsum_sm + (j & 1) * 4 * BN;
 #pragma unroll
         for (int i = 0; i < NCH; ++i) {
@@ -480,8 +481,8 @@ tc_gemm_persist_kernel(const __grid_constant__ TcGemmArgs g) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int cc = q * 8 + e * 2;
-              const float x0 = live ? __uint_as_float(v[i][cc]) * elu_grad_from_output(__low2float(hp[e])) : 0.0f;
-              const float x1 = live ? __uint_as_float(v[i][cc + 1]) * elu_grad_from_output(__high2float(hp[e])) : 0.0f;
+              const float x0 = __uint_as_float(v[i][cc]) * elu_grad_from_output(__low2float(hp[e]));
+              const float x1 = __uint_as_float(v[i][cc + 1]) * elu_grad_from_output(__high2float(hp[e]));
               f[cc] = x0;
               f[cc + 1] = x1;
               op[e] = pack_bf16x2(x0, x1);
