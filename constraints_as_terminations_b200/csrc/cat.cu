@@ -5,21 +5,24 @@
 // CaT.add/get_probs :39-82) and the reward/dones lines of CaTEnv.step (U/cat/cat_env.py:102-121).
 //
 // Data flow (N envs in tiles of 32, K constraint columns, S statistics slots):
-//   cat_eval_kernel : one CTA per 32-env tile, lane = env, G = 1..8 warps sharing the tile.  The tile's rows of
-//                     every source tensor are copied verbatim into shared memory by the bulk async-copy engine
-//                     (cp.async.bulk + mbarrier, one copy per source, no per-element staging instructions).
-//                     Contact-force peaks are computed once per (history tensor, body) pair into a shared table
-//                     and the command gates of all terms once per warp into a bit mask; then warp w evaluates
-//                     columns w, w+G, ... of every term (warp-uniform op dispatch hoisted out of the column
-//                     loop), writes the raw constraint into a shared [K][32] tile and the column maximum over
-//                     the 32 envs (one CREDUX.MAX.F32 per column) into a shared row.  The tile leaves as ONE
-//                     bulk async store into the workspace (C_T, tile-major [n_tiles][K][32]); each CTA issues at
-//                     most one atomicMax per column into one of up to 64 scratch rows and the last CTA
-//                     (two-level ticket) applies the clamp + Polyak update to running_max[K] (:55-61).
-//   cat_apply_kernel: one CTA per 32 envs (lane = env), 8 warps split the statistics slots.  Reads the tile's K
+//   cat_eval_kernel : persistent CTAs walk the 32-env tiles (lane = env, up to 16 warps per CTA).  The tile's rows
+//                     of every source tensor are copied verbatim into shared memory by the bulk async-copy engine
+//                     (cp.async.bulk + mbarrier; every source has its own issuing lane, no per-element staging
+//                     instructions), double buffered: tile i+1 lands while tile i is evaluated.  Contact-force
+//                     peaks are computed once per (history tensor, body) pair into a shared table (dealt to the
+//                     warps); then every TERM is evaluated by one warp -- its prologue (sources, scalars, command
+//                     gate) runs once per tile, the op switch sits outside the column loop, terms are ranked by
+//                     cost at plan time and dealt in snake order -- which writes the raw constraints into a shared
+//                     [K][32] tile and the column maxima over the 32 envs (one CREDUX.MAX.F32 per column) into a
+//                     shared row.  The tile leaves as ONE bulk async store into the workspace (C_T, tile-major
+//                     [n_tiles][K][32]); at the end each CTA issues at most one atomicMax per column into one of up
+//                     to 64 scratch rows and the last CTA (two-level ticket) applies the clamp + Polyak update to
+//                     running_max[K] (:55-61).
+//   cat_apply_kernel: one CTA per 32 envs (lane = env), the warps split the statistics slots.  Reads the tile's K
 //                     constraint values back (coalesced, L2 hits), maps violations to probabilities (:64-72),
 //                     takes the per-term and overall row max (:82,:225), updates the two per-term episode
-//                     statistics (:226-227) and writes cstr_prob plus, optionally, the scaled reward / float dones.
+//                     statistics (:226-227) and writes cstr_prob plus, optionally, the scaled reward / float dones
+//                     and -- fused reset -- the episode means of the envs flagged in reset_buf (:190-211).
 //
 // The cross-env column max is a true global dependency (probability of env i depends on the max over
 // all envs of this step), hence two phases.  HBM-bound streaming work: no tensor cores involved.
@@ -44,7 +47,7 @@ bool pdl_enabled() {
 constexpr int kTile = 32;          // envs per CTA in the eval and apply kernels (one per lane)
 constexpr int kEvalMaxWarps = 16;  // eval kernel: 1, 2, 4, 8 or 16 warps share a tile (chosen per launch)
 constexpr int kApplyMaxWarps = 16; // apply kernel: one warp per statistics slot, at most 16 (chosen per launch)
-constexpr int kApplyThreads = 64;
+constexpr int kApplyThreads = 64;   // cat_probs_kernel (debug matrix): one thread per env
 
 // sqrt(x^2 + y^2 + z^2) the way torch.norm reduces a short contiguous dim on CPU and CUDA:
 // sequential fused multiply-adds from a zero accumulator, then a correctly rounded sqrt.

@@ -77,3 +77,21 @@ def test_empty_manager_returns_empty_tensor():
     out = mgr.compute()
     assert isinstance(out, torch.Tensor) and out.numel() == 0
     assert mgr.reset() == {}
+
+
+def test_lazy_stats_dict_behaves_like_the_reference_dict():
+    """`fused_reset_stats()` hands out a dict that splits the packed statistics vector on first access."""
+    import torch
+
+    from constraints_as_terminations_b200.constraint_manager import _LazyStats
+
+    keys = ["Episode_Constraint_violation/a", "Episode_Constraint_probability/a"]
+    d = _LazyStats(keys, torch.tensor([25.0, 0.5]))
+    assert dict.__len__(d) == 0  # nothing materialised yet
+    assert "Episode_Constraint_violation/a" in d and len(d) == 2 and list(d) == keys
+    assert float(d[keys[0]]) == 25.0 and float(d.get(keys[1])) == 0.5 and d[keys[0]].ndim == 0
+    merged = {}
+    merged.update(_LazyStats(keys, torch.tensor([1.0, 2.0])))  # extras["log"].update(info) as in CaTEnv._reset_idx
+    assert list(merged) == keys and float(merged[keys[1]]) == 2.0
+    d[keys[0]] = d[keys[0]].unsqueeze(0)  # the trainer's logging loop rewrites entries in place (ppo.py:241-244)
+    assert d[keys[0]].shape == (1,)
