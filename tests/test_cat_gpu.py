@@ -51,7 +51,7 @@ def test_manager_matches_reference_golden(golden_dir, fixture):
     assert torch.equal(torch.stack([mgr._cstr_mean_values[k] for k in mgr.active_terms]).cpu(), gold["mean_values"])
 
 
-@pytest.mark.parametrize("num_envs", [1, 31, 33, 1000, 4096])
+@pytest.mark.parametrize("num_envs", [1, 31, 33, 1000, 4096, 20011])  # 20011: 626 tiles = up to 3 per persistent CTA, the last one ragged
 def test_manager_matches_oracle(num_envs):
     steps = 5
     cpu_env = se.SyntheticSolo12Env(num_envs, device="cpu", seed=11, pool=1)
