@@ -1,0 +1,61 @@
+"""bench.py contract checks that need no GPU: the reference arm prints ONE JSON line with the driver's keys, the GPU arm
+refuses to run without a device (no CPU fallback), and the flops attribution of the roofline object adds up."""
+
+import json
+import os
+import subprocess
+import sys
+from types import SimpleNamespace
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(*args):
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True, cwd=ROOT, timeout=600)
+
+
+def test_reference_arm_prints_one_json_line():
+    proc = _run("--impl", "reference", "--envs", "64", "--steps", "1", "--warmup", "0")
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    lines = [l for l in proc.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "env_steps_per_sec" and d["unit"] == "env-steps/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    proc = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                          capture_output=True, text=True, cwd=ROOT, env=env, timeout=120)
+    assert proc.returncode == 0 and proc.stdout.strip() == ""
+
+
+def test_gpu_arm_has_no_cpu_fallback():
+    if torch.cuda.is_available():
+        import pytest
+
+        pytest.skip("CUDA present")
+    proc = _run("--steps", "1", "--warmup", "3")
+    assert proc.returncode != 0 and "no CPU fallback" in (proc.stderr + proc.stdout)
+
+
+def test_gemm_flops_attribution_adds_up():
+    sys.path.insert(0, ROOT)
+    import bench
+
+    tr = SimpleNamespace(num_envs=4096, T=24, batch_size=4096 * 24, minibatch_size=16384, cfg=SimpleNamespace(updates_epochs=5))
+    flops = bench._gemm_flops_by_kernel(tr)
+    opt_rows, roll_rows = 5 * 4096 * 24, 4096 * 25
+    mac_fwd = 2 * (64 * 512 + 512 * 256 + 256 * 128)   # both nets, obs padded to 64 (0.7508 MFLOP/sample with 45)
+    mac_dgrad = 2 * (256 * 128 + 512 * 256)
+    fwd = sum(v for k, v in flops.items() if "<0," in k)
+    dgrad = sum(v for k, v in flops.items() if "<1," in k)
+    assert fwd == 2.0 * mac_fwd * (opt_rows + roll_rows)
+    assert dgrad == 2.0 * mac_dgrad * opt_rows
+    # the minibatch launches of layers 1-2 and both dgrads have more than 2 x 148 tiles: persistent kernel
+    assert set(flops) == {"tc_gemm_persist_kernel<0, 128>", "tc_gemm_kernel<0, 128>", "tc_gemm_persist_kernel<1, 128>"}
