@@ -369,7 +369,7 @@ def run_ours(args):
     losses = trainer.losses()
     prof, prof_total = kernel_profile(trainer, record=(rank == 0))
     dominant = dominant_kernel_roofline(prof, prof_total, trainer, peaks) if rank == 0 else None
-    working_set = sum(t.numel() * t.element_size() for t in (trainer.obs, trainer.obs16, trainer.actions, trainer.rewards, trainer.dones, trainer.values, trainer.advantages, trainer.returns, trainer.train_ws))
+    working_set = sum(t.numel() * t.element_size() for t in (trainer.obs, trainer.obs_op, trainer.actions, trainer.rewards, trainer.dones, trainer.values, trainer.advantages, trainer.returns, trainer.train_ws))
     del env, trainer
     torch.cuda.empty_cache()
 

@@ -45,6 +45,22 @@ NO_SOURCE = 0xFF
 # catb200_gae_variant
 GAE_RLGAMES, GAE_SKRL = 0, 1
 
+# catb200_prec: operand precision of the hidden-layer GEMMs
+PREC_BF16, PREC_TF32 = 0, 1
+PREC_NAMES = {"bf16": PREC_BF16, "tf32": PREC_TF32}
+
+
+def default_precision() -> str:
+    """`CATB200_GEMM_PREC=tf32|bf16` (default tf32: the reference's GPU numerics, scripts/clean_rl/train.py:86-87)."""
+    name = os.environ.get("CATB200_GEMM_PREC", "tf32").lower()
+    if name not in PREC_NAMES:
+        raise ValueError(f"CATB200_GEMM_PREC must be tf32 or bf16, got {name!r}")
+    return name
+
+
+def operand_dtype(prec: int) -> torch.dtype:
+    return torch.float32 if prec == PREC_TF32 else torch.bfloat16
+
 
 class Source(C.Structure):
     _fields_ = [
@@ -114,6 +130,7 @@ class MlpDims(C.Structure):
         ("h2", C.c_int32),
         ("h3", C.c_int32),
         ("obs_pad", C.c_int32),
+        ("prec", C.c_int32),
     ]
 
 
@@ -123,9 +140,24 @@ class MlpLayout(C.Structure):
         ("w", (C.c_int64 * 4) * 2),
         ("b", (C.c_int64 * 4) * 2),
         ("logstd", C.c_int64),
-        ("n_w16", C.c_int64),
-        ("w16", (C.c_int64 * 3) * 2),
-        ("wt16", (C.c_int64 * 3) * 2),
+        ("n_wc", C.c_int64),
+        ("wc", (C.c_int64 * 3) * 2),
+        ("wtc", (C.c_int64 * 3) * 2),
+    ]
+
+
+class CommandCfg(C.Structure):
+    _fields_ = [
+        ("lin_vel_x", C.c_float * 2),
+        ("lin_vel_y", C.c_float * 2),
+        ("ang_vel_z", C.c_float * 2),
+        ("heading", C.c_float * 2),
+        ("velocity_deadzone", C.c_float),
+        ("heading_control_stiffness", C.c_float),
+        ("rel_heading_envs", C.c_float),
+        ("rel_standing_envs", C.c_float),
+        ("p_step", C.c_float),
+        ("heading_command", C.c_int32),
     ]
 
 
@@ -210,7 +242,7 @@ SIGNATURES = {
     "catb200_cat_reset_workspace_bytes": (_SZ, []),
     "catb200_cat_reset_stats": (C.c_int, [_P, _I32, _P, _P, _I32, _I32, _P, _P, _P, _P, _SZ, _P]),
     "catb200_rms_workspace_bytes": (_SZ, [_I32]),
-    "catb200_rms_forward": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _F, _I32, _P, _P, _I32, _P, _SZ, _P]),
+    "catb200_rms_forward": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _F, _I32, _P, _P, _I32, _I32, _P, _SZ, _P]),
     "catb200_rollout_append": (C.c_int, [_P, _P, _P, _I32, _P, _P, _P, _P]),
     "catb200_gae_workspace_bytes": (_SZ, []),
     "catb200_gae": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _F, _F, _P, _P, _P, _P, _P, _SZ, _P]),
@@ -218,9 +250,9 @@ SIGNATURES = {
     "catb200_gae_float_dones": (C.c_int, [_I32, _P, _P, _P, _P, _P, _I32, _I32, _F, _F, _P, _P, _I32, _P, _SZ, _P]),
     "catb200_mlp_layout": (C.c_int, [C.POINTER(MlpDims), C.POINTER(MlpLayout)]),
     "catb200_mlp_cast_weights": (C.c_int, [C.POINTER(MlpDims), _P, _P, _P]),
-    "catb200_obs_to_bf16": (C.c_int, [_P, _I64, _I32, _I32, _P, _P]),
+    "catb200_obs_to_operand": (C.c_int, [C.POINTER(MlpDims), _P, _I64, _P, _P]),
     "catb200_mlp_workspace_bytes": (_SZ, [C.POINTER(MlpDims), _I32, _I32]),
-    "catb200_mlp_act": (C.c_int, [C.POINTER(MlpDims), _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "catb200_mlp_act": (C.c_int, [C.POINTER(MlpDims), _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "catb200_ppo_minibatch_grad": (
         C.c_int,
         [C.POINTER(MlpDims), C.POINTER(PpoHparams), _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P],
@@ -229,6 +261,12 @@ SIGNATURES = {
         C.c_int,
         [C.POINTER(MlpDims), _P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _P, _P, _P],
     ),
+    "catb200_philox4x32_10": (C.c_int, [_P, _P, _P]),
+    "catb200_random_permutation_host": (C.c_int, [_I64, C.c_uint64, C.c_uint64, _P]),
+    "catb200_random_permutation": (C.c_int, [_I64, _P, _P, _P]),
+    "catb200_bernoulli_mask": (C.c_int, [_P, _I32, _P, _P, _P, _P, _P]),
+    "catb200_command_update": (C.c_int, [C.POINTER(CommandCfg), _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "catb200_push_select": (C.c_int, [_I32, _F, _P, _P, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -30,8 +30,8 @@ extern unsigned long long g_launch_count;
     CATB200_CUDA_TRY(cudaPeekAtLastError());       \
   } while (0)
 
-// mlp.cu: refresh the bf16 compute copies (W and W^T of the hidden layers) from the fp32 master parameters
-int launch_cast_weights(const catb200_mlp_dims_t* dims, const float* params, void* w16, cudaStream_t st);
+// mlp.cu: refresh the compute copies (W and W^T of the hidden layers, operand precision) from the fp32 master parameters
+int launch_cast_weights(const catb200_mlp_dims_t* dims, const float* params, void* wc, cudaStream_t st);
 
 // ---- programmatic dependent launch (PDL) --------------------------------------------------------------
 // The update path is a chain of ~14 short dependent kernels per minibatch.  With PDL the next kernel's CTAs

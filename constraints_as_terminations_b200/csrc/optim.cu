@@ -5,7 +5,7 @@
 // launches over the 377k-element flat buffers:
 //   grad_norm_kernel : sum of squares (double) -> total norm, clip coefficient, Adam bias corrections
 //   adam_kernel      : scaled gradient -> moments -> parameter update (float4), zeroes the gradient for the
-//                      next minibatch; then the tiled cast kernel refreshes the bf16 copies (W and W^T).
+//                      next minibatch; then the tiled cast kernel refreshes the operand copies (W and W^T).
 #include "common.cuh"
 #include "mma.cuh"
 
@@ -104,9 +104,9 @@ using namespace catb200;
 extern "C" {
 
 int catb200_adam_step(const catb200_mlp_dims_t* dims, float* params, float* grads, float* exp_avg, float* exp_avg_sq,
-                      void* w16, const float* lr_dev, int32_t* step_dev, float max_grad_norm, float beta1, float beta2,
+                      void* wc, const float* lr_dev, int32_t* step_dev, float max_grad_norm, float beta1, float beta2,
                       float eps, float grad_scale, float* grad_norm_out, void* opt_ws, void* stream) {
-  if (!dims || !params || !grads || !exp_avg || !exp_avg_sq || !w16 || !lr_dev || !step_dev || !opt_ws)
+  if (!dims || !params || !grads || !exp_avg || !exp_avg_sq || !wc || !lr_dev || !step_dev || !opt_ws)
     return CATB200_ERR_INVALID_ARGUMENT;
   catb200_mlp_layout_t P;
   int rc = catb200_mlp_layout(dims, &P);
@@ -123,7 +123,7 @@ int catb200_adam_step(const catb200_mlp_dims_t* dims, float* params, float* grad
   const long long threads = n / 4 + 4;
   CATB200_CUDA_TRY(launch_pdl(adam_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, st, a));
   CATB200_LAUNCH_CHECK();
-  rc = launch_cast_weights(dims, params, w16, st);  // refresh the bf16 copies the tensor-core GEMMs read
+  rc = launch_cast_weights(dims, params, wc, st);  // refresh the operand copies the tensor-core GEMMs read
   if (rc != CATB200_OK) return rc;
   return CATB200_OK;
 }

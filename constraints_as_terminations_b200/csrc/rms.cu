@@ -101,8 +101,8 @@ rms_moments_kernel(const float* __restrict__ x, long long rows, int dim, float* 
 
 __global__ void __launch_bounds__(kRmsThreads)
 rms_normalize_kernel(const float* __restrict__ x, long long rows, int dim, const float* __restrict__ mean,
-                     const float* __restrict__ var, float eps, float* __restrict__ out, bf16* __restrict__ out16,
-                     int pad16) {
+                     const float* __restrict__ var, float eps, float* __restrict__ out, void* __restrict__ out_op,
+                     int pad_op, int op_prec) {
   const int rows_per_pass = kRmsThreads / dim;
   const int active = rows_per_pass * dim;
   if (threadIdx.x >= active) return;
@@ -115,9 +115,18 @@ rms_normalize_kernel(const float* __restrict__ x, long long rows, int dim, const
     const long long k = r * dim + col;
     const float y = __fdiv_rn(__fsub_rn(x[k], m), d);
     out[k] = y;
-    if (out16 != nullptr) {  // bf16 copy in the zero-padded row layout the first GEMM layer reads
-      out16[r * pad16 + col] = __float2bfloat16(y);
-      if (col + dim < pad16) out16[r * pad16 + dim + col] = __float2bfloat16(0.0f);  // pad16 - dim <= dim
+    if (out_op != nullptr) {  // operand copy in the zero-padded row layout the first GEMM layer reads
+      if (op_prec == CATB200_PREC_BF16) {
+        bf16* o = static_cast<bf16*>(out_op);
+        o[r * pad_op + col] = __float2bfloat16(y);
+        if (col + dim < pad_op) o[r * pad_op + dim + col] = __float2bfloat16(0.0f);  // pad_op - dim <= dim
+      } else {  // fp32 rounded to tf32 (cvt.rna), what tcgen05.mma kind::tf32 reads exactly
+        float* o = static_cast<float*>(out_op);
+        uint32_t t;
+        asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(t) : "f"(y));
+        o[r * pad_op + col] = __uint_as_float(t);
+        if (col + dim < pad_op) o[r * pad_op + dim + col] = 0.0f;
+      }
     }
   }
 }
@@ -141,10 +150,11 @@ extern "C" {
 size_t catb200_rms_workspace_bytes(int32_t dim) { return dim > 0 ? 256 + sizeof(double) * 2 * (size_t)dim : 0; }
 
 int catb200_rms_forward(const float* x, int64_t rows, int32_t dim, float* mean, float* var, float* count, float eps,
-                        int32_t update, float* out, void* out16, int32_t pad16, void* workspace,
+                        int32_t update, float* out, void* out_op, int32_t pad_op, int32_t op_prec, void* workspace,
                         size_t workspace_bytes, void* stream) {
   if (!x || rows <= 0 || dim <= 0 || dim > kRmsThreads || !mean || !var || !count) return CATB200_ERR_INVALID_ARGUMENT;
-  if (out16 && (!out || pad16 < dim || pad16 - dim > dim)) return CATB200_ERR_INVALID_ARGUMENT;
+  if (out_op && (!out || pad_op < dim || pad_op - dim > dim)) return CATB200_ERR_INVALID_ARGUMENT;
+  if (out_op && op_prec != CATB200_PREC_BF16 && op_prec != CATB200_PREC_TF32) return CATB200_ERR_INVALID_ARGUMENT;
   cudaStream_t st = as_stream(stream);
   const int rows_per_pass = kRmsThreads / dim;
   long long want = (rows + rows_per_pass - 1) / rows_per_pass;
@@ -158,7 +168,7 @@ int catb200_rms_forward(const float* x, int64_t rows, int32_t dim, float* mean, 
   }
   if (out) {
     const int grid = (int)min((long long)kNumSMs * 8, max(1ll, (want + 1) / 2));
-    rms_normalize_kernel<<<grid, kRmsThreads, 0, st>>>(x, rows, dim, mean, var, eps, out, static_cast<bf16*>(out16), pad16);
+    rms_normalize_kernel<<<grid, kRmsThreads, 0, st>>>(x, rows, dim, mean, var, eps, out, out_op, pad_op, op_prec);
     CATB200_LAUNCH_CHECK();
   }
   return CATB200_OK;

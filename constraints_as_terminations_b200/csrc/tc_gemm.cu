@@ -1,20 +1,23 @@
-// 5th-generation tensor-core GEMMs for the actor-critic MLP (sm_100a: tcgen05.mma + TMEM + TMA).
+// 5th-generation tensor-core GEMMs for the actor-critic MLP (sm_100a: tcgen05.mma + TMEM + TMA), templated on the
+// operand precision (PrecT in tc_ptx.cuh): tf32 (fp32 storage, kind::tf32 -- the reference's GPU numerics,
+// scripts/clean_rl/train.py:86-87) or bf16 (kind::f16).  Both nets (0 critic, 1 actor) are batched into every launch.
 //
-// One warp-specialised kernel, three modes (both nets batched over blockIdx.z):
-//   kFwd   : C[M,N]  = ELU(A[M,K] B[N,K]^T + bias)            A, B K-major            (hidden layers, forward)
-//   kDgrad : C[M,N]  = (A[M,K] B[N,K]^T) * ELU'(H[M,N]), db += colsum      K-major    (dZ_{l-1} from dZ_l, W_l^T)
-//   kWgrad : P[s,N,K] = sum_{m in split s} dZ[m,N]^T Hin[m,K]  A, B MN-major          (weight-gradient partials)
+//   mlp_gemm_kernel<kTcFwd>   : C[M,N] = ELU(A[M,K] B[N,K]^T + bias)           A, B K-major   (hidden layers, forward)
+//   mlp_gemm_kernel<kTcDgrad> : C[M,N] = (A[M,K] B[N,K]^T) * ELU'(H[M,N])      A, B K-major   (dZ_{l-1} from dZ_l, W_l^T)
+//   mlp_wgrad_kernel          : dW[outs,ins] += dZ^T Hin, db[outs] += dZ^T 1   A, B MN-major  (no transposed copies)
 //
-// CTA = one 128 x BN accumulator tile living in TMEM (128 lanes x BN fp32 columns).
-//   warp 0      : TMA producer  - cp.async.bulk.tensor 2D boxes (64 elements = 128 B inner, SWIZZLE_128B)
-//                                 into a 4-stage shared-memory ring, completion on mbarriers
-//   warp 1      : TMEM allocator + MMA issuer - one elected lane issues tcgen05.mma.cta_group::1.kind::f16
-//                                 (M = 128, N = BN, K = 16) from shared-memory matrix descriptors;
-//                                 tcgen05.commit releases ring slots and finally signals the epilogue
-//   warps 2..5  : epilogue      - tcgen05.ld (32 lanes x 32 columns per instruction) -> registers ->
-//                                 bias/ELU or ELU'-scale (+ recursive-halving column sums) or fp32 partials
-// Several CTAs are resident per SM (<= 96 KiB of shared memory, BN <= 128 TMEM columns each), so one CTA's
-// epilogue overlaps another CTA's main loop without a persistent scheduler.
+// mlp_gemm_kernel is persistent: one CTA per SM walks the 128 x 128 output tiles with three decoupled roles
+//   warp 0     TMA producer : cp.async.bulk.tensor boxes (128-byte rows, SWIZZLE_128B) into a 4-stage ring that runs
+//                             across tile boundaries
+//   warp 1     MMA issuer   : one elected lane issues tcgen05.mma (M = 128, N = 128, 32 bytes of K per instruction)
+//                             into one of two TMEM accumulator stages
+//   warps 2-9  epilogue     : tcgen05.ld -> registers -> bias/ELU or ELU'-scale -> per-warp swizzled slab in shared
+//                             memory -> ONE TMA tensor store per 32 x 128-byte slab.  In dgrad the slab first receives
+//                             the H values by TMA, so ELU' needs no strided global loads.
+// mlp_wgrad_kernel is one (tile, row range) per CTA: split over the minibatch rows so the launch fills the machine, the
+// fp32 tile leaves TMEM straight into the gradient accumulators with red.global.add.v4.f32 (no partial-sum buffers,
+// no reduction kernel), and the bias gradient is the same A operand multiplied by a tile of ones (N = 16), so the
+// dgrad epilogue carries no column sums.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -27,313 +30,52 @@
 namespace catb200 {
 
 constexpr int kTcThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (2 warps per TMEM lane quarter)
-constexpr int kTcStages = 3;     // ring slots at most (fewer when the reduction is short)
-constexpr int kTcBK = 64;  // reduction elements per stage (= 4 UMMA K-steps of 16)
-
-template <int MODE, int BN>
-struct TcSmem {
-  static constexpr int kABytes = 128 * kTcBK * 2;  // 16 KiB: 128 (M) x 64 (K) bf16, or 2 boxes of 64 x 64 (MN-major)
-  static constexpr int kBBytes = BN * kTcBK * 2;
-  static constexpr int kStage = kABytes + kBBytes;
-  static constexpr int kAux = 256 /*barriers*/ + 4 * BN * 4 /*bias tile (fwd) or 4 x BN column-sum scratch (dgrad)*/;
-  static constexpr int total(int stages) { return stages * kStage + 1024 /*alignment slack*/ + kAux; }
-};
-
-template <int MODE, int BN>
-__global__ void __launch_bounds__(kTcThreads, 2)
-tc_gemm_kernel(const __grid_constant__ TcGemmArgs g) {
-  using S = TcSmem<MODE, BN>;
-  extern __shared__ uint8_t smem_raw[];
-  pdl_launch_dependents();  // let the next kernel of the chain get resident while this one runs
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t tiles = (raw + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
-  const int stages = g.stages;
-  const uint32_t bars = tiles + stages * S::kStage;
-  const uint32_t full_bar = bars, empty_bar = bars + 8 * kTcStages, tmem_full_bar = bars + 16 * kTcStages;
-  const uint32_t tmem_slot = bars + 16 * kTcStages + 8;
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
-  float* bias_sm = reinterpret_cast<float*>(smem_raw + (bars + 256 - raw));
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int z = blockIdx.z;
-  const CUtensorMap* mapA = &g.mapA[z];
-  const CUtensorMap* mapB = &g.mapB[z];
-
-  // tile coordinates and reduction range
-  int row_base, col_base, k_begin, k_blocks;
-  if (MODE == kTcWgrad) {
-    const int k_tiles = g.N / BN;  // output columns (input features) per BN tile
-    row_base = (blockIdx.x / k_tiles) * 128;  // dW rows (output features of the layer)
-    col_base = (blockIdx.x % k_tiles) * BN;
-    k_begin = blockIdx.y * g.m_range;
-    const int k_end = min(g.K, k_begin + g.m_range);
-    k_blocks = max(0, (k_end - k_begin + kTcBK - 1) / kTcBK);
-  } else {
-    row_base = blockIdx.x * 128;
-    col_base = blockIdx.y * BN;
-    k_begin = 0;
-    k_blocks = g.K / kTcBK;
-  }
-
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];\n" ::"l"(mapA));
-    asm volatile("prefetch.tensormap [%0];\n" ::"l"(mapB));
-    for (int s = 0; s < stages; ++s) {
-      mbar_init(full_bar + 8 * s, 1);
-      mbar_init(empty_bar + 8 * s, 1);
-    }
-    mbar_init(tmem_full_bar, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, BN);
-  // everything above (barriers, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail;
-  // from here on global data produced by it is read
-  pdl_wait();
-  if (MODE == kTcFwd && warp >= 2) {
-    for (int c = threadIdx.x - 64; c < BN; c += kTcThreads - 64) bias_sm[c] = __ldg(g.bias[z] + col_base + c);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (elect_one()) {
-      for (int kb = 0; kb < k_blocks; ++kb) {
-        const int s = kb % stages;
-        mbar_wait(empty_bar + 8 * s, ((kb / stages) & 1) ^ 1);
-        const uint32_t sa = tiles + s * S::kStage, sb = sa + S::kABytes;
-        mbar_expect_tx(full_bar + 8 * s, S::kStage);
-        const int k0 = k_begin + kb * kTcBK;
-        if (MODE == kTcWgrad) {
-          // MN-major operands: boxes of 64 (contiguous features) x 64 (reduction rows), 8 KiB each
-          for (int h = 0; h < 2; ++h) tma_load_2d(sa + h * 8192, mapA, full_bar + 8 * s, row_base + h * 64, k0);
-          for (int h = 0; h < BN / 64; ++h) tma_load_2d(sb + h * 8192, mapB, full_bar + 8 * s, col_base + h * 64, k0);
-        } else {
-          tma_load_2d(sa, mapA, full_bar + 8 * s, k0, row_base);  // 64 (K) x 128 rows
-          tma_load_2d(sb, mapB, full_bar + 8 * s, k0, col_base);  // 64 (K) x BN rows
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc(128, BN, MODE == kTcWgrad, MODE == kTcWgrad);
-    for (int kb = 0; kb < k_blocks; ++kb) {
-      const int s = kb % stages;
-      mbar_wait(full_bar + 8 * s, (kb / stages) & 1);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t sa = tiles + s * S::kStage, sb = sa + S::kABytes;
-#pragma unroll
-        for (int k = 0; k < kTcBK / 16; ++k) {
-          uint64_t da, db;
-          if (MODE == kTcWgrad) {
-            // MN-major SW128: 64-feature chunks LBO = 8 KiB apart, 8-row reduction groups SBO = 1 KiB apart;
-            // one UMMA K-step (16 reduction rows) = 2 KiB further
-            da = make_smem_desc(sa + k * 2048, 8192, 1024);
-            db = make_smem_desc(sb + k * 2048, 8192, 1024);
-          } else {
-            // K-major SW128: rows are 128 B, 8-row groups SBO = 1 KiB apart; one K-step = 32 B further
-            da = make_smem_desc(sa + k * 32, 16, 1024);
-            db = make_smem_desc(sb + k * 32, 16, 1024);
-          }
-          umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-        }
-      }
-      __syncwarp();
-      if (elect_one()) {
-        umma_commit(empty_bar + 8 * s);                         // frees the ring slot once these MMAs retire
-        if (kb == k_blocks - 1) umma_commit(tmem_full_bar);    // accumulator complete -> epilogue
-      }
-      __syncwarp();
-    }
-  } else {
-    // ===================== epilogue (warps 2..9) =====================
-    // TMEM lanes 32*quarter .. +31 are the ones a warp may read (quarter = warp % 4); the two warps of a
-    // quarter split the BN columns in halves.  Both 32-column chunks of a half are fetched before one wait.
-    const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
-    constexpr int HC = BN / 2;       // columns per warp
-    constexpr int NCH = HC / 32;     // 32-column chunks per warp (1 or 2)
-    const int row = row_base + quarter * 32 + lane;
-    const int c_first = half * HC;
-    // dgrad: the forward activations whose ELU' scales the result are fetched while the MMAs still run
-    uint4 hv[NCH][4];
-    if (MODE == kTcDgrad) {
-      const bf16* __restrict__ hrow = g.H[z] + (size_t)row * g.ldc + col_base + c_first;
-#pragma unroll
-      for (int i = 0; i < NCH; ++i)
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          hv[i][q] = row < g.M ? __ldg(reinterpret_cast<const uint4*>(hrow + i * 32 + q * 8)) : make_uint4(0, 0, 0, 0);
-    }
-    if (k_blocks > 0) {
-      if (lane == 0) mbar_wait(tmem_full_bar, 0);  // one sleeping lane per warp instead of 256 pollers
-      __syncwarp();
-      mbar_wait(tmem_full_bar, 0);                 // already complete: a single acquire per thread
-      tc_fence_after();
-    }
-    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + c_first;
-    uint32_t v[NCH][32];
-    if (k_blocks > 0) {
-#pragma unroll
-      for (int i = 0; i < NCH; ++i) tmem_ld32(taddr + i * 32, v[i]);
-#pragma unroll
-      for (int i = 0; i < NCH; ++i) tmem_ld_wait(v[i]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < NCH; ++i)
-#pragma unroll
-        for (int e = 0; e < 32; ++e) v[i][e] = 0u;
-    }
-    // Output path (fwd / dgrad): the warp's 32 rows x 64 columns (128 B per row) are written into the ring's
-    // first stage -- free by now, all MMAs have retired -- in the SWIZZLE_128B layout and leave with ONE TMA
-    // tensor store per warp: full 128-byte lines instead of 32 scattered 16-byte stores per instruction.
-    // box `half` = columns [half*64, half*64+64) of the tile: [128 rows][128 B], 16 KiB, rows of this warp at +quarter*4 KiB
-    const int trow = quarter * 32 + lane;  // row inside the 128-row tile
-    const uint32_t cbox = tiles + half * 16384;
-    if (MODE == kTcFwd) {
-#pragma unroll
-      for (int i = 0; i < NCH; ++i) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 o;
-          uint32_t* op = reinterpret_cast<uint32_t*>(&o);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int cc = q * 8 + e * 2;
-            const float x0 = __uint_as_float(v[i][cc]) + bias_sm[c_first + i * 32 + cc];
-            const float x1 = __uint_as_float(v[i][cc + 1]) + bias_sm[c_first + i * 32 + cc + 1];
-            op[e] = pack_bf16x2(elu_fast(x0), elu_fast(x1));
-          }
-          st_shared_v4(cbox + trow * 128 + (((i * 4 + q) ^ (trow & 7)) << 4), o);
-        }
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        tma_store_2d(&g.mapC[z], cbox + quarter * 4096, col_base + c_first, row_base + quarter * 32);
-        tma_store_commit_and_wait();
-      }
-      __syncwarp();
-    } else if (MODE == kTcDgrad) {
-      const bool live = row < g.M;
-#pragma unroll
-      for (int i = 0; i < NCH; ++i) {
-        float f[32];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&hv[i][q]);
-          uint4 o;
-          uint32_t* op = reinterpret_cast<uint32_t*>(&o);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int cc = q * 8 + e * 2;
-            const float x0 = live ? __uint_as_float(v[i][cc]) * elu_grad_from_output(__low2float(hp[e])) : 0.0f;
-            const float x1 = live ? __uint_as_float(v[i][cc + 1]) * elu_grad_from_output(__high2float(hp[e])) : 0.0f;
-            f[cc] = x0;
-            f[cc + 1] = x1;
-            op[e] = pack_bf16x2(x0, x1);
-          }
-          st_shared_v4(cbox + trow * 128 + (((i * 4 + q) ^ (trow & 7)) << 4), o);
-        }
-        // column sums over this warp's 32 rows by recursive halving: after the 5 rounds lane l holds the
-        // sum of column (i*32 + l)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const bool upper = (lane & o) != 0;
-#pragma unroll
-          for (int j = 0; j < o; ++j) {
-            const float send = upper ? f[j] : f[j + o];
-            const float keep = upper ? f[j + o] : f[j];
-            f[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-          }
-        }
-        bias_sm[quarter * BN + c_first + i * 32 + lane] = f[0];  // per-quarter column sums -> shared scratch
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        tma_store_2d(&g.mapC[z], cbox + quarter * 4096, col_base + c_first, row_base + quarter * 32);
-        tma_store_commit_and_wait();
-      }
-      // the four row quarters cover the same columns: combine them in shared memory and issue ONE atomic per
-      // column per CTA (same-address atomics from many CTAs serialise in L2, tens of ns each)
-      asm volatile("bar.sync 1, 256;\n" ::: "memory");  // the 8 epilogue warps only
-      const int et = threadIdx.x - 64;
-      if (et < BN)
-        atomicAdd(g.dbias[z] + col_base + et, (bias_sm[et] + bias_sm[BN + et]) + (bias_sm[2 * BN + et] + bias_sm[3 * BN + et]));
-    } else {
-      // weight-gradient partial: fp32 [128 rows (layer outputs) x BN (layer inputs)]
-      float* __restrict__ prow = g.part[z] + ((size_t)blockIdx.y * g.M + row) * g.N + col_base + c_first;
-#pragma unroll
-      for (int i = 0; i < NCH; ++i)
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<uint4*>(prow + i * 32 + q * 4) = make_uint4(v[i][q * 4], v[i][q * 4 + 1], v[i][q * 4 + 2], v[i][q * 4 + 3]);
-    }
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
-  }
-}
-
-// ---- persistent variant (forward / dgrad) ----------------------------------------------------------------------
-// ncu on the one-tile-per-CTA kernel above: a 128 x 128 x 256 tile needs 0.5 us of tensor-pipe time but its CTA lives
-// ~15 us (prologue: barrier init, TMEM allocation, descriptor fetch; then load -> MMA -> TMEM read -> epilogue -> store
-// strictly one after the other), so the tensor pipe is 5-10 % busy even with two CTAs per SM.  Here ONE CTA per SM
-// walks the tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (n fastest, so CTAs that run side by side share the A
-// tile in L2) with the three roles decoupled across tiles:
-//   warp 0   TMA producer: keeps the 4-stage ring full across tile boundaries (running k-block counter)
-//   warp 1   MMA issuer  : accumulates tile j into TMEM stage j & 1 (2 x BN columns allocated once)
-//   warps 2-9 epilogue   : drain stage j & 1 (tcgen05.ld), hand it back (tmem_empty barrier, one arrival per warp)
-//                          and do the bias/ELU or ELU'-scale math + TMA store while the MMAs of tile j + 1 run.
-// The output staging area is separate from the ring (the ring is never idle any more).
+constexpr int kEpiWarps = kTcThreads / 32 - 2;
+constexpr int kRowBytes = 128;                 // one SWIZZLE_128B row
+constexpr int kATileBytes = 128 * kRowBytes;   // 16 KiB: 128 rows (M or N) x 128 bytes of K
+constexpr int kSlabBytes = 32 * kRowBytes;     // 4 KiB: one epilogue warp's 32 rows x 128 bytes of output
 constexpr int kPStages = 4;
 
-template <int MODE, int BN>
 struct PSmem {
-  static constexpr int kABytes = 128 * kTcBK * 2, kBBytes = BN * kTcBK * 2, kStage = kABytes + kBBytes;
-  static constexpr int kOut = 2 * 2 * 16384;                    // 2 tiles x two [128 rows][64 cols] bf16 boxes, SWIZZLE_128B
-  static constexpr int kAux = 256 + 2 * 4 * BN * 4;             // barriers + double-buffered 4 x BN column-sum scratch
-  static constexpr int kTotal = kPStages * kStage + kOut + 1024 /*alignment slack*/ + kAux;
+  static constexpr int kStage = 2 * kATileBytes;                  // A tile + B tile (BN = 128)
+  static constexpr int kSlabs = kEpiWarps * 2 * kSlabBytes;       // two slabs per epilogue warp
+  static constexpr int kBars = 8 * (2 * kPStages + 4 + 2 * kEpiWarps);
+  static constexpr int kBias = 2 * kEpiWarps * 64 * 4;            // double-buffered 64 bias values per warp
+  static constexpr int kTotal = kPStages * kStage + kSlabs + ((kBars + 15) & ~15) + 16 + kBias + 1024 /*alignment slack*/;
 };
 
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
-}
-
-template <int MODE, int BN>
+template <int MODE, int PREC>
 __global__ void __launch_bounds__(kTcThreads, 1)
-tc_gemm_persist_kernel(const __grid_constant__ TcGemmArgs g) {
-  using S = PSmem<MODE, BN>;
-  static_assert(MODE == kTcFwd || MODE == kTcDgrad, "persistent kernel: forward / dgrad only");
+mlp_gemm_kernel(const __grid_constant__ TcGemmArgs g) {
+  using P = PrecT<PREC>;
+  using S = PSmem;
+  constexpr int BN = 128;
+  constexpr int CH = kRowBytes / (int)sizeof(typename P::T);  // output columns per slab row: 64 bf16 / 32 fp32
+  constexpr int NCHUNK = 64 / CH;                             // slabs per warp and tile: 1 / 2
   extern __shared__ uint8_t smem_raw[];
   pdl_launch_dependents();
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t tiles = (raw + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
-  const uint32_t out_sm = tiles + kPStages * S::kStage;
-  const uint32_t bars = out_sm + S::kOut;
+  const uint32_t slabs = tiles + kPStages * S::kStage;
+  const uint32_t bars = slabs + S::kSlabs;
   const uint32_t full_bar = bars, empty_bar = bars + 8 * kPStages;
   const uint32_t tfull_bar = bars + 16 * kPStages, tempty_bar = tfull_bar + 16;
-  const uint32_t tmem_slot = tempty_bar + 16;
+  const uint32_t h_bar = tempty_bar + 16;  // [kEpiWarps][2]
+  const uint32_t tmem_slot = bars + ((S::kBars + 15) & ~15);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
-  float* colsum_sm = reinterpret_cast<float*>(smem_raw + (bars + 256 - raw));  // [2][4][BN]
+  float* bias_sm = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - raw));  // [2][kEpiWarps][64]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = g.N / BN, tiles_m = (g.M + 127) / 128;
   const int per_net = tiles_m * tiles_n, total = 2 * per_net;
-  const int k_blocks = g.K / kTcBK;
+  const int k_blocks = g.K / P::kBK;
 
   if (warp == 0 && lane == 0) {
     for (int z = 0; z < 2; ++z) {
       asm volatile("prefetch.tensormap [%0];\n" ::"l"(&g.mapA[z]));
       asm volatile("prefetch.tensormap [%0];\n" ::"l"(&g.mapB[z]));
       asm volatile("prefetch.tensormap [%0];\n" ::"l"(&g.mapC[z]));
+      if (MODE == kTcDgrad) asm volatile("prefetch.tensormap [%0];\n" ::"l"(&g.mapH[z]));
     }
     for (int s = 0; s < kPStages; ++s) {
       mbar_init(full_bar + 8 * s, 1);
@@ -341,11 +83,14 @@ tc_gemm_persist_kernel(const __grid_constant__ TcGemmArgs g) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar + 8 * a, 1);
-      mbar_init(tempty_bar + 8 * a, kTcThreads / 32 - 2);  // one arrival per epilogue warp
+      mbar_init(tempty_bar + 8 * a, kEpiWarps);  // one arrival per epilogue warp
     }
+    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(h_bar + 8 * i, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+  // everything above (barriers, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail;
+  // from here on global data produced by it is read
   pdl_wait();
   tc_fence_before();
   __syncthreads();
@@ -362,16 +107,16 @@ tc_gemm_persist_kernel(const __grid_constant__ TcGemmArgs g) {
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {
           const uint32_t s = it % kPStages;
           mbar_wait(empty_bar + 8 * s, ((it / kPStages) & 1) ^ 1);
-          const uint32_t sa = tiles + s * S::kStage, sb = sa + S::kABytes;
+          const uint32_t sa = tiles + s * S::kStage, sb = sa + kATileBytes;
           mbar_expect_tx(full_bar + 8 * s, S::kStage);
-          tma_load_2d(sa, &g.mapA[z], full_bar + 8 * s, kb * kTcBK, row_base);  // 64 (K) x 128 rows
-          tma_load_2d(sb, &g.mapB[z], full_bar + 8 * s, kb * kTcBK, col_base);  // 64 (K) x BN rows
+          tma_load_2d(sa, &g.mapA[z], full_bar + 8 * s, kb * P::kBK, row_base);  // 128 bytes of K x 128 rows
+          tma_load_2d(sb, &g.mapB[z], full_bar + 8 * s, kb * P::kBK, col_base);
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc(128, BN, false, false);
+    constexpr uint32_t idesc = make_idesc(P::kFmt, 128, BN, false, false);
     uint32_t it = 0, j = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
       const uint32_t a = j & 1;
@@ -382,13 +127,13 @@ tc_gemm_persist_kernel(const __grid_constant__ TcGemmArgs g) {
         mbar_wait(full_bar + 8 * s, (it / kPStages) & 1);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t sa = tiles + s * S::kStage, sb = sa + S::kABytes;
+          const uint32_t sa = tiles + s * S::kStage, sb = sa + kATileBytes;
 #pragma unroll
-          for (int k = 0; k < kTcBK / 16; ++k) {
+          for (int k = 0; k < P::kBK / P::kUmmaK; ++k) {
             // K-major SW128: rows are 128 B, 8-row groups SBO = 1 KiB apart; one K-step = 32 B further
             const uint64_t da = make_smem_desc(sa + k * 32, 16, 1024);
             const uint64_t db = make_smem_desc(sb + k * 32, 16, 1024);
-            umma_bf16(tmem_base + a * BN, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma<PREC>(tmem_base + a * BN, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
         }
         __syncwarp();
@@ -401,33 +146,36 @@ tc_gemm_persist_kernel(const __grid_constant__ TcGemmArgs g) {
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
-    const int quarter = warp & 3;      // TMEM lanes 32 * quarter .. + 31 are the ones this warp may read
-    const int half = (warp - 2) >> 2;  // the two warps of a quarter split the BN columns in halves
-    constexpr int HC = BN / 2, NCH = HC / 32;
-    const int c_first = half * HC;
-    const int trow = quarter * 32 + lane;  // row inside the 128-row tile
+    const int ew = warp - 2;
+    const int quarter = warp & 3;  // TMEM lanes 32 * quarter .. + 31 are the ones this warp may read
+    const int half = ew >> 2;      // the two warps of a quarter split the BN columns in halves
+    const int c_first = half * 64;
+    const uint32_t my_slabs = slabs + ew * 2 * kSlabBytes;
+    const uint32_t my_hbar = h_bar + ew * 16;
+    const uint32_t lane_row = lane * kRowBytes, lane_x = lane & 7;
     uint32_t j = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
       const int z = t / per_net, r = t - z * per_net;
       const int row_base = (r / tiles_n) * 128, col_base = (r % tiles_n) * BN;
-      const int row = row_base + trow;
       const uint32_t a = j & 1;
-      const uint32_t cbox = out_sm + a * 32768 + half * 16384;  // output staging alternates with the tile parity
-      // dgrad: the forward activations whose ELU' scales the result are fetched while the MMAs still run
-      uint4 hv[NCH][4];
+      // slab buffer of chunk c: fp32 has two 32-column chunks per tile (buffer c, used once per tile); bf16 has one
+      // 64-column chunk (buffer j & 1, used every other tile).  Before a buffer is refilled, the TMA store that last
+      // read it must have finished reading: bulk groups complete in order, so "at most n pending" is enough.
+      float* bsm = bias_sm + ((j & 1) * kEpiWarps + ew) * 64;
       if (MODE == kTcDgrad) {
-        const bf16* __restrict__ hrow = g.H[z] + (size_t)row * g.ldc + col_base + c_first;
+        // H values of this warp's slabs arrive by TMA while the MMAs still run
+        if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < NCH; ++i)
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            hv[i][q] = row < g.M ? __ldg(reinterpret_cast<const uint4*>(hrow + i * 32 + q * 8)) : make_uint4(0, 0, 0, 0);
-      }
-      // forward: this warp's 64 bias values, fetched coalesced (2 loads per lane) into the warp's own scratch row while
-      // the MMAs still run; the epilogue then reads them back as 16-byte broadcasts.  (Per-element warp-uniform global
-      // loads cost a descriptor setup each: ncu counted 17 thread instructions per output element with them.)
-      float* bsm = colsum_sm + (((j & 1) * 8 + (warp - 2)) * 64);
-      if (MODE == kTcFwd) {
+          for (int c = 0; c < NCHUNK; ++c) {
+            const uint32_t buf = NCHUNK == 2 ? (uint32_t)c : (j & 1);
+            if (NCHUNK == 2 && c == 1) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
+            mbar_expect_tx(my_hbar + 8 * buf, kSlabBytes);
+            tma_load_2d(my_slabs + buf * kSlabBytes, &g.mapH[z], my_hbar + 8 * buf, col_base + c_first + c * CH, row_base + quarter * 32);
+          }
+        }
+      } else {
+        // this warp's 64 bias values, fetched coalesced into its own scratch row; the math reads them as broadcasts
         const float* __restrict__ bp = g.bias[z] + col_base + c_first;
         bsm[lane] = __ldg(bp + lane);
         bsm[32 + lane] = __ldg(bp + 32 + lane);
@@ -437,95 +185,79 @@ tc_gemm_persist_kernel(const __grid_constant__ TcGemmArgs g) {
       mbar_wait(tfull_bar + 8 * a, (j >> 1) & 1);                 // already complete: a single acquire per thread
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * BN + c_first;
-      uint32_t v[NCH][32];
-#pragma unroll
-      for (int i = 0; i < NCH; ++i) tmem_ld32(taddr + i * 32, v[i]);
-#pragma unroll
-      for (int i = 0; i < NCH; ++i) tmem_ld_wait(v[i]);
+      uint32_t v[2][32];
+      tmem_ld32(taddr, v[0]);
+      tmem_ld32(taddr + 32, v[1]);
+      tmem_ld_wait(v[0]);
+      tmem_ld_wait(v[1]);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar + 8 * a);  // the MMA warp may overwrite this stage (tile j + 2)
 
-      if (MODE == kTcFwd) {
 #pragma unroll
-        for (int i = 0; i < NCH; ++i) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 b0 = *reinterpret_cast<const float4*>(bsm + i * 32 + q * 8);
-            const float4 b1 = *reinterpret_cast<const float4*>(bsm + i * 32 + q * 8 + 4);
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            uint4 o;
-            uint32_t* op = reinterpret_cast<uint32_t*>(&o);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int cc = q * 8 + e * 2;
-              const float x0 = __uint_as_float(v[i][cc]) + bb[e * 2];
-              const float x1 = __uint_as_float(v[i][cc + 1]) + bb[e * 2 + 1];
-              op[e] = pack_bf16x2(elu_fast(x0), elu_fast(x1));
-            }
-            st_shared_v4(cbox + trow * 128 + (((i * 4 + q) ^ (trow & 7)) << 4), o);
+      for (int c = 0; c < NCHUNK; ++c) {
+        const uint32_t buf = NCHUNK == 2 ? (uint32_t)c : (j & 1);
+        const uint32_t slab = my_slabs + buf * kSlabBytes;
+        if (MODE == kTcDgrad) {
+          mbar_wait(my_hbar + 8 * buf, NCHUNK == 2 ? (j & 1) : ((j >> 1) & 1));
+        } else {
+          if (lane == 0) {
+            if (NCHUNK == 2 && c == 1) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
           }
+          __syncwarp();
         }
-      } else {
-        // rows beyond M need no masking: TMA zero-fills them in the A tile, so their accumulators are exactly 0 (and
-        // their ELU' factor is 1: hv was set to 0), i.e. they add nothing to the column sums; the TMA store clips them
-        float* colsum = colsum_sm + (j & 1) * 4 * BN;
 #pragma unroll
-        for (int i = 0; i < NCH; ++i) {
-          float f[32];
+        for (int q = 0; q < 8; ++q) {  // 16-byte chunk q of this thread's 128-byte row
+          const uint32_t addr = slab + lane_row + ((q ^ lane_x) << 4);
+          uint4 o;
+          if (PREC == kPrecTf32) {
+            float x[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&hv[i][q]);
-            uint4 o;
-            uint32_t* op = reinterpret_cast<uint32_t*>(&o);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int cc = q * 8 + e * 2;
-              const float x0 = __uint_as_float(v[i][cc]) * elu_grad_from_output(__low2float(hp[e]));
-              const float x1 = __uint_as_float(v[i][cc + 1]) * elu_grad_from_output(__high2float(hp[e]));
-              f[cc] = x0;
-              f[cc + 1] = x1;
-              op[e] = pack_bf16x2(x0, x1);
+            for (int e = 0; e < 4; ++e) x[e] = __uint_as_float(v[c][q * 4 + e]);
+            if (MODE == kTcFwd) {
+              const float4 b = *reinterpret_cast<const float4*>(bsm + c * 32 + q * 4);
+              x[0] = elu_fast(x[0] + b.x); x[1] = elu_fast(x[1] + b.y); x[2] = elu_fast(x[2] + b.z); x[3] = elu_fast(x[3] + b.w);
+            } else {
+              const uint4 h = ld_shared_v4(addr);
+              x[0] *= elu_grad_from_output(__uint_as_float(h.x)); x[1] *= elu_grad_from_output(__uint_as_float(h.y));
+              x[2] *= elu_grad_from_output(__uint_as_float(h.z)); x[3] *= elu_grad_from_output(__uint_as_float(h.w));
             }
-            st_shared_v4(cbox + trow * 128 + (((i * 4 + q) ^ (trow & 7)) << 4), o);
-          }
-          // column sums over this warp's 32 rows by recursive halving: lane l ends with the sum of column i*32 + l
+            o = make_uint4(__float_as_uint(round_tf32(x[0])), __float_as_uint(round_tf32(x[1])),
+                           __float_as_uint(round_tf32(x[2])), __float_as_uint(round_tf32(x[3])));
+          } else {
+            float x[8];
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const bool upper = (lane & o) != 0;
+            for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[q >> 2][(q & 3) * 8 + e]);
+            if (MODE == kTcFwd) {
+              const float4 b0 = *reinterpret_cast<const float4*>(bsm + q * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(bsm + q * 8 + 4);
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-            for (int jj = 0; jj < o; ++jj) {
-              const float send = upper ? f[jj] : f[jj + o];
-              const float keep = upper ? f[jj + o] : f[jj];
-              f[jj] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+              for (int e = 0; e < 8; ++e) x[e] = elu_fast(x[e] + bb[e]);
+            } else {
+              const uint4 h = ld_shared_v4(addr);
+              const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&h);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                x[2 * e] *= elu_grad_from_output(__low2float(hp[e]));
+                x[2 * e + 1] *= elu_grad_from_output(__high2float(hp[e]));
+              }
             }
+            o = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
           }
-          colsum[quarter * BN + c_first + i * 32 + lane] = f[0];
+          st_shared_v4(addr, o);
         }
-      }
-      // this warp's 32 rows x 64 columns leave with ONE TMA tensor store.  The slab is this warp's own and there are
-      // two of them: only the store issued one tile ago (which read the slab the next tile will overwrite) has to be
-      // done before going on, the one just issued drains behind the next tile's math; no CTA-wide barrier involved
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        tma_store_2d(&g.mapC[z], cbox + quarter * 4096, col_base + c_first, row_base + quarter * 32);
-        asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
-      }
-      __syncwarp();
-      if (MODE == kTcDgrad) {
-        // the four row quarters cover the same columns: combine them in shared memory and issue ONE atomic per
-        // column per tile.  The scratch alternates between two buffers: a warp that races ahead writes tile j + 1's
-        // sums into the other one, and reaches tile j + 2 only through tile j + 1's barrier.
-        asm volatile("bar.sync 1, 256;\n" ::: "memory");  // the 8 epilogue warps only
-        const float* colsum = colsum_sm + (j & 1) * 4 * BN;
-        const int et = threadIdx.x - 64;
-        if (et < BN)
-          atomicAdd(g.dbias[z] + col_base + et, (colsum[et] + colsum[BN + et]) + (colsum[2 * BN + et] + colsum[3 * BN + et]));
+        // rows beyond M need no masking: TMA zero-fills them in the A tile (accumulators exactly 0) and clips the store
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&g.mapC[z], slab, col_base + c_first + c * CH, row_base + quarter * 32);
+          asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+        }
       }
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");  // staging read out before exit
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");  // stores complete before exit
     tc_fence_before();
   }
   __syncthreads();
@@ -535,13 +267,152 @@ tc_gemm_persist_kernel(const __grid_constant__ TcGemmArgs g) {
   }
 }
 
+// ---- weight gradient ---------------------------------------------------------------------------------------------
+constexpr int kWgStages = 3;
+
+template <int BN>
+struct WgSmem {
+  static constexpr int kStage = (128 + BN) * kRowBytes;  // (128 dZ + BN input features) x kBK rows x element size
+  static constexpr int kOnes = 2048;                     // 16 rows x 128 B of ones (K-major B operand of the bias MMA)
+  static constexpr int kTotal = kWgStages * kStage + kOnes + 256 /*barriers + tmem slot*/ + 1024 /*alignment slack*/;
+};
+
+template <int PREC, int BN>
+__global__ void __launch_bounds__(kTcThreads, 2)
+mlp_wgrad_kernel(const __grid_constant__ TcWgradArgs g) {
+  using P = PrecT<PREC>;
+  using T = typename P::T;
+  using S = WgSmem<BN>;
+  constexpr int CH = kRowBytes / (int)sizeof(T);   // features per 128-byte row: 64 / 32
+  constexpr int kBoxBytes = P::kBK * kRowBytes;    // one TMA box: CH features x kBK rows (8 / 4 KiB)
+  constexpr int kTmemCols = BN == 128 ? 256 : 128; // BN accumulator columns + 16 for the bias MMA, power of two
+  extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t tiles = (raw + 1023u) & ~1023u;
+  const uint32_t ones = tiles + kWgStages * S::kStage;
+  const uint32_t bars = ones + S::kOnes;
+  const uint32_t full_bar = bars, empty_bar = bars + 8 * kWgStages, tmem_full_bar = bars + 16 * kWgStages;
+  const uint32_t tmem_slot = tmem_full_bar + 8;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int z = blockIdx.z;
+  const int n_tiles = g.ins_pad / BN;
+  const int row_base = (blockIdx.x / n_tiles) * 128;  // dW rows = output features of the layer
+  const int col_base = (blockIdx.x % n_tiles) * BN;   // dW columns = input features
+  const bool with_bias = col_base == 0;                // one column tile per row tile also produces db
+  const int k_begin = blockIdx.y * g.m_range;
+  const int k_end = min(g.rows, k_begin + g.m_range);
+  const int k_blocks = max(0, (k_end - k_begin + P::kBK - 1) / P::kBK);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&g.mapA[z]));
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&g.mapB[z]));
+    for (int s = 0; s < kWgStages; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  if (warp >= 2) {  // the tile of ones, written through the generic proxy and published to the async proxy
+    T* op = reinterpret_cast<T*>(smem_raw + (ones - raw));
+    const T one = PREC == kPrecTf32 ? T(1.0f) : T(__float2bfloat16(1.0f));
+    for (int i = threadIdx.x - 64; i < S::kOnes / (int)sizeof(T); i += kTcThreads - 64) op[i] = one;
+    fence_proxy_async_smem();
+  }
+  pdl_wait();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        const int s = kb % kWgStages;
+        mbar_wait(empty_bar + 8 * s, ((kb / kWgStages) & 1) ^ 1);
+        const uint32_t sa = tiles + s * S::kStage, sb = sa + kATileBytes;
+        mbar_expect_tx(full_bar + 8 * s, S::kStage);
+        const int k0 = k_begin + kb * P::kBK;
+        // MN-major operands: boxes of CH contiguous features x kBK reduction rows; rows beyond the matrix are zero-filled
+        for (int h = 0; h < 128 / CH; ++h) tma_load_2d(sa + h * kBoxBytes, &g.mapA[z], full_bar + 8 * s, row_base + h * CH, k0);
+        for (int h = 0; h < BN / CH; ++h) tma_load_2d(sb + h * kBoxBytes, &g.mapB[z], full_bar + 8 * s, col_base + h * CH, k0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc(P::kFmt, 128, BN, true, true);
+    constexpr uint32_t idesc_ones = make_idesc(P::kFmt, 128, 16, true, false);
+    for (int kb = 0; kb < k_blocks; ++kb) {
+      const int s = kb % kWgStages;
+      mbar_wait(full_bar + 8 * s, (kb / kWgStages) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = tiles + s * S::kStage, sb = sa + kATileBytes;
+        const uint64_t d1 = make_smem_desc(ones, 16, 1024);  // K-major, 16 rows x 128 B, every element 1
+#pragma unroll
+        for (int k = 0; k < P::kBK / P::kUmmaK; ++k) {
+          // MN-major SW128: CH-feature chunks LBO = one box apart, 8-row reduction groups SBO = 1 KiB apart;
+          // one K-step (kUmmaK reduction rows) = kUmmaK * 128 B further
+          const uint64_t da = make_smem_desc(sa + k * P::kUmmaK * kRowBytes, kBoxBytes, 1024);
+          const uint64_t db = make_smem_desc(sb + k * P::kUmmaK * kRowBytes, kBoxBytes, 1024);
+          umma<PREC>(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          if (with_bias) umma<PREC>(tmem_base + BN, da, d1, idesc_ones, (kb | k) != 0 ? 1u : 0u);
+        }
+      }
+      __syncwarp();
+      if (elect_one()) {
+        umma_commit(empty_bar + 8 * s);
+        if (kb == k_blocks - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+    }
+  } else if (k_blocks > 0) {
+    // ===================== epilogue (warps 2..9): TMEM -> red.global.add =====================
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int HC = BN / 2, NCH = HC / 32;
+    const int row = row_base + quarter * 32 + lane;
+    const int c_first = half * HC;
+    if (lane == 0) mbar_wait(tmem_full_bar, 0);
+    __syncwarp();
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    uint32_t v[NCH][32];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) tmem_ld32(taddr + c_first + i * 32, v[i]);
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) tmem_ld_wait(v[i]);
+    float* __restrict__ grow = g.gw[z] + (size_t)row * g.ins_pad + col_base + c_first;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i)
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        red_add_v4(grow + i * 32 + q * 4, __uint_as_float(v[i][q * 4]), __uint_as_float(v[i][q * 4 + 1]),
+                   __uint_as_float(v[i][q * 4 + 2]), __uint_as_float(v[i][q * 4 + 3]));
+    if (with_bias && half == 0) {
+      uint32_t b[8];
+      tmem_ld8(taddr + BN, b);
+      red_add(g.gb[z] + row, __uint_as_float(b[0]));
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-int encode_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
-                     uint32_t box_outer);
 
 static EncodeTiledFn encoder() {
   static EncodeTiledFn fn = nullptr;
@@ -558,106 +429,89 @@ struct TmapKey {
   const void* ptr;
   uint64_t inner, outer, ld;
   uint32_t bi, bo;
+  int prec;
 };
 struct TmapEntry {
   TmapKey key;
   CUtensorMap map;
 };
-static TmapEntry g_tmap_cache[128];
+static TmapEntry g_tmap_cache[256];
 static int g_tmap_count = 0;
 
-// bf16 row-major [outer, inner] with leading dimension ld (elements); box = [box_outer, box_inner].
+static int encode_tmap(CUtensorMap* map, int prec, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
+                       uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = encoder();
+  if (!fn) return CATB200_ERR_UNSUPPORTED;
+  const uint64_t esz = prec == kPrecTf32 ? 4 : 2;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * esz};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, prec == kPrecTf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? CATB200_OK : CATB200_ERR_CUDA;
+}
+
 // Encodings are memoised: the trainer reuses a handful of (pointer, shape) combinations every step.
-int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
-                   uint32_t box_outer) {
+int make_tmap(CUtensorMap* map, int prec, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+              uint32_t box_outer) {
   for (int i = 0; i < g_tmap_count; ++i) {
     const TmapKey& k = g_tmap_cache[i].key;
-    if (k.ptr == ptr && k.inner == inner && k.outer == outer && k.ld == ld && k.bi == box_inner && k.bo == box_outer) {
+    if (k.ptr == ptr && k.inner == inner && k.outer == outer && k.ld == ld && k.bi == box_inner && k.bo == box_outer && k.prec == prec) {
       *map = g_tmap_cache[i].map;
       return CATB200_OK;
     }
   }
-  int rc = encode_tmap_bf16(map, ptr, inner, outer, ld, box_inner, box_outer);
+  int rc = encode_tmap(map, prec, ptr, inner, outer, ld, box_inner, box_outer);
   if (rc == CATB200_OK) {
-    const int slot = g_tmap_count < 128 ? g_tmap_count++ : 127;
-    g_tmap_cache[slot].key = TmapKey{ptr, inner, outer, ld, box_inner, box_outer};
+    const int slot = g_tmap_count < 256 ? g_tmap_count++ : 255;
+    g_tmap_cache[slot].key = TmapKey{ptr, inner, outer, ld, box_inner, box_outer, prec};
     g_tmap_cache[slot].map = *map;
   }
   return rc;
 }
 
-int encode_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
-                     uint32_t box_outer) {
-  EncodeTiledFn fn = encoder();
-  if (!fn) return CATB200_ERR_UNSUPPORTED;
-  cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {ld * 2};
-  cuuint32_t box[2] = {box_inner, box_outer};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? CATB200_OK : CATB200_ERR_CUDA;
-}
-
-template <int MODE, int BN>
-static int launch_one(TcGemmArgs g, dim3 grid, cudaStream_t st) {
-  using S = TcSmem<MODE, BN>;
+template <int MODE, int PREC>
+static int launch_gemm(const TcGemmArgs& g, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    CATB200_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::total(kTcStages)));
+    CATB200_CUDA_TRY(cudaFuncSetAttribute(mlp_gemm_kernel<MODE, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, PSmem::kTotal));
     attr = true;
   }
-  // ring depth: no more slots than reduction blocks (a K = 64 layer needs one), which keeps several CTAs per SM
-  const int red = MODE == kTcWgrad ? g.m_range : g.K;
-  g.stages = max(1, min(kTcStages, (red + kTcBK - 1) / kTcBK));
-  CATB200_CUDA_TRY(launch_pdl(tc_gemm_kernel<MODE, BN>, grid, dim3(kTcThreads), (size_t)S::total(g.stages), st, g));
+  const int total = 2 * ((g.M + 127) / 128) * (g.N / 128);
+  CATB200_CUDA_TRY(launch_pdl(mlp_gemm_kernel<MODE, PREC>, dim3(min(total, kNumSMs)), dim3(kTcThreads), (size_t)PSmem::kTotal, st, g));
   CATB200_LAUNCH_CHECK();
   return CATB200_OK;
 }
 
-// persistent kernel for launches whose tiles do not all fit on the machine at once (two one-tile CTAs per SM);
-// CATB200_TC_PERSIST=0: always one tile per CTA
-static bool use_persistent(int total_tiles) {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = std::getenv("CATB200_TC_PERSIST");
-    v = (e && e[0] == '0') ? 0 : 1;
-  }
-  return v == 1 && total_tiles > 2 * kNumSMs;
+int tc_gemm_launch(int mode, int prec, const TcGemmArgs& g, cudaStream_t st) {
+  const int bk = prec == kPrecTf32 ? 32 : 64;
+  if (g.N % 128 || g.K % bk || g.M <= 0) return CATB200_ERR_UNSUPPORTED;
+  if (mode == kTcFwd) return prec == kPrecTf32 ? launch_gemm<kTcFwd, kPrecTf32>(g, st) : launch_gemm<kTcFwd, kPrecBf16>(g, st);
+  return prec == kPrecTf32 ? launch_gemm<kTcDgrad, kPrecTf32>(g, st) : launch_gemm<kTcDgrad, kPrecBf16>(g, st);
 }
 
-template <int MODE, int BN>
-static int launch_persist(TcGemmArgs g, int total_tiles, cudaStream_t st) {
-  using S = PSmem<MODE, BN>;
+template <int PREC, int BN>
+static int launch_wgrad(const TcWgradArgs& g, int splits, cudaStream_t st) {
+  using S = WgSmem<BN>;
   static bool attr = false;
   if (!attr) {
-    CATB200_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_persist_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    CATB200_CUDA_TRY(cudaFuncSetAttribute(mlp_wgrad_kernel<PREC, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     attr = true;
   }
-  g.stages = kPStages;
-  CATB200_CUDA_TRY(launch_pdl(tc_gemm_persist_kernel<MODE, BN>, dim3(min(total_tiles, kNumSMs)), dim3(kTcThreads), (size_t)S::kTotal, st, g));
+  const dim3 grid((g.outs / 128) * (g.ins_pad / BN), splits, 2);
+  CATB200_CUDA_TRY(launch_pdl(mlp_wgrad_kernel<PREC, BN>, grid, dim3(kTcThreads), (size_t)S::kTotal, st, g));
   CATB200_LAUNCH_CHECK();
   return CATB200_OK;
 }
 
-int tc_gemm_launch(int mode, const TcGemmArgs& g, int splits, cudaStream_t st) {
-  if (mode == kTcFwd) {
-    if (g.N % 128) return CATB200_ERR_UNSUPPORTED;
-    const int total = 2 * ((g.M + 127) / 128) * (g.N / 128);
-    if (use_persistent(total)) return launch_persist<kTcFwd, 128>(g, total, st);
-    return launch_one<kTcFwd, 128>(g, dim3((g.M + 127) / 128, g.N / 128, 2), st);
-  }
-  if (mode == kTcDgrad) {
-    if (g.N % 128) return CATB200_ERR_UNSUPPORTED;
-    const int total = 2 * ((g.M + 127) / 128) * (g.N / 128);
-    if (use_persistent(total)) return launch_persist<kTcDgrad, 128>(g, total, st);
-    return launch_one<kTcDgrad, 128>(g, dim3((g.M + 127) / 128, g.N / 128, 2), st);
-  }
-  // wgrad: g.M = layer outputs (dW rows), g.N = padded layer inputs (dW cols), g.K = minibatch rows
-  if (g.M % 128) return CATB200_ERR_UNSUPPORTED;
-  if (g.N % 128 == 0) return launch_one<kTcWgrad, 128>(g, dim3((g.M / 128) * (g.N / 128), splits, 2), st);
-  if (g.N % 64 == 0) return launch_one<kTcWgrad, 64>(g, dim3((g.M / 128) * (g.N / 64), splits, 2), st);
+int tc_wgrad_launch(int prec, const TcWgradArgs& g, int splits, cudaStream_t st) {
+  if (g.outs % 128 || splits <= 0) return CATB200_ERR_UNSUPPORTED;
+  if (g.ins_pad % 128 == 0)
+    return prec == kPrecTf32 ? launch_wgrad<kPrecTf32, 128>(g, splits, st) : launch_wgrad<kPrecBf16, 128>(g, splits, st);
+  if (g.ins_pad % 64 == 0)
+    return prec == kPrecTf32 ? launch_wgrad<kPrecTf32, 64>(g, splits, st) : launch_wgrad<kPrecBf16, 64>(g, splits, st);
   return CATB200_ERR_UNSUPPORTED;
 }
 

@@ -76,6 +76,13 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
 }
@@ -125,11 +132,76 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   return d;
 }
 
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (1 << 4), A/B bf16 (1 << 7, 1 << 10),
-// a_major bit 15, b_major bit 16 (1 = MN-major), N >> 3 in [17,23), M >> 4 in [24,29).
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn_major, bool b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (1 << 4), A / B format in [7,10) / [10,13)
+// (0 = f16, 1 = bf16, 2 = tf32), a_major bit 15, b_major bit 16 (1 = MN-major), N >> 3 in [17,23), M >> 4 in [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, int M, int N, bool a_mn_major, bool b_mn_major) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- operand precision of the hidden-layer GEMMs ------------------------------------------------------------
+// kPrecTf32 (default): fp32 storage, operands rounded to tf32 (10-bit mantissa) where they are stored, tcgen05.mma
+//   kind::tf32, fp32 accumulation -- the reference's own GPU numerics (scripts/clean_rl/train.py:86-87).
+// kPrecBf16: bf16 storage and operands (kind::f16), fp32 accumulation -- half the operand bytes, 8-bit mantissa.
+// Either way one shared-memory row of an operand tile is 128 bytes (SWIZZLE_128B) and one UMMA K-step is 32 bytes.
+enum Prec { kPrecBf16 = 0, kPrecTf32 = 1 };
+
+template <int PREC>
+struct PrecT;
+template <>
+struct PrecT<kPrecBf16> {
+  using T = bf16;
+  static constexpr int kBK = 64;     // reduction elements per 128-byte row = per pipeline stage
+  static constexpr int kUmmaK = 16;  // reduction elements per tcgen05.mma
+  static constexpr uint32_t kFmt = 1;
+};
+template <>
+struct PrecT<kPrecTf32> {
+  using T = float;
+  static constexpr int kBK = 32;
+  static constexpr int kUmmaK = 8;
+  static constexpr uint32_t kFmt = 2;
+};
+
+template <int PREC>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (PREC == kPrecBf16) umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+  else umma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
+}
+
+// round-to-nearest fp32 -> tf32 (low 13 mantissa bits cleared); operands are rounded where they are stored so that
+// the tensor core's own truncation of the fp32 bit pattern never discards anything
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+// fire-and-forget vector reduction into global memory (sm_90+): 16 bytes per instruction
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add(float* addr, float a) {
+  asm volatile("red.global.add.f32 [%0], %1;\n" ::"l"(addr), "f"(a) : "memory");
+}
+// 32 lanes x 8 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+               :
+               : "memory");
 }
 
 }  // namespace catb200

@@ -47,12 +47,13 @@ def rms_forward(
     out: torch.Tensor | None = None,
     normalize: bool = True,
     workspace: Workspace | None = None,
-    out16: torch.Tensor | None = None,
+    out_op: torch.Tensor | None = None,
     validate: bool = True,
 ) -> torch.Tensor | None:
     """x: [rows, dim] or [rows] (dim = 1).  Updates (mean, var, count) in place when `update`, then
     returns (x - mean) / sqrt(var + eps) with the updated statistics (written to `out` if given).
-    `out16` (bf16 [rows, pad]) additionally receives the zero-padded bf16 copy the MLP reads."""
+    `out_op` (bf16 or fp32 [rows, pad]) additionally receives the zero-padded tensor-core operand copy the MLP
+    reads (fp32 = rounded to tf32)."""
     dim = 1 if x.ndim == 1 else x.shape[-1]
     rows = x.numel() // dim
     if validate:
@@ -68,8 +69,8 @@ def rms_forward(
             _f32c(out, "out")
             if out.numel() != x.numel():
                 raise ValueError("out must have as many elements as x")
-            if out16 is not None and (out16.dtype != torch.bfloat16 or not out16.is_contiguous() or out16.numel() % rows):
-                raise ValueError("out16 must be a contiguous bf16 tensor [rows, pad]")
+            if out_op is not None and (out_op.dtype not in (torch.bfloat16, torch.float32) or not out_op.is_contiguous() or out_op.numel() % rows):
+                raise ValueError("out_op must be a contiguous bf16 / fp32 tensor [rows, pad]")
     lib = L.load()
     ws_ptr, ws_bytes = None, 0
     if update:
@@ -79,8 +80,8 @@ def rms_forward(
     L.check(
         lib.catb200_rms_forward(
             x.data_ptr(), rows, dim, mean.data_ptr(), var.data_ptr(), count.data_ptr(), eps, int(update),
-            out.data_ptr() if normalize else None, L.ptr(out16), (out16.numel() // rows) if out16 is not None else 0,
-            ws_ptr, ws_bytes, L.stream(),
+            out.data_ptr() if normalize else None, L.ptr(out_op), (out_op.numel() // rows) if out_op is not None else 0,
+            L.PREC_TF32 if out_op is not None and out_op.dtype == torch.float32 else L.PREC_BF16, ws_ptr, ws_bytes, L.stream(),
         ),
         "rms_forward",
     )  # fmt: skip
@@ -173,12 +174,19 @@ def gae(
 # --------------------------------------------------------------------------------------------------
 # actor-critic MLP, PPO minibatch gradient, Adam  (reference cleanrl/ppo.py:71-123,294-354)
 # --------------------------------------------------------------------------------------------------
-def make_dims(obs_dim: int, act_dim: int, hidden=(512, 256, 128)) -> L.MlpDims:
+def make_dims(obs_dim: int, act_dim: int, hidden=(512, 256, 128), precision: str | None = None) -> L.MlpDims:
+    """`precision`: "tf32" (default; env CATB200_GEMM_PREC) or "bf16" -- operand type of the hidden-layer GEMMs."""
     d = L.MlpDims()
     d.obs_dim, d.act_dim = int(obs_dim), int(act_dim)
     d.h1, d.h2, d.h3 = (int(h) for h in hidden)
     d.obs_pad = (int(obs_dim) + 63) // 64 * 64
+    d.prec = L.PREC_NAMES[(precision or L.default_precision()).lower()]
     return d
+
+
+def weight_copies(dims, layout, device) -> torch.Tensor:
+    """Zeroed buffer for the operand-precision compute copies of the hidden-layer weights."""
+    return torch.zeros(layout.n_wc, dtype=L.operand_dtype(dims.prec), device=device)
 
 
 def mlp_layout(dims: L.MlpDims) -> L.MlpLayout:
@@ -187,20 +195,30 @@ def mlp_layout(dims: L.MlpDims) -> L.MlpLayout:
     return layout
 
 
-def cast_weights(dims, params: torch.Tensor, w16: torch.Tensor) -> None:
+def _check_operand(dims, t: torch.Tensor, what: str) -> None:
+    L.require_cuda(t, what)
+    if t.dtype != L.operand_dtype(dims.prec) or not t.is_contiguous():
+        raise TypeError(f"{what} must be a contiguous {L.operand_dtype(dims.prec)} tensor for this precision, got {t.dtype}")
+
+
+def cast_weights(dims, params: torch.Tensor, wc: torch.Tensor) -> None:
     _f32c(params, "params")
-    L.require_cuda(w16, "w16")
-    L.check(L.load().catb200_mlp_cast_weights(dims, params.data_ptr(), w16.data_ptr(), L.stream()), "mlp_cast_weights")
+    _check_operand(dims, wc, "wc")
+    L.check(L.load().catb200_mlp_cast_weights(dims, params.data_ptr(), wc.data_ptr(), L.stream()), "mlp_cast_weights")
 
 
-def obs_to_bf16(obs: torch.Tensor, obs_pad: int, out: torch.Tensor | None = None) -> torch.Tensor:
+def obs_to_operand(dims, obs: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """fp32 [..., obs_dim] -> operand [..., obs_pad] (bf16, or fp32 rounded to tf32), zero padded."""
     _f32c(obs, "obs")
-    rows, dim = obs.numel() // obs.shape[-1], obs.shape[-1]
+    if obs.shape[-1] != dims.obs_dim:
+        raise ValueError(f"obs has {obs.shape[-1]} features, expected {dims.obs_dim}")
+    rows = obs.numel() // dims.obs_dim
     if out is None:
-        out = torch.empty((*obs.shape[:-1], obs_pad), dtype=torch.bfloat16, device=obs.device)
-    if out.dtype != torch.bfloat16 or not out.is_contiguous() or out.numel() != rows * obs_pad:
-        raise ValueError("obs16 output must be a contiguous bf16 tensor [rows, obs_pad]")
-    L.check(L.load().catb200_obs_to_bf16(obs.data_ptr(), rows, dim, obs_pad, out.data_ptr(), L.stream()), "obs_to_bf16")
+        out = torch.empty((*obs.shape[:-1], dims.obs_pad), dtype=L.operand_dtype(dims.prec), device=obs.device)
+    _check_operand(dims, out, "obs_op")
+    if out.numel() != rows * dims.obs_pad:
+        raise ValueError("obs_op output must hold [rows, obs_pad] elements")
+    L.check(L.load().catb200_obs_to_operand(dims, obs.data_ptr(), rows, out.data_ptr(), L.stream()), "obs_to_operand")
     return out
 
 
@@ -211,15 +229,22 @@ def mlp_workspace(dims, rows: int, training: bool, device) -> torch.Tensor:
     return L.zeros_workspace(need, device)
 
 
-def mlp_act(dims, obs16, params, w16, ws, noise=None, action_in=None, action=None, logprob=None, value=None, mean_out=None,
-            validate: bool = True):  # fmt: skip
-    rows = obs16.numel() // dims.obs_pad
-    for t, name in () if not validate else ((noise, "noise"), (action_in, "action_in"), (action, "action"), (logprob, "logprob"), (value, "value"), (mean_out, "mean_out")):  # fmt: skip
-        if t is not None:
-            _f32c(t, name)
+def mlp_act(dims, obs_op, params, wc, ws, noise=None, action_in=None, action=None, logprob=None, value=None, mean_out=None,
+            rng_state=None, validate: bool = True):  # fmt: skip
+    """`noise` [rows, act_dim] supplies Normal.sample()'s eps; `rng_state` (2 x int64 on the device: seed, offset) lets the
+    head kernel draw it from Philox instead (and advances the offset)."""
+    rows = obs_op.numel() // dims.obs_pad
+    if validate:
+        _check_operand(dims, obs_op, "obs_op")
+        _check_operand(dims, wc, "wc")
+        for t, name in ((noise, "noise"), (action_in, "action_in"), (action, "action"), (logprob, "logprob"), (value, "value"), (mean_out, "mean_out")):  # fmt: skip
+            if t is not None:
+                _f32c(t, name)
+        if rng_state is not None and (rng_state.dtype != torch.int64 or rng_state.numel() != 2 or not rng_state.is_cuda):
+            raise TypeError("rng_state must be a CUDA int64 tensor {seed, offset}")
     L.check(
         L.load().catb200_mlp_act(
-            dims, obs16.data_ptr(), rows, params.data_ptr(), w16.data_ptr(), L.ptr(noise), L.ptr(action_in),
+            dims, obs_op.data_ptr(), rows, params.data_ptr(), wc.data_ptr(), L.ptr(noise), L.ptr(rng_state), L.ptr(action_in),
             L.ptr(action), L.ptr(logprob), L.ptr(value), L.ptr(mean_out), ws.data_ptr(), ws.numel() * 8, L.stream(),
         ),
         "mlp_act",
@@ -233,9 +258,11 @@ def make_hparams(clip_coef=0.2, ent_coef=0.001, vf_coef=2.0, norm_adv=True, clip
     return hp
 
 
-def ppo_minibatch_grad(dims, hp, mb_inds, obs16_all, actions_all, logprobs_all, advantages_all, returns_all, values_all,
-                       norm_stats, params, w16, grads, loss_acc, ws) -> None:  # fmt: skip
+def ppo_minibatch_grad(dims, hp, mb_inds, obs_op_all, actions_all, logprobs_all, advantages_all, returns_all, values_all,
+                       norm_stats, params, wc, grads, loss_acc, ws) -> None:  # fmt: skip
     L.require_cuda(mb_inds, "mb_inds")
+    _check_operand(dims, obs_op_all, "obs_op_all")
+    _check_operand(dims, wc, "wc")
     if mb_inds.dtype != torch.int64 or not mb_inds.is_contiguous():
         raise TypeError("mb_inds must be a contiguous int64 tensor")
     for t, name in ((actions_all, "actions"), (logprobs_all, "logprobs"), (advantages_all, "advantages"), (returns_all, "returns"),
@@ -243,22 +270,22 @@ def ppo_minibatch_grad(dims, hp, mb_inds, obs16_all, actions_all, logprobs_all, 
         _f32c(t, name)
     L.check(
         L.load().catb200_ppo_minibatch_grad(
-            dims, hp, mb_inds.numel(), mb_inds.data_ptr(), obs16_all.data_ptr(), actions_all.data_ptr(),
+            dims, hp, mb_inds.numel(), mb_inds.data_ptr(), obs_op_all.data_ptr(), actions_all.data_ptr(),
             logprobs_all.data_ptr(), advantages_all.data_ptr(), returns_all.data_ptr(), values_all.data_ptr(),
-            norm_stats.data_ptr(), params.data_ptr(), w16.data_ptr(), grads.data_ptr(), loss_acc.data_ptr(),
+            norm_stats.data_ptr(), params.data_ptr(), wc.data_ptr(), grads.data_ptr(), loss_acc.data_ptr(),
             ws.data_ptr(), ws.numel() * 8, L.stream(),
         ),
         "ppo_minibatch_grad",
     )  # fmt: skip
 
 
-def adam_step(dims, params, grads, exp_avg, exp_avg_sq, w16, lr_dev, step_dev, opt_ws, max_grad_norm=1.0,
+def adam_step(dims, params, grads, exp_avg, exp_avg_sq, wc, lr_dev, step_dev, opt_ws, max_grad_norm=1.0,
               betas=(0.9, 0.999), eps=1e-5, grad_scale=1.0, grad_norm_out=None) -> None:  # fmt: skip
     for t, name in ((params, "params"), (grads, "grads"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq"), (lr_dev, "lr")):
         _f32c(t, name)
     L.check(
         L.load().catb200_adam_step(
-            dims, params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), w16.data_ptr(),
+            dims, params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), wc.data_ptr(),
             lr_dev.data_ptr(), step_dev.data_ptr(), max_grad_norm, betas[0], betas[1], eps, grad_scale,
             L.ptr(grad_norm_out), opt_ws.data_ptr(), L.stream(),
         ),
@@ -316,3 +343,40 @@ def gae_float_dones(
         "gae_float_dones",
     )  # fmt: skip
     return advantages, returns
+
+
+# --------------------------------------------------------------------------------------------------
+# device-side random draws (Philox4x32-10)
+# --------------------------------------------------------------------------------------------------
+def make_rng_state(seed: int, device, offset: int = 0) -> torch.Tensor:
+    """{seed, offset} as two int64 on the device (the kernels read them as uint64 and advance the offset)."""
+    return torch.tensor([int(seed) & 0x7FFFFFFFFFFFFFFF, int(offset)], dtype=torch.int64, device=device)
+
+
+def random_permutation(n: int, rng_state: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Pseudo-random permutation of 0..n-1 (replaces torch.randperm, reference cleanrl/ppo.py:295): keyed Feistel
+    bijection + cycle walking, one launch, no sort."""
+    L.require_cuda(rng_state, "rng_state")
+    if out is None:
+        out = torch.empty(n, dtype=torch.int64, device=rng_state.device)
+    if out.dtype != torch.int64 or not out.is_contiguous() or out.numel() != n:
+        raise TypeError("out must be a contiguous int64 tensor with n entries")
+    L.check(L.load().catb200_random_permutation(n, rng_state.data_ptr(), out.data_ptr(), L.stream()), "random_permutation")
+    return out
+
+
+def bernoulli_mask(p: torch.Tensor, rng_state: torch.Tensor, with_ids: bool = False):
+    """mask = (u < p) with Philox uniforms; with_ids also returns (ids buffer [n], count [1]) where ids[:count] are the
+    ascending positions of the set entries."""
+    _f32c(p, "p")
+    n = p.numel()
+    mask = torch.empty(n, dtype=torch.uint8, device=p.device)
+    ids = count = None
+    if with_ids:
+        ids = torch.empty(n, dtype=torch.int64, device=p.device)
+        count = torch.zeros(1, dtype=torch.int32, device=p.device)
+    L.check(
+        L.load().catb200_bernoulli_mask(p.data_ptr(), n, rng_state.data_ptr(), mask.data_ptr(), L.ptr(ids), L.ptr(count), L.stream()),
+        "bernoulli_mask",
+    )
+    return (mask.view(torch.bool), ids, count) if with_ids else mask.view(torch.bool)

@@ -9,12 +9,15 @@ Public names and behaviour follow `exts/cat_envs/cat_envs/tasks/utils/cleanrl/pp
     PPO(envs, ppo_cfg, run_path)              :126-372 the training loop (float `dones`, time-out aware GAE)
 
 Execution model (one process per GPU):
-  rollout step  : pre  = [randn] -> 3 batched GEMM launches -> head kernel (sample, log-prob, value)
+  rollout step  : pre  = 3 batched tcgen05 GEMM launches -> head kernel (Philox sample, log-prob, value)
                   env.step(action)   (Isaac Lab + the fused ConstraintManager kernels)
-                  post = append -> running moments -> normalise (+bf16 copy)
-  update        : 1 GAE(+value statistics) launch, then per minibatch `catb200_ppo_minibatch_grad`
-                  (gather, 3 fwd GEMMs, head/loss, 3 wgrad + 2 dgrad GEMMs, reduce) [-> NCCL allreduce of the
-                  flat 1.5 MB gradient] -> `catb200_adam_step` (norm, clip, Adam, bf16 weight refresh)
+                  post = append -> running moments -> normalise (+ operand copy for the first GEMM)
+  update        : 1 GAE(+value statistics) launch, then per epoch a Feistel/Philox permutation and per minibatch
+                  `catb200_ppo_minibatch_grad` (gather, 3 fwd GEMMs, head/loss, 3 wgrad + 2 dgrad GEMMs, fold)
+                  [-> NCCL allreduce of the flat 1.5 MB gradient] -> `catb200_adam_step` (norm, clip, Adam,
+                  operand-precision weight refresh)
+Hidden-layer GEMM operands are tf32 by default (fp32 storage; the reference's GPU numerics,
+scripts/clean_rl/train.py:86-87) or bf16 (`precision="bf16"` / CATB200_GEMM_PREC=bf16).
 No tensor math runs in python; there is no eager fallback (CPU tensors raise).
 """
 
@@ -48,11 +51,11 @@ class RunningMeanStd(nn.Module):
             self._ws = ops.Workspace(self.running_mean.device)
         return self._ws
 
-    def forward(self, obs, update=True, out=None, out16=None, validate=True):
+    def forward(self, obs, update=True, out=None, out_op=None, validate=True):
         obs = obs if obs.is_contiguous() else obs.contiguous()
         return ops.rms_forward(
             obs, self.running_mean, self.running_var, self.count, self.epsilon, update=update, out=out,
-            workspace=self._workspace(), out16=out16, validate=validate,
+            workspace=self._workspace(), out_op=out_op, validate=validate,
         )  # fmt: skip
 
     def update(self, x):
@@ -74,7 +77,7 @@ class Agent(nn.Module):
 
     HIDDEN = (512, 256, 128)
 
-    def __init__(self, envs, device=None):
+    def __init__(self, envs, device=None, precision=None):
         super().__init__()
         obs_shape = envs.unwrapped.single_observation_space["policy"].shape
         act_shape = envs.unwrapped.single_action_space.shape
@@ -96,10 +99,11 @@ class Agent(nn.Module):
         self.obs_rms = RunningMeanStd(shape=obs_shape)
         self.value_rms = RunningMeanStd(shape=())
 
-        self.dims = ops.make_dims(self.obs_dim, self.act_dim, self.HIDDEN)
+        self.dims = ops.make_dims(self.obs_dim, self.act_dim, self.HIDDEN, precision=precision)
+        self.precision = "tf32" if self.dims.prec == L.PREC_TF32 else "bf16"
         self.layout = ops.mlp_layout(self.dims)
         self._flat = None
-        self._w16 = None
+        self._wc = None  # operand-precision compute copies of the hidden-layer weights (W and W^T)
         self._act_ws = None
         self._ws_need: dict = {}
         self._noise = None
@@ -126,7 +130,7 @@ class Agent(nn.Module):
         for p, off in self._param_slots():
             p.data = flat[off : off + p.numel()].view(p.shape)
         self._flat = flat
-        self._w16 = torch.zeros(self.layout.n_w16, dtype=torch.bfloat16, device=device)
+        self._wc = ops.weight_copies(self.dims, self.layout, device)
         self._act_ws = None
         if device.type == "cuda":
             self.sync_weights()
@@ -144,10 +148,10 @@ class Agent(nn.Module):
         return self._flat
 
     def sync_weights(self) -> None:
-        """Refresh the bf16 compute copies after the fp32 parameters were written from outside
+        """Refresh the operand-precision compute copies after the fp32 parameters were written from outside
         (load_state_dict, manual edits).  The Adam kernel keeps them fresh during training."""
         if self._flat is not None and self._flat.is_cuda:
-            ops.cast_weights(self.dims, self._flat, self._w16)
+            ops.cast_weights(self.dims, self._flat, self._wc)
 
     # -- inference ---------------------------------------------------------------------------------
     def _workspace(self, rows):
@@ -158,26 +162,31 @@ class Agent(nn.Module):
             self._act_ws = L.zeros_workspace(need, self._flat.device)
         return self._act_ws
 
-    def _as_obs16(self, x):
-        if x.dtype == torch.bfloat16 and x.shape[-1] == self.dims.obs_pad:
+    def _as_operand(self, x):
+        """Observations as the first GEMM reads them: [rows, obs_pad] in the operand precision (already converted
+        rows -- the trainer's padded rollout copy -- pass through)."""
+        if x.shape[-1] == self.dims.obs_pad and x.dtype == L.operand_dtype(self.dims.prec):
             return x
         x = x.float() if x.dtype != torch.float32 else x
-        return ops.obs_to_bf16(x if x.is_contiguous() else x.contiguous(), self.dims.obs_pad)
+        return ops.obs_to_operand(self.dims, x if x.is_contiguous() else x.contiguous())
 
     def get_value(self, x):
-        obs16 = self._as_obs16(x)
-        rows = obs16.numel() // self.dims.obs_pad
-        value = torch.empty((rows, 1), dtype=torch.float32, device=obs16.device)
-        ops.mlp_act(self.dims, obs16, self._flat, self._w16, self._workspace(rows), value=value)
+        obs_op = self._as_operand(x)
+        rows = obs_op.numel() // self.dims.obs_pad
+        value = torch.empty((rows, 1), dtype=torch.float32, device=obs_op.device)
+        ops.mlp_act(self.dims, obs_op, self._flat, self._wc, self._workspace(rows), value=value)
         return value
 
-    def get_action_and_value(self, x, action=None, deterministic=False, out=None, validate=True):
+    def get_action_and_value(self, x, action=None, deterministic=False, out=None, validate=True, rng_state=None, workspace=None):
         """-> (action, log-prob summed over action dims, entropy summed over action dims, value [N,1]).
 
-        `out=(action, logprob, value)` lets the trainer write straight into its rollout buffers."""
-        obs16 = self._as_obs16(x)
-        rows = obs16.numel() // self.dims.obs_pad
-        dev = obs16.device
+        `out=(action, logprob, value)` lets the trainer write straight into its rollout buffers; `rng_state`
+        (ops.make_rng_state) draws Normal.sample()'s noise inside the head kernel instead of torch's generator;
+        `workspace` is caller-owned activation scratch (the trainer's CUDA graphs must not share the Agent's,
+        which is regrown on demand)."""
+        obs_op = self._as_operand(x)
+        rows = obs_op.numel() // self.dims.obs_pad
+        dev = obs_op.device
         if out is None:
             act_out = torch.empty((rows, self.act_dim), dtype=torch.float32, device=dev)
             logprob = torch.empty(rows, dtype=torch.float32, device=dev)
@@ -185,12 +194,14 @@ class Agent(nn.Module):
         else:
             act_out, logprob, value = out
         noise = None
-        if action is None and not deterministic:  # Normal.sample's eps, from torch's generator
+        sample = action is None and not deterministic
+        if sample and rng_state is None:  # Normal.sample's eps, from torch's generator
             if self._noise is None or self._noise.shape[0] != rows or self._noise.device != dev:
                 self._noise = torch.empty((rows, self.act_dim), dtype=torch.float32, device=dev)
             noise = self._noise.normal_()
         ops.mlp_act(
-            self.dims, obs16, self._flat, self._w16, self._workspace(rows), noise=noise,
+            self.dims, obs_op, self._flat, self._wc, workspace if workspace is not None else self._workspace(rows),
+            noise=noise, rng_state=rng_state if sample else None,
             action_in=None if action is None else action.contiguous(), action=act_out, logprob=logprob, value=value,
             validate=validate,
         )  # fmt: skip
@@ -225,7 +236,7 @@ class Agent(nn.Module):
 class PPOTrainer:
     """State and steps of the training loop; `PPO()` below drives it exactly like the reference function."""
 
-    def __init__(self, envs, cfg, device=None, seed=None, use_graphs=True, distributed=True):
+    def __init__(self, envs, cfg, device=None, seed=None, use_graphs=True, distributed=True, precision=None):
         self.envs = envs
         self.cfg = cfg
         env = envs.unwrapped
@@ -239,7 +250,7 @@ class PPOTrainer:
         # distributed=False keeps this trainer rank-local even inside an initialised process group (bench probes)
         self.world, self.rank = (cdist.world_size(), cdist.rank()) if distributed else (1, 0)
 
-        self.agent = Agent(envs, device=self.device)
+        self.agent = Agent(envs, device=self.device, precision=precision)
         if self.world > 1:  # rank 0 seeds everybody (the reference's multi-process front-ends do the same)
             cdist.broadcast_params(self.agent.parameters_flat(), src=0)
             self.agent.sync_weights()
@@ -250,7 +261,8 @@ class PPOTrainer:
 
         f32 = dict(dtype=torch.float32, device=dev)
         self.obs = torch.zeros((T + 1, N, O), **f32)
-        self.obs16 = torch.zeros((T + 1, N, dims.obs_pad), dtype=torch.bfloat16, device=dev)
+        # the normalised observations once more as the first GEMM reads them: zero-padded rows in the operand precision
+        self.obs_op = torch.zeros((T + 1, N, dims.obs_pad), dtype=L.operand_dtype(dims.prec), device=dev)
         self.actions = torch.zeros((T, N, A), **f32)
         self.logprobs = torch.zeros((T, N), **f32)
         self.rewards = torch.zeros((T, N), **f32)
@@ -274,6 +286,13 @@ class PPOTrainer:
         self.train_ws = ops.mlp_workspace(dims, self.minibatch_size, True, dev)
         self.gae_ws = ops.Workspace(dev)
         self.perm = torch.zeros(self.batch_size, dtype=torch.int64, device=dev)
+        # private activation scratch of the rollout policy / bootstrap value: CUDA graphs bake its address in, so it
+        # must not be the Agent's own workspace (public Agent calls with other batch sizes regrow that one)
+        self.act_ws = ops.mlp_workspace(dims, N, False, dev)
+        # device-side Philox state {seed, offset}: action noise and minibatch permutations (graph-capturable)
+        base_seed = int(seed if seed is not None else getattr(cfg, "seed", 0))
+        self.rng_state = ops.make_rng_state(base_seed * 1000003 + 7919 * self.rank + 1, dev)
+        self.device_rng = os.environ.get("CATB200_DEVICE_RNG", "1") != "0"
         self.hp = ops.make_hparams(cfg.clip_coef, cfg.ent_coef, cfg.vf_coef, cfg.norm_adv, cfg.clip_vloss)
         self.global_step = 0
         self.iteration = 0
@@ -281,9 +300,9 @@ class PPOTrainer:
         # every minibatch replay as graphs around the eager NCCL all-reduce (CATB200_MULTI_GPU_GRAPHS=0 -> all eager).
         self.use_graphs = bool(use_graphs) and (self.world == 1 or os.environ.get("CATB200_MULTI_GPU_GRAPHS", "1") != "0")
         self._split_graphs = None  # multi-GPU: (per-minibatch gradient graphs, optimizer graph)
-        self._epoch_graph = None
-        self._graph_launches = 0  # kernels recorded in the epoch graph
-        self._graph_replays = 0
+        self._epoch_graphs: dict = {}  # in-graph shuffle? -> (graph, kernels recorded)
+        self._captured_launches = 0  # kernels recorded (not executed) while capturing epoch graphs
+        self._replayed_launches = 0  # kernels executed by epoch-graph replays
         self._eager_epochs = 0
         self._policy_graphs: dict = {}
         self._policy_graph_launches = 0
@@ -305,22 +324,28 @@ class PPOTrainer:
     def _ingest_obs(self, raw_obs, slot):
         raw_obs = raw_obs.float() if raw_obs.dtype != torch.float32 else raw_obs
         # update + normalise (ppo.py:187,225); the same kernel also emits the bf16 rows the MLP reads
-        self.agent.obs_rms(raw_obs, update=True, out=self.obs[slot], out16=self.obs16[slot], validate=self._validate)
+        self.agent.obs_rms(raw_obs, update=True, out=self.obs[slot], out_op=self.obs_op[slot], validate=self._validate)
 
     def _policy(self, t):
         """Agent.get_action_and_value on slot t -> actions[t], logprobs[t], values[t] (ppo.py:208-212);
-        after the first iteration the 5 launches (noise + 3 GEMMs + head) replay as one CUDA graph per slot."""
+        after the first iteration the launches (3 GEMMs + head with in-kernel Philox noise) replay as one CUDA graph
+        per slot."""
+        rng = self.rng_state if self.device_rng else None
         if not self.use_graphs or self.iteration < 2:
             self.agent.get_action_and_value(
-                self.obs16[t], out=(self.actions[t], self.logprobs[t], self.values[t]), validate=self._validate
-            )
+                self.obs_op[t], out=(self.actions[t], self.logprobs[t], self.values[t]), validate=self._validate,
+                rng_state=rng, workspace=self.act_ws,
+            )  # fmt: skip
             return
         graph = self._policy_graphs.get(t)
         if graph is None:
             graph = torch.cuda.CUDAGraph()
             before = L.launch_count()
             with torch.cuda.graph(graph):
-                self.agent.get_action_and_value(self.obs16[t], out=(self.actions[t], self.logprobs[t], self.values[t]), validate=False)
+                self.agent.get_action_and_value(
+                    self.obs_op[t], out=(self.actions[t], self.logprobs[t], self.values[t]), validate=False,
+                    rng_state=rng, workspace=self.act_ws,
+                )  # fmt: skip
             self._policy_graph_launches = L.launch_count() - before
             self._policy_captures += 1
             self._policy_graphs[t] = graph
@@ -359,7 +384,7 @@ class PPOTrainer:
         `bootstrap=False` keeps whatever `self.next_value` holds (replaying a recorded rollout)."""
         a = self.agent
         if bootstrap:
-            ops.mlp_act(a.dims, self.obs16[self.T], a.parameters_flat(), a._w16, a._workspace(self.num_envs), value=self.next_value)
+            ops.mlp_act(a.dims, self.obs_op[self.T], a.parameters_flat(), a._wc, self.act_ws, value=self.next_value)
         vr = a.value_rms
         self.value_rms_state[0:1].copy_(vr.running_mean.reshape(1))
         self.value_rms_state[1:2].copy_(vr.running_var.reshape(1))
@@ -377,15 +402,15 @@ class PPOTrainer:
         a = self.agent
         B = self.batch_size
         ops.ppo_minibatch_grad(
-            a.dims, self.hp, mb_inds, self.obs16.view(-1, a.dims.obs_pad), self.actions.view(B, -1),
+            a.dims, self.hp, mb_inds, self.obs_op.view(-1, a.dims.obs_pad), self.actions.view(B, -1),
             self.logprobs.view(B), self.advantages.view(B), self.returns.view(B), self.values.view(B), self.norm_stats,
-            a.parameters_flat(), a._w16, self.grads, self.loss_acc, self.train_ws,
+            a.parameters_flat(), a._wc, self.grads, self.loss_acc, self.train_ws,
         )  # fmt: skip
 
     def _minibatch_opt(self):
         a = self.agent
         ops.adam_step(
-            a.dims, a.parameters_flat(), self.grads, self.exp_avg, self.exp_avg_sq, a._w16, self.lr_dev, self.step_dev,
+            a.dims, a.parameters_flat(), self.grads, self.exp_avg, self.exp_avg_sq, a._wc, self.lr_dev, self.step_dev,
             self.opt_ws, max_grad_norm=self.cfg.max_grad_norm, eps=1e-5, grad_scale=1.0 / self.world,
             grad_norm_out=self.grad_norm,
         )  # fmt: skip
@@ -424,7 +449,16 @@ class PPOTrainer:
             opt.replay()
         self._split_replays += 1
 
-    def _epoch(self):
+    def _shuffle(self):
+        """b_inds = randperm(batch) of this epoch (ppo.py:295): one Feistel/Philox launch into self.perm."""
+        if self.device_rng:
+            ops.random_permutation(self.batch_size, self.rng_state, out=self.perm)
+        else:
+            self.perm.copy_(torch.randperm(self.batch_size, device=self.device))
+
+    def _epoch(self, shuffle=False):
+        if shuffle:
+            self._shuffle()
         for start in range(0, self.batch_size, self.minibatch_size):
             self._minibatch(self.perm[start : start + self.minibatch_size])
 
@@ -432,38 +466,45 @@ class PPOTrainer:
         """All epochs x minibatches of one iteration (ppo.py:290-354).  `perms` (one index permutation per
         epoch) replaces the `torch.randperm` draws, for replaying a recorded run."""
         self.loss_acc.zero_()
+        # the permutation launch is part of the epoch graph when it is drawn on the device (its Philox offset lives
+        # in device memory); recorded permutations (`perms`) and torch.randperm are copied in before the replay
+        in_graph_shuffle = perms is None and self.device_rng
         for epoch in range(int(self.cfg.updates_epochs)):
             if perms is not None:
                 self.perm.copy_(perms[epoch])
-            else:
-                self.perm.copy_(torch.randperm(self.batch_size, device=self.device))
+            elif not in_graph_shuffle:
+                self._shuffle()
             if self.use_graphs and self.world > 1 and self._eager_epochs >= 1:
+                if in_graph_shuffle:
+                    self._shuffle()
                 self._epoch_split_graphs()
                 self._eager_epochs += 1
                 continue
-            if self.use_graphs and self._epoch_graph is None and self._eager_epochs >= 1:
+            key = bool(in_graph_shuffle)
+            if self.use_graphs and key not in self._epoch_graphs and self._eager_epochs >= 1:
                 # the first epoch ever ran eagerly (it also set the kernel attributes); record the identical
                 # launch sequence once and replay it from now on
                 graph = torch.cuda.CUDAGraph()
                 before = L.launch_count()
                 with torch.cuda.graph(graph):
-                    self._epoch()
-                self._graph_launches = L.launch_count() - before
-                self._epoch_graph = graph
-            if self._epoch_graph is not None:
-                self._epoch_graph.replay()
-                self._graph_replays += 1
+                    self._epoch(shuffle=key)
+                self._epoch_graphs[key] = (graph, L.launch_count() - before)
+                self._captured_launches += L.launch_count() - before
+            if key in self._epoch_graphs:
+                graph, n = self._epoch_graphs[key]
+                graph.replay()
+                self._replayed_launches += n
                 self._eager_epochs += 1
             else:
-                self._epoch()
+                self._epoch(shuffle=key)
                 self._eager_epochs += 1
 
     def kernel_launches(self) -> int:
         """libcatb200 kernels executed so far by this process (graph replays included)."""
-        captured = self._graph_launches * (1 if self._epoch_graph is not None else 0)
+        captured = self._captured_launches
         captured += self._policy_graph_launches * self._policy_captures
         captured += self._split_captured
-        replayed = self._graph_launches * self._graph_replays + self._policy_graph_launches * self._policy_replays
+        replayed = self._replayed_launches + self._policy_graph_launches * self._policy_replays
         replayed += self._split_launches * self._split_replays
         return L.launch_count() - captured + replayed
 
@@ -471,7 +512,7 @@ class PPOTrainer:
         """Slot T (the bootstrap observation / dones) becomes slot 0 of the next rollout (ppo.py:203-205)."""
         T = self.T
         self.obs[0].copy_(self.obs[T])
-        self.obs16[0].copy_(self.obs16[T])
+        self.obs_op[0].copy_(self.obs_op[T])
         self.dones[0].copy_(self.dones[T])
         self.true_dones[0].copy_(self.true_dones[T])
 

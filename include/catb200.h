@@ -196,13 +196,14 @@ size_t catb200_rms_workspace_bytes(int32_t dim);
  * RunningMeanStd.forward(x, update=True) for x [rows, dim] (dim = 1 for scalars):
  * batch mean / biased variance, Chan merge into (mean[dim], var[dim], count[1]) and
  * out = (x - mean) / sqrt(var + eps) with the *updated* statistics.  `out` may alias x or be NULL
- * (update only).  update == 0 skips the statistics and only normalises.  If out16 != NULL the normalised
- * rows are also written as bf16 [rows, pad16] (zero padded; dim <= pad16 <= 2 * dim), the layout the
- * first MLP layer reads, so the rollout needs no separate conversion pass.
+ * (update only).  update == 0 skips the statistics and only normalises.  If out_op != NULL the normalised
+ * rows are also written as the zero-padded tensor-core operand [rows, pad_op] (dim <= pad_op <= 2 * dim) of
+ * precision op_prec (catb200_prec: bf16, or fp32 rounded to tf32), the layout the first MLP layer reads, so the
+ * rollout needs no separate conversion pass.
  */
 int catb200_rms_forward(const float* x, int64_t rows, int32_t dim, float* mean, float* var, float* count,
-                        float eps, int32_t update, float* out, void* out16, int32_t pad16, void* workspace,
-                        size_t workspace_bytes, void* stream);
+                        float eps, int32_t update, float* out, void* out_op, int32_t pad_op, int32_t op_prec,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Post-step rollout append (U/cleanrl/ppo.py:203-205,215-216,225 for step t):
@@ -259,50 +260,62 @@ int catb200_gae_float_dones(int32_t variant, const float* rewards, const float* 
  * log-std (ppo.py:97).  Master parameters, gradients and Adam moments are flat fp32 buffers laid out in
  * the reference's `agent.parameters()` order (critic, actor_mean, actor_logstd) so that the python
  * `Agent` exposes them as views with the reference's state_dict keys.  The hidden-layer GEMMs run on the
- * tensor cores with bf16 operands / fp32 accumulation from bf16 copies of the weights that the Adam
- * kernel refreshes; heads, loss and optimizer math are fp32.
+ * tensor cores (tcgen05) from compute copies of the weights that the Adam kernel refreshes, in the precision
+ * dims->prec names:
+ *   CATB200_PREC_TF32  fp32 storage, operands rounded to tf32, fp32 accumulation: the reference's own GPU
+ *                      numerics (torch.backends.cuda.matmul.allow_tf32, scripts/clean_rl/train.py:86-87)
+ *   CATB200_PREC_BF16  bf16 operands and stored activations, fp32 accumulation (half the bytes, 8-bit mantissa)
+ * Heads, loss and optimizer math are fp32 either way.  "operand" below = element of that precision
+ * (4 bytes / 2 bytes).
  * ---------------------------------------------------------------------------------------------- */
+typedef enum { CATB200_PREC_BF16 = 0, CATB200_PREC_TF32 = 1 } catb200_prec;
+
 typedef struct {
   int32_t obs_dim; /* 45                                  */
   int32_t act_dim; /* 12 (<= 16)                          */
   int32_t h1, h2, h3; /* 512, 256, 128: multiples of 128  */
   int32_t obs_pad; /* obs_dim rounded up to 64            */
+  int32_t prec;    /* catb200_prec                        */
 } catb200_mlp_dims_t;
 
-/* Offsets (in elements) into the flat fp32 parameter vector and into the bf16 weight-copy buffer.
+/* Offsets (in elements) into the flat fp32 parameter vector and into the operand-precision weight-copy buffer.
  * Index 0 = critic, 1 = actor for every [2] array. */
 typedef struct {
   int64_t n_params;                 /* total fp32 parameters (377241 for Solo12)                 */
   int64_t w[2][4], b[2][4];         /* weight / bias offset of layer 0..3 of net 0/1             */
   int64_t logstd;                   /* offset of actor_logstd [act_dim]                          */
-  int64_t n_w16;                    /* total bf16 elements of the compute copies                 */
-  int64_t w16[2][3];                /* W_l   [out, in_pad] bf16, l = 0..2                        */
-  int64_t wt16[2][3];               /* W_l^T [in, out]     bf16, l = 1..2 (entry 0 unused = -1)  */
+  int64_t n_wc;                     /* total operand elements of the compute copies              */
+  int64_t wc[2][3];                 /* W_l   [out, in_pad], l = 0..2                             */
+  int64_t wtc[2][3];                /* W_l^T [in, out],     l = 1..2 (entry 0 unused = -1)       */
 } catb200_mlp_layout_t;
 
 int catb200_mlp_layout(const catb200_mlp_dims_t* dims, catb200_mlp_layout_t* layout);
 
-/* bf16 compute copies (W and W^T of the hidden layers) from the fp32 master parameters. */
-int catb200_mlp_cast_weights(const catb200_mlp_dims_t* dims, const float* params, void* w16, void* stream);
+/* Compute copies (W and W^T of the hidden layers, operand precision) from the fp32 master parameters. */
+int catb200_mlp_cast_weights(const catb200_mlp_dims_t* dims, const float* params, void* wc, void* stream);
 
-/* fp32 [rows, obs_dim] -> bf16 [rows, obs_pad] (zero padded), the layout the first GEMM reads. */
-int catb200_obs_to_bf16(const float* obs, int64_t rows, int32_t obs_dim, int32_t obs_pad, void* obs16,
-                        void* stream);
+/* fp32 [rows, obs_dim] -> operand [rows, obs_pad] (zero padded), the layout the first GEMM reads. */
+int catb200_obs_to_operand(const catb200_mlp_dims_t* dims, const float* obs, int64_t rows, void* obs_op,
+                           void* stream);
 
 /* Bytes of activation scratch for a forward (training = 0) or forward + backward (training = 1) pass
- * over `rows` samples. */
+ * over `rows` samples.  The scratch must be zero-initialised once; the kernels leave what must stay zero zeroed. */
 size_t catb200_mlp_workspace_bytes(const catb200_mlp_dims_t* dims, int32_t rows, int32_t training);
 
 /*
  * Agent.get_action_and_value(x) for the rollout (ppo.py:104-119,208-212): both MLPs forward, then
  *   action = action_in                    if action_in != NULL (evaluate given actions), else
- *   action = mean + exp(logstd) * noise   (noise ~ N(0,1) supplied by the caller; NULL -> action = mean)
+ *   action = mean + exp(logstd) * noise   noise ~ N(0,1): supplied by the caller (`noise`), or drawn on the device
+ *                                         from rng_state (Philox4x32-10 + Box-Muller, element (row, j) = counter
+ *                                         offset + row * act_dim + j; the offset is advanced by rows * act_dim);
+ *                                         both NULL -> action = mean
  *   logprob = sum_j Normal(mean_j, std_j).log_prob(action_j),  value = critic(x)
- * obs16: bf16 [rows, obs_pad].  Any of action / logprob / value / mean_out may be NULL.
+ * obs_op: operand [rows, obs_pad].  Any of action / logprob / value / mean_out may be NULL.
  */
-int catb200_mlp_act(const catb200_mlp_dims_t* dims, const void* obs16, int32_t rows, const float* params,
-                    const void* w16, const float* noise, const float* action_in, float* action, float* logprob,
-                    float* value, float* mean_out, void* workspace, size_t workspace_bytes, void* stream);
+int catb200_mlp_act(const catb200_mlp_dims_t* dims, const void* obs_op, int32_t rows, const float* params,
+                    const void* wc, const float* noise, uint64_t* rng_state, const float* action_in, float* action,
+                    float* logprob, float* value, float* mean_out, void* workspace, size_t workspace_bytes,
+                    void* stream);
 
 typedef struct {
   float clip_coef, ent_coef, vf_coef;
@@ -311,32 +324,89 @@ typedef struct {
 
 /*
  * Forward + backward of one PPO minibatch (ppo.py:298-352 up to loss.backward()):
- * gathers rows mb_inds[0..mb_rows) of the flattened rollout (obs16_all bf16 [B, obs_pad], actions_all
+ * gathers rows mb_inds[0..mb_rows) of the flattened rollout (obs_op_all operand [B, obs_pad], actions_all
  * [B, act_dim], logprobs_all / advantages_all / returns_all / values_all [B]), normalises advantages per
  * minibatch (unbiased std + 1e-8), normalises returns / old values / new values with norm_stats
  * (see catb200_gae), evaluates the clipped policy loss, clipped value loss and entropy bonus and
  * accumulates d loss / d params into `grads` (flat fp32, must be zero on entry; catb200_adam_step
  * leaves it zeroed).  loss_acc[8] += {pg_loss, v_loss, entropy, approx_kl, clipfrac, old_approx_kl,
  * loss, 1} for this minibatch (running sums the trainer reads once per iteration).
+ * The weight gradients of the hidden layers are summed with floating-point atomics (red.global.add): their
+ * last bits depend on the order in which CTAs retire.
  */
 int catb200_ppo_minibatch_grad(const catb200_mlp_dims_t* dims, const catb200_ppo_hparams_t* hp, int32_t mb_rows,
-                               const int64_t* mb_inds, const void* obs16_all, const float* actions_all,
+                               const int64_t* mb_inds, const void* obs_op_all, const float* actions_all,
                                const float* logprobs_all, const float* advantages_all, const float* returns_all,
                                const float* values_all, const float* norm_stats, const float* params,
-                               const void* w16, float* grads, float* loss_acc, void* workspace,
+                               const void* wc, float* grads, float* loss_acc, void* workspace,
                                size_t workspace_bytes, void* stream);
 
 /*
  * clip_grad_norm_(all params, max_grad_norm) + Adam step (ppo.py:353-354; torch.optim.Adam with
- * eps, betas, no weight decay), then zero `grads` and refresh the bf16 weight copies.
+ * eps, betas, no weight decay), then zero `grads` and refresh the operand-precision weight copies.
  * grads are first multiplied by grad_scale (1 / world_size after a sum-allreduce).
  * lr_dev: device float; step_dev: device int32 step counter (incremented here).
  * opt_ws: 64 bytes of zero-initialised device scratch.
  */
 int catb200_adam_step(const catb200_mlp_dims_t* dims, float* params, float* grads, float* exp_avg,
-                      float* exp_avg_sq, void* w16, const float* lr_dev, int32_t* step_dev, float max_grad_norm,
+                      float* exp_avg_sq, void* wc, const float* lr_dev, int32_t* step_dev, float max_grad_norm,
                       float beta1, float beta2, float eps, float grad_scale, float* grad_norm_out, void* opt_ws,
                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Device-side random draws (Philox4x32-10; csrc/philox.cuh, CPU restatement oracle/philox_oracle.py)
+ *
+ * rng_state: two uint64 in device memory, {seed, offset}.  Every function below reads the state on the device,
+ * uses the counters [offset, offset + consumed) of its own Philox stream and advances offset by `consumed`, so
+ * calls can be captured in CUDA graphs and replayed with fresh numbers.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Host-side (no GPU) evaluation of the Philox4x32-10 block function the kernels inline: counter4 / key2 / out4 are
+ * raw 32-bit words in Random123 order, so its published known-answer vectors apply directly. */
+int catb200_philox4x32_10(const uint32_t* counter4, const uint32_t* key2, uint32_t* out4);
+/* Host-side evaluation of catb200_random_permutation for a given (seed, offset). */
+int catb200_random_permutation_host(int64_t n, uint64_t seed, uint64_t offset, int64_t* out);
+
+/* out[0..n) = a pseudo-random permutation of 0..n-1 (replaces torch.randperm, U/cleanrl/ppo.py:295): keyed 6-round
+ * Feistel bijection of [0, 2^ceil(log2 n)) with cycle walking; consumes 2 counters. */
+int catb200_random_permutation(int64_t n, uint64_t* rng_state, int64_t* out, void* stream);
+
+/* mask[i] = (u_i < p[i]) for i < n, u_i uniform in (0,1) (counter offset + i; consumes n).  If ids != NULL, also
+ * ids[0..*count) = ascending positions of the set entries (= mask.nonzero().flatten()).  The optional stochastic
+ * termination mode of the CaT env: p = constraint probabilities (north_star; the reference itself keeps `dones`
+ * as a probability, U/cat/cat_env.py:107). */
+int catb200_bernoulli_mask(const float* p, int32_t n, uint64_t* rng_state, uint8_t* mask, int64_t* ids,
+                           int32_t* count, void* stream);
+
+/* UniformVelocityCommandWithDeadzone._update_command (U/mdp/commands.py:39-93). */
+typedef struct {
+  float lin_vel_x[2], lin_vel_y[2], ang_vel_z[2], heading[2]; /* cfg.ranges.*                            */
+  float velocity_deadzone;                                    /* commands.py:100                         */
+  float heading_control_stiffness;
+  float rel_heading_envs, rel_standing_envs;
+  float p_step;            /* env.physics_dt / env.max_episode_length_s (commands.py:71-73,81-83)       */
+  int32_t heading_command; /* cfg.heading_command                                                        */
+} catb200_command_cfg_t;
+
+/*
+ * vel_command_b [N,3] in place: heading-error yaw rate for heading envs, dead zone, Bernoulli resampling
+ * (p = 0.01 for still commands, p_step otherwise) with uniform redraws in the cfg ranges, Bernoulli yaw flip.
+ * Env i uses uniforms u[i][0..8): 0 resample, 1-3 lin_x / lin_y / ang_z, 4 heading, 5 is_heading, 6 is_standing,
+ * 7 yaw flip -- from u_ext [N,8] if given (parity tests), else Philox (consumes 8 N).  resampled [N] (optional)
+ * receives the resample mask (the caller resets time_left / command_counter for those, as CommandTerm._resample does).
+ */
+int catb200_command_update(const catb200_command_cfg_t* cfg, int32_t num_envs, float* vel_command_b,
+                           float* heading_target, const float* heading_w, uint8_t* is_heading_env,
+                           uint8_t* is_standing_env, const float* u_ext, uint64_t* rng_state, uint8_t* resampled,
+                           void* stream);
+
+/*
+ * push_by_setting_velocity_with_random_envs (U/mdp/events.py:59-96): pushed[i] = (u[i][0] < p_push); pushed envs get
+ * root_vel_w[i][k] = lo[k] + (hi[k] - lo[k]) * u[i][1 + k], k = 0..5 (x, y, z, roll, pitch, yaw); the others keep
+ * their velocity.  u from u_ext [N,7] or Philox (consumes 8 N).
+ */
+int catb200_push_select(int32_t num_envs, float p_push, const float* range_lo, const float* range_hi,
+                        float* root_vel_w, const float* u_ext, uint64_t* rng_state, uint8_t* pushed, void* stream);
 
 #ifdef __cplusplus
 }

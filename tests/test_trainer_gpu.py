@@ -34,10 +34,13 @@ def test_state_dict_keys_match_reference(golden_dir):
         assert torch.equal(v.cpu(), g["final_state"][k]), k
     # parameters live in one flat vector that the kernels update in place
     assert agent.critic[0].weight.data_ptr() == agent.parameters_flat().data_ptr()
-    # the bf16 compute copies followed the load
+    # the operand-precision compute copies followed the load (default precision tf32: fp32 rounded to 10 mantissa bits)
     w = agent.actor_mean[2].weight
     lay = agent.layout
-    assert torch.equal(agent._w16[lay.w16[1][1] : lay.w16[1][1] + w.numel()].view_as(w), w.to(torch.bfloat16))
+    assert agent.precision == "tf32"
+    got = agent._wc[lay.wc[1][1] : lay.wc[1][1] + w.numel()].view_as(w)
+    torch.testing.assert_close(got, w.detach(), rtol=2**-11, atol=0)
+    assert int((got.view(torch.int32) & 0x1FFF).abs().max()) == 0
 
 
 def test_trainer_replays_reference_iteration(golden_dir):
@@ -49,13 +52,13 @@ def test_trainer_replays_reference_iteration(golden_dir):
     tr.agent.load_state_dict(g["init_state"])
     # recorded rollout -> trainer buffers (slot T = bootstrap obs / next_done)
     tr.obs[:T].copy_(g["obs"]); tr.obs[T].copy_(g["next_obs"])
-    ops.obs_to_bf16(tr.obs.view(-1, se.OBS_DIM), tr.agent.dims.obs_pad, out=tr.obs16.view(-1, tr.agent.dims.obs_pad))
+    ops.obs_to_operand(tr.agent.dims, tr.obs.view(-1, se.OBS_DIM), out=tr.obs_op.view(-1, tr.agent.dims.obs_pad))
     tr.actions.copy_(g["actions"]); tr.logprobs.copy_(g["logprobs"]); tr.rewards.copy_(g["rewards"]); tr.values.copy_(g["values"])
     tr.dones[:T].copy_(g["dones"]); tr.dones[T].copy_(g["next_done"])
     tr.true_dones[:T].copy_(g["true_dones"]); tr.true_dones[T].copy_(g["next_true_done"])
-    # our own bootstrap value (bf16 tensor-core MLP) vs the reference's fp32 one
+    # our own bootstrap value (tf32 tensor-core MLP) vs the reference's fp32 one
     tr.compute_gae(bootstrap=True)
-    torch.testing.assert_close(tr.next_value.cpu(), g["next_value"].reshape(-1), rtol=3e-2, atol=3e-2)
+    torch.testing.assert_close(tr.next_value.cpu(), g["next_value"].reshape(-1), rtol=4e-3, atol=4e-3)
     # with the recorded bootstrap value GAE is bit-exact and the value statistics agree to 1e-5
     tr.agent.load_state_dict(g["init_state"])
     tr.next_value.copy_(g["next_value"].reshape(-1))
@@ -73,17 +76,17 @@ def test_trainer_replays_reference_iteration(golden_dir):
     tr.update(perms=[p.to(DEV) for p in g["perms"]])
     losses = tr.losses()
     n_mb = len(g["perms"]) * (n * T // cfg_d["minibatch_size"])
-    # bf16 tensor-core numerics vs the reference's fp32 CPU run: losses to 2e-2 (relative or absolute)
-    assert losses["mean_pg_loss"] == pytest.approx(g["sum_pg_loss"] / n_mb, rel=2e-2, abs=2e-3)
-    assert losses["mean_v_loss"] == pytest.approx(g["sum_v_loss"] / n_mb, rel=2e-2, abs=2e-3)
+    # tf32 tensor-core numerics vs the reference's fp32 CPU run: losses to 3e-3 (relative or absolute)
+    assert losses["mean_pg_loss"] == pytest.approx(g["sum_pg_loss"] / n_mb, rel=3e-3, abs=3e-4)
+    assert losses["mean_v_loss"] == pytest.approx(g["sum_v_loss"] / n_mb, rel=3e-3, abs=3e-4)
     assert losses["mean_entropy_loss"] == pytest.approx(g["sum_entropy_loss"] / n_mb, rel=1e-4)
     # parameter update after the 6 Adam steps: same direction and size as the reference's
     init = torch.cat([g["init_state"][k].reshape(-1) for k in g["init_state"] if "_rms." not in k])
     want = torch.cat([g["final_state"][k].reshape(-1) for k in g["final_state"] if "_rms." not in k]) - init
     got = torch.cat([v.detach().cpu().reshape(-1) for k, v in tr.agent.state_dict().items() if "_rms." not in k]) - init
     cos = float(torch.dot(got, want) / (got.norm() * want.norm()))
-    assert cos > 0.97, f"update direction cosine {cos:.4f}"
-    assert float(got.norm() / want.norm()) == pytest.approx(1.0, abs=0.05)
+    assert cos > 0.995, f"update direction cosine {cos:.4f}"
+    assert float(got.norm() / want.norm()) == pytest.approx(1.0, abs=0.02)
 
 
 def _make_trainer(n, T, mb, graphs, seed):

@@ -24,7 +24,7 @@ def main():
     # host-side cost of the rollout pieces (no syncs: pure python + launch overhead)
     for t in range(tr.T):
         a = time.perf_counter()
-        tr.agent.get_action_and_value(tr.obs16[t], out=(tr.actions[t], tr.logprobs[t], tr.values[t]))
+        tr.agent.get_action_and_value(tr.obs_op[t], out=(tr.actions[t], tr.logprobs[t], tr.values[t]))
         b = time.perf_counter()
         out = env.step(tr.actions[t])
         c = time.perf_counter()
