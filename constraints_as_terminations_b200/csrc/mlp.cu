@@ -828,8 +828,9 @@ int catb200_ppo_minibatch_grad(const catb200_mlp_dims_t* dims, const catb200_ppo
       TcWgradArgs t = {};
       for (int z = 0; z < 2; ++z) {
         const void* Hin = l == 0 ? X : static_cast<const void*>(ws + L.H[z][l - 1]);
-        rc = make_tmap(&t.mapA[z], prec, ws + L.dZ[z][l], x.out[l], M, x.out[l], ch, bk);
-        if (rc == CATB200_OK) rc = make_tmap(&t.mapB[z], prec, Hin, x.in_pad[l], M, x.in_pad[l], ch, bk);
+        const int swz32 = prec == kPrecTf32 ? 1 : 0;  // MN-major 32-bit operands: 32-byte-granular swizzle
+        rc = make_tmap(&t.mapA[z], prec, ws + L.dZ[z][l], x.out[l], M, x.out[l], ch, bk, swz32);
+        if (rc == CATB200_OK) rc = make_tmap(&t.mapB[z], prec, Hin, x.in_pad[l], M, x.in_pad[l], ch, bk, swz32);
         if (rc != CATB200_OK) return rc;
         t.gw[z] = reinterpret_cast<float*>(ws + L.gacc[z][l]);
         t.gb[z] = grads + P.b[z][l];

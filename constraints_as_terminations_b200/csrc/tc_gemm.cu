@@ -356,10 +356,13 @@ mlp_wgrad_kernel(const __grid_constant__ TcWgradArgs g) {
         const uint64_t d1 = make_smem_desc(ones, 16, 1024);  // K-major, 16 rows x 128 B, every element 1
 #pragma unroll
         for (int k = 0; k < P::kBK / P::kUmmaK; ++k) {
-          // MN-major SW128: CH-feature chunks LBO = one box apart, 8-row reduction groups SBO = 1 KiB apart;
-          // one K-step (kUmmaK reduction rows) = kUmmaK * 128 B further
-          const uint64_t da = make_smem_desc(sa + k * P::kUmmaK * kRowBytes, kBoxBytes, 1024);
-          const uint64_t db = make_smem_desc(sb + k * P::kUmmaK * kRowBytes, kBoxBytes, 1024);
+          // MN-major: CH-feature chunks LBO = one box apart; one K-step (kUmmaK reduction rows) = kUmmaK * 128 B
+          // further.  bf16: SWIZZLE_128B, 8-row reduction groups SBO = 1 KiB apart.  tf32: the tensor core takes
+          // MN-major 32-bit operands only in the 32-byte-granular swizzle (4-row groups, SBO = 512 B).
+          constexpr uint32_t lt = PREC == kPrecTf32 ? kLayoutSw128Base32 : kLayoutSw128;
+          constexpr uint32_t sbo = PREC == kPrecTf32 ? 512 : 1024;
+          const uint64_t da = make_smem_desc(sa + k * P::kUmmaK * kRowBytes, kBoxBytes, sbo, lt);
+          const uint64_t db = make_smem_desc(sb + k * P::kUmmaK * kRowBytes, kBoxBytes, sbo, lt);
           umma<PREC>(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           if (with_bias) umma<PREC>(tmem_base + BN, da, d1, idesc_ones, (kb | k) != 0 ? 1u : 0u);
         }
@@ -429,7 +432,7 @@ struct TmapKey {
   const void* ptr;
   uint64_t inner, outer, ld;
   uint32_t bi, bo;
-  int prec;
+  int prec, swz32;
 };
 struct TmapEntry {
   TmapKey key;
@@ -439,7 +442,7 @@ static TmapEntry g_tmap_cache[256];
 static int g_tmap_count = 0;
 
 static int encode_tmap(CUtensorMap* map, int prec, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
-                       uint32_t box_inner, uint32_t box_outer) {
+                       uint32_t box_inner, uint32_t box_outer, int swz32) {
   EncodeTiledFn fn = encoder();
   if (!fn) return CATB200_ERR_UNSUPPORTED;
   const uint64_t esz = prec == kPrecTf32 ? 4 : 2;
@@ -448,25 +451,27 @@ static int encode_tmap(CUtensorMap* map, int prec, const void* ptr, uint64_t inn
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, prec == kPrecTf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                  const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swz32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? CATB200_OK : CATB200_ERR_CUDA;
 }
 
 // Encodings are memoised: the trainer reuses a handful of (pointer, shape) combinations every step.
 int make_tmap(CUtensorMap* map, int prec, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
-              uint32_t box_outer) {
+              uint32_t box_outer, int swz32) {
   for (int i = 0; i < g_tmap_count; ++i) {
     const TmapKey& k = g_tmap_cache[i].key;
-    if (k.ptr == ptr && k.inner == inner && k.outer == outer && k.ld == ld && k.bi == box_inner && k.bo == box_outer && k.prec == prec) {
+    if (k.ptr == ptr && k.inner == inner && k.outer == outer && k.ld == ld && k.bi == box_inner && k.bo == box_outer &&
+        k.prec == prec && k.swz32 == swz32) {
       *map = g_tmap_cache[i].map;
       return CATB200_OK;
     }
   }
-  int rc = encode_tmap(map, prec, ptr, inner, outer, ld, box_inner, box_outer);
+  int rc = encode_tmap(map, prec, ptr, inner, outer, ld, box_inner, box_outer, swz32);
   if (rc == CATB200_OK) {
     const int slot = g_tmap_count < 256 ? g_tmap_count++ : 255;
-    g_tmap_cache[slot].key = TmapKey{ptr, inner, outer, ld, box_inner, box_outer, prec};
+    g_tmap_cache[slot].key = TmapKey{ptr, inner, outer, ld, box_inner, box_outer, prec, swz32};
     g_tmap_cache[slot].map = *map;
   }
   return rc;

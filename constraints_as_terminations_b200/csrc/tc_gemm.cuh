@@ -24,7 +24,7 @@ struct TcGemmArgs {
 // weight gradient dW[outs, ins] += dZ[rows, outs]^T Hin[rows, ins] over a range of minibatch rows, and
 // db[outs] += column sums of dZ (a second, 8-column MMA against a tile of ones).
 struct TcWgradArgs {
-  CUtensorMap mapA[2];  // dZ  [rows, outs]: load boxes CH (features) x kBK (rows)
+  CUtensorMap mapA[2];  // dZ  [rows, outs]: load boxes CH (features) x kBK (rows); tf32: SWIZZLE_128B_ATOM_32B
   CUtensorMap mapB[2];  // Hin [rows, ins_pad]: same box shape
   float* gw[2];         // fp32 accumulators [outs, ins_pad] (16-byte aligned rows): red.global.add.v4.f32
   float* gb[2];         // bias gradient [outs]
@@ -33,9 +33,10 @@ struct TcWgradArgs {
 };
 
 // 2-D tensor map over a row-major [outer, inner] matrix of bf16 (prec 0) or fp32 (prec 1) elements with leading
-// dimension ld (elements); box = [box_outer, box_inner], SWIZZLE_128B.  Encodings are memoised.
+// dimension ld (elements); box = [box_outer, box_inner], SWIZZLE_128B (swz32 != 0: SWIZZLE_128B_ATOM_32B, the layout
+// MN-major 32-bit tensor-core operands need).  Encodings are memoised.
 int make_tmap(CUtensorMap* map, int prec, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
-              uint32_t box_outer);
+              uint32_t box_outer, int swz32 = 0);
 int tc_gemm_launch(int mode, int prec, const TcGemmArgs& g, cudaStream_t st);
 int tc_wgrad_launch(int prec, const TcWgradArgs& g, int splits, cudaStream_t st);
 

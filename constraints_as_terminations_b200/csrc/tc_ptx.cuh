@@ -121,14 +121,18 @@ __device__ __forceinline__ float elu_fast(float v) {
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address >> 4 in bits [0,14),
 // leading byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version 1 in [46,48),
-// layout type SWIZZLE_128B (= 2) in [61,64).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout type in [61,64): SWIZZLE_128B = 2 (16-byte chunks XOR-ed with the row index, 8-row atoms) or
+// SWIZZLE_128B_BASE32B = 1 (32-byte chunks, 4-row atoms: the only layout the tensor core accepts for MN-major
+// 32-bit operands; TMA writes it with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).
+constexpr uint32_t kLayoutSw128 = 2, kLayoutSw128Base32 = 1;
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type = kLayoutSw128) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout_type << 61;
   return d;
 }
 

