@@ -3,7 +3,7 @@
 
     python bench.py --gpus 1 --steps 20 --warmup 5                     # this repo's CUDA path (1 GPU)
     torchrun --nproc-per-node N ... bench.py --gpus N --steps K --warmup W   # one rank per GPU, NCCL
-    python bench.py --impl reference --steps K --warmup W              # reference arm: CPU oracle port
+    python bench.py --impl reference --steps K --warmup W              # reference arm: the unmodified reference on the host cores
 
 A "step" is one full PPO iteration on the trainer side of Isaac-Velocity-CaT-Flat-Solo12-v0 with the
 reference's hyper-parameters: 24 env steps x num_envs (policy forward + sampling, the 13-term constraint
@@ -14,7 +14,11 @@ the same tensors (`constraints_as_terminations_b200/synthetic_env.py`); the numb
 env-steps/s and says so in `data`.
 
 Prints ONE JSON line (rank 0).  `value` has the env state already resident in HBM; `e2e` feeds every env
-step's state from pinned host memory (H2D inside the timed region) and reads the losses back (D2H).
+step's state from pinned host memory (H2D inside the timed region) and reads the losses back (D2H).  Beside them:
+`roofline` (dominant kernel of the step), `rooflines` (HBM-bound kernels timed alone, incl. 65 536 / 1 M envs),
+`sweep` (BASELINE.json configs 3-5: 16 384 / 65 536 envs per GPU and the 16-term stress layout), `cpu_baseline` (the
+unmodified reference on the host cores, bounded sample) and `gpu_eager_baseline` (the unmodified reference's torch-eager
+code with CUDA tensors on this B200, TF32 on: the practically relevant "before").
 """
 
 from __future__ import annotations
@@ -36,6 +40,21 @@ METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
 
 
+def workload_config(envs_per_gpu, world):
+    """`config` of the JSON line: identical for both arms (same keys, same values) for the same command line."""
+    T, mb = 24, min(16384, envs_per_gpu * 24)
+    return {
+        "workload": f"Isaac-Velocity-CaT-Flat-Solo12-v0 trainer side, {envs_per_gpu} envs/GPU, CleanRL PPO cfg (T=24, 5 epochs x {envs_per_gpu * T // mb} minibatches of {mb})",
+        "envs_per_gpu": envs_per_gpu, "num_steps": T, "constraint_terms": 13, "constraint_columns": 78,
+        "minibatch": mb, "epochs": 5,
+        "parallelism": f"dp{world} (one env shard per GPU, 1 gradient allreduce per optimizer step)",
+        "l2": "per-step working set (rollout buffers + minibatch activations, > 300 MB) exceeds the 126 MB L2: inputs larger than L2",
+    }  # fmt: skip
+
+
+DATA = "synthetic Solo12 state (no Isaac Sim physics): trainer-side env-steps/s"
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
@@ -55,7 +74,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "40", "-i", str(self.index)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "10", "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
             )  # fmt: skip
             self.thread = threading.Thread(target=self._read, daemon=True)
@@ -86,6 +105,9 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------
 # this repo's arm
 # ----------------------------------------------------------------------------------------------------------
+PRECISION = None  # --precision: tf32 (default) | bf16
+
+
 def make_trainer(num_envs, device, seed, host_fed=False, pool=8, graphs=True, distributed=True):
     from constraints_as_terminations_b200 import PPOTrainer, solo12_flat_ppo_cfg
     from constraints_as_terminations_b200 import synthetic_env as se
@@ -95,7 +117,7 @@ def make_trainer(num_envs, device, seed, host_fed=False, pool=8, graphs=True, di
     env.load_managers()
     cfg = solo12_flat_ppo_cfg(logger=None)
     torch.manual_seed(cfg.seed + seed)
-    trainer = PPOTrainer(env, cfg, device=device, use_graphs=graphs, distributed=distributed)
+    trainer = PPOTrainer(env, cfg, device=device, use_graphs=graphs, distributed=distributed, precision=PRECISION)
     trainer.start()
     return env, trainer
 
@@ -171,7 +193,7 @@ def _host_fed_env_cls():
 HostFedEnv = None
 
 
-def timed_iterations(trainer, steps, warmup, world, device, read_losses):
+def timed_iterations(trainer, steps, warmup, world, device, read_losses, sample_clocks=True):
     for _ in range(warmup):
         trainer.train_iteration()
         if read_losses:
@@ -180,8 +202,9 @@ def timed_iterations(trainer, steps, warmup, world, device, read_losses):
     if world > 1:
         torch.distributed.barrier()
     launches0 = trainer.kernel_launches()
-    sampler = ClockSampler(device.index or 0)
-    sampler.start()
+    sampler = ClockSampler(device.index or 0) if sample_clocks else None
+    if sampler:
+        sampler.start()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     start.record()
@@ -197,7 +220,7 @@ def timed_iterations(trainer, steps, warmup, world, device, read_losses):
         t = torch.tensor([ms], device=device)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         ms = float(t)
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     return ms, trainer.kernel_launches() - launches0, clocks
 
 
@@ -230,37 +253,34 @@ def kernel_profile(trainer, iters=2, record=True):
     return dict(sorted(rows.items(), key=lambda kv: -kv[1]["us"])), total
 
 
-# tensor-core flops per sample of the three tcgen05 GEMM modes (both nets, obs padded to 64): SURVEY.md §8d
-_MAC_FWD = 2 * (64 * 512 + 512 * 256 + 256 * 128)   # also the weight-gradient GEMMs
-_MAC_DGRAD = 2 * (256 * 128 + 512 * 256)
-
-
 def _traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures."""
-    path = os.path.join(ROOT, "profiles", "r1b_traffic.json")
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of the
+    CURRENT kernels (profiles/r2_traffic.json names the ncu CSV each value came from).  ncu flushes the caches before
+    every replay, so these are cold-cache figures: an upper bound on what the same launch moves inside the step."""
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
     return json.load(open(path)) if os.path.isfile(path) else {}
 
 
 def _gemm_flops_by_kernel(trainer):
-    """Tensor-core flops per iteration attributed to each tcgen05 kernel name.  Forward / dgrad launches with more
-    than 2 x 148 output tiles run the persistent kernel, the others (rollout-sized launches, the 256 -> 128 layer)
-    the one-tile-per-CTA kernel (tc_gemm.cu: use_persistent)."""
+    """ALGORITHMIC tensor-core flops per iteration attributed to each tcgen05 kernel name (csrc/tc_gemm.cu): layer 0
+    counted at K = 45 (SURVEY.md §8d: 0.7508 MFLOP/sample forward), not at the K = 64 the padded operand rows carry;
+    both nets (critic + actor) run in every launch.  mlp_gemm_kernel<0, P> = forward, <1, P> = dgrad,
+    mlp_wgrad_kernel<P, BN> = weight gradients (BN = 64 for the 45 -> 512 layer, 128 otherwise)."""
     n, T = trainer.num_envs, trainer.T
     opt_rows = trainer.batch_size * int(trainer.cfg.updates_epochs)  # minibatch rows per iteration
-    mb = trainer.minibatch_size
-    layers = [(64, 512), (512, 256), (256, 128)]  # (K, N) of the hidden layers, both nets batched per launch
+    p = 1 if trainer.agent.precision == "tf32" else 0
+    layers = [(45, 512), (512, 256), (256, 128)]  # (K, N) of the hidden layers
     flops = {}
 
-    def add(kind, rows_per_launch, total_rows, k, n_out):
-        tiles = 2 * ((rows_per_launch + 127) // 128) * (n_out // 128)
-        name = f"tc_gemm_persist_kernel<{kind}, 128>" if tiles > 2 * 148 else f"tc_gemm_kernel<{kind}, 128>"
+    def add(name, total_rows, k, n_out):
         flops[name] = flops.get(name, 0.0) + 2.0 * 2 * k * n_out * total_rows
 
     for k, n_out in layers:
-        add(0, mb, opt_rows, k, n_out)          # update forward
-        add(0, n, n * (T + 1), k, n_out)        # rollout policy + bootstrap value
+        add(f"mlp_gemm_kernel<0, {p}>", opt_rows + n * (T + 1), k, n_out)   # update forward + rollout policy + bootstrap
     for k, n_out in layers[1:]:
-        add(1, mb, opt_rows, n_out, k)          # dgrad: dZ_l [M, N_l] x W_l -> [M, K_l]
+        add(f"mlp_gemm_kernel<1, {p}>", opt_rows, n_out, k)                # dgrad: dZ_l [M, N_l] x W_l -> [M, K_l]
+    for k, n_out in layers:
+        add(f"mlp_wgrad_kernel<{p}, {64 if k < 128 else 128}>", opt_rows, k, n_out)
     return flops
 
 
@@ -272,11 +292,17 @@ def dominant_kernel_roofline(prof, total_us, trainer, peaks):
     name, row = next(iter(prof.items()))
     out = {"kernel": name, "share_of_step": row["share"], "us_per_step": row["us"], "launches_per_step": row["launches"]}
     if name in flops:
-        peak = peaks.get("bf16_tflops_sustained") or peaks["bf16_tflops"]
+        bf16_peak = peaks.get("bf16_tflops_sustained") or peaks["bf16_tflops"]
+        tf32 = trainer.agent.precision == "tf32"
+        # kind::tf32 issues half the MACs per tcgen05.mma of kind::f16 (K = 8 vs 16 per instruction at the same
+        # dispatch rate; nominal 1.1 vs 2.25 PFLOP/s dense, B200_PROFILING.md): peak = half the MEASURED bf16 rate
+        peak = bf16_peak * (0.5 if tf32 else 1.0)
         ach = flops[name] / (row["us"] * 1e-6) / 1e12
         out.update({"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                    "flops_per_step": flops[name], "traffic": _traffic().get(name),
-                    "peak_source": peaks["source"] + " (sustained bf16: the kernel runs inside a long step)"})
+                    "frac_of_measured_bf16_peak": ach / bf16_peak,
+                    "flops_per_step": flops[name], "traffic": (_traffic().get(name) or {}).get("bytes_per_launch"),
+                    "traffic_source": (_traffic().get(name) or {}).get("source"),
+                    "peak_source": peaks["source"] + (" (sustained bf16 cuBLAS rate x 0.5: tf32 operands; the kernel runs inside a long step)" if tf32 else " (sustained bf16: the kernel runs inside a long step)")})
     return out
 
 
@@ -323,23 +349,69 @@ def kernel_rooflines(device, num_envs, peaks):
         nbytes = 940 * n
         out[f"cat_step@{n}"] = {"bound": "hbm", "achieved": nbytes / sec / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": nbytes / sec / 1e9 / peaks["hbm_gbs"], "us": sec * 1e6, "bytes": nbytes, "launches": 2}
         del env, mgr
-    # one PPO optimizer step on a 16384-row minibatch (gather, 3 fwd + 2 dgrad + 3 wgrad tcgen05 GEMMs, head/loss,
-    # reduce, clip + Adam + weight cast): 2.2525 MFLOP/sample of tensor work
+    # a6: running observation moments + normalise (+ operand copy) + rollout append: 428 B/env-step
+    from constraints_as_terminations_b200 import RunningMeanStd
+    from constraints_as_terminations_b200 import _lib as L
+
+    roof_a6 = {}
+    for n in sorted({num_envs, 65536, 1 << 20}):
+        rms = RunningMeanStd(shape=(se.OBS_DIM,)).to(device)
+        raw = torch.randn(n, se.OBS_DIM, device=device)
+        norm, out_op = torch.empty_like(raw), torch.empty(n, 64, dtype=L.operand_dtype(L.PREC_NAMES[PRECISION or L.default_precision()]), device=device)
+        rew, done, tout = torch.rand(n, device=device), torch.rand(n, device=device), torch.zeros(n, dtype=torch.bool, device=device)
+        r_t, d_t, td_t = torch.empty(n, device=device), torch.empty(n, device=device), torch.empty(n, device=device)
+
+        def a6():
+            ops.rollout_append(rew, done, tout, r_t, d_t, td_t)
+            rms(raw, update=True, out=norm, out_op=out_op)
+
+        sec = time_kernel(a6)
+        nbytes = 428 * n
+        roof_a6[f"obs_norm_append@{n}"] = {"bound": "hbm", "achieved": nbytes / sec / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": nbytes / sec / 1e9 / peaks["hbm_gbs"], "us": sec * 1e6, "bytes": nbytes, "launches": 3}
+        del rms, raw, out_op
+    # one PPO optimizer step on a 16384-row minibatch (gather, 3 fwd + 2 dgrad + 3 wgrad tcgen05 GEMMs, head/loss, fold,
+    # grad norm, Adam + operand-copy refresh): 2.2525 MFLOP/sample of tensor work
     env, tr = make_trainer(num_envs, device, seed=0, graphs=False, distributed=False)  # rank-local probe
     tr.train_iteration()
     mb = tr.minibatch_size
     perm = torch.randperm(tr.batch_size, device=device)
+    before = L.launch_count()
+    tr._minibatch(perm[:mb])
+    launches = L.launch_count() - before
     sec = time_kernel(lambda: tr._minibatch(perm[:mb]), reps=10)
     flops = 2.2525e6 * mb
-    out[f"ppo_minibatch_step@{mb}"] = {"bound": "tensor", "achieved": flops / sec / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": flops / sec / 1e12 / peaks["bf16_tflops"], "us": sec * 1e6, "flops": flops, "launches": 14}
+    tf32 = tr.agent.precision == "tf32"
+    peak = peaks["bf16_tflops"] * (0.5 if tf32 else 1.0)
+    out[f"ppo_minibatch_step@{mb}"] = {"bound": "tensor", "achieved": flops / sec / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": flops / sec / 1e12 / peak, "us": sec * 1e6, "flops": flops, "launches": launches,
+                                       "peak_source": "measured burst bf16 cuBLAS rate" + (" x 0.5 (tf32 operands)" if tf32 else "")}
     del env, tr
-    # DRAM traffic per launch from the committed `ncu --set full` captures (profiles/), where available
-    tpath = os.path.join(ROOT, "profiles", "r1b_traffic.json")
-    if os.path.isfile(tpath):
-        for k, v in json.load(open(tpath)).items():
-            if k in out:
-                out[k]["traffic"] = v
+    out.update(roof_a6)
+    # DRAM traffic per launch from the committed `ncu --set full` captures of the current kernels, where available
+    for k, v in _traffic().items():
+        if k in out:
+            out[k]["traffic"] = v.get("bytes_per_launch")
+            out[k]["traffic_source"] = v.get("source")
     return out
+
+
+def sweep_point(num_envs, device, rank, world, stress, graphs, steps=4, warmup=3):
+    """One point of the north_star size sweep (BASELINE.json configs 3-5): full PPO iterations at `num_envs` envs per GPU."""
+    from constraints_as_terminations_b200 import PPOTrainer, solo12_flat_ppo_cfg
+    from constraints_as_terminations_b200 import synthetic_env as se
+
+    env = se.SyntheticSolo12Env(num_envs, device=device, seed=rank, pool=2, constraints_cfg=se.solo12_constraints_cfg(stress=stress))
+    env.load_managers()
+    cfg = solo12_flat_ppo_cfg(logger=None)
+    tr = PPOTrainer(env, cfg, device=device, use_graphs=graphs, precision=PRECISION)
+    tr.start()
+    ms, _, _ = timed_iterations(tr, steps, warmup, world, device, read_losses=False, sample_clocks=False)
+    n_terms = len(env.constraint_manager.active_terms)
+    del env, tr
+    torch.cuda.empty_cache()
+    return {
+        "envs_per_gpu": num_envs, "constraint_terms": n_terms, "constraint_columns": 93 if stress else 78, "n_gpus": world,
+        "value": num_envs * 24 * world * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
+    }  # fmt: skip
 
 
 def run_ours(args):
@@ -367,16 +439,16 @@ def run_ours(args):
     ms, launches, clocks = timed_iterations(trainer, args.steps, args.warmup, world, device, read_losses=False)
     value = N * T * world * args.steps / (ms * 1e-3)
     losses = trainer.losses()
+    precision = trainer.agent.precision
     prof, prof_total = kernel_profile(trainer, record=(rank == 0))
     dominant = dominant_kernel_roofline(prof, prof_total, trainer, peaks) if rank == 0 else None
-    working_set = sum(t.numel() * t.element_size() for t in (trainer.obs, trainer.obs_op, trainer.actions, trainer.rewards, trainer.dones, trainer.values, trainer.advantages, trainer.returns, trainer.train_ws))
     del env, trainer
     torch.cuda.empty_cache()
 
     # ---- e2e: host-resident env state, H2D each env step, D2H of the losses each iteration
     env, trainer = make_trainer(N, device, seed=rank, host_fed=True, graphs=not args.no_graphs)
     e_steps = max(3, args.steps // 2)
-    e_ms, _, _ = timed_iterations(trainer, e_steps, max(3, args.warmup // 2), world, device, read_losses=True)
+    e_ms, _, _ = timed_iterations(trainer, e_steps, max(3, args.warmup // 2), world, device, read_losses=True, sample_clocks=False)
     e2e = {
         "value": N * T * world * e_steps / (e_ms * 1e-3),
         "unit": UNIT,
@@ -389,41 +461,65 @@ def run_ours(args):
     del env, trainer
     torch.cuda.empty_cache()
 
-    line = None
-    if rank == 0:
-        roof = kernel_rooflines(device, N, peaks)
-        cpu = cpu_baseline(N, sample_steps=4, sample_minibatches=2)
-        main = dominant
-        main["note"] = main.get("note") or ("dominant kernel of the step by device time (torch.profiler/CUPTI over 2 iterations of the timed workload); "
-                        "HBM-bound kernels (GAE, CaT) timed alone with CUDA events are in `rooflines`")
-        gae_main = roof[f"gae@{N}"]
-        gae_main["note"] = f"{gae_main['bytes']/1e6:.2f} MB per launch: launch-latency bound at {N} envs; see the 65536 / 1M-env entries"
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "fp32 (CaT/GAE/moments/loss/Adam), bf16 operands + fp32 accumulate (hidden-layer GEMMs)",
-            "data": "synthetic Solo12 state (no Isaac Sim physics): trainer-side env-steps/s",
-            "config": {
-                "workload": "Isaac-Velocity-CaT-Flat-Solo12-v0 trainer side, 4096 envs/GPU, CleanRL PPO cfg (T=24, 5 epochs x 6 minibatches of 16384)",
-                "envs_per_gpu": N, "num_steps": T, "constraint_terms": 13, "constraint_columns": 78,
-                "minibatch": 16384, "epochs": 5, "parallelism": f"dp{world} (one env shard per GPU, 1 gradient allreduce per optimizer step)",
-                "l2": f"per-step working set {working_set/1e6:.0f} MB > 126 MB L2 (inputs larger than L2)",
-                "cuda_graphs": not args.no_graphs,
-            },
-            "e2e": e2e,
-            "gpu_launches": launches,
-            "clocks": clocks,
-            "roofline": main,
-            "rooflines": roof,
-            "kernel_shares": {k: {"share": round(v["share"], 4), "us_per_step": round(v["us"], 1), "launches_per_step": v["launches"]} for k, v in list(prof.items())[:16]},
-            "cpu_baseline": cpu,
-            "losses": losses,
+    # ---- north_star size sweep (every rank takes part: the iterations contain the gradient all-reduce)
+    sweep = None
+    if not args.no_sweep:
+        sweep = {
+            "note": "full PPO iterations (24 env steps + GAE + 5 epochs of 16384-row minibatches), same precision / graphs as the headline; BASELINE.json configs 3-5",
+            "points": [
+                sweep_point(16384, device, rank, world, stress=False, graphs=not args.no_graphs),
+                sweep_point(65536, device, rank, world, stress=False, graphs=not args.no_graphs),
+                sweep_point(65536, device, rank, world, stress=True, graphs=not args.no_graphs),
+            ],
         }  # fmt: skip
-    if world > 1:
+
+    # a second precision beside the headline (bf16 operands when the headline is tf32, and vice versa), same workload
+    other = None
+    if not args.no_sweep:
+        global PRECISION
+        keep, PRECISION = PRECISION, ("bf16" if precision == "tf32" else "tf32")
+        env, trainer = make_trainer(N, device, seed=rank, graphs=not args.no_graphs)
+        o_ms, _, _ = timed_iterations(trainer, max(3, args.steps // 2), 3, world, device, read_losses=False, sample_clocks=False)
+        other = {"precision": PRECISION, "value": N * T * world * max(3, args.steps // 2) / (o_ms * 1e-3), "unit": UNIT, "ms_per_step": o_ms / max(3, args.steps // 2)}
+        PRECISION = keep
+        del env, trainer
+        torch.cuda.empty_cache()
+
+    if world > 1:  # the remaining legs are rank-local: let the other ranks go
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
-    if line is not None:
-        print(json.dumps(line))
+    if rank != 0:
+        return
+    roof = kernel_rooflines(device, N, peaks)
+    cpu = gpu_eager = None
+    if world == 1 and not args.no_baselines:
+        gpu_eager = gpu_eager_baseline(N, device)
+        cpu = cpu_baseline(N)
+    main = dominant
+    main["note"] = main.get("note") or ("dominant kernel of the step by device time (torch.profiler/CUPTI over 2 iterations of the timed workload); "
+                    "HBM-bound kernels (GAE, CaT, obs normalisation) timed alone with CUDA events are in `rooflines`")
+    gemm = "tf32 operands (fp32 storage rounded to tf32, tcgen05 kind::tf32) + fp32 accumulate" if precision == "tf32" else "bf16 operands + fp32 accumulate"
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": f"fp32 (CaT/GAE/moments/heads/loss/Adam), {gemm} (hidden-layer GEMMs: the reference's GPU numerics are TF32 matmuls)",
+        "data": DATA,
+        "config": workload_config(N, world),
+        "precision": precision,
+        "cuda_graphs": not args.no_graphs,
+        "e2e": e2e,
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": main,
+        "rooflines": roof,
+        "kernel_shares": {k: {"share": round(v["share"], 4), "us_per_step": round(v["us"], 1), "launches_per_step": v["launches"]} for k, v in list(prof.items())[:18]},
+        "sweep": sweep,
+        "other_precision": other,
+        "cpu_baseline": cpu,
+        "gpu_eager_baseline": gpu_eager,
+        "losses": losses,
+    }  # fmt: skip
+    print(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -498,7 +594,8 @@ class CpuReferencePath:
 def pick_threads(num_envs):
     """torch's CPU ops on these small tensors do not scale to every core of a big host (128 threads make
     one env step ~100x slower than 8-16 do), so give the CPU arm the thread count that is fastest for it:
-    time one env step + one minibatch at a few counts up to all cores and keep the best."""
+    time one env step + one minibatch of the oracle port (the same op mix) at a few counts up to all cores and keep
+    the best."""
     cores = os.cpu_count() or 1
     candidates = sorted({min(cores, c) for c in (8, 16, 32, 64, cores)})
     ref = CpuReferencePath(num_envs)
@@ -524,69 +621,97 @@ def pick_threads(num_envs):
     return best, cores
 
 
-def cpu_baseline(num_envs, sample_steps=4, sample_minibatches=2):
-    """Bounded sample of the same workload on the host cores; extrapolated to a full iteration."""
-    threads, cores = pick_threads(num_envs)
+def reference_kind():
+    """"reference": the unmodified reference (from /root/reference, or the archive oracle/build_ref.py packed) runs;
+    "port": it is not reachable on this box and the oracle port stands in."""
+    from oracle import ref_loader
+
+    return "reference" if ref_loader.reference_available() else "port"
+
+
+def run_cpu_reference(num_envs, steps, warmup):
+    """Full PPO iterations of the reference on the host cores: warmup untimed, then exactly `steps` timed.
+    -> (seconds for the `steps` iterations, kind, threads, cores, description)"""
+    threads, cores = pick_threads(min(num_envs, 4096))
+    kind = reference_kind()
+    if kind == "reference":
+        from oracle import ref_runner
+
+        r = ref_runner.run_reference_trainer(num_envs, steps, warmup, device="cpu")
+        what = (f"the UNMODIFIED reference (ConstraintManager / CaT / term functions / curriculum / PPO() of {r['reference_root']}) "
+                f"driven through its own API on the synthetic Solo12 state, torch CPU, {threads} threads (fastest of the counts tried on a {cores}-core host)")
+        return r["seconds"], kind, threads, cores, what
     ref = CpuReferencePath(num_envs)
-    ref.env_step(0)  # warm-up
-    t0 = time.perf_counter()
-    for t in range(sample_steps):
-        ref.env_step(t)
-    t_step = (time.perf_counter() - t0) / sample_steps
-    t0 = time.perf_counter()
-    ref.gae()
-    t_gae = time.perf_counter() - t0
-    perm = torch.randperm(num_envs * 24)
     mb = min(16384, num_envs * 24)
-    ref.minibatch(perm[:mb])  # warm-up
+
+    def one_iteration():
+        for t in range(24):
+            ref.env_step(t)
+        ref.gae()
+        for _ in range(5):
+            perm = torch.randperm(num_envs * 24)
+            for i in range(max(1, num_envs * 24 // mb)):
+                ref.minibatch(perm[i * mb : (i + 1) * mb])
+
+    for _ in range(warmup):
+        one_iteration()
     t0 = time.perf_counter()
-    for i in range(sample_minibatches):
-        ref.minibatch(perm[i * mb : (i + 1) * mb] if (i + 1) * mb <= perm.numel() else perm[:mb])
-    t_mb = (time.perf_counter() - t0) / sample_minibatches
-    n_mb = 5 * max(1, num_envs * 24 // mb)
-    t_iter = 24 * t_step + t_gae + n_mb * t_mb
+    for _ in range(steps):
+        one_iteration()
+    what = f"oracle PORT of the reference path (the reference tree is not reachable on this box), torch CPU, {threads} threads (fastest of the counts tried on a {cores}-core host)"
+    return time.perf_counter() - t0, kind, threads, cores, what
+
+
+def cpu_baseline(num_envs):
+    """Bounded sample inside the GPU arm's run: 1 warm-up + 3 full PPO iterations of the reference on the host cores
+    (every iteration complete: 24 env steps, GAE, 5 epochs x 6 minibatches -- nothing extrapolated)."""
+    from oracle import ref_runner
+
+    steps, warmup = 3, 1
+    with ref_runner._device_choice(False):  # the reference picks its device with torch.cuda.is_available(): host cores here
+        seconds, kind, threads, cores, what = run_cpu_reference(num_envs, steps, warmup)
     return {
-        "value": num_envs * 24 / t_iter, "unit": UNIT, "cores": threads, "kind": "port",
-        "sample": f"{sample_steps} env steps ({t_step*1e3:.1f} ms each) + 1 GAE ({t_gae*1e3:.1f} ms) + {sample_minibatches} minibatches of {mb} ({t_mb*1e3:.1f} ms each), extrapolated to 24 steps + GAE + {n_mb} minibatches = {t_iter:.2f} s per iteration; torch CPU oracle port, {threads} threads (fastest of the counts tried on a {cores}-core host)",
+        "value": num_envs * 24 * steps / seconds, "unit": UNIT, "cores": threads, "kind": kind,
+        "sample": f"{steps} full PPO iterations after {warmup} warm-up ({seconds / steps:.2f} s each) of the headline workload; {what}",
+    }  # fmt: skip
+
+
+def gpu_eager_baseline(num_envs, device):
+    """The practically relevant "before" (SURVEY.md §8d last row): the unmodified reference's own
+    torch-eager code with CUDA tensors on this B200, TF32 matmuls on as scripts/clean_rl/train.py:86-87 sets them."""
+    if reference_kind() != "reference":
+        return {"unavailable": "reference tree not reachable on this box (oracle/_ref/ref_hotpath.tar.gz missing)"}
+    from oracle import ref_runner
+
+    steps, warmup = 5, 2
+    r = ref_runner.run_reference_trainer(num_envs, steps, warmup, device=str(device), tf32=True)
+    torch.cuda.empty_cache()
+    return {
+        "value": r["env_steps_per_sec"], "unit": UNIT, "ms_per_step": r["seconds_per_iteration"] * 1e3, "steps": steps, "warmup": warmup,
+        "kind": "reference", "numerics": "fp32 storage, TF32 matmuls (torch.backends.cuda.matmul.allow_tf32 = True)",
+        "what": f"reference PPO() + ConstraintManager from {r['reference_root']}, eager torch on {device}, same synthetic Solo12 state and hyper-parameters as the headline; wall clock with device syncs",
     }  # fmt: skip
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path (oracle port) on this box's host cores.  Each step is a
-    bounded sample of one iteration: the full 24-step rollout + GAE + one of the five epochs (6 minibatches);
-    the other four epochs repeat identical work and are accounted for by scaling that epoch's time."""
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores, same workload as the
+    GPU arm's command line: `--gpus N` shards of `--envs` envs each (one process, N x envs envs), full PPO iterations,
+    W untimed then exactly K timed."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = max(1, int(os.environ.get("WORLD_SIZE", str(args.gpus))))
     N, T = args.envs, 24
-    threads, cores = pick_threads(N)
-    ref = CpuReferencePath(N)
-    mb = min(16384, N * T)
-    n_mb_epoch = max(1, N * T // mb)
-
-    def one_step():
-        t0 = time.perf_counter()
-        for t in range(T):
-            ref.env_step(t)
-        ref.gae()
-        t1 = time.perf_counter()
-        perm = torch.randperm(N * T)
-        for i in range(n_mb_epoch):
-            ref.minibatch(perm[i * mb : (i + 1) * mb])
-        t2 = time.perf_counter()
-        return (t1 - t0) + 5 * (t2 - t1)
-
-    for _ in range(args.warmup):
-        one_step()
-    total = sum(one_step() for _ in range(args.steps))
-    value = N * T * args.steps / total
-    sample = f"per step: full 24-step rollout + GAE + 1 of 5 epochs ({n_mb_epoch} minibatches of {mb}) measured, epoch time x5; torch CPU oracle port, {threads} threads (fastest of the counts tried on a {cores}-core host)"
+    total_envs = N * world
+    seconds, kind, threads, cores, what = run_cpu_reference(total_envs, args.steps, args.warmup)
+    value = total_envs * T * args.steps / seconds
+    sample = f"{args.steps} full PPO iterations after {args.warmup} warm-up on {total_envs} envs ({world} shard(s) of {N}): {what}"
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic Solo12 state (no Isaac Sim physics): trainer-side env-steps/s",
-        "config": {"workload": "Isaac-Velocity-CaT-Flat-Solo12-v0 trainer side, 4096 envs, CleanRL PPO cfg (T=24, 5 epochs x 6 minibatches of 16384)", "envs_per_gpu": N},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": seconds / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": DATA,
+        "config": workload_config(N, world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))  # fmt: skip
 
@@ -599,9 +724,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
     ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--precision", default=None, choices=["tf32", "bf16"], help="operand precision of the hidden-layer GEMMs (default tf32)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the 16384 / 65536-env sweep and the second-precision leg")
+    ap.add_argument("--no-baselines", action="store_true", help="skip cpu_baseline and gpu_eager_baseline")
     args = ap.parse_args()
+    global PRECISION
+    PRECISION = args.precision
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
+        os.environ["CUDA_VISIBLE_DEVICES"] = ""  # the reference arm runs on the host cores (CUDA is initialised lazily)
         run_reference(args)
     else:
         run_ours(args)

@@ -172,3 +172,16 @@ except Exception:  # noqa: BLE001 - any import failure means "use the shims"
                 term_cfg.func = term_cfg.func(cfg=term_cfg, env=self._env)
             if not callable(term_cfg.func):
                 raise AttributeError(f"The term '{term_name}' is not callable. Received: {term_cfg.func}")
+            # the static check Isaac Lab performs: the function's parameters beyond the first `min_argc` must be exactly
+            # the keys of `params` (plus whatever has a default)
+            func_static = term_cfg.func.__call__ if isinstance(term_cfg.func, ManagerTermBase) else term_cfg.func
+            sig = inspect.signature(func_static).parameters
+            with_defaults = [a for a in sig if sig[a].default is not inspect.Parameter.empty]
+            without_defaults = [a for a in sig if sig[a].default is inspect.Parameter.empty]
+            args = without_defaults + with_defaults
+            term_params = list(term_cfg.params.keys())
+            if len(args) > min_argc and set(args[min_argc:]) != set(term_params + with_defaults):
+                raise ValueError(
+                    f"The term '{term_name}' expects mandatory parameters: {without_defaults[min_argc:]}"
+                    f" and optional parameters: {with_defaults}, but received: {term_params}."
+                )

@@ -14,9 +14,10 @@ fused constraint kernels:
   episode lengths and merges them into `extras["log"]` (reference :178-182), delegating everything else to
   `ManagerBasedRLEnv._reset_idx` instead of re-implementing it.
 
-Isaac Lab is not importable where this repository is built and tested, so this module is exercised only
-through `SyntheticSolo12Env`, which mirrors the same three hooks; with Isaac Lab present it subclasses the real
-`ManagerBasedRLEnv`.
+Isaac Lab is not importable where this repository is built and tested; `tests/test_cat_env_gpu.py` executes this
+module (constructor, load_managers, step, _reset_idx) on a test double of `ManagerBasedRLEnv` backed by the synthetic
+Solo12 state, against the oracle of the reference's step; `SyntheticSolo12Env` mirrors the same three hooks for the
+trainer-side runs.  With Isaac Lab present it subclasses the real `ManagerBasedRLEnv`.
 """
 
 from __future__ import annotations
@@ -27,7 +28,7 @@ import torch
 
 from .constraint_manager import ConstraintManager
 
-try:  # pragma: no cover - needs Isaac Lab / Isaac Sim
+try:
     from isaaclab.envs.manager_based_rl_env import ManagerBasedRLEnv
 
     HAVE_ISAACLAB_ENV = True
@@ -36,7 +37,7 @@ except Exception:  # noqa: BLE001
     HAVE_ISAACLAB_ENV = False
 
 
-class CaTEnv(ManagerBasedRLEnv):  # pragma: no cover - needs Isaac Lab / Isaac Sim
+class CaTEnv(ManagerBasedRLEnv):
     """Manager-based RL env whose `terminated` output is the CaT termination probability."""
 
     def __init__(self, *args, **kwargs):

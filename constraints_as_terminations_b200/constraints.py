@@ -19,6 +19,8 @@ from __future__ import annotations
 from collections.abc import Callable
 from dataclasses import dataclass, field
 
+import inspect
+
 import torch
 
 from . import _lib as L
@@ -98,6 +100,9 @@ def _term(spec_fn):
     func.__name__ = spec_fn.__name__
     func.__qualname__ = spec_fn.__qualname__
     func.__doc__ = spec_fn.__doc__
+    # Isaac Lab's ManagerBase._resolve_common_term_cfg checks `inspect.signature(func)` against the keys of
+    # `term_cfg.params`: expose the reference's own signature (env, limit, asset_cfg, ...) -> Tensor, not (env, **params)
+    func.__signature__ = inspect.signature(spec_fn).replace(return_annotation=torch.Tensor)
     func.fused_spec = spec_fn
     return func
 

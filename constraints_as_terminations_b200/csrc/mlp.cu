@@ -18,6 +18,7 @@
 
 #include "common.cuh"
 #include "mma.cuh"
+#include "optim.cuh"
 #include "philox.cuh"
 #include "tc_gemm.cuh"
 #include "tc_ptx.cuh"
@@ -81,20 +82,43 @@ __global__ void __launch_bounds__(256) fold_grads_kernel(const __grid_constant__
   pdl_launch_dependents();
   pdl_wait();
   const int seg = blockIdx.y;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (seg < r.n_segments) {
+    // four padded columns per thread (one 16-byte load of the accumulator); the gradient values are fetched before the
+    // accumulator is zeroed so that both loads are in flight together (the pointers may alias as far as the compiler knows)
     const int N = r.N[seg], Kpad = r.Kpad[seg], Kt = r.Ktrue[seg];
-    if (e >= N * Kpad) return;
-    const int n = e / Kpad, k = e - n * Kpad;
-    const float v = r.acc[seg][e];
-    r.acc[seg][e] = 0.0f;
-    if (k < Kt) r.grad[seg][(size_t)n * Kt + k] += v;  // the padded input columns of layer 0 are dropped
+    float4* __restrict__ acc4 = reinterpret_cast<float4*>(r.acc[seg]);
+    float* __restrict__ grad = r.grad[seg];
+    const int quads = N * Kpad / 4, qpr = Kpad / 4;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += gridDim.x * blockDim.x) {
+      const int n = q / qpr, k = (q - n * qpr) * 4;
+      const float4 v = acc4[q];
+      float* gp = grad + (size_t)n * Kt + k;
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+      float g[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) g[i] = k + i < Kt ? gp[i] : 0.0f;
+      acc4[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (k + i < Kt) gp[i] = g[i] + vv[i];  // the padded input columns of layer 0 are dropped
+    }
     return;
   }
-  // ---- head segment: sum the per-CTA rows, route every value to its gradient slot / loss accumulator
-  if (e >= kHeadValues * 32) return;
+  // ---- head segment: sum the per-CTA rows, route every value to its gradient slot / loss accumulator.
+  // One CTA per 32 consecutive values: its 8 warps split the rows (a single thread walking all ~148 rows is a chain of
+  // dependent-latency loads: 20 us per launch) and combine through shared memory.
+  __shared__ float part_s[8][32];
+  const int warp = threadIdx.x >> 5, ln = threadIdx.x & 31;
+  const int e = blockIdx.x * 32 + ln;
+  if (blockIdx.x * 32 >= kHeadValues * 32) return;
+  float acc = 0.0f;
+  for (int c = warp; c < r.head_rows; c += 8) acc += r.head_part[(size_t)c * kHeadValues * 32 + e];
+  part_s[warp][ln] = acc;
+  __syncthreads();
+  if (warp != 0) return;
   float t = 0.0f;
-  for (int c = 0; c < r.head_rows; ++c) t += r.head_part[(size_t)c * kHeadValues * 32 + e];
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += part_s[w][ln];
   const int v = e >> 5, lane = e & 31;
   const float inv_M = 1.0f / (float)r.M;
   if (v < kHvW4c) {
@@ -537,6 +561,75 @@ __global__ void __launch_bounds__(256) cast_weights_kernel(const __grid_constant
   }
 }
 
+// Adam fused with the operand-copy refresh.  blockIdx.y < 6: one hidden weight matrix, 32 x 32 tiles as in
+// cast_weights_kernel (update every element, write it back, emit W [rows, cols_pad] and W^T [cols, rows] in operand
+// precision); blockIdx.y == 6: everything else of the flat vector (biases, heads, log-std: `n_rest` elements in at most
+// 8 contiguous ranges), one thread per element.
+struct AdamCastArgs {
+  CastSeg seg[6];
+  long long seg_off[6];      // flat offset of each hidden weight matrix
+  long long rest_begin[8];   // flat ranges [begin, begin + len) outside the hidden matrices
+  int rest_len[8];
+  int n_rest_ranges;
+  AdamState a;
+};
+
+template <int PREC>
+__global__ void __launch_bounds__(256) adam_cast_kernel(const __grid_constant__ AdamCastArgs c) {
+  using T = typename PrecT<PREC>::T;
+  pdl_launch_dependents();
+  pdl_wait();
+  const AdamState& a = c.a;
+  const float clip = a.sc->clip_coef * a.grad_scale;
+  const float step_size = __ldg(a.lr) * a.sc->step_size_scale;
+  const float bc2_sqrt = a.sc->bc2_sqrt;
+  if (blockIdx.y == 6) {
+    int e = blockIdx.x * 256 + threadIdx.y * 32 + threadIdx.x;
+    for (int r = 0; r < c.n_rest_ranges; ++r) {
+      if (e < c.rest_len[r]) {
+        const long long i = c.rest_begin[r] + e;
+        adam_one(a.params[i], a.grads[i], a.m[i], a.v[i], clip, step_size, bc2_sqrt, a.beta1, a.beta2, a.eps);
+        return;
+      }
+      e -= c.rest_len[r];
+    }
+    return;
+  }
+  const CastSeg& s = c.seg[blockIdx.y];
+  const long long base = c.seg_off[blockIdx.y];
+  const int tiles_c = (s.cols_pad + 31) / 32, tiles_r = s.rows / 32;
+  if ((int)blockIdx.x >= tiles_c * tiles_r) return;
+  const int tr = blockIdx.x / tiles_c, tc = blockIdx.x % tiles_c;
+  __shared__ float tile[32][33];
+  T* dst = static_cast<T*>(s.dst);
+  T* dst_t = static_cast<T*>(s.dst_t);
+  auto conv = [](float v) -> T {
+    if (PREC == kPrecBf16) return T(__float2bfloat16(v));
+    return T(round_tf32(v));
+  };
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = tr * 32 + threadIdx.y + i * 8, k = tc * 32 + threadIdx.x;
+    float v = 0.0f;
+    if (k < s.cols) {
+      const long long e = base + (long long)r * s.cols + k;
+      v = a.params[e];
+      float g = a.grads[e], m = a.m[e], vv = a.v[e];
+      adam_one(v, g, m, vv, clip, step_size, bc2_sqrt, a.beta1, a.beta2, a.eps);
+      a.params[e] = v; a.grads[e] = g; a.m[e] = m; a.v[e] = vv;
+    }
+    tile[threadIdx.y + i * 8][threadIdx.x] = v;
+    if (k < s.cols_pad) dst[(size_t)r * s.cols_pad + k] = conv(v);
+  }
+  if (dst_t == nullptr) return;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = tc * 32 + threadIdx.y + i * 8, r = tr * 32 + threadIdx.x;
+    if (k < s.cols) dst_t[(size_t)k * s.rows + r] = conv(tile[threadIdx.x][threadIdx.y + i * 8]);
+  }
+}
+
 // advances the device-side Philox offset after a sampling launch (keeps the launch graph-capturable)
 __global__ void rng_bump_kernel(unsigned long long* rng_state, unsigned long long n) { rng_state[1] += n; }
 
@@ -675,6 +768,50 @@ int launch_cast_weights(const catb200_mlp_dims_t* dims, const float* params, voi
     }
   if (dims->prec == kPrecTf32) CATB200_CUDA_TRY(launch_pdl(cast_weights_kernel<kPrecTf32>, dim3(max_tiles, 6), dim3(32, 8), 0, st, c));
   else CATB200_CUDA_TRY(launch_pdl(cast_weights_kernel<kPrecBf16>, dim3(max_tiles, 6), dim3(32, 8), 0, st, c));
+  CATB200_LAUNCH_CHECK();
+  return CATB200_OK;
+}
+
+int launch_adam_cast(const catb200_mlp_dims_t* dims, const AdamState& a, void* wcv, cudaStream_t st) {
+  catb200_mlp_layout_t P;
+  fill_layout(dims, &P);
+  Dims x = make_dims(dims);
+  const size_t es = esize(dims);
+  char* wc = static_cast<char*>(wcv);
+  AdamCastArgs c = {};
+  int max_tiles = 1;
+  for (int z = 0; z < 2; ++z)
+    for (int l = 0; l < 3; ++l) {
+      CastSeg& s = c.seg[z * 3 + l];
+      s.src = a.params + P.w[z][l];
+      s.dst = wc + P.wc[z][l] * es;
+      s.dst_t = l > 0 ? wc + P.wtc[z][l] * es : nullptr;
+      s.rows = x.out[l]; s.cols = x.in[l]; s.cols_pad = x.in_pad[l];
+      c.seg_off[z * 3 + l] = P.w[z][l];
+      max_tiles = max(max_tiles, (s.rows / 32) * ((s.cols_pad + 31) / 32));
+    }
+  // the rest of the flat vector: the gaps between consecutive hidden matrices (b0 | b1 | b2, head weight, head bias) and
+  // what follows the last one (actor b2, head, log-std)
+  int n_rest = 0;
+  long long cursor = 0;
+  for (int z = 0; z < 2; ++z)
+    for (int l = 0; l < 3; ++l) {
+      if (P.w[z][l] > cursor) {
+        c.rest_begin[c.n_rest_ranges] = cursor;
+        c.rest_len[c.n_rest_ranges] = (int)(P.w[z][l] - cursor);
+        n_rest += c.rest_len[c.n_rest_ranges++];
+      }
+      cursor = P.w[z][l] + (long long)x.out[l] * x.in[l];
+    }
+  if (P.n_params > cursor) {
+    c.rest_begin[c.n_rest_ranges] = cursor;
+    c.rest_len[c.n_rest_ranges] = (int)(P.n_params - cursor);
+    n_rest += c.rest_len[c.n_rest_ranges++];
+  }
+  c.a = a;
+  max_tiles = max(max_tiles, (n_rest + 255) / 256);
+  if (dims->prec == kPrecTf32) CATB200_CUDA_TRY(launch_pdl(adam_cast_kernel<kPrecTf32>, dim3(max_tiles, 7), dim3(32, 8), 0, st, c));
+  else CATB200_CUDA_TRY(launch_pdl(adam_cast_kernel<kPrecBf16>, dim3(max_tiles, 7), dim3(32, 8), 0, st, c));
   CATB200_LAUNCH_CHECK();
   return CATB200_OK;
 }
@@ -870,9 +1007,8 @@ int catb200_ppo_minibatch_grad(const catb200_mlp_dims_t* dims, const catb200_ppo
   fold.logstd = params + P.logstd; fold.loss_acc = loss_acc;
   fold.A = dims->act_dim; fold.h3 = dims->h3; fold.M = M;
   fold.ent_coef = hp->ent_coef; fold.vf_coef = hp->vf_coef;
-  int max_elems = kHeadValues * 32;
-  for (int sgm = 0; sgm < fold.n_segments; ++sgm) max_elems = max(max_elems, fold.N[sgm] * fold.Kpad[sgm]);
-  CATB200_CUDA_TRY(launch_pdl(fold_grads_kernel, dim3((max_elems + 255) / 256, fold.n_segments + 1), dim3(256), 0, st, fold));
+  // x: 76 CTAs cover the head segment (one per 32 values); the weight segments walk their quads with a grid stride
+  CATB200_CUDA_TRY(launch_pdl(fold_grads_kernel, dim3(kHeadValues, fold.n_segments + 1), dim3(256), 0, st, fold));
   CATB200_LAUNCH_CHECK();
   return CATB200_OK;
 }

@@ -1,0 +1,37 @@
+// Optimizer pieces shared by optim.cu (global-norm clip) and mlp.cu (Adam fused with the operand-copy refresh).
+#pragma once
+
+#include "common.cuh"
+
+namespace catb200 {
+
+struct OptScratch {  // 64 bytes of caller-provided zero-initialised device memory
+  unsigned int ticket;
+  float clip_coef, total_norm, step_size_scale, bc2_sqrt;
+  float pad[3];
+  double sumsq;
+  double pad2[3];
+};
+
+// torch.optim.Adam (no weight decay, not amsgrad), one element; zeroes the gradient for the next minibatch
+__device__ __forceinline__ void adam_one(float& p, float& g, float& m, float& v, float clip, float step_size,
+                                         float bc2_sqrt, float beta1, float beta2, float eps) {
+  const float gs = g * clip;
+  g = 0.0f;
+  m = m + (gs - m) * (1.0f - beta1);            // exp_avg.lerp_(grad, 1 - beta1)
+  v = v * beta2 + (1.0f - beta2) * gs * gs;     // mul_(beta2).addcmul_(g, g, value = 1 - beta2)
+  const float denom = sqrtf(v) / bc2_sqrt + eps;  // (exp_avg_sq.sqrt() / bias_correction2_sqrt).add_(eps)
+  p = p - step_size * (m / denom);                // addcdiv_(exp_avg, denom, value = -step_size)
+}
+
+struct AdamState {
+  float* params; float* grads; float* m; float* v;
+  const float* lr; const OptScratch* sc;
+  float beta1, beta2, eps, grad_scale;
+};
+
+// mlp.cu: Adam over the whole flat parameter vector AND the operand-precision compute copies (W, W^T) of the six
+// hidden matrices in one launch -- the tiled cast kernel with the update applied to every element on its way through.
+int launch_adam_cast(const catb200_mlp_dims_t* dims, const AdamState& a, void* wc, cudaStream_t st);
+
+}  // namespace catb200

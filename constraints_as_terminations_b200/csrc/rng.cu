@@ -119,14 +119,15 @@ command_update_kernel(const catb200_command_cfg_t c, int n, float* __restrict__ 
   // random resampling (commands.py:67-78): p = 0.01 for still commands, dt / T_episode otherwise
   const float nrm = sqrtf(fmaf(w, w, fmaf(y, y, x * x)));
   const float no_vel = nrm < c.velocity_deadzone ? 1.0f : 0.0f;
-  const float p = 0.01f * no_vel + c.p_step * (1.0f - no_vel);
+  const float p = __fadd_rn(__fmul_rn(0.01f, no_vel), __fmul_rn(c.p_step, 1.0f - no_vel));
   const bool res = u[0] < p;
   if (res) {  // UniformVelocityCommand._resample_command (Isaac Lab, third party): uniform draws in the cfg ranges
-    x = c.lin_vel_x[0] + (c.lin_vel_x[1] - c.lin_vel_x[0]) * u[1];
-    y = c.lin_vel_y[0] + (c.lin_vel_y[1] - c.lin_vel_y[0]) * u[2];
-    w = c.ang_vel_z[0] + (c.ang_vel_z[1] - c.ang_vel_z[0]) * u[3];
+    // lo + (hi - lo) * u with separately rounded multiply and add (no FMA contraction), like the eager tensor ops
+    x = __fadd_rn(c.lin_vel_x[0], __fmul_rn(c.lin_vel_x[1] - c.lin_vel_x[0], u[1]));
+    y = __fadd_rn(c.lin_vel_y[0], __fmul_rn(c.lin_vel_y[1] - c.lin_vel_y[0], u[2]));
+    w = __fadd_rn(c.ang_vel_z[0], __fmul_rn(c.ang_vel_z[1] - c.ang_vel_z[0], u[3]));
     if (c.heading_command) {
-      heading_target[i] = c.heading[0] + (c.heading[1] - c.heading[0]) * u[4];
+      heading_target[i] = __fadd_rn(c.heading[0], __fmul_rn(c.heading[1] - c.heading[0], u[4]));
       is_heading[i] = u[5] <= c.rel_heading_envs ? 1 : 0;
     }
     is_standing[i] = u[6] <= c.rel_standing_envs ? 1 : 0;
@@ -157,7 +158,7 @@ push_select_kernel(int n, float p_push, const float* __restrict__ lo, const floa
   const bool push = u[0] < p_push;
   if (push) {
 #pragma unroll
-    for (int k = 0; k < 6; ++k) root_vel_w[(size_t)i * 6 + k] = lo[k] + (hi[k] - lo[k]) * u[1 + k];
+    for (int k = 0; k < 6; ++k) root_vel_w[(size_t)i * 6 + k] = __fadd_rn(lo[k], __fmul_rn(hi[k] - lo[k], u[1 + k]));
   }
   pushed[i] = push ? 1 : 0;
 }

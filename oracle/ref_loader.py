@@ -1,12 +1,15 @@
-"""ORACLE tooling (build container only): import the *real* reference modules from /root/reference.
+"""ORACLE tooling: import the *real* reference modules.
 
-The reference is pure Python on top of Isaac Lab, which is not installed, so its three CaT modules
-are loaded from where they lie under a synthetic package with `sys.modules` stubs for the five
-Isaac Lab names and `prettytable`.  `cleanrl/ppo.py` needs no stubs.
+The reference is pure Python on top of Isaac Lab, which is not installed, so its CaT modules are loaded
+from where they lie under a synthetic package with `sys.modules` stubs for the five Isaac Lab names and
+`prettytable`.  `cleanrl/ppo.py` needs no stubs.
 
-Nothing is copied: files are executed from /root/reference.  This loader is used only by
-`oracle/make_golden.py` (to produce `tests/golden/`) and by tests that are skipped when
-/root/reference is absent (e.g. on the GPU box).
+Where the files come from, in this order: $CAT_REFERENCE_ROOT, /root/reference (the build container),
+oracle/_ref/ref_hotpath.tar.gz (a git-ignored archive that `oracle/build_ref.py` -- run by `__graft_entry__.build()`
+whenever /root/reference is present -- packs from the handful of reference files on the hot path, so that the unmodified
+reference also travels to the GPU box; nothing of it is committed; it is unpacked into a temporary directory here).  Used by
+`oracle/make_golden.py` (fixtures), `oracle/ref_runner.py` (the reference arm of bench.py) and by tests that skip
+when no reference tree is found.
 """
 
 from __future__ import annotations
@@ -16,8 +19,34 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("CAT_REFERENCE_ROOT", "/root/reference")
-_UTILS = os.path.join(REFERENCE_ROOT, "exts/cat_envs/cat_envs/tasks/utils")
+_REL_UTILS = "exts/cat_envs/cat_envs/tasks/utils"
+LOCAL_ARCHIVE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "ref_hotpath.tar.gz")
+
+
+def _unpack_local() -> str | None:
+    if not os.path.isfile(LOCAL_ARCHIVE):
+        return None
+    import atexit
+    import shutil
+    import tarfile
+    import tempfile
+
+    root = tempfile.mkdtemp(prefix="cat_ref_")
+    atexit.register(shutil.rmtree, root, ignore_errors=True)
+    with tarfile.open(LOCAL_ARCHIVE, "r:gz") as tar:
+        tar.extractall(root)
+    return root
+
+
+def _find_root() -> str:
+    for root in (os.environ.get("CAT_REFERENCE_ROOT"), "/root/reference"):
+        if root and os.path.isfile(os.path.join(root, _REL_UTILS, "cat/constraint_manager.py")):
+            return root
+    return _unpack_local() or os.environ.get("CAT_REFERENCE_ROOT", "/root/reference")
+
+
+REFERENCE_ROOT = _find_root()
+_UTILS = os.path.join(REFERENCE_ROOT, _REL_UTILS)
 
 
 def reference_available() -> bool:

@@ -24,7 +24,11 @@ def test_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "env_steps_per_sec" and d["unit"] == "env-steps/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    sys.path.insert(0, ROOT)
+    import bench
+
+    assert d["config"] == bench.workload_config(64, 1)  # the same dict the GPU arm prints for the same command line
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
@@ -48,14 +52,15 @@ def test_gemm_flops_attribution_adds_up():
     sys.path.insert(0, ROOT)
     import bench
 
-    tr = SimpleNamespace(num_envs=4096, T=24, batch_size=4096 * 24, minibatch_size=16384, cfg=SimpleNamespace(updates_epochs=5))
+    tr = SimpleNamespace(num_envs=4096, T=24, batch_size=4096 * 24, minibatch_size=16384, cfg=SimpleNamespace(updates_epochs=5),
+                         agent=SimpleNamespace(precision="tf32"))
     flops = bench._gemm_flops_by_kernel(tr)
     opt_rows, roll_rows = 5 * 4096 * 24, 4096 * 25
-    mac_fwd = 2 * (64 * 512 + 512 * 256 + 256 * 128)   # both nets, obs padded to 64 (0.7508 MFLOP/sample with 45)
+    mac_fwd = 2 * (45 * 512 + 512 * 256 + 256 * 128)   # both nets, layer 0 at its true K = 45
     mac_dgrad = 2 * (256 * 128 + 512 * 256)
-    fwd = sum(v for k, v in flops.items() if "<0," in k)
-    dgrad = sum(v for k, v in flops.items() if "<1," in k)
-    assert fwd == 2.0 * mac_fwd * (opt_rows + roll_rows)
-    assert dgrad == 2.0 * mac_dgrad * opt_rows
-    # the minibatch launches of layers 1-2 and both dgrads have more than 2 x 148 tiles: persistent kernel
-    assert set(flops) == {"tc_gemm_persist_kernel<0, 128>", "tc_gemm_kernel<0, 128>", "tc_gemm_persist_kernel<1, 128>"}
+    assert set(flops) == {"mlp_gemm_kernel<0, 1>", "mlp_gemm_kernel<1, 1>", "mlp_wgrad_kernel<1, 64>", "mlp_wgrad_kernel<1, 128>"}
+    assert flops["mlp_gemm_kernel<0, 1>"] == 2.0 * mac_fwd * (opt_rows + roll_rows)
+    assert flops["mlp_gemm_kernel<1, 1>"] == 2.0 * mac_dgrad * opt_rows
+    assert flops["mlp_wgrad_kernel<1, 64>"] + flops["mlp_wgrad_kernel<1, 128>"] == 2.0 * mac_fwd * opt_rows
+    # 750 848 FLOP/sample forward = the hidden layers on the tensor cores + the fp32 heads (128 -> 12, 128 -> 1)
+    assert 2.0 * mac_fwd + 2 * (128 * 12 + 128) == 750848

@@ -7,6 +7,10 @@ arithmetic of the hidden-layer GEMMs (tf32 operands, fp32 accumulation vs fp32 o
 two runs drift apart slowly; the test bounds that drift on the quantities the reference logs (U/cleanrl/ppo.py:356-366):
 policy loss, value loss, entropy, approx KL, and on the parameters themselves.  The reference's own GPU runs carry the
 same kind of difference against its CPU runs (TF32 matmuls, scripts/clean_rl/train.py:86-87).
+
+PPO training is sensitive to perturbations (clip / max branches flip, Adam normalises tiny gradients), so the band is
+not guessed: the fp32 oracle trainer is run again from weights perturbed by 2^-11 relative -- the resolution of a tf32
+operand -- and the drift of the CUDA trainer from the oracle must stay within 2x the drift between those two fp32 runs.
 """
 
 import os
@@ -126,7 +130,7 @@ def _run(precision):
     got = tr.agent.parameters_flat().detach().cpu()
     want = ora.flat()
     p0 = torch.cat([init[k].reshape(-1) for k in init if "_rms." not in k])
-    return rows, got, want, p0
+    return rows, got, want, p0, init, seed, cfg.learning_rate
 
 
 def _table(rows, got, want, p0, name):
@@ -150,24 +154,52 @@ def _table(rows, got, want, p0, name):
     return pg, vl, kl, en, cf, cos, rel
 
 
+def _natural_drift(init, seed, lr):
+    """Per-metric max |difference| over the run between the fp32 oracle trainer and itself started from weights
+    perturbed by 2^-11 relative (two perturbation signs; the larger drift counts)."""
+    def run(pert):
+        g = torch.Generator().manual_seed(123)
+        sd = {k: (v * (1 + pert * torch.randn(v.shape, generator=g)) if v.is_floating_point() and "_rms." not in k else v) for k, v in init.items()}
+        o = OracleTrainer(sd, seed, lr, ITERS)
+        return [o.iterate() for _ in range(ITERS)], o.flat()
+
+    base, base_p = run(0.0)
+    drift = {k: 0.0 for k in ("pg_loss", "v_loss", "entropy", "approx_kl", "clipfrac")}
+    prel = 0.0
+    for pert in (2.0**-11, -(2.0**-11)):
+        rows, p = run(pert)
+        for k in drift:
+            drift[k] = max(drift[k], max(abs(x[k] - y[k]) for x, y in zip(rows, base)))
+        prel = max(prel, float((p - base_p).norm()))
+    return drift, prel
+
+
 def test_tf32_trainer_tracks_the_fp32_oracle_trainer():
-    pg, vl, kl, en, cf, cos, rel = _table(*_run("tf32"), "tf32")
+    rows, got, want, p0, init, seed, lr = _run("tf32")
+    pg, vl, kl, en, cf, cos, rel = _table(rows, got, want, p0, "tf32")
     # iteration 1 (same parameters on both sides, only the GEMM arithmetic differs): logged scalars agree to 1e-4
     assert abs(pg[0, 0] - pg[0, 1]) < 1e-4 and abs(vl[0, 0] - vl[0, 1]) < 1e-4 * max(1.0, vl[0, 1]) and abs(kl[0, 0] - kl[0, 1]) < 1e-5
-    # bands for the whole run (measured drift in profiles/r2_equivalence_tf32.txt is about half of each): value loss 2 %
-    # (+ 2e-3), policy loss -- a mean of O(1) mixed-sign terms that itself is only ~1e-2 -- 5e-3 absolute, approx KL 1e-3
-    # absolute (values 1e-4 .. 8e-3), clip fraction 0.02, entropy 3e-3 relative, and after 600 Adam steps the two
-    # parameter vectors have moved the same way (cosine of the updates > 0.99, difference < 15 % of the update)
-    assert np.all(np.abs(vl[:, 0] - vl[:, 1]) <= 0.02 * np.abs(vl[:, 1]) + 2e-3), "value-loss trajectory"
-    assert np.all(np.abs(pg[:, 0] - pg[:, 1]) <= 5e-3), "policy-loss trajectory"
-    assert np.all(np.abs(kl[:, 0] - kl[:, 1]) <= 1e-3), "approx-KL trajectory"
-    assert np.all(np.abs(en[:, 0] - en[:, 1]) <= 3e-3 * np.abs(en[:, 1])), "entropy trajectory"
-    assert np.all(np.abs(cf[:, 0] - cf[:, 1]) <= 0.02), "clip-fraction trajectory"
+    # whole run: within 2x the drift between two fp32 runs that differ by a tf32-sized perturbation of the weights
+    nat, nat_p = _natural_drift(init, seed, lr)
+    gpu = {"pg_loss": np.abs(pg[:, 0] - pg[:, 1]).max(), "v_loss": np.abs(vl[:, 0] - vl[:, 1]).max(), "entropy": np.abs(en[:, 0] - en[:, 1]).max(),
+           "approx_kl": np.abs(kl[:, 0] - kl[:, 1]).max(), "clipfrac": np.abs(cf[:, 0] - cf[:, 1]).max()}  # fmt: skip
+    gpu_p = float((got - want).norm())
+    lines = ["max |difference| over the run:  metric   CUDA tf32 vs fp32 oracle   fp32 oracle vs fp32 oracle perturbed by 2^-11"]
+    for k in nat:
+        lines.append(f"   {k:10s} {gpu[k]:.3e}   {nat[k]:.3e}")
+    lines.append(f"   |params|   {gpu_p:.3e}   {nat_p:.3e}")
+    print("\n".join(lines))
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):
+        open(os.path.join(out_dir, "equivalence_tf32.txt"), "a").write("\n".join(lines) + "\n")
+    for k in nat:
+        assert gpu[k] <= 2.0 * nat[k] + 1e-4, f"{k}: CUDA-vs-oracle drift {gpu[k]:.3e} exceeds 2x the fp32 perturbation drift {nat[k]:.3e}"
+    assert gpu_p <= 2.0 * nat_p
     assert cos > 0.99 and rel < 0.15
 
 
 def test_bf16_trainer_drift_is_recorded():
     """The bf16 operand mode next to it, for the record (no band claimed beyond the first iteration and the direction)."""
-    pg, vl, kl, en, cf, cos, rel = _table(*_run("bf16"), "bf16")
+    pg, vl, kl, en, cf, cos, rel = _table(*_run("bf16")[:4], "bf16")
     assert abs(pg[0, 0] - pg[0, 1]) < 2e-3 and abs(vl[0, 0] - vl[0, 1]) < 2e-2 * max(1.0, vl[0, 1])
     assert cos > 0.9

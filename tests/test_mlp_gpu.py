@@ -85,7 +85,7 @@ TOL = {
     "tf32": dict(fwd_emul=2e-3, fwd_mean_abs=1e-4, fwd_fp32=4e-3, loss_emul=5e-4, loss_fp32=2e-3, grad_emul=2e-3, grad_fp32=5e-3,
                  w_mult=3.0, b_mult=4.0, logstd_mult=4.0),
     "bf16": dict(fwd_emul=1e-2, fwd_mean_abs=5e-4, fwd_fp32=3e-2, loss_emul=2e-3, loss_fp32=2e-2, grad_emul=1.5e-2, grad_fp32=6e-2,
-                 w_mult=3.5, b_mult=4.0, logstd_mult=5.0),
+                 w_mult=3.5, b_mult=5.0, logstd_mult=8.0),
 }
 PRECS = ["tf32", "bf16"]
 
