@@ -261,6 +261,13 @@ SIGNATURES = {
         C.c_int,
         [C.POINTER(MlpDims), _P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _P, _P, _P],
     ),
+    "catb200_adam_apply": (C.c_int, [C.POINTER(MlpDims), _P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _P, _P]),
+    "catb200_peer_arena_bytes": (_SZ, [_I64]),
+    "catb200_peer_alloc": (C.c_int, [_SZ, C.POINTER(_P), _P]),
+    "catb200_peer_open": (C.c_int, [_P, C.POINTER(_P)]),
+    "catb200_peer_close": (C.c_int, [_P]),
+    "catb200_peer_free": (C.c_int, [_P]),
+    "catb200_grad_allreduce_norm": (C.c_int, [_P, _I32, _I32, _I64, _I32, _P, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P]),
     "catb200_philox4x32_10": (C.c_int, [_P, _P, _P]),
     "catb200_random_permutation_host": (C.c_int, [_I64, C.c_uint64, C.c_uint64, _P]),
     "catb200_random_permutation": (C.c_int, [_I64, _P, _P, _P]),

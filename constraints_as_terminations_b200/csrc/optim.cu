@@ -75,4 +75,13 @@ int catb200_adam_step(const catb200_mlp_dims_t* dims, float* params, float* grad
   return CATB200_OK;
 }
 
+// The Adam half alone (clip coefficient and bias corrections already in opt_ws: written by catb200_grad_allreduce_norm)
+int catb200_adam_apply(const catb200_mlp_dims_t* dims, float* params, float* grads, float* exp_avg, float* exp_avg_sq,
+                       void* wc, const float* lr_dev, float beta1, float beta2, float eps, float grad_scale, void* opt_ws,
+                       void* stream) {
+  if (!dims || !params || !grads || !exp_avg || !exp_avg_sq || !wc || !lr_dev || !opt_ws) return CATB200_ERR_INVALID_ARGUMENT;
+  AdamState a = {params, grads, exp_avg, exp_avg_sq, lr_dev, static_cast<OptScratch*>(opt_ws), beta1, beta2, eps, grad_scale};
+  return launch_adam_cast(dims, a, wc, as_stream(stream));
+}
+
 }  // extern "C"

@@ -10,6 +10,7 @@ clip + Adam kernels (`catb200_adam_step(grad_scale=...)`), so every rank clips w
 
 from __future__ import annotations
 
+import ctypes as C
 import os
 
 import torch
@@ -57,3 +58,84 @@ def allreduce_grads(flat_grads: torch.Tensor) -> float:
 def shard_seed(base_seed: int) -> int:
     """Per-rank seed, like the reference's distributed front-ends (`scripts/skrl/train.py:116-117`)."""
     return base_seed + rank()
+
+
+class _RawCuda:
+    """Zero-copy torch view of raw device memory (the __cuda_array_interface__ protocol)."""
+
+    def __init__(self, ptr: int, n_floats: int):
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+class PeerGradExchange:
+    """One-shot gradient all-reduce over NVLink peer memory, fused with the gradient norm (csrc/peer.cu).
+
+    Every rank cudaMallocs one peer-visible block ([flags][arena 0][arena 1]); the 64-byte IPC handles travel once
+    through `torch.distributed.all_gather_object` (host plumbing) and every rank maps its peers' blocks.  After that the
+    exchange is ONE kernel per optimizer step and rank (`reduce`), with no library collective and no host
+    synchronisation, so a whole epoch of minibatches replays as a single CUDA graph on every rank."""
+
+    def __init__(self, n_params: int, device: torch.device):
+        from . import _lib as L
+
+        self.L, self.lib = L, L.load()
+        self.rank, self.world = rank(), world_size()
+        if self.world > 8:
+            raise RuntimeError("PeerGradExchange supports up to 8 ranks (one NVSwitch domain)")
+        self.n = int(n_params)
+        self.n_pad = (self.n + 63) // 64 * 64
+        self.device = device
+        nbytes = self.lib.catb200_peer_arena_bytes(self.n)
+        own = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        L.check(self.lib.catb200_peer_alloc(nbytes, C.byref(own), handle), "peer_alloc")
+        self._own = own.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle))
+        self._bases = (C.c_void_p * self.world)()
+        self._opened = []
+        for p, h in enumerate(handles):
+            if p == self.rank:
+                self._bases[p] = self._own
+                continue
+            ptr = C.c_void_p()
+            buf = (C.c_uint8 * 64).from_buffer_copy(h)
+            L.check(self.lib.catb200_peer_open(buf, C.byref(ptr)), f"peer_open(rank {p})")
+            self._bases[p] = ptr.value
+            self._opened.append(ptr.value)
+        arenas = self._own + 64 * 4
+        self.arena = [torch.as_tensor(_RawCuda(arenas + i * self.n_pad * 4, self.n), device=device) for i in range(2)]
+        self.grad_sum = torch.zeros(self.n, dtype=torch.float32, device=device)
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+        self.err = torch.zeros(1, dtype=torch.int32, device=device)
+        dist.barrier()  # nobody touches a peer block before everybody has mapped everything
+
+    def reduce(self, parity: int, step_dev, opt_ws, max_grad_norm=1.0, betas=(0.9, 0.999), grad_norm_out=None) -> torch.Tensor:
+        """Sum of every rank's arena `parity` -> self.grad_sum (+ clip coefficient / bias corrections in opt_ws)."""
+        L = self.L
+        L.check(
+            self.lib.catb200_grad_allreduce_norm(
+                self._bases, self.rank, self.world, self.n, int(parity), self.grad_sum.data_ptr(), 1.0 / self.world,
+                max_grad_norm, betas[0], betas[1], step_dev.data_ptr(), L.ptr(grad_norm_out), opt_ws.data_ptr(),
+                self.epoch.data_ptr(), self.err.data_ptr(), L.stream(),
+            ),
+            "grad_allreduce_norm",
+        )  # fmt: skip
+        return self.grad_sum
+
+    def check(self) -> None:
+        """Raise if a handshake timed out or the arena parity went out of step (one device->host read)."""
+        code = int(self.err.item())
+        if code:
+            raise RuntimeError(f"peer gradient exchange failed on rank {self.rank}: " + {1: "a peer did not arrive within 2 s", 2: "arena parity out of step"}.get(code, str(code)))
+
+    def close(self) -> None:
+        if getattr(self, "_own", None):
+            torch.cuda.synchronize(self.device)
+            if dist.is_initialized():
+                dist.barrier()
+            for ptr in self._opened:
+                self.lib.catb200_peer_close(ptr)
+            self.arena = None
+            self.lib.catb200_peer_free(self._own)
+            self._own = None

@@ -293,6 +293,20 @@ def adam_step(dims, params, grads, exp_avg, exp_avg_sq, wc, lr_dev, step_dev, op
     )  # fmt: skip
 
 
+def adam_apply(dims, params, grads, exp_avg, exp_avg_sq, wc, lr_dev, opt_ws, betas=(0.9, 0.999), eps=1e-5, grad_scale=1.0) -> None:
+    """The Adam + operand-copy half of `adam_step`; the clip coefficient / bias corrections are already in `opt_ws`
+    (written by the peer-memory all-reduce, dist.PeerGradExchange.reduce)."""
+    for t, name in ((params, "params"), (grads, "grads"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq"), (lr_dev, "lr")):
+        _f32c(t, name)
+    L.check(
+        L.load().catb200_adam_apply(
+            dims, params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), wc.data_ptr(),
+            lr_dev.data_ptr(), betas[0], betas[1], eps, grad_scale, opt_ws.data_ptr(), L.stream(),
+        ),
+        "adam_apply",
+    )  # fmt: skip
+
+
 # --------------------------------------------------------------------------------------------------
 # single-`dones` GAE of the rl_games / skrl front-ends  (reference rl_games/cat_common.py:96-104,
 # skrl/ppo.py:397-442)

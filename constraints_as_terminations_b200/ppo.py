@@ -276,6 +276,13 @@ class PPOTrainer:
         self.value_rms_state = torch.tensor([0.0, 1.0, 1.0], **f32)  # mean, var, count of agent.value_rms
 
         self.grads = torch.zeros(lay.n_params, **f32)
+        # several ranks: the gradient of minibatch k is accumulated straight into arena k & 1 of a peer-visible block and
+        # exchanged by ONE kernel per optimizer step over NVLink (dist.PeerGradExchange); CATB200_PEER_ALLREDUCE=0 or an
+        # odd number of minibatches per epoch falls back to torch.distributed's NCCL all-reduce between two graphs
+        self.peer = None
+        n_mb = -(-self.batch_size // self.minibatch_size)
+        if self.world > 1 and dev.type == "cuda" and os.environ.get("CATB200_PEER_ALLREDUCE", "1") != "0" and n_mb % 2 == 0:
+            self.peer = cdist.PeerGradExchange(lay.n_params, dev)
         self.exp_avg = torch.zeros(lay.n_params, **f32)
         self.exp_avg_sq = torch.zeros(lay.n_params, **f32)
         self.lr_dev = torch.tensor(float(cfg.learning_rate), **f32)
@@ -312,6 +319,8 @@ class PPOTrainer:
         self._split_captured = 0
         self._split_replays = 0
         self._validate = True  # argument checks of the ops wrappers; switched off after the first iteration
+        # thread_local: with a process group alive, the NCCL watchdog thread may query events while this thread captures
+        self._capture_mode = "thread_local" if self.world > 1 else "global"
 
     # -- rollout -------------------------------------------------------------------------------------
     def start(self):
@@ -341,7 +350,7 @@ class PPOTrainer:
         if graph is None:
             graph = torch.cuda.CUDAGraph()
             before = L.launch_count()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, capture_error_mode=self._capture_mode):
                 self.agent.get_action_and_value(
                     self.obs_op[t], out=(self.actions[t], self.logprobs[t], self.values[t]), validate=False,
                     rng_state=rng, workspace=self.act_ws,
@@ -398,13 +407,13 @@ class PPOTrainer:
         vr.running_var.copy_(self.value_rms_state[1])
         vr.count.copy_(self.value_rms_state[2])
 
-    def _minibatch_grad(self, mb_inds):
+    def _minibatch_grad(self, mb_inds, grads=None):
         a = self.agent
         B = self.batch_size
         ops.ppo_minibatch_grad(
             a.dims, self.hp, mb_inds, self.obs_op.view(-1, a.dims.obs_pad), self.actions.view(B, -1),
             self.logprobs.view(B), self.advantages.view(B), self.returns.view(B), self.values.view(B), self.norm_stats,
-            a.parameters_flat(), a._wc, self.grads, self.loss_acc, self.train_ws,
+            a.parameters_flat(), a._wc, self.grads if grads is None else grads, self.loss_acc, self.train_ws,
         )  # fmt: skip
 
     def _minibatch_opt(self):
@@ -415,9 +424,19 @@ class PPOTrainer:
             grad_norm_out=self.grad_norm,
         )  # fmt: skip
 
-    def _minibatch(self, mb_inds):
+    def _minibatch(self, mb_inds, index=0):
+        """One optimizer step on minibatch number `index` of the epoch (ppo.py:298-354)."""
+        if self.peer is not None:
+            # gradient into the peer-visible arena of this minibatch's parity; ONE kernel exchanges it with every rank over
+            # NVLink, sums in rank order and produces the clip coefficient; Adam then consumes the private sum
+            a, parity = self.agent, index & 1
+            self._minibatch_grad(mb_inds, grads=self.peer.arena[parity])
+            gsum = self.peer.reduce(parity, self.step_dev, self.opt_ws, max_grad_norm=self.cfg.max_grad_norm, grad_norm_out=self.grad_norm)
+            ops.adam_apply(a.dims, a.parameters_flat(), gsum, self.exp_avg, self.exp_avg_sq, a._wc, self.lr_dev, self.opt_ws,
+                           eps=1e-5, grad_scale=1.0 / self.world)  # fmt: skip
+            return
         self._minibatch_grad(mb_inds)
-        if self.world > 1:  # the one exchange step: sum-allreduce of the flat 1.5 MB gradient over NVLink
+        if self.world > 1:  # the one exchange step: sum-allreduce of the flat 1.5 MB gradient over NVLink (NCCL)
             cdist.allreduce_grads(self.grads)
         self._minibatch_opt()
 
@@ -459,8 +478,8 @@ class PPOTrainer:
     def _epoch(self, shuffle=False):
         if shuffle:
             self._shuffle()
-        for start in range(0, self.batch_size, self.minibatch_size):
-            self._minibatch(self.perm[start : start + self.minibatch_size])
+        for index, start in enumerate(range(0, self.batch_size, self.minibatch_size)):
+            self._minibatch(self.perm[start : start + self.minibatch_size], index)
 
     def update(self, perms=None):
         """All epochs x minibatches of one iteration (ppo.py:290-354).  `perms` (one index permutation per
@@ -474,7 +493,7 @@ class PPOTrainer:
                 self.perm.copy_(perms[epoch])
             elif not in_graph_shuffle:
                 self._shuffle()
-            if self.use_graphs and self.world > 1 and self._eager_epochs >= 1:
+            if self.use_graphs and self.world > 1 and self.peer is None and self._eager_epochs >= 1:
                 if in_graph_shuffle:
                     self._shuffle()
                 self._epoch_split_graphs()
@@ -486,7 +505,7 @@ class PPOTrainer:
                 # launch sequence once and replay it from now on
                 graph = torch.cuda.CUDAGraph()
                 before = L.launch_count()
-                with torch.cuda.graph(graph):
+                with torch.cuda.graph(graph, capture_error_mode=self._capture_mode):
                     self._epoch(shuffle=key)
                 self._epoch_graphs[key] = (graph, L.launch_count() - before)
                 self._captured_launches += L.launch_count() - before
@@ -536,6 +555,8 @@ class PPOTrainer:
     def losses(self) -> dict:
         """Mean losses over the minibatches of the last update (one device->host read)."""
         acc = self.loss_acc.cpu()
+        if self.peer is not None:
+            self.peer.check()
         n = max(float(acc[7]), 1.0)
         return {
             "mean_pg_loss": float(acc[0]) / n,

@@ -353,6 +353,42 @@ int catb200_adam_step(const catb200_mlp_dims_t* dims, float* params, float* grad
                       float beta1, float beta2, float eps, float grad_scale, float* grad_norm_out, void* opt_ws,
                       void* stream);
 
+/* The Adam + operand-copy-refresh half of catb200_adam_step alone, for callers that obtained the clip coefficient and the
+ * bias corrections in opt_ws from catb200_grad_allreduce_norm (multi-GPU). */
+int catb200_adam_apply(const catb200_mlp_dims_t* dims, float* params, float* grads, float* exp_avg, float* exp_avg_sq,
+                       void* wc, const float* lr_dev, float beta1, float beta2, float eps, float grad_scale,
+                       void* opt_ws, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU gradient exchange over NVLink peer memory  (one exchange step per optimizer step)
+ *
+ * Each rank owns one peer-visible allocation of catb200_peer_arena_bytes(n_params) bytes:
+ *   [flags: 64 x uint32][gradient arena 0: n_pad floats][gradient arena 1: n_pad floats],  n_pad = n_params rounded up to 64.
+ * Minibatch k accumulates its flat gradient into arena k & 1 (`grads` of catb200_ppo_minibatch_grad points there).
+ * catb200_grad_allreduce_norm is then ONE kernel per rank: flag handshake with every peer over NVLink, rank-ordered sum
+ * of the world arenas of that parity into the private `grad_sum` (bit-identical on every rank), squared norm -> clip
+ * coefficient / Adam bias corrections in opt_ws (what catb200_adam_step's first launch does on one GPU), and zeroing of
+ * the caller's other arena for the next minibatch.  No host synchronisation, no library collective: graph-capturable.
+ * ---------------------------------------------------------------------------------------------- */
+size_t catb200_peer_arena_bytes(int64_t n_params);
+/* cudaMalloc + zero + cudaIpcGetMemHandle (64 bytes, to be sent to the peers by any host channel). */
+int catb200_peer_alloc(size_t bytes, void** ptr, uint8_t* ipc_handle64);
+/* Map a peer's allocation (cudaIpcOpenMemHandle, peer access enabled lazily) / unmap it / free an own allocation. */
+int catb200_peer_open(const uint8_t* ipc_handle64, void** ptr);
+int catb200_peer_close(void* ptr);
+int catb200_peer_free(void* ptr);
+/*
+ * peer_bases[world]: base pointer of every rank's allocation as mapped in THIS process (own one at index `rank`).
+ * parity: arena to reduce; must equal (*epoch_dev & 1), epoch_dev being a device-side counter of completed calls that
+ * the kernel increments.  err_dev (device int32, caller-zeroed) becomes 1 if a peer did not arrive within ~2 s, 2 on a
+ * parity mismatch -- the kernel never spins forever.  grad_sum [n_params] receives the summed gradient; the remaining
+ * arguments are those of catb200_adam_step's norm / clip stage.
+ */
+int catb200_grad_allreduce_norm(void* const* peer_bases, int32_t rank, int32_t world, int64_t n_params, int32_t parity,
+                                float* grad_sum, float grad_scale, float max_grad_norm, float beta1, float beta2,
+                                int32_t* step_dev, float* grad_norm_out, void* opt_ws, uint32_t* epoch_dev,
+                                int32_t* err_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Device-side random draws (Philox4x32-10; csrc/philox.cuh, CPU restatement oracle/philox_oracle.py)
  *
