@@ -267,6 +267,250 @@ mlp_gemm_kernel(const __grid_constant__ TcGemmArgs g) {
   }
 }
 
+// ---- 256-row tiles (minibatch-sized launches) -----------------------------------------------------------------------
+// With fp32 operands a 128 x 128 tile moves 32 KiB of operands per 32 reduction elements and the launch is bound by
+// L2 -> SM operand traffic (~10 TB/s chip-wide), not by the tensor pipe: ncu shows 36 % tensor activity on the
+// 512 -> 256 layer while 300 MB cross the L2 for 8.6 GFLOP.  This variant gives one CTA a 256 x BN tile as two 128-row
+// accumulators that share every B stage (BN = 256: 64 KiB per k-block for four times the MACs of the 128 x 128 tile,
+// i.e. half the operand bytes per flop; BN = 128 for the 128-wide layer: 48 KiB for twice the MACs).  BN = 256 fills all
+// 512 TMEM columns with one accumulator stage (the epilogue of a tile does not overlap the next tile's MMAs -- launches
+// of this size have 1-2 tiles per CTA); BN = 128 keeps two stages.  Roles, slabs and the dgrad H path are those of
+// mlp_gemm_kernel; each epilogue warp walks its 32 rows x BN/2 columns of both accumulators slab by slab.
+template <int BN>
+struct P2Smem {
+  static constexpr int kStages = BN == 256 ? 2 : 3;
+  static constexpr int kStage = 2 * kATileBytes + BN * kRowBytes;   // two A tiles + one B tile
+  static constexpr int kSlabs = kEpiWarps * 2 * kSlabBytes;
+  static constexpr int kBars = 8 * (2 * kStages + 4 + 2 * kEpiWarps);
+  static constexpr int kBias = 2 * kEpiWarps * (BN / 2) * 4;        // double-buffered BN/2 bias values per warp
+  static constexpr int kTotal = kStages * kStage + kSlabs + ((kBars + 15) & ~15) + 16 + kBias + 1024 /*alignment slack*/;
+};
+
+template <int MODE, int PREC, int BN>
+__global__ void __launch_bounds__(kTcThreads, 1)
+mlp_gemm256_kernel(const __grid_constant__ TcGemmArgs g) {
+  using P = PrecT<PREC>;
+  using S = P2Smem<BN>;
+  constexpr int kStages = S::kStages;
+  constexpr int kAccStages = 512 / (2 * BN);                  // TMEM accumulator stages: 1 (BN = 256) or 2
+  constexpr int CH = kRowBytes / (int)sizeof(typename P::T);  // output columns per slab row: 64 bf16 / 32 fp32
+  constexpr int LD = CH / 32;                                 // 32-column TMEM loads per slab
+  constexpr int NSLAB = 2 * (BN / 2) / CH;                    // slabs per warp and tile (both accumulators)
+  extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t tiles = (raw + 1023u) & ~1023u;
+  const uint32_t slabs = tiles + kStages * S::kStage;
+  const uint32_t bars = slabs + S::kSlabs;
+  const uint32_t full_bar = bars, empty_bar = bars + 8 * kStages;
+  const uint32_t tfull_bar = bars + 16 * kStages, tempty_bar = tfull_bar + 16;
+  const uint32_t h_bar = tempty_bar + 16;  // [kEpiWarps][2]
+  const uint32_t tmem_slot = bars + ((S::kBars + 15) & ~15);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+  float* bias_sm = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - raw));  // [2][kEpiWarps][BN / 2]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_n = g.N / BN, tiles_m = (g.M + 255) / 256;
+  const int per_net = tiles_m * tiles_n, total = 2 * per_net;
+  const int k_blocks = g.K / P::kBK;
+
+  if (warp == 0 && lane == 0) {
+    for (int z = 0; z < 2; ++z) {
+      asm volatile("prefetch.tensormap [%0];\n" ::"l"(&g.mapA[z]));
+      asm volatile("prefetch.tensormap [%0];\n" ::"l"(&g.mapB[z]));
+      asm volatile("prefetch.tensormap [%0];\n" ::"l"(&g.mapC[z]));
+      if (MODE == kTcDgrad) asm volatile("prefetch.tensormap [%0];\n" ::"l"(&g.mapH[z]));
+    }
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar + 8 * a, 1);
+      mbar_init(tempty_bar + 8 * a, kEpiWarps);
+    }
+    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(h_bar + 8 * i, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  pdl_wait();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int z = t / per_net, r = t - z * per_net;
+        const int row_base = (r / tiles_n) * 256, col_base = (r % tiles_n) * BN;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const uint32_t s = it % kStages;
+          mbar_wait(empty_bar + 8 * s, ((it / kStages) & 1) ^ 1);
+          const uint32_t sa = tiles + s * S::kStage, sb = sa + 2 * kATileBytes;
+          mbar_expect_tx(full_bar + 8 * s, S::kStage);
+          tma_load_2d(sa, &g.mapA[z], full_bar + 8 * s, kb * P::kBK, row_base);                     // rows   0..127 of the tile
+          tma_load_2d(sa + kATileBytes, &g.mapA[z], full_bar + 8 * s, kb * P::kBK, row_base + 128);  // rows 128..255 (zero-filled beyond M)
+#pragma unroll
+          for (int h = 0; h < BN / 128; ++h) tma_load_2d(sb + h * kATileBytes, &g.mapB[z], full_bar + 8 * s, kb * P::kBK, col_base + h * 128);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc(P::kFmt, 128, BN, false, false);
+    uint32_t it = 0, j = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
+      const uint32_t a = j % kAccStages;
+      mbar_wait(tempty_bar + 8 * a, ((j / kAccStages) & 1) ^ 1);  // the epilogue has drained this accumulator stage
+      tc_fence_after();
+      for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+        const uint32_t s = it % kStages;
+        mbar_wait(full_bar + 8 * s, (it / kStages) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = tiles + s * S::kStage, sb = sa + 2 * kATileBytes;
+#pragma unroll
+          for (int k = 0; k < P::kBK / P::kUmmaK; ++k) {
+            const uint64_t db = make_smem_desc(sb + k * 32, 16, 1024);  // BN rows of 128 B, 8-row groups 1 KiB apart
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+              const uint64_t da = make_smem_desc(sa + sub * kATileBytes + k * 32, 16, 1024);
+              umma<PREC>(tmem_base + a * 2 * BN + sub * BN, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+          }
+        }
+        __syncwarp();
+        if (elect_one()) {
+          umma_commit(empty_bar + 8 * s);
+          if (kb == k_blocks - 1) umma_commit(tfull_bar + 8 * a);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9) =====================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;
+    const int c_first = half * (BN / 2);
+    const uint32_t my_slabs = slabs + ew * 2 * kSlabBytes;
+    const uint32_t my_hbar = h_bar + ew * 16;
+    const uint32_t lane_row = lane * kRowBytes, lane_x = lane & 7;
+    uint32_t j = 0, n_slab = 0;  // n_slab: running slab counter of this warp (buffer = n_slab & 1, H-barrier phase = n_slab >> 1)
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
+      const int z = t / per_net, r = t - z * per_net;
+      const int row_base = (r / tiles_n) * 256, col_base = (r % tiles_n) * BN;
+      const uint32_t a = j % kAccStages;
+      float* bsm = bias_sm + ((j & 1) * kEpiWarps + ew) * (BN / 2);
+      // slab i of the tile: accumulator sub = i / (NSLAB / 2), columns c_first + (i % (NSLAB / 2)) * CH
+      auto slab_col = [&](int i) { return col_base + c_first + (i % (NSLAB / 2)) * CH; };
+      auto slab_row = [&](int i) { return row_base + (i / (NSLAB / 2)) * 128 + quarter * 32; };
+      if (MODE == kTcDgrad) {
+        if (lane == 0) {  // H of the first slab, in flight while the MMAs still run
+          asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
+          const uint32_t buf = n_slab & 1;
+          mbar_expect_tx(my_hbar + 8 * buf, kSlabBytes);
+          tma_load_2d(my_slabs + buf * kSlabBytes, &g.mapH[z], my_hbar + 8 * buf, slab_col(0), slab_row(0));
+        }
+      } else {
+        const float* __restrict__ bp = g.bias[z] + col_base + c_first;
+#pragma unroll
+        for (int c = lane; c < BN / 2; c += 32) bsm[c] = __ldg(bp + c);
+      }
+      if (lane == 0) mbar_wait(tfull_bar + 8 * a, (j / kAccStages) & 1);
+      __syncwarp();
+      mbar_wait(tfull_bar + 8 * a, (j / kAccStages) & 1);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * 2 * BN + c_first;
+#pragma unroll 1
+      for (int i = 0; i < NSLAB; ++i, ++n_slab) {
+        const uint32_t buf = n_slab & 1;
+        const uint32_t slab = my_slabs + buf * kSlabBytes;
+        const int sub = i / (NSLAB / 2), ci = i % (NSLAB / 2);
+        uint32_t v[LD][32];
+#pragma unroll
+        for (int l = 0; l < LD; ++l) tmem_ld32(tbase + sub * BN + ci * CH + l * 32, v[l]);
+        if (MODE == kTcDgrad) {
+          if (lane == 0 && i + 1 < NSLAB) {  // H of the next slab: its buffer was last read by the store of slab i - 1
+            asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+            const uint32_t nb = buf ^ 1;
+            mbar_expect_tx(my_hbar + 8 * nb, kSlabBytes);
+            tma_load_2d(my_slabs + nb * kSlabBytes, &g.mapH[z], my_hbar + 8 * nb, slab_col(i + 1), slab_row(i + 1));
+          }
+          mbar_wait(my_hbar + 8 * buf, (n_slab >> 1) & 1);
+        } else {
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");  // store of slab i - 2 (same buffer)
+          __syncwarp();
+        }
+#pragma unroll
+        for (int l = 0; l < LD; ++l) tmem_ld_wait(v[l]);
+        if (i == NSLAB - 1) {  // last TMEM read of this tile: hand the accumulator stage back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar + 8 * a);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint32_t addr = slab + lane_row + ((q ^ lane_x) << 4);
+          uint4 o;
+          if (PREC == kPrecTf32) {
+            float x[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] = __uint_as_float(v[0][q * 4 + e]);
+            if (MODE == kTcFwd) {
+              const float4 b = *reinterpret_cast<const float4*>(bsm + ci * CH + q * 4);
+              x[0] = elu_fast(x[0] + b.x); x[1] = elu_fast(x[1] + b.y); x[2] = elu_fast(x[2] + b.z); x[3] = elu_fast(x[3] + b.w);
+            } else {
+              const uint4 h = ld_shared_v4(addr);
+              x[0] *= elu_grad_from_output(__uint_as_float(h.x)); x[1] *= elu_grad_from_output(__uint_as_float(h.y));
+              x[2] *= elu_grad_from_output(__uint_as_float(h.z)); x[3] *= elu_grad_from_output(__uint_as_float(h.w));
+            }
+            o = make_uint4(__float_as_uint(round_tf32(x[0])), __float_as_uint(round_tf32(x[1])),
+                           __float_as_uint(round_tf32(x[2])), __float_as_uint(round_tf32(x[3])));
+          } else {
+            float x[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[(q >> 2) % LD][(q & 3) * 8 + e]);
+            if (MODE == kTcFwd) {
+              const float4 b0 = *reinterpret_cast<const float4*>(bsm + ci * CH + q * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(bsm + ci * CH + q * 8 + 4);
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) x[e] = elu_fast(x[e] + bb[e]);
+            } else {
+              const uint4 h = ld_shared_v4(addr);
+              const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&h);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                x[2 * e] *= elu_grad_from_output(__low2float(hp[e]));
+                x[2 * e + 1] *= elu_grad_from_output(__high2float(hp[e]));
+              }
+            }
+            o = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+          }
+          st_shared_v4(addr, o);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&g.mapC[z], slab, slab_col(i), slab_row(i));
+          asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+        }
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ---- weight gradient ---------------------------------------------------------------------------------------------
 constexpr int kWgStages = 3;
 
@@ -490,11 +734,49 @@ static int launch_gemm(const TcGemmArgs& g, cudaStream_t st) {
   return CATB200_OK;
 }
 
+template <int MODE, int PREC, int BN>
+static int launch_gemm256(const TcGemmArgs& g, cudaStream_t st) {
+  using S = P2Smem<BN>;
+  static bool attr = false;
+  if (!attr) {
+    CATB200_CUDA_TRY(cudaFuncSetAttribute(mlp_gemm256_kernel<MODE, PREC, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    attr = true;
+  }
+  const int total = 2 * ((g.M + 255) / 256) * (g.N / BN);
+  CATB200_CUDA_TRY(launch_pdl(mlp_gemm256_kernel<MODE, PREC, BN>, dim3(min(total, kNumSMs)), dim3(kTcThreads), (size_t)S::kTotal, st, g));
+  CATB200_LAUNCH_CHECK();
+  return CATB200_OK;
+}
+
+// 256-row tiles: opt-in (CATB200_TILE256=1) for launches that still fill most of the machine with them.  Measured on
+// the B200 (profiles/README.md, round 2): half the operand bytes, but no faster than the 128 x 128 tiles -- 22.2 vs
+// 19.5 us per forward launch, 25.8 vs 22.7 us per dgrad launch at 16384 rows: with BN = 256 the single accumulator stage
+// serialises load -> MMA -> epilogue per tile, and 256 tiles on 148 SMs quantise to two waves.  The 128 x 128 kernel runs
+// at ~13 TB/s of L2 -> SM operand traffic, the chip's L2 cap; halving the bytes WITH overlap needs cta_group::2 pairs.
+static bool use_tile256(int M, int N) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("CATB200_TILE256");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  const int bn = N % 256 == 0 ? 256 : 128;
+  return v == 1 && 2 * ((M + 255) / 256) * (N / bn) >= 96;
+}
+
+template <int MODE, int PREC>
+static int launch_gemm_any(const TcGemmArgs& g, cudaStream_t st) {
+  if (use_tile256(g.M, g.N)) {
+    if (g.N % 256 == 0) return launch_gemm256<MODE, PREC, 256>(g, st);
+    return launch_gemm256<MODE, PREC, 128>(g, st);
+  }
+  return launch_gemm<MODE, PREC>(g, st);
+}
+
 int tc_gemm_launch(int mode, int prec, const TcGemmArgs& g, cudaStream_t st) {
   const int bk = prec == kPrecTf32 ? 32 : 64;
   if (g.N % 128 || g.K % bk || g.M <= 0) return CATB200_ERR_UNSUPPORTED;
-  if (mode == kTcFwd) return prec == kPrecTf32 ? launch_gemm<kTcFwd, kPrecTf32>(g, st) : launch_gemm<kTcFwd, kPrecBf16>(g, st);
-  return prec == kPrecTf32 ? launch_gemm<kTcDgrad, kPrecTf32>(g, st) : launch_gemm<kTcDgrad, kPrecBf16>(g, st);
+  if (mode == kTcFwd) return prec == kPrecTf32 ? launch_gemm_any<kTcFwd, kPrecTf32>(g, st) : launch_gemm_any<kTcFwd, kPrecBf16>(g, st);
+  return prec == kPrecTf32 ? launch_gemm_any<kTcDgrad, kPrecTf32>(g, st) : launch_gemm_any<kTcDgrad, kPrecBf16>(g, st);
 }
 
 template <int PREC, int BN>

@@ -190,7 +190,8 @@ def _minibatch(agent, B, M, seed, margin=None):
 
 
 @pytest.mark.parametrize("prec,margin", [("tf32", 0.01), ("tf32", None), ("bf16", None)])
-@pytest.mark.parametrize("B,M", [(24 * 1024, 16384), (3000, 1000), (768, 512), (7000, 5000)])  # 5000: ragged last tile on the persistent GEMMs
+# 5000: ragged last 128-row tile
+@pytest.mark.parametrize("B,M", [(24 * 1024, 16384), (3000, 1000), (768, 512), (7000, 5000)])
 def test_minibatch_gradient_matches_oracle(B, M, prec, margin):
     """tf32 / margin 0.01: every sample of the minibatch takes the same PPO branches as in the fp32 oracle -> the
     gradient agrees with fp32 to 5e-3 (rel. Frobenius), what tf32 operand rounding allows.  Without the margin a few
@@ -258,6 +259,34 @@ def test_minibatch_gradient_matches_oracle(B, M, prec, margin):
         # log-std gradient: a sum of mixed-sign per-sample terms (cancellation) -> judged norm-wise
         r = float((got[ls] - want[ls]).norm() / want[ls].norm())
         assert r < T["logstd_mult"] * gtol, f"{name}: log-std gradient relative error {r:.3e}"
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_tile256_kernels_match_the_default_tiles():
+    """The opt-in 256-row-tile GEMM kernels (CATB200_TILE256=1, read once per process -> a subprocess) give the same
+    gradient as the default 128 x 128 tiles on a ragged 16500-row minibatch."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import torch, sys; sys.path.insert(0, %r)\n"
+        "from tests import test_mlp_gpu as T\n"
+        "from constraints_as_terminations_b200 import ops\n"
+        "agent = T.make_agent(seed=1); dims, layout, params, wc = T.device_agent(agent, 'tf32')\n"
+        "obs, actions, logp, adv, returns, values, ns, idx = T._minibatch(agent, 20000, 16500, seed=5)\n"
+        "g = torch.zeros(layout.n_params, device='cuda:0'); la = torch.zeros(8, device='cuda:0')\n"
+        "ops.ppo_minibatch_grad(dims, ops.make_hparams(), idx.cuda(), ops.obs_to_operand(dims, obs.cuda()), actions.cuda(), logp.cuda(), adv.cuda(),"
+        " returns.cuda(), values.cuda(), ns.cuda(), params, wc, g, la, ops.mlp_workspace(dims, 16500, True, 'cuda:0'))\n"
+        "torch.save(g.cpu(), sys.argv[1])\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for flag in ("0", "1"):
+        path = f"/tmp/catb200_tile256_{flag}.pt"
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=dict(os.environ, CATB200_TILE256=flag), timeout=300)
+        outs.append(torch.load(path))
+    rel = float((outs[0] - outs[1]).norm() / outs[0].norm())
+    assert rel < 1e-5, rel  # same products, same fp32 accumulation per tile row; only the atomics order of wgrad differs
 
 
 @pytest.mark.parametrize("prec", PRECS)
