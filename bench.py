@@ -187,6 +187,10 @@ def _host_fed_env_cls():
             self.load_state(self._staging[buf][k])
             self._count += 1
 
+        def pointer_key(self):  # which staging set / step the current state tensors belong to
+            it, k = divmod(self._count - 1, self.STEPS)
+            return (it & 1, k)
+
     return HostFed
 
 

@@ -119,6 +119,7 @@ class CatParams(C.Structure):
         ("min_p", C.c_float),
         ("floor_max", C.c_float),
         ("span", C.c_float * MAX_TERMS),
+        ("span_dev", C.c_void_p),
     ]
 
 

@@ -482,6 +482,13 @@ class ConstraintManager(ManagerBase):
         self._raw_cache = None
         self._reset_ws = None
         self._fused_out = None
+        # max_p - min_p per term in device memory (the kernels read it there: a CUDA graph of the step stays current when
+        # the curriculum changes max_p), refreshed from a pinned host mirror with an asynchronous copy
+        self._span_dev = torch.zeros(L.MAX_TERMS, dtype=torch.float, device=dev)
+        self._span_host = torch.zeros(L.MAX_TERMS, dtype=torch.float)
+        if torch.device(dev).type == "cuda":
+            self._span_host = self._span_host.pin_memory()
+        self._params.span_dev = self._span_dev.data_ptr()
 
     # -- reference API -----------------------------------------------------------------------------
     def __str__(self) -> str:
@@ -547,7 +554,7 @@ class ConstraintManager(ManagerBase):
         self._launch(None, None)
         return self._cstr_prob_buf
 
-    def compute_step(self, raw_reward: torch.Tensor, reset_buf: torch.Tensor | None, fuse_reset: bool = False):
+    def compute_step(self, raw_reward: torch.Tensor, reset_buf: torch.Tensor | None, fuse_reset: bool = False, fused_out=None):
         """`compute()` fused with the reward / dones lines of `CaTEnv.step` (reference cat_env.py:100-107,118-121).
 
         Returns `(reward_buf, dones)`: reward = clip(raw_reward * (1 - cstr_prob), min=0) and
@@ -557,7 +564,8 @@ class ConstraintManager(ManagerBase):
         `fuse_reset=True` additionally performs `reset(ids of the envs flagged in reset_buf)` inside the same two
         launches (the order of `CaTEnv.step`: compute at cat_env.py:100, `constraint_manager.reset` at :181 via
         `_reset_idx`), reading `env.episode_length_buf` before anybody zeroes it; `fused_reset_stats()` then returns
-        what `reset()` would have.
+        what `reset()` would have.  `fused_out` (float32 [2 * n_terms]) receives those statistics instead of a fresh
+        tensor (a caller that replays the step from a CUDA graph needs the address to be its own).
         """
         L.require_cuda(raw_reward, "raw_reward")
         if raw_reward.dtype != torch.float32 or not raw_reward.is_contiguous():
@@ -571,15 +579,17 @@ class ConstraintManager(ManagerBase):
                 reset_buf = reset_buf.contiguous()
         if fuse_reset and reset_buf is None:
             raise ValueError("compute_step(fuse_reset=True) needs reset_buf")
-        self._launch(raw_reward, reset_buf, fuse_reset=fuse_reset)
+        self._launch(raw_reward, reset_buf, fuse_reset=fuse_reset, fused_out=fused_out)
         return self._reward_buf, self._dones_buf
 
-    def fused_reset_stats(self) -> dict[str, torch.Tensor]:
+    def fused_reset_stats(self, packed=None) -> dict[str, torch.Tensor]:
         """Episode statistics gathered by the last `compute_step(..., fuse_reset=True)`: same keys / values as
-        `reset(env_ids)` for the envs that were flagged in its `reset_buf` (NaN if none was)."""
-        if self._fused_out is None:
+        `reset(env_ids)` for the envs that were flagged in its `reset_buf` (NaN if none was).  `packed`: the `fused_out`
+        buffer of a graph-replayed step."""
+        packed = self._fused_out if packed is None else packed
+        if packed is None:
             raise RuntimeError("no compute_step(fuse_reset=True) has run yet")
-        return _LazyStats(self._stat_keys, self._fused_out)
+        return _LazyStats(self._stat_keys, packed)
 
     def reset(self, env_ids: Sequence[int] | None = None) -> dict[str, torch.Tensor]:
         """Episode statistics of the envs being reset, then clear them (reference :190-211)."""
@@ -666,11 +676,21 @@ class ConstraintManager(ManagerBase):
 
     def _refresh_max_p(self):
         min_p = self.cat.min_p
+        changed = False
         for i, term_cfg in enumerate(self._term_cfgs):  # re-read every step like the reference (:217)
             mp = term_cfg.max_p
             if mp != self._max_p_cache[i]:
                 self._max_p_cache[i] = mp
                 self._params.span[i] = mp - min_p
+                self._span_host[i] = self._params.span[i]  # the fp32 value ctypes rounded to
+                changed = True
+        if changed:  # stream-ordered before the next launch / graph replay; no host synchronisation
+            self._span_dev.copy_(self._span_host, non_blocking=True)
+
+    def refresh_params(self) -> None:
+        """Host-side part of a step for callers that replay the launches of `compute_step` from a CUDA graph: pick up
+        `max_p` changes (curriculum, `set_term_cfg`) into the device-side table the captured kernels read."""
+        self._refresh_max_p()
 
     def _episode_lengths(self) -> torch.Tensor:
         ep_len = self._env.episode_length_buf
@@ -679,7 +699,7 @@ class ConstraintManager(ManagerBase):
         L.require_cuda(ep_len, "episode_length_buf")
         return ep_len
 
-    def _launch(self, raw_reward, reset_buf, fuse_reset=False):
+    def _launch(self, raw_reward, reset_buf, fuse_reset=False, fused_out=None):
         if not self._term_names:
             self._cstr_prob_buf = torch.tensor([], device=self._device)
             self._computed = False
@@ -692,7 +712,7 @@ class ConstraintManager(ManagerBase):
             if self._reset_ws is None:
                 self._reset_ws = L.zeros_workspace(L.load().catb200_cat_reset_workspace_bytes(), dev)
             # a fresh output per call: the dict handed out by fused_reset_stats() may be kept by the caller (extras["log"])
-            self._fused_out = torch.empty(2 * len(self._term_names), dtype=torch.float, device=dev)
+            self._fused_out = fused_out if fused_out is not None else torch.empty(2 * len(self._term_names), dtype=torch.float, device=dev)
             ep_len = self._episode_lengths()
             L.check(
                 L.load().catb200_cat_step_reset(

@@ -537,7 +537,7 @@ cat_apply_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_const
     float es2 = 0.0f, mv2 = 0.0f;
     if (live) {
       const int c0 = plan.slot_col_begin[slot], c1 = plan.slot_col_begin[slot + 1];
-      const float span = prm.span[slot];
+      const float span = prm.span_dev ? __ldg(prm.span_dev + slot) : prm.span[slot];
       const size_t k = (size_t)slot * num_envs + i;
       const float es = episode_sums[k], mv = mean_values[k];  // requested before the columns: all in flight together
       float tmax = -INFINITY;
@@ -591,7 +591,8 @@ cat_probs_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_const
     const int c0 = plan.slot_col_begin[slot], c1 = plan.slot_col_begin[slot + 1];
     for (int col = c0; col < c1; ++col) {
       const float c = c_t[((size_t)(i / kTile) * plan.n_cols + col) * kTile + (i % kTile)];
-      probs_out[(size_t)i * plan.n_cols + col] = violation_prob(c, running_max[col], prm.min_p, prm.span[slot]);
+      probs_out[(size_t)i * plan.n_cols + col] =
+          violation_prob(c, running_max[col], prm.min_p, prm.span_dev ? __ldg(prm.span_dev + slot) : prm.span[slot]);
     }
   }
 }

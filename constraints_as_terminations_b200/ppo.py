@@ -312,6 +312,8 @@ class PPOTrainer:
         self._replayed_launches = 0  # kernels executed by epoch-graph replays
         self._eager_epochs = 0
         self._policy_graphs: dict = {}
+        self._step_graphs: dict = {}  # (slot, state-pointer key) -> (graph, kernels recorded, reset-statistics buffer)
+        self.step_graphs = os.environ.get("CATB200_STEP_GRAPHS", "1") != "0"
         self._policy_graph_launches = 0
         self._policy_captures = 0
         self._policy_replays = 0
@@ -361,20 +363,65 @@ class PPOTrainer:
         graph.replay()
         self._policy_replays += 1
 
+    def _post_step(self, t, next_obs, reward, next_done, timeouts):
+        """rewards[t], dones / true_dones[t + 1] (ppo.py:215-224) and the normalised next observation (ppo.py:225)."""
+        if next_done.dtype != torch.float32:
+            next_done = next_done.to(torch.float)
+        if reward.dtype != torch.float32 or not reward.is_contiguous():
+            reward = reward.float().contiguous()
+        if timeouts.dtype not in (torch.bool, torch.uint8) or not timeouts.is_contiguous():
+            timeouts = (timeouts != 0).contiguous()
+        ops.rollout_append(reward, next_done, timeouts, self.rewards[t], self.dones[t + 1], self.true_dones[t + 1], validate=self._validate)
+        self._ingest_obs(next_obs["policy"], t + 1)
+
+    def _graphable_env(self):
+        env = self.envs.unwrapped
+        return all(hasattr(env, m) for m in ("step_host", "step_device", "step_finish_host", "pointer_key")) and env.pointer_key() is not None
+
+    def _rollout_step_graphed(self, t):
+        """The whole env step -- policy, the env's device half (fused constraint step), append, observation statistics
+        and normalisation -- as ONE CUDA-graph launch.  Needs an env that separates its host bookkeeping from its kernels
+        (`step_host` / `step_device` / `step_finish_host`) and names the state tensors the step reads (`pointer_key`):
+        the synthetic env does; with Isaac Lab's own `step` in between only the policy is graphed."""
+        env = self.envs.unwrapped
+        env.step_host()
+        key = (t, env.pointer_key())
+        entry = self._step_graphs.get(key)
+        if entry is None:
+            if len(self._step_graphs) >= 512:
+                self._step_graphs.clear()
+            graph = torch.cuda.CUDAGraph()
+            stats = torch.empty(2 * max(1, len(getattr(env.constraint_manager, "active_terms", []))), dtype=torch.float, device=self.device)
+            before = L.launch_count()
+            with torch.cuda.graph(graph, capture_error_mode=self._capture_mode):
+                self.agent.get_action_and_value(
+                    self.obs_op[t], out=(self.actions[t], self.logprobs[t], self.values[t]), validate=False,
+                    rng_state=self.rng_state if self.device_rng else None, workspace=self.act_ws,
+                )  # fmt: skip
+                env.step_device(uniform=True, fused_out=stats)
+                self._post_step(t, env.obs_buf, env.reward_buf, env._dones, env.reset_time_outs)
+            entry = self._step_graphs[key] = (graph, L.launch_count() - before, stats)
+            self._captured_launches += entry[1]
+        graph, n, stats = entry
+        graph.replay()
+        self._replayed_launches += n
+        if env._resetting and env.constraint_manager is not None:  # the statistics of this step's resets: this graph's own buffer
+            env.extras["log"] = env.constraint_manager.fused_reset_stats(stats)
+        env.step_finish_host()
+        info = env.extras
+        info["true_dones"] = env.reset_time_outs
+        return info
+
     def rollout_step(self, t):
         """One env step of the rollout (reference ppo.py:201-230)."""
         self.global_step += self.num_envs * self.world
         # obs[t], dones[t], true_dones[t] are already in place (slot t was filled by the previous post-step)
+        if self.use_graphs and self.step_graphs and self.iteration >= 2 and not self._validate and self._graphable_env():
+            return self._rollout_step_graphed(t)
         self._policy(t)
         next_obs, reward, next_done, timeouts, info = self.envs.step(self.actions[t])
-        if next_done.dtype != torch.float32:
-            next_done = next_done.to(torch.float)
-        ops.rollout_append(
-            reward if reward.is_contiguous() else reward.contiguous(), next_done, timeouts,
-            self.rewards[t], self.dones[t + 1], self.true_dones[t + 1], validate=self._validate,
-        )  # fmt: skip
+        self._post_step(t, next_obs, reward, next_done, timeouts)
         info["true_dones"] = timeouts
-        self._ingest_obs(next_obs["policy"], t + 1)
         return info
 
     def collect_rollout(self):

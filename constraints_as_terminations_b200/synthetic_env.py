@@ -227,27 +227,62 @@ class SyntheticSolo12Env:
 
     def step(self, action: torch.Tensor):
         """Trainer-visible part of `CaTEnv.step` (reference cat_env.py:92-147) on synthetic state."""
+        resetting = self.step_host()
+        self.step_device(resetting)
+        self.step_finish_host()
+        return self.obs_buf, self.reward_buf, self._dones, self.reset_time_outs, self.extras
+
+    # The step in two halves, so that a trainer can replay the device half from a CUDA graph (one launch per env step):
+    #   step_host()   : everything the host does -- state pointers, host-side counters, the time-out schedule (a host
+    #                   mirror of the episode lengths: no device read), the curriculum and the extras["log"] dict;
+    #   step_device() : every kernel -- counters, time-outs, the fused constraint step (+ reset statistics), the zeroing
+    #                   of the reset envs' episode lengths.  With `uniform=True` it does the same launches whether or not
+    #                   anybody resets this step (what a graph records once must be valid for every replay);
+    #   step_finish_host() : the curriculum of the envs that reset (reference: inside _reset_idx, i.e. after this step's
+    #                   constraint computation -- the new max_p takes effect from the next step on).
+    def pointer_key(self):
+        """Identifies the set of state tensors `step_device()` reads after the last `step_host()` (a CUDA graph of the
+        device half is valid for exactly one such set)."""
+        return self._cursor
+
+    def step_host(self) -> bool:
         self._advance()
-        self.episode_length_buf += 1
         self.common_step_counter += 1
-        # time-outs (Isaac Lab's termination manager in the real env); the host mirror of the episode
-        # lengths tells whether anything resets this step without reading the device
         self._phase_np += 1
         due = self._phase_np >= self.max_episode_length
-        self.reset_time_outs = self.episode_length_buf >= self.max_episode_length
+        resetting = bool(due.any())
+        mgr = self.constraint_manager
+        if resetting:
+            self.extras["log"] = dict()
+            self._phase_np[due] = 0
+        if mgr is not None:
+            mgr.refresh_params()
+        self._resetting = resetting
+        return resetting
+
+    def step_finish_host(self) -> None:
+        if self._resetting and self.constraint_manager is not None:
+            self._curriculum()
+
+    def step_device(self, resetting: bool | None = None, uniform: bool = False, fused_out=None):
+        resetting = self._resetting if resetting is None else resetting
+        self.episode_length_buf += 1
+        # time-outs (Isaac Lab's termination manager in the real env)
+        torch.ge(self.episode_length_buf, self.max_episode_length, out=self.reset_time_outs)
         self.reset_buf = self.reset_time_outs
         mgr = self.constraint_manager
-        resetting = bool(due.any())
+        fuse = (resetting or uniform) and self.fuse_reset
         if mgr is not None:
             # when some env resets this step, its episode statistics are gathered by the same two launches
-            self.reward_buf, dones = mgr.compute_step(self._raw_reward, self.reset_buf, fuse_reset=resetting and self.fuse_reset)
+            self.reward_buf, self._dones = mgr.compute_step(self._raw_reward, self.reset_buf, fuse_reset=fuse, fused_out=fused_out)
         else:
             self.reward_buf = self._raw_reward
-            dones = self.reset_buf.float()
-        if resetting:
-            self._reset_masked(self.reset_buf)
-            self._phase_np[due] = 0
-        return self.obs_buf, self.reward_buf, dones, self.reset_time_outs, self.extras
+            self._dones = self.reset_buf.float()
+        if resetting or uniform:
+            if mgr is not None and resetting:
+                # (assigned, not .update()d: the fused statistics stay one packed device vector until somebody reads them)
+                self.extras["log"] = mgr.fused_reset_stats(fused_out) if fuse else mgr.reset_masked(self.reset_buf)
+            self.episode_length_buf.masked_fill_(self.reset_buf, 0)
 
     def _curriculum(self):
         mgr = self.constraint_manager

@@ -122,6 +122,10 @@ typedef struct {
   float min_p;         /* fl32(min_p)                                        :72 */
   float floor_max;     /* fl32(1e-6) clamp of the column max                 :55 */
   float span[CATB200_MAX_TERMS]; /* fl32(max_p - min_p) per term (double subtraction)  :72 */
+  /* If not NULL: device array of CATB200_MAX_TERMS floats that replaces span[] -- the curriculum changes max_p at run
+   * time (U/cat/curriculums.py:37-41); with the table in device memory a CUDA graph of the step keeps seeing the
+   * current values (the host refreshes it with an asynchronous copy), whereas by-value arguments are frozen in it. */
+  const float* span_dev;
 } catb200_cat_params_t;
 
 /* Validates a plan and fills the derived fields (shared-memory layout, division magics). */

@@ -37,7 +37,7 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(L.Source) == 32
     assert ctypes.sizeof(L.Term) == 56
     assert ctypes.sizeof(L.Plan) < 3072 + 64
-    assert ctypes.sizeof(L.CatParams) == 16 + 4 * L.MAX_TERMS
+    assert ctypes.sizeof(L.CatParams) == 16 + 4 * L.MAX_TERMS + 8
 
 
 def test_ctypes_layout_matches_header_compiled_as_c(tmp_path):

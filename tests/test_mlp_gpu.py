@@ -261,7 +261,6 @@ def test_minibatch_gradient_matches_oracle(B, M, prec, margin):
         assert r < T["logstd_mult"] * gtol, f"{name}: log-std gradient relative error {r:.3e}"
 
 
-@pytest.mark.parametrize("prec", PRECS)
 def test_tile256_kernels_match_the_default_tiles():
     """The opt-in 256-row-tile GEMM kernels (CATB200_TILE256=1, read once per process -> a subprocess) give the same
     gradient as the default 128 x 128 tiles on a ragged 16500-row minibatch."""
