@@ -915,7 +915,7 @@ int catb200_ppo_minibatch_grad(const catb200_mlp_dims_t* dims, const catb200_ppo
   Dims x = make_dims(dims);
   const size_t es = esize(dims);
   const int ch = ch_elems(dims), prec = dims->prec;
-  const int bk = ch;  // reduction rows per wgrad pipeline stage
+  const int bk = 64;  // reduction rows per TMA box of the weight-gradient kernel (tc_gemm.cu: kWgRows)
   cudaStream_t st = as_stream(stream);
   char* ws = static_cast<char*>(workspace);
   const char* wc = static_cast<const char*>(wcv);

@@ -512,23 +512,31 @@ mlp_gemm256_kernel(const __grid_constant__ TcGemmArgs g) {
 }
 
 // ---- weight gradient ---------------------------------------------------------------------------------------------
-constexpr int kWgStages = 3;
+// Weight-gradient pipeline: a stage holds kWgRows = 64 reduction rows of the 128 dZ features and the BN input features
+// (TMA boxes of one 128-byte feature chunk x 64 rows: 8 KiB per box in tf32 -- with 32-row boxes the 4 KiB requests, six
+// per stage, bounded the 45 -> 512 layer).  The launches have at most one CTA per SM (tiles x splits <= 148), so the bytes
+// in flight per SM are stages x stage size: the ring is as deep as 192 KiB of shared memory allow (three 32 KiB stages
+// streamed only 64 GB/s per SM).
+constexpr int kWgRows = 64;
 
-template <int BN>
+template <int PREC, int BN>
 struct WgSmem {
-  static constexpr int kStage = (128 + BN) * kRowBytes;  // (128 dZ + BN input features) x kBK rows x element size
+  static constexpr int kStage = (128 + BN) * kWgRows * (int)sizeof(typename PrecT<PREC>::T);
+  static constexpr int kStages = 196608 / kStage;        // 3 (tf32, BN 128), 4 (tf32, BN 64), 6 / 8 (bf16)
   static constexpr int kOnes = 2048;                     // 16 rows x 128 B of ones (K-major B operand of the bias MMA)
-  static constexpr int kTotal = kWgStages * kStage + kOnes + 256 /*barriers + tmem slot*/ + 1024 /*alignment slack*/;
+  static constexpr int kTotal = kStages * kStage + kOnes + 256 /*barriers + tmem slot*/ + 1024 /*alignment slack*/;
 };
 
 template <int PREC, int BN>
-__global__ void __launch_bounds__(kTcThreads, 2)
+__global__ void __launch_bounds__(kTcThreads, 1)
 mlp_wgrad_kernel(const __grid_constant__ TcWgradArgs g) {
   using P = PrecT<PREC>;
   using T = typename P::T;
-  using S = WgSmem<BN>;
+  using S = WgSmem<PREC, BN>;
+  constexpr int kWgStages = S::kStages;
   constexpr int CH = kRowBytes / (int)sizeof(T);   // features per 128-byte row: 64 / 32
-  constexpr int kBoxBytes = P::kBK * kRowBytes;    // one TMA box: CH features x kBK rows (8 / 4 KiB)
+  constexpr int kBoxBytes = kWgRows * kRowBytes;   // one TMA box: CH features x 64 rows (8 KiB)
+  constexpr int kABytes = (128 / CH) * kBoxBytes;  // the 128 dZ features of a stage
   constexpr int kTmemCols = BN == 128 ? 256 : 128; // BN accumulator columns + 16 for the bias MMA, power of two
   extern __shared__ uint8_t smem_raw[];
   pdl_launch_dependents();
@@ -548,7 +556,7 @@ mlp_wgrad_kernel(const __grid_constant__ TcWgradArgs g) {
   const bool with_bias = col_base == 0;                // one column tile per row tile also produces db
   const int k_begin = blockIdx.y * g.m_range;
   const int k_end = min(g.rows, k_begin + g.m_range);
-  const int k_blocks = max(0, (k_end - k_begin + P::kBK - 1) / P::kBK);
+  const int k_blocks = max(0, (k_end - k_begin + kWgRows - 1) / kWgRows);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(&g.mapA[z]));
@@ -579,10 +587,10 @@ mlp_wgrad_kernel(const __grid_constant__ TcWgradArgs g) {
       for (int kb = 0; kb < k_blocks; ++kb) {
         const int s = kb % kWgStages;
         mbar_wait(empty_bar + 8 * s, ((kb / kWgStages) & 1) ^ 1);
-        const uint32_t sa = tiles + s * S::kStage, sb = sa + kATileBytes;
+        const uint32_t sa = tiles + s * S::kStage, sb = sa + kABytes;
         mbar_expect_tx(full_bar + 8 * s, S::kStage);
-        const int k0 = k_begin + kb * P::kBK;
-        // MN-major operands: boxes of CH contiguous features x kBK reduction rows; rows beyond the matrix are zero-filled
+        const int k0 = k_begin + kb * kWgRows;
+        // MN-major operands: boxes of CH contiguous features x 64 reduction rows; rows beyond the matrix are zero-filled
         for (int h = 0; h < 128 / CH; ++h) tma_load_2d(sa + h * kBoxBytes, &g.mapA[z], full_bar + 8 * s, row_base + h * CH, k0);
         for (int h = 0; h < BN / CH; ++h) tma_load_2d(sb + h * kBoxBytes, &g.mapB[z], full_bar + 8 * s, col_base + h * CH, k0);
       }
@@ -596,10 +604,10 @@ mlp_wgrad_kernel(const __grid_constant__ TcWgradArgs g) {
       mbar_wait(full_bar + 8 * s, (kb / kWgStages) & 1);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t sa = tiles + s * S::kStage, sb = sa + kATileBytes;
+        const uint32_t sa = tiles + s * S::kStage, sb = sa + kABytes;
         const uint64_t d1 = make_smem_desc(ones, 16, 1024);  // K-major, 16 rows x 128 B, every element 1
 #pragma unroll
-        for (int k = 0; k < P::kBK / P::kUmmaK; ++k) {
+        for (int k = 0; k < kWgRows / P::kUmmaK; ++k) {
           // MN-major: CH-feature chunks LBO = one box apart; one K-step (kUmmaK reduction rows) = kUmmaK * 128 B
           // further.  bf16: SWIZZLE_128B, 8-row reduction groups SBO = 1 KiB apart.  tf32: the tensor core takes
           // MN-major 32-bit operands only in the 32-byte-granular swizzle (4-row groups, SBO = 512 B).
@@ -781,7 +789,7 @@ int tc_gemm_launch(int mode, int prec, const TcGemmArgs& g, cudaStream_t st) {
 
 template <int PREC, int BN>
 static int launch_wgrad(const TcWgradArgs& g, int splits, cudaStream_t st) {
-  using S = WgSmem<BN>;
+  using S = WgSmem<PREC, BN>;
   static bool attr = false;
   if (!attr) {
     CATB200_CUDA_TRY(cudaFuncSetAttribute(mlp_wgrad_kernel<PREC, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
