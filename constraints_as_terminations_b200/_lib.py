@@ -162,6 +162,29 @@ class CommandCfg(C.Structure):
     ]
 
 
+class ObsTerm(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p),
+        ("row_stride", C.c_int32),
+        ("n_cols", C.c_int32),
+        ("n_min", C.c_float),
+        ("n_max", C.c_float),
+        ("noise_span", C.c_float),
+        ("ids", C.c_uint8 * 32),
+        ("scale", C.c_float * 32),
+    ]
+
+
+class ObsPlan(C.Structure):
+    _fields_ = [
+        ("n_terms", C.c_int32),
+        ("n_cols", C.c_int32),
+        ("terms", ObsTerm * 8),
+        ("col_term", C.c_uint8 * 64),
+        ("col_idx", C.c_uint8 * 64),
+    ]
+
+
 class PpoHparams(C.Structure):
     _fields_ = [
         ("clip_coef", C.c_float),
@@ -275,6 +298,7 @@ SIGNATURES = {
     "catb200_bernoulli_mask": (C.c_int, [_P, _I32, _P, _P, _P, _P, _P]),
     "catb200_command_update": (C.c_int, [C.POINTER(CommandCfg), _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "catb200_push_select": (C.c_int, [_I32, _F, _P, _P, _P, _P, _P, _P, _P]),
+    "catb200_obs_assemble": (C.c_int, [C.POINTER(ObsPlan), _I32, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -138,6 +138,9 @@ def _build(env, term_specs) -> _BuiltPlan:
         ids = _ids_list(spec.ids, id_space)
         if any(i < 0 or i >= id_space for i in ids):
             raise ValueError(f"term '{name}': ids {ids} out of range for a source with {id_space} entries")
+        if any(i > 255 for i in ids):  # catb200_term_t.ids is uint8: ctypes would truncate silently
+            raise ValueError(f"term '{name}': element index {max(ids)} > 255 cannot be selected by a fused term (ids are 8-bit); "
+                             "slice the source tensor first or use a python term")
         chunks = [ids] if spec.single_column else [ids[k : k + L.MAX_IDS] for k in range(0, len(ids), L.MAX_IDS)]
         if spec.single_column and len(ids) > L.MAX_IDS:
             raise RuntimeError(f"term '{name}': more than {L.MAX_IDS} bodies in one reducing term")
@@ -581,6 +584,18 @@ class ConstraintManager(ManagerBase):
             raise ValueError("compute_step(fuse_reset=True) needs reset_buf")
         self._launch(raw_reward, reset_buf, fuse_reset=fuse_reset, fused_out=fused_out)
         return self._reward_buf, self._dones_buf
+
+    def sample_terminations(self, rng_state: torch.Tensor, probs: torch.Tensor | None = None, with_ids: bool = True):
+        """OPTIONAL stochastic termination mode (default off; the reference itself never samples: it hands the
+        probability to the trainer as a float `dones`, U/cat/cat_env.py:107, and GAE uses it as a soft discount).
+        Draws mask[i] ~ Bernoulli(p[i]) for the probabilities of the last `compute()` / `compute_step()` (or `probs`)
+        from the device Philox stream `rng_state` (ops.make_rng_state): mask[i] = (u_i < p[i]).  Returns
+        (mask bool [N], ids int64 [N] buffer, count int32 [1]) -- ids[:count] are the terminated env indices in ascending
+        order, bit-exact against oracle/philox_oracle.py -- or just the mask."""
+        from . import ops
+
+        p = self._dones_buf if probs is None and self._computed else (self._cstr_prob_buf if probs is None else probs)
+        return ops.bernoulli_mask(p, rng_state, with_ids=with_ids)
 
     def fused_reset_stats(self, packed=None) -> dict[str, torch.Tensor]:
         """Episode statistics gathered by the last `compute_step(..., fuse_reset=True)`: same keys / values as

@@ -163,6 +163,26 @@ push_select_kernel(int n, float p_push, const float* __restrict__ lo, const floa
   pushed[i] = push ? 1 : 0;
 }
 
+// ---- policy observation assembly (S12/cat_flat_env_cfg.py:137-172 through Isaac Lab's ObservationManager) ---------
+__global__ void __launch_bounds__(256)
+obs_assemble_kernel(const __grid_constant__ catb200_obs_plan_t plan, int n, float* __restrict__ out,
+                    const float* __restrict__ u_ext, const unsigned long long* __restrict__ rng_state) {
+  const long long total = (long long)n * plan.n_cols;
+  unsigned long long seed = 0, off = 0;
+  if (!u_ext && rng_state) { seed = rng_state[0]; off = rng_state[1]; }
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e / plan.n_cols), c = (int)(e - (long long)i * plan.n_cols);
+    const catb200_obs_term_t& t = plan.terms[plan.col_term[c]];
+    const int k = plan.col_idx[c];
+    float v = __ldg(t.src + (size_t)i * t.row_stride + t.ids[k]);
+    if (t.n_max > t.n_min) {  // data + rand * (n_max - n_min) + n_min, each operation rounded separately like the eager ops
+      const float u = u_ext ? u_ext[e] : philox_uniform(seed, kStreamUniform, off + (unsigned long long)e);
+      v = __fadd_rn(__fadd_rn(v, __fmul_rn(u, t.noise_span)), t.n_min);
+    }
+    out[e] = __fmul_rn(v, t.scale[k]);
+  }
+}
+
 }  // namespace catb200
 
 using namespace catb200;
@@ -242,6 +262,35 @@ int catb200_command_update(const catb200_command_cfg_t* cfg, int32_t num_envs, f
   CATB200_LAUNCH_CHECK();
   if (!u_ext) {
     rng_advance_kernel<<<1, 1, 0, st>>>((unsigned long long*)rng_state, 8ull * num_envs);
+    CATB200_LAUNCH_CHECK();
+  }
+  return CATB200_OK;
+}
+
+int catb200_obs_assemble(catb200_obs_plan_t* plan, int32_t num_envs, float* obs_out, const float* u_ext,
+                         uint64_t* rng_state, void* stream) {
+  if (!plan || num_envs <= 0 || !obs_out) return CATB200_ERR_INVALID_ARGUMENT;
+  if (plan->n_terms <= 0 || plan->n_terms > CATB200_OBS_MAX_TERMS) return CATB200_ERR_INVALID_ARGUMENT;
+  int col = 0;
+  bool noisy = false;
+  for (int t = 0; t < plan->n_terms; ++t) {
+    const catb200_obs_term_t& term = plan->terms[t];
+    if (!term.src || term.n_cols <= 0 || term.n_cols > 32 || col + term.n_cols > CATB200_OBS_MAX_COLS) return CATB200_ERR_INVALID_ARGUMENT;
+    noisy = noisy || term.n_max > term.n_min;
+    for (int k = 0; k < term.n_cols; ++k, ++col) {
+      plan->col_term[col] = (uint8_t)t;
+      plan->col_idx[col] = (uint8_t)k;
+    }
+  }
+  plan->n_cols = col;
+  if (noisy && !u_ext && !rng_state) return CATB200_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = as_stream(stream);
+  const long long total = (long long)num_envs * col;
+  obs_assemble_kernel<<<(int)min((total + 255) / 256, (long long)kNumSMs * 16), 256, 0, st>>>(*plan, num_envs, obs_out, u_ext,
+                                                                                             (const unsigned long long*)rng_state);
+  CATB200_LAUNCH_CHECK();
+  if (noisy && !u_ext) {
+    rng_advance_kernel<<<1, 1, 0, st>>>((unsigned long long*)rng_state, (unsigned long long)total);
     CATB200_LAUNCH_CHECK();
   }
   return CATB200_OK;

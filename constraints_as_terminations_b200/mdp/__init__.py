@@ -3,6 +3,7 @@ dead zone / Bernoulli resampling / yaw flip and the random push event, as fused 
 
 from .commands import UniformVelocityCommandWithDeadzone, UniformVelocityCommandWithDeadzoneCfg, update_velocity_command
 from .events import push_by_setting_velocity_with_random_envs, select_pushes
+from .observations import ObservationAssembler, ObsTermSpec, solo12_policy_terms
 
 __all__ = [
     "UniformVelocityCommandWithDeadzone",
@@ -10,4 +11,7 @@ __all__ = [
     "update_velocity_command",
     "push_by_setting_velocity_with_random_envs",
     "select_pushes",
+    "ObservationAssembler",
+    "ObsTermSpec",
+    "solo12_policy_terms",
 ]

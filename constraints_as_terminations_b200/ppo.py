@@ -631,8 +631,9 @@ def _make_writer(ppo_cfg, run_path):
 
 def PPO(envs, ppo_cfg, run_path):
     """Train; same signature, logging keys and checkpoint files as the reference (ppo.py:126-372)."""
-    writer = _make_writer(ppo_cfg, run_path)
-    if not os.path.exists(run_path):
+    # one writer / log directory per job: rank 0's (every rank of the reference's distributed front-ends logs for itself)
+    writer = _make_writer(ppo_cfg, run_path) if cdist.rank() == 0 else None
+    if cdist.rank() == 0 and not os.path.exists(run_path):
         os.makedirs(run_path)
     trainer = PPOTrainer(envs, ppo_cfg)
     device = trainer.device

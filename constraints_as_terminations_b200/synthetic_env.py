@@ -149,6 +149,7 @@ class SyntheticSolo12Env:
         constraints_cfg=None,
         curriculum: bool = True,
         adversarial: bool = False,
+        stochastic_terminations: bool = False,
     ):
         self.num_envs = int(num_envs)
         self.device = torch.device(device)
@@ -158,6 +159,10 @@ class SyntheticSolo12Env:
         self.cfg = SimpleNamespace(constraints=constraints_cfg)
         self.extras: dict = {}
         self._curriculum_on = curriculum
+        # optional mode: `dones` becomes a hard 0 / 1 mask sampled from the constraint probability (device Philox);
+        # default off = the reference's behaviour (float probability, soft discount in GAE)
+        self.stochastic_terminations = bool(stochastic_terminations)
+        self._term_rng = None
         self.fuse_reset = True  # gather the reset statistics inside the constraint step (False: separate reset launch)
 
         self.scene = _Scene(robot=_Articulation(), contact_forces=_ContactSensor())
@@ -278,6 +283,13 @@ class SyntheticSolo12Env:
         else:
             self.reward_buf = self._raw_reward
             self._dones = self.reset_buf.float()
+        if self.stochastic_terminations and mgr is not None:
+            if self._term_rng is None:
+                from . import ops
+
+                self._term_rng = ops.make_rng_state(0x7E57, self.device)
+            self.termination_mask = mgr.sample_terminations(self._term_rng, probs=self._dones, with_ids=False)
+            self._dones = self.termination_mask.float()
         if resetting or uniform:
             if mgr is not None and resetting:
                 # (assigned, not .update()d: the fused statistics stay one packed device vector until somebody reads them)

@@ -97,7 +97,7 @@ typedef struct {
   uint16_t col_offset; /* first column of this term in the [N,K] layout                     */
   uint16_t reserved2;  /* filled by finalize: entry k = index of the term with the k-th largest evaluation cost */
   float p0, p1, p2;
-  uint8_t ids[CATB200_MAX_IDS];
+  uint8_t ids[CATB200_MAX_IDS]; /* element / body indices into the source row: 8-bit, i.e. rows of at most 256 entries */
 } catb200_term_t;
 
 typedef struct {
@@ -447,6 +447,37 @@ int catb200_command_update(const catb200_command_cfg_t* cfg, int32_t num_envs, f
  */
 int catb200_push_select(int32_t num_envs, float p_push, const float* range_lo, const float* range_hi,
                         float* root_vel_w, const float* u_ext, uint64_t* rng_state, uint8_t* pushed, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Policy observation assembly  (S12/cat_flat_env_cfg.py:137-172)
+ *
+ * The 45-d policy observation of the Solo12 task is six ObservationTermCfg's of Isaac Lab's ObservationManager: a column
+ * selection of a state tensor, additive uniform noise (AdditiveUniformNoiseCfg: data + rand * (n_max - n_min) + n_min),
+ * then a per-term or per-column scale, concatenated.  One launch assembles all terms for all envs; the uniforms come from
+ * the device Philox stream (element (env, column) = counter offset + env * n_cols + column; consumes N * n_cols) or from
+ * u_ext [N, n_cols] (parity tests).
+ * ---------------------------------------------------------------------------------------------- */
+#define CATB200_OBS_MAX_TERMS 8
+#define CATB200_OBS_MAX_COLS 64
+typedef struct {
+  const float* src;      /* [N, ...] state tensor, row stride in elements below                  */
+  int32_t row_stride;
+  int32_t n_cols;        /* columns this term contributes                                        */
+  float n_min, n_max;    /* uniform noise bounds; n_min == n_max: no noise                       */
+  float noise_span;      /* fl32(n_max - n_min), the subtraction done in double like python does */
+  uint8_t ids[32];       /* source column of each output column                                  */
+  float scale[32];       /* per output column                                                    */
+} catb200_obs_term_t;
+
+typedef struct {
+  int32_t n_terms, n_cols;
+  catb200_obs_term_t terms[CATB200_OBS_MAX_TERMS];
+  uint8_t col_term[CATB200_OBS_MAX_COLS]; /* filled by the call: term of each output column      */
+  uint8_t col_idx[CATB200_OBS_MAX_COLS];  /* filled by the call: index of the column in its term  */
+} catb200_obs_plan_t;
+
+int catb200_obs_assemble(catb200_obs_plan_t* plan, int32_t num_envs, float* obs_out, const float* u_ext,
+                         uint64_t* rng_state, void* stream);
 
 #ifdef __cplusplus
 }

@@ -8,6 +8,9 @@ explicit so that any generator can drive it: `torch.bernoulli(p)` becomes `u < p
                    ranges and is_heading / is_standing as `uniform <= rel_*_envs`) -> parity there is UNPINNED, anchored on
                    the reference's call site commands.py:77-78.
   select_pushes  : push_by_setting_velocity_with_random_envs, U/mdp/events.py:59-96.
+  assemble_obs   : the policy observation group of S12/cat_flat_env_cfg.py:137-172 as Isaac Lab's ObservationManager
+                   computes it (third party: per term gather -> AdditiveUniformNoise `data + rand * (n_max - n_min) + n_min`
+                   -> scale -> concatenate; parity UNPINNED there, anchored on the cfg's constants).
 Only tests/ may import this module.
 """
 
@@ -64,3 +67,19 @@ def select_pushes(root_vel_w, u, *, physics_dt, max_episode_length_s, velocity_r
     sample = ranges[:, 0] + (ranges[:, 1] - ranges[:, 0]) * u[:, 1:7]  # sample_uniform :91-93
     vel[pushed] = sample[pushed]
     return pushed, vel
+
+
+def assemble_obs(sources, terms, u):
+    """sources: list of [N, D] tensors; terms: list of dicts {ids, noise (lo, hi) | None, scale}; u: [N, n_cols] uniforms."""
+    cols, c = [], 0
+    for src, t in zip(sources, terms):
+        ids = list(range(src.shape[1])) if t["ids"] is None else list(t["ids"])
+        data = src[:, ids]
+        if t["noise"] is not None:
+            lo, hi = t["noise"]
+            data = data + u[:, c : c + len(ids)] * (hi - lo) + lo  # AdditiveUniformNoiseCfg / uniform_noise
+        scale = t["scale"]
+        data = data * (torch.tensor(scale, dtype=torch.float32) if isinstance(scale, (tuple, list)) else scale)
+        cols.append(data)
+        c += len(ids)
+    return torch.cat(cols, dim=1)

@@ -53,6 +53,8 @@ def test_ctypes_layout_matches_header_compiled_as_c(tmp_path):
         "catb200_mlp_layout_t": L.MlpLayout,
         "catb200_ppo_hparams_t": L.PpoHparams,
         "catb200_command_cfg_t": L.CommandCfg,
+        "catb200_obs_term_t": L.ObsTerm,
+        "catb200_obs_plan_t": L.ObsPlan,
     }
     lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "catb200.h"', "int main(void) {"]
     for cname, cls in mirrors.items():

@@ -250,3 +250,38 @@ def test_fused_step_reset_equals_step_then_reset(num_envs):
             torch.testing.assert_close(out_a[k], out_b[k], rtol=1e-6, atol=1e-8, equal_nan=True)
     with pytest.raises(ValueError):
         mgrs[0].compute_step(raw_reward, None, fuse_reset=True)
+
+
+def test_optional_stochastic_termination_mask_is_the_documented_philox_draw():
+    """north_star's "sampling the stochastic termination mask ... bit-exact for the termination-mask indices": optional
+    mode (default off -- the reference keeps `dones` a probability).  mask[i] = (u_i < dones[i]) with u from Philox4x32-10;
+    probabilities are bit-exact against the oracle, so the index list is too."""
+    from constraints_as_terminations_b200 import ops
+    from oracle import philox_oracle
+
+    n, seed = 5000, 31337
+    cpu_env = se.SyntheticSolo12Env(n, device="cpu", seed=2, pool=1)
+    gpu_env = se.SyntheticSolo12Env(n, device=DEV, seed=2, pool=1)
+    oracle = cat_oracle.ManagerOracle(cpu_env, cat_oracle.terms_from_cfg(se.solo12_constraints_cfg(), resolve_scene=cpu_env.scene))
+    mgr = ConstraintManager(se.solo12_constraints_cfg(), gpu_env)
+    rng = ops.make_rng_state(seed, DEV)
+    reset = torch.zeros(n, dtype=torch.bool)
+    reset[::97] = True
+    offset = 0
+    for _ in range(3):
+        want_p = oracle.compute()
+        _, want_dones = cat_oracle.step_epilogue(cpu_env._raw_reward, want_p, reset)
+        mgr.compute_step(gpu_env._raw_reward, reset.to(DEV))
+        mask, ids, count = mgr.sample_terminations(rng)
+        want_mask = philox_oracle.bernoulli_mask(want_dones.numpy(), seed, offset)
+        offset += n
+        assert torch.equal(mask.cpu(), torch.from_numpy(want_mask))
+        assert torch.equal(ids[: int(count)].cpu(), torch.from_numpy(want_mask).nonzero().flatten())
+        assert mask.cpu()[reset].all()  # hard resets (dones == 1) always terminate
+    assert rng.cpu().tolist() == [seed, 3 * n]
+    # the env-level switch: hard 0 / 1 dones, every reset env included
+    env = se.SyntheticSolo12Env(512, device=DEV, seed=0, pool=2, episode_length=5, constraints_cfg=se.solo12_constraints_cfg(), stochastic_terminations=True)
+    env.load_managers()
+    for _ in range(6):
+        _, _, dones, time_outs, _ = env.step(torch.zeros(512, se.ACT_DIM, device=DEV))
+        assert set(dones.unique().tolist()) <= {0.0, 1.0} and bool(dones[time_outs].eq(1).all())

@@ -105,3 +105,30 @@ def test_push_event_term_writes_all_envs_without_an_index_list():
     v = written["v"]
     assert bool(((v[pushed][:, 0] >= 1.0) & (v[pushed][:, 0] <= 2.0)).all()) and float(v[pushed][:, 1:].abs().max()) == 0.0
     assert torch.equal(v[~pushed], asset.data.root_vel_w[~pushed])
+
+
+def test_observation_assembly_matches_the_oracle():
+    """The 45-d Solo12 policy observation (cat_flat_env_cfg.py:137-172) in one launch: bit-exact against the CPU
+    restatement with shared uniforms, and with the uniforms the Philox restatement yields for the device draws."""
+    from constraints_as_terminations_b200 import synthetic_env as se
+
+    n = 3000
+    g = torch.Generator().manual_seed(1)
+    ang, cmd, grav = torch.randn(n, 3, generator=g), torch.randn(n, 3, generator=g), torch.randn(n, 3, generator=g)
+    jp, jv, act = torch.randn(n, 12, generator=g), 8 * torch.randn(n, 12, generator=g), torch.randn(n, 12, generator=g)
+    joint_ids = [0, 1, 2, 3, 4, 5, 9, 10, 11, 6, 7, 8]  # FL, FR, HR, HL in an (FL, FR, HL, HR) articulation
+    robot = types.SimpleNamespace(data=types.SimpleNamespace(root_ang_vel_b=ang.to(DEV), projected_gravity_b=grav.to(DEV), joint_pos=jp.to(DEV), joint_vel=jv.to(DEV)))
+    env = types.SimpleNamespace(scene={"robot": robot}, command_manager=types.SimpleNamespace(get_command=lambda name: cmd.to(DEV)),
+                                action_manager=types.SimpleNamespace(_action=act.to(DEV)))  # fmt: skip
+    terms = mdp.solo12_policy_terms(joint_ids)
+    asm = mdp.ObservationAssembler(terms, DEV, seed=77)
+    spec = [{"ids": t.ids, "noise": t.noise, "scale": t.scale} for t in terms]
+    sources = [ang, cmd, grav, jp, jv, act]
+    u = torch.rand(n, se.OBS_DIM, generator=g)
+    got = asm.assemble(env, uniforms=u.to(DEV))
+    assert got.shape == (n, se.OBS_DIM)
+    assert torch.equal(got.cpu(), mdp_oracle.assemble_obs(sources, spec, u))
+    got = asm.assemble(env)  # device Philox, offset 0
+    u = torch.from_numpy(philox_oracle.uniform(77, philox_oracle.STREAM_UNIFORM, 0, n * se.OBS_DIM).reshape(n, se.OBS_DIM).copy())
+    assert torch.equal(got.cpu(), mdp_oracle.assemble_obs(sources, spec, u))
+    assert asm.rng_state.cpu().tolist() == [77, n * se.OBS_DIM]
