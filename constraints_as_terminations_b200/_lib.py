@@ -285,6 +285,11 @@ SIGNATURES = {
         C.c_int,
         [C.POINTER(MlpDims), _P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _P, _P, _P],
     ),
+    "catb200_ppo_minibatch_update": (
+        C.c_int,
+        [C.POINTER(MlpDims), C.POINTER(PpoHparams), _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ,
+         _P, _P, _P, _P, _F, _F, _F, _F, _F, _P, _P, _P],
+    ),
     "catb200_adam_apply": (C.c_int, [C.POINTER(MlpDims), _P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _P, _P]),
     "catb200_peer_arena_bytes": (_SZ, [_I64]),
     "catb200_peer_alloc": (C.c_int, [_SZ, C.POINTER(_P), _P]),

@@ -78,63 +78,64 @@ struct FoldArgs {
   float ent_coef, vf_coef;
 };
 
-__global__ void __launch_bounds__(256) fold_grads_kernel(const __grid_constant__ FoldArgs r) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int seg = blockIdx.y;
-  if (seg < r.n_segments) {
-    // four padded columns per thread (one 16-byte load of the accumulator); the gradient values are fetched before the
-    // accumulator is zeroed so that both loads are in flight together (the pointers may alias as far as the compiler knows)
-    const int N = r.N[seg], Kpad = r.Kpad[seg], Kt = r.Ktrue[seg];
-    float4* __restrict__ acc4 = reinterpret_cast<float4*>(r.acc[seg]);
-    float* __restrict__ grad = r.grad[seg];
-    const int quads = N * Kpad / 4, qpr = Kpad / 4;
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += gridDim.x * blockDim.x) {
-      const int n = q / qpr, k = (q - n * qpr) * 4;
-      const float4 v = acc4[q];
-      float* gp = grad + (size_t)n * Kt + k;
-      const float vv[4] = {v.x, v.y, v.z, v.w};
-      float g[4];
+// One 16-byte quad of a padded accumulator: added into the flat gradient, accumulator zeroed; returns the sum of squares of
+// the (up to four) final gradient values.  The gradient values are fetched before the accumulator is zeroed so that both
+// loads are in flight together (the pointers may alias as far as the compiler knows).
+__device__ __forceinline__ float fold_weight_quad(const FoldArgs& r, int seg, int q) {
+  const int Kpad = r.Kpad[seg], Kt = r.Ktrue[seg];
+  float4* __restrict__ acc4 = reinterpret_cast<float4*>(r.acc[seg]);
+  const int qpr = Kpad / 4;
+  const int n = q / qpr, k = (q - n * qpr) * 4;
+  const float4 v = acc4[q];
+  float* gp = r.grad[seg] + (size_t)n * Kt + k;
+  const float vv[4] = {v.x, v.y, v.z, v.w};
+  float g[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) g[i] = k + i < Kt ? gp[i] : 0.0f;
-      acc4[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  for (int i = 0; i < 4; ++i) g[i] = k + i < Kt ? gp[i] : 0.0f;
+  acc4[q] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  float ss = 0.0f;
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (k + i < Kt) gp[i] = g[i] + vv[i];  // the padded input columns of layer 0 are dropped
+  for (int i = 0; i < 4; ++i)
+    if (k + i < Kt) {  // the padded input columns of layer 0 are dropped
+      const float t = g[i] + vv[i];
+      gp[i] = t;
+      ss = fmaf(t, t, ss);
     }
-    return;
-  }
-  // ---- head segment: sum the per-CTA rows, route every value to its gradient slot / loss accumulator.
-  // One CTA per 32 consecutive values: its 8 warps split the rows (a single thread walking all ~148 rows is a chain of
-  // dependent-latency loads: 20 us per launch) and combine through shared memory.
-  __shared__ float part_s[8][32];
+  return ss;
+}
+
+// Head segment, one CTA (256 threads) per 32 consecutive values of the head kernel's per-CTA rows: the 8 warps split the
+// rows (a single thread walking all ~148 rows is a chain of dependent-latency loads: 20 us per launch), combine through
+// shared memory, and warp 0 routes every value to its gradient slot / loss accumulator.  Returns (in warp 0) the square of
+// the final gradient value this thread wrote, 0 elsewhere.
+__device__ __forceinline__ float fold_head_group(const FoldArgs& r, int group, float (*part_s)[32]) {
   const int warp = threadIdx.x >> 5, ln = threadIdx.x & 31;
-  const int e = blockIdx.x * 32 + ln;
-  if (blockIdx.x * 32 >= kHeadValues * 32) return;
+  const int e = group * 32 + ln;
   float acc = 0.0f;
   for (int c = warp; c < r.head_rows; c += 8) acc += r.head_part[(size_t)c * kHeadValues * 32 + e];
   part_s[warp][ln] = acc;
   __syncthreads();
-  if (warp != 0) return;
+  if (warp != 0) return 0.0f;
   float t = 0.0f;
 #pragma unroll
   for (int w = 0; w < 8; ++w) t += part_s[w][ln];
   const int v = e >> 5, lane = e & 31;
   const float inv_M = 1.0f / (float)r.M;
+  float fin = 0.0f;
   if (v < kHvW4c) {
     const int j = v >> 2, f = v & 3;
-    if (j < r.A) r.gW4a[j * r.h3 + lane * 4 + f] += t;
+    if (j < r.A) { float* p = r.gW4a + j * r.h3 + lane * 4 + f; fin = *p + t; *p = fin; }
   } else if (v < kHvB4a) {
-    r.gW4c[lane * 4 + (v - kHvW4c)] += t;
+    float* p = r.gW4c + lane * 4 + (v - kHvW4c); fin = *p + t; *p = fin;
   } else if (v == kHvB4a) {  // per-action-dim scalars live in the even lane of pair (2j, 2j+1)
-    if ((lane & 1) == 0 && (lane >> 1) < r.A) r.gb4a[lane >> 1] += t;
+    if ((lane & 1) == 0 && (lane >> 1) < r.A) { float* p = r.gb4a + (lane >> 1); fin = *p + t; *p = fin; }
   } else if (v == kHvLogstd) {
     // policy part + d(-ent_coef * mean entropy)/d logstd_j = -ent_coef (entropy is sample independent)
-    if ((lane & 1) == 0 && (lane >> 1) < r.A) r.glogstd[lane >> 1] += t - r.ent_coef;
+    if ((lane & 1) == 0 && (lane >> 1) < r.A) { float* p = r.glogstd + (lane >> 1); fin = *p + (t - r.ent_coef); *p = fin; }
   } else if (lane == 0) {
     const int k = v - kHvScalars;  // g_b4c, pg, v, kl, clip, old_kl
     if (k == 0) {
-      r.gb4c[0] += t;
+      fin = r.gb4c[0] + t; r.gb4c[0] = fin;
     } else if (k == 1) {
       r.loss_acc[0] += t * inv_M;
       // entropy = sum_j (0.5 + 0.5 log(2 pi) + logstd_j); also the per-minibatch counter and total loss
@@ -154,6 +155,20 @@ __global__ void __launch_bounds__(256) fold_grads_kernel(const __grid_constant__
       r.loss_acc[5] += t * inv_M;
     }
   }
+  return fin * fin;
+}
+
+__global__ void __launch_bounds__(256) fold_grads_kernel(const __grid_constant__ FoldArgs r) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int seg = blockIdx.y;
+  if (seg < r.n_segments) {
+    const int quads = r.N[seg] * r.Kpad[seg] / 4;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += gridDim.x * blockDim.x) fold_weight_quad(r, seg, q);
+    return;
+  }
+  __shared__ float part_s[8][32];
+  if ((int)blockIdx.x < kHeadValues) fold_head_group(r, blockIdx.x, part_s);
 }
 
 // ---- minibatch gather + advantage statistics -----------------------------------------------------------
@@ -574,33 +589,17 @@ struct AdamCastArgs {
   AdamState a;
 };
 
+// one 32 x 32 tile of hidden matrix `seg`: Adam on every element, W [rows, cols_pad] and W^T [cols, rows] in operand
+// precision on the way (tx = lane, ty = warp of a 256-thread CTA; `tile` is the CTA's transpose buffer)
 template <int PREC>
-__global__ void __launch_bounds__(256) adam_cast_kernel(const __grid_constant__ AdamCastArgs c) {
+__device__ __forceinline__ void adam_cast_tile(const AdamCastArgs& c, int seg, int t, int tx, int ty, float clip, float step_size,
+                                               float bc2_sqrt, float (*tile)[33]) {
   using T = typename PrecT<PREC>::T;
-  pdl_launch_dependents();
-  pdl_wait();
   const AdamState& a = c.a;
-  const float clip = a.sc->clip_coef * a.grad_scale;
-  const float step_size = __ldg(a.lr) * a.sc->step_size_scale;
-  const float bc2_sqrt = a.sc->bc2_sqrt;
-  if (blockIdx.y == 6) {
-    int e = blockIdx.x * 256 + threadIdx.y * 32 + threadIdx.x;
-    for (int r = 0; r < c.n_rest_ranges; ++r) {
-      if (e < c.rest_len[r]) {
-        const long long i = c.rest_begin[r] + e;
-        adam_one(a.params[i], a.grads[i], a.m[i], a.v[i], clip, step_size, bc2_sqrt, a.beta1, a.beta2, a.eps);
-        return;
-      }
-      e -= c.rest_len[r];
-    }
-    return;
-  }
-  const CastSeg& s = c.seg[blockIdx.y];
-  const long long base = c.seg_off[blockIdx.y];
-  const int tiles_c = (s.cols_pad + 31) / 32, tiles_r = s.rows / 32;
-  if ((int)blockIdx.x >= tiles_c * tiles_r) return;
-  const int tr = blockIdx.x / tiles_c, tc = blockIdx.x % tiles_c;
-  __shared__ float tile[32][33];
+  const CastSeg& s = c.seg[seg];
+  const long long base = c.seg_off[seg];
+  const int tiles_c = (s.cols_pad + 31) / 32;
+  const int tr = t / tiles_c, tc = t % tiles_c;
   T* dst = static_cast<T*>(s.dst);
   T* dst_t = static_cast<T*>(s.dst_t);
   auto conv = [](float v) -> T {
@@ -609,7 +608,7 @@ __global__ void __launch_bounds__(256) adam_cast_kernel(const __grid_constant__ 
   };
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int r = tr * 32 + threadIdx.y + i * 8, k = tc * 32 + threadIdx.x;
+    const int r = tr * 32 + ty + i * 8, k = tc * 32 + tx;
     float v = 0.0f;
     if (k < s.cols) {
       const long long e = base + (long long)r * s.cols + k;
@@ -618,15 +617,158 @@ __global__ void __launch_bounds__(256) adam_cast_kernel(const __grid_constant__ 
       adam_one(v, g, m, vv, clip, step_size, bc2_sqrt, a.beta1, a.beta2, a.eps);
       a.params[e] = v; a.grads[e] = g; a.m[e] = m; a.v[e] = vv;
     }
-    tile[threadIdx.y + i * 8][threadIdx.x] = v;
+    tile[ty + i * 8][tx] = v;
     if (k < s.cols_pad) dst[(size_t)r * s.cols_pad + k] = conv(v);
   }
   if (dst_t == nullptr) return;
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int k = tc * 32 + threadIdx.y + i * 8, r = tr * 32 + threadIdx.x;
-    if (k < s.cols) dst_t[(size_t)k * s.rows + r] = conv(tile[threadIdx.x][threadIdx.y + i * 8]);
+    const int k = tc * 32 + ty + i * 8, r = tr * 32 + tx;
+    if (k < s.cols) dst_t[(size_t)k * s.rows + r] = conv(tile[tx][ty + i * 8]);
+  }
+}
+
+// element e of "everything else" (biases, heads, log-std)
+__device__ __forceinline__ void adam_rest(const AdamCastArgs& c, int e, float clip, float step_size, float bc2_sqrt) {
+  const AdamState& a = c.a;
+  for (int r = 0; r < c.n_rest_ranges; ++r) {
+    if (e < c.rest_len[r]) {
+      const long long i = c.rest_begin[r] + e;
+      adam_one(a.params[i], a.grads[i], a.m[i], a.v[i], clip, step_size, bc2_sqrt, a.beta1, a.beta2, a.eps);
+      return;
+    }
+    e -= c.rest_len[r];
+  }
+}
+
+template <int PREC>
+__global__ void __launch_bounds__(256) adam_cast_kernel(const __grid_constant__ AdamCastArgs c) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const AdamState& a = c.a;
+  const float clip = a.sc->clip_coef * a.grad_scale;
+  const float step_size = __ldg(a.lr) * a.sc->step_size_scale;
+  const float bc2_sqrt = a.sc->bc2_sqrt;
+  if (blockIdx.y == 6) {
+    adam_rest(c, blockIdx.x * 256 + threadIdx.y * 32 + threadIdx.x, clip, step_size, bc2_sqrt);
+    return;
+  }
+  const CastSeg& s = c.seg[blockIdx.y];
+  if ((int)blockIdx.x >= ((s.cols_pad + 31) / 32) * (s.rows / 32)) return;
+  __shared__ float tile[32][33];
+  adam_cast_tile<PREC>(c, blockIdx.y, blockIdx.x, threadIdx.x, threadIdx.y, clip, step_size, bc2_sqrt, tile);
+}
+
+// ---- the whole optimizer step of one minibatch as ONE launch (single GPU) --------------------------------------------
+// fold (padded accumulators + head rows -> flat gradient) | squared norm of the flat gradient  -- grid barrier --
+// clip coefficient, bias corrections | Adam on every element + operand copies.  Replaces fold_grads_kernel +
+// grad_norm_kernel + adam_cast_kernel (11 + 6 + 6 us of three latency-bound launches over 1.5 MB).  One CTA per SM, all
+// co-resident (grid <= kNumSMs, 256 threads, < 6 KiB of shared memory): the barrier is an arrival counter in the
+// optimizer scratch that only ever grows (arrival ticket / grid = generation), the sum of squares is reset by the last CTA
+// that has read it (ticket), so the scratch is clean for the next launch and for catb200_adam_step.
+struct OptStepArgs {
+  FoldArgs f;
+  AdamCastArgs c;
+  int quad_prefix[7];          // fold segments: prefix sums of their 16-byte quads
+  int tile_prefix[7];          // hidden matrices: prefix sums of their 32 x 32 tiles
+  long long bias_begin[6];     // hidden-layer bias gradients (written by mlp_wgrad_kernel directly): flat offsets
+  int bias_len[6];
+  int n_rest;
+  float max_norm;
+  int* step;
+  float* grad_norm_out;
+  OptScratch* sc;
+};
+
+template <int PREC>
+__global__ void __launch_bounds__(256) opt_step_kernel(const __grid_constant__ OptStepArgs r) {
+  __shared__ float part_s[8][32];
+  __shared__ float tile[32][33];
+  __shared__ double red_s[8];
+  __shared__ float coef_s[3];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gtid = blockIdx.x * 256 + tid, gthreads = gridDim.x * 256;
+  const float gscale = r.c.a.grad_scale;
+  OptScratch* sc = r.sc;
+  const int step0 = *r.step;  // CTA 0 advances it only after the barrier below
+
+  // ---- phase A: fold + sum of squares of every element of the flat gradient
+  double ss = 0.0;
+  const int total_quads = r.quad_prefix[r.f.n_segments];
+  for (int q = gtid; q < total_quads; q += gthreads) {
+    int seg = 0;
+    while (q >= r.quad_prefix[seg + 1]) ++seg;
+    ss += (double)fold_weight_quad(r.f, seg, q - r.quad_prefix[seg]);
+  }
+  if ((int)blockIdx.x < kHeadValues) ss += (double)fold_head_group(r.f, blockIdx.x, part_s);
+  {  // hidden-layer biases, dealt from the far end of the grid (the first 76 CTAs carry the head rows)
+    int e = (gridDim.x - 1 - blockIdx.x) * 256 + tid;
+    for (int b = 0; b < 6; ++b) {
+      if (e < r.bias_len[b]) {
+        const float g = r.c.a.grads[r.bias_begin[b] + e];
+        ss += (double)g * (double)g;
+        break;
+      }
+      e -= r.bias_len[b];
+    }
+  }
+  ss *= (double)gscale * (double)gscale;
+  ss = warp_sum(ss);
+  if (lane == 0) red_s[warp] = ss;
+  __syncthreads();
+  // ---- grid barrier (release: every thread's writes of this CTA are ordered before thread 0's fence + arrival)
+  if (tid == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red_s[w];
+    atomicAdd(&sc->sumsq, t);
+    __threadfence();
+    unsigned int* bar = reinterpret_cast<unsigned int*>(&sc->pad[0]);
+    const unsigned int ticket = atomicAdd(bar, 1u);
+    const unsigned int target = (ticket / gridDim.x + 1u) * gridDim.x;
+    const long long t0 = clock64();
+    while ((int)(*reinterpret_cast<volatile unsigned int*>(bar) - target) < 0) {
+      if (clock64() - t0 > 4000000000ll) __trap();  // a CTA that never arrived (not co-resident): fail, do not hang
+    }
+    __threadfence();
+    const double tot = *reinterpret_cast<volatile double*>(&sc->sumsq);
+    const float norm = (float)sqrt(tot);
+    // torch.nn.utils.clip_grad_norm_: clip_coef = max_norm / (total_norm + 1e-6), clamped to 1
+    const float clip_coef = fminf(r.max_norm / (norm + 1e-6f), 1.0f);
+    const int t1 = step0 + 1;
+    const double bc1 = 1.0 - pow((double)r.c.a.beta1, (double)t1), bc2 = 1.0 - pow((double)r.c.a.beta2, (double)t1);
+    coef_s[0] = clip_coef * gscale;
+    coef_s[1] = __ldg(r.c.a.lr) * (float)(1.0 / bc1);
+    coef_s[2] = (float)sqrt(bc2);
+    if (blockIdx.x == 0) {
+      sc->clip_coef = clip_coef;
+      sc->total_norm = norm;
+      sc->step_size_scale = (float)(1.0 / bc1);
+      sc->bc2_sqrt = (float)sqrt(bc2);
+      *r.step = t1;
+      if (r.grad_norm_out) *r.grad_norm_out = norm;
+    }
+    // the last CTA to have read the sum resets it
+    __threadfence();
+    if (atomicAdd(&sc->ticket, 1u) == gridDim.x - 1) {
+      sc->ticket = 0u;
+      sc->sumsq = 0.0;
+    }
+  }
+  __syncthreads();
+  const float clip = coef_s[0], step_size = coef_s[1], bc2_sqrt = coef_s[2];
+
+  // ---- phase C: Adam + operand copies
+  const int n_tiles = r.tile_prefix[6], n_items = n_tiles + (r.n_rest + 255) / 256;
+  for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+    if (w < n_tiles) {
+      int seg = 0;
+      while (w >= r.tile_prefix[seg + 1]) ++seg;
+      __syncthreads();  // the previous tile's transpose reads are done
+      adam_cast_tile<PREC>(r.c, seg, w - r.tile_prefix[seg], lane, warp, clip, step_size, bc2_sqrt, tile);
+    } else {
+      adam_rest(r.c, (w - n_tiles) * 256 + tid, clip, step_size, bc2_sqrt);
+    }
   }
 }
 
@@ -772,13 +914,15 @@ int launch_cast_weights(const catb200_mlp_dims_t* dims, const float* params, voi
   return CATB200_OK;
 }
 
-int launch_adam_cast(const catb200_mlp_dims_t* dims, const AdamState& a, void* wcv, cudaStream_t st) {
+// segments / ranges of the flat vector for the Adam kernels; returns the grid width adam_cast_kernel needs
+static int fill_adam_cast_args(const catb200_mlp_dims_t* dims, const AdamState& a, void* wcv, AdamCastArgs* out) {
   catb200_mlp_layout_t P;
   fill_layout(dims, &P);
   Dims x = make_dims(dims);
   const size_t es = esize(dims);
   char* wc = static_cast<char*>(wcv);
-  AdamCastArgs c = {};
+  AdamCastArgs& c = *out;
+  c = AdamCastArgs{};
   int max_tiles = 1;
   for (int z = 0; z < 2; ++z)
     for (int l = 0; l < 3; ++l) {
@@ -809,7 +953,12 @@ int launch_adam_cast(const catb200_mlp_dims_t* dims, const AdamState& a, void* w
     n_rest += c.rest_len[c.n_rest_ranges++];
   }
   c.a = a;
-  max_tiles = max(max_tiles, (n_rest + 255) / 256);
+  return max(max_tiles, (n_rest + 255) / 256);
+}
+
+int launch_adam_cast(const catb200_mlp_dims_t* dims, const AdamState& a, void* wcv, cudaStream_t st) {
+  AdamCastArgs c;
+  const int max_tiles = fill_adam_cast_args(dims, a, wcv, &c);
   if (dims->prec == kPrecTf32) CATB200_CUDA_TRY(launch_pdl(adam_cast_kernel<kPrecTf32>, dim3(max_tiles, 7), dim3(32, 8), 0, st, c));
   else CATB200_CUDA_TRY(launch_pdl(adam_cast_kernel<kPrecBf16>, dim3(max_tiles, 7), dim3(32, 8), 0, st, c));
   CATB200_LAUNCH_CHECK();
@@ -898,11 +1047,16 @@ int catb200_mlp_act(const catb200_mlp_dims_t* dims, const void* obs_op, int32_t 
   return CATB200_OK;
 }
 
-int catb200_ppo_minibatch_grad(const catb200_mlp_dims_t* dims, const catb200_ppo_hparams_t* hp, int32_t mb_rows,
-                               const int64_t* mb_inds, const void* obs_op_all, const float* actions_all,
-                               const float* logprobs_all, const float* advantages_all, const float* returns_all,
-                               const float* values_all, const float* norm_stats, const float* params, const void* wcv,
-                               float* grads, float* loss_acc, void* workspace, size_t workspace_bytes, void* stream) {
+}  // extern "C"
+
+// forward + backward of one minibatch; the fold of the padded accumulators / head rows into `grads` is launched here, or
+// -- defer_fold != NULL -- described there for the caller's fused optimizer-step kernel
+static int minibatch_backward(const catb200_mlp_dims_t* dims, const catb200_ppo_hparams_t* hp, int32_t mb_rows,
+                              const int64_t* mb_inds, const void* obs_op_all, const float* actions_all,
+                              const float* logprobs_all, const float* advantages_all, const float* returns_all,
+                              const float* values_all, const float* norm_stats, const float* params, const void* wcv,
+                              float* grads, float* loss_acc, void* workspace, size_t workspace_bytes, void* stream,
+                              FoldArgs* defer_fold) {
   if (!dims_ok(dims)) return CATB200_ERR_UNSUPPORTED;
   if (!hp || mb_rows <= 0 || !mb_inds || !obs_op_all || !actions_all || !logprobs_all || !advantages_all || !returns_all ||
       !values_all || !norm_stats || !params || !wcv || !grads || !loss_acc || !workspace)
@@ -1007,8 +1161,60 @@ int catb200_ppo_minibatch_grad(const catb200_mlp_dims_t* dims, const catb200_ppo
   fold.logstd = params + P.logstd; fold.loss_acc = loss_acc;
   fold.A = dims->act_dim; fold.h3 = dims->h3; fold.M = M;
   fold.ent_coef = hp->ent_coef; fold.vf_coef = hp->vf_coef;
+  if (defer_fold) {
+    *defer_fold = fold;
+    return CATB200_OK;
+  }
   // x: 76 CTAs cover the head segment (one per 32 values); the weight segments walk their quads with a grid stride
   CATB200_CUDA_TRY(launch_pdl(fold_grads_kernel, dim3(kHeadValues, fold.n_segments + 1), dim3(256), 0, st, fold));
+  CATB200_LAUNCH_CHECK();
+  return CATB200_OK;
+}
+
+extern "C" {
+
+int catb200_ppo_minibatch_grad(const catb200_mlp_dims_t* dims, const catb200_ppo_hparams_t* hp, int32_t mb_rows,
+                               const int64_t* mb_inds, const void* obs_op_all, const float* actions_all,
+                               const float* logprobs_all, const float* advantages_all, const float* returns_all,
+                               const float* values_all, const float* norm_stats, const float* params, const void* wcv,
+                               float* grads, float* loss_acc, void* workspace, size_t workspace_bytes, void* stream) {
+  return minibatch_backward(dims, hp, mb_rows, mb_inds, obs_op_all, actions_all, logprobs_all, advantages_all, returns_all,
+                            values_all, norm_stats, params, wcv, grads, loss_acc, workspace, workspace_bytes, stream, nullptr);
+}
+
+int catb200_ppo_minibatch_update(const catb200_mlp_dims_t* dims, const catb200_ppo_hparams_t* hp, int32_t mb_rows,
+                                 const int64_t* mb_inds, const void* obs_op_all, const float* actions_all,
+                                 const float* logprobs_all, const float* advantages_all, const float* returns_all,
+                                 const float* values_all, const float* norm_stats, float* params, void* wcv, float* grads,
+                                 float* loss_acc, void* workspace, size_t workspace_bytes, float* exp_avg, float* exp_avg_sq,
+                                 const float* lr_dev, int32_t* step_dev, float max_grad_norm, float beta1, float beta2,
+                                 float eps, float grad_scale, float* grad_norm_out, void* opt_ws, void* stream) {
+  if (!exp_avg || !exp_avg_sq || !lr_dev || !step_dev || !opt_ws) return CATB200_ERR_INVALID_ARGUMENT;
+  OptStepArgs o = {};
+  int rc = minibatch_backward(dims, hp, mb_rows, mb_inds, obs_op_all, actions_all, logprobs_all, advantages_all, returns_all,
+                              values_all, norm_stats, params, wcv, grads, loss_acc, workspace, workspace_bytes, stream, &o.f);
+  if (rc != CATB200_OK) return rc;
+  catb200_mlp_layout_t P;
+  fill_layout(dims, &P);
+  Dims x = make_dims(dims);
+  AdamState a = {params, grads, exp_avg, exp_avg_sq, lr_dev, static_cast<OptScratch*>(opt_ws), beta1, beta2, eps, grad_scale};
+  fill_adam_cast_args(dims, a, wcv, &o.c);
+  for (int s = 0; s < o.f.n_segments; ++s) o.quad_prefix[s + 1] = o.quad_prefix[s] + o.f.N[s] * o.f.Kpad[s] / 4;
+  for (int s = 0; s < 6; ++s) o.tile_prefix[s + 1] = o.tile_prefix[s] + (o.c.seg[s].rows / 32) * ((o.c.seg[s].cols_pad + 31) / 32);
+  for (int z = 0; z < 2; ++z)
+    for (int l = 0; l < 3; ++l) {
+      o.bias_begin[z * 3 + l] = P.b[z][l];
+      o.bias_len[z * 3 + l] = x.out[l];
+    }
+  for (int i = 0; i < o.c.n_rest_ranges; ++i) o.n_rest += o.c.rest_len[i];
+  o.max_norm = max_grad_norm;
+  o.step = step_dev;
+  o.grad_norm_out = grad_norm_out;
+  o.sc = static_cast<OptScratch*>(opt_ws);
+  cudaStream_t st = as_stream(stream);
+  // a plain (fully stream-ordered) launch of one CTA per SM: all CTAs are co-resident, which the grid barrier needs
+  if (dims->prec == kPrecTf32) opt_step_kernel<kPrecTf32><<<kNumSMs, 256, 0, st>>>(o);
+  else opt_step_kernel<kPrecBf16><<<kNumSMs, 256, 0, st>>>(o);
   CATB200_LAUNCH_CHECK();
   return CATB200_OK;
 }

@@ -511,6 +511,286 @@ mlp_gemm256_kernel(const __grid_constant__ TcGemmArgs g) {
   }
 }
 
+// ---- CTA pairs: 256 x 256 tiles on two SMs (cta_group::2) -----------------------------------------------------------
+// The 128 x 128 kernel is bound by L2 -> SM operand traffic (fp32 operands: 32 KiB per 128 x 128 x 32 MACs, ~13 TB/s
+// chip-wide at 16384 rows).  A CTA pair (a 2-CTA cluster = the two SMs of a TPC) computes one 256 x 256 tile with
+// tcgen05.mma.cta_group::2: each CTA stages ITS 128 rows of A and ITS 128 of the 256 B rows -- the same 32 KiB per
+// k-block and CTA as before, for twice the MACs: half the operand bytes per flop, and unlike the single-CTA 256-row
+// variant above each CTA's accumulator is 256 columns, so two TMEM stages fit and the epilogue keeps overlapping the
+// next tile's MMAs.
+//   both CTAs : warp 0 = TMA producer for its own A rows / B half (the loads complete on the LEADER's full barrier,
+//               which expects both CTAs' bytes); warps 2-9 = epilogue of its own 128 rows (slabs / dgrad H path as in
+//               mlp_gemm_kernel); arrivals on the leader's tmem_empty barrier come from both CTAs' epilogue warps
+//   leader    : warp 1 issues the pair's MMAs; tcgen05.commit multicasts "ring slot free" and "accumulator complete" to
+//               the barriers of both CTAs
+// Epilogue: ncu / timing of the first version (8 epilogue warps) showed these kernels bound by the EPILOGUE, not by
+// operands -- a dgrad tile cost ~9 us per CTA however few bytes the main loop moved, because every 32 x 32 slab waited a
+// full L2 round trip for its H values and only 8 warps were there to overlap anything.  tf32 therefore runs 16 epilogue
+// warps (4 per TMEM lane quarter, 64 columns = two slabs each) and requests the H slabs of the NEXT tile while the
+// current one is still being computed; bf16 (half the bytes per element, 64-column slabs) keeps 8.
+template <int PREC>
+struct P2cCfg {
+  static constexpr int kEpi = PREC == kPrecTf32 ? 16 : 8;      // epilogue warps
+  static constexpr int kThreads = 64 + 32 * kEpi;
+  static constexpr int kStages = PREC == kPrecTf32 ? 2 : 3;    // 16 epilogue warps' slabs (128 KiB) leave room for two 32 KiB stages
+  static constexpr int kStage = 2 * kATileBytes;                // this CTA's 128 A rows + its 128 B rows, 128 B of K each
+  static constexpr int kSlabs = kEpi * 2 * kSlabBytes;          // two slabs per epilogue warp
+  static constexpr int kBars = 8 * (2 * kStages + 4 + 2 * kEpi);
+  static constexpr int kBias = kEpi * 64 * 4;                   // 64 bias values per warp (bf16: per half of its 128 columns)
+  // no alignment slack: the kernel has no static shared memory, so the dynamic window starts 1024-byte aligned (checked)
+  static constexpr int kTotal = kStages * kStage + kSlabs + ((kBars + 15) & ~15) + 16 + kBias;
+  static_assert(kTotal <= 232448, "shared memory budget");
+};
+
+template <int MODE, int PREC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P2cCfg<PREC>::kThreads, 1)
+mlp_gemm2cta_kernel(const __grid_constant__ TcGemmArgs g) {
+  using P = PrecT<PREC>;
+  using S = P2cCfg<PREC>;
+  constexpr int BN = 256;
+  constexpr int kEpi = S::kEpi, k2Stages = S::kStages;
+  constexpr int CH = kRowBytes / (int)sizeof(typename P::T);
+  constexpr int LD = CH / 32;
+  constexpr int WCOLS = BN / (kEpi / 4);  // columns per epilogue warp: 64 (fp32) / 128 (bf16)
+  constexpr int NSLAB = WCOLS / CH;       // = 2 slabs per warp and tile
+  static_assert(NSLAB == 2, "the H prefetch below assumes two slabs per warp and tile");
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t tiles = raw;
+  const uint32_t slabs = tiles + k2Stages * S::kStage;
+  const uint32_t bars = slabs + S::kSlabs;
+  const uint32_t full_bar = bars, empty_bar = bars + 8 * k2Stages;
+  const uint32_t tfull_bar = bars + 16 * k2Stages, tempty_bar = tfull_bar + 16;
+  const uint32_t h_bar = tempty_bar + 16;  // [kEpi][2]
+  const uint32_t tmem_slot = bars + ((S::kBars + 15) & ~15);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+  float* bias_sm = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - raw));  // [kEpi][64], private to each warp
+  if (raw & 1023u) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta = cluster_ctarank();  // 0 = leader
+  const int n_pairs = gridDim.x / 2, pair = blockIdx.x / 2;
+  const int tiles_n = g.N / BN, tiles_m = (g.M + 255) / 256;
+  const int per_net = tiles_m * tiles_n, total = 2 * per_net;
+  const int k_blocks = g.K / P::kBK;
+
+  if (warp == 0 && lane == 0) {
+    for (int z = 0; z < 2; ++z) {
+      asm volatile("prefetch.tensormap [%0];\n" ::"l"(&g.mapA[z]));
+      asm volatile("prefetch.tensormap [%0];\n" ::"l"(&g.mapB[z]));
+      asm volatile("prefetch.tensormap [%0];\n" ::"l"(&g.mapC[z]));
+      if (MODE == kTcDgrad) asm volatile("prefetch.tensormap [%0];\n" ::"l"(&g.mapH[z]));
+    }
+    for (int s = 0; s < k2Stages; ++s) {
+      mbar_init(full_bar + 8 * s, 1);   // the leader's producer arrives (with both CTAs' byte count); used on the leader only
+      mbar_init(empty_bar + 8 * s, 1);  // one multicast commit per use
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar + 8 * a, 1);
+      mbar_init(tempty_bar + 8 * a, 2 * kEpi);  // the epilogue warps of BOTH CTAs; used on the leader only
+    }
+    for (int i = 0; i < 2 * kEpi; ++i) mbar_init(h_bar + 8 * i, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2cta(tmem_slot, 512);
+  tc_fence_before();
+  cluster_sync_all();  // barriers of both CTAs initialised and visible cluster-wide, TMEM allocated
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (elect_one()) {
+      uint32_t it = 0;
+      for (int t = pair; t < total; t += n_pairs) {
+        const int z = t / per_net, r = t - z * per_net;
+        const int row_base = (r / tiles_n) * 256 + (int)cta * 128, col_base = (r % tiles_n) * BN + (int)cta * 128;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const uint32_t s = it % k2Stages;
+          mbar_wait(empty_bar + 8 * s, ((it / k2Stages) & 1) ^ 1);
+          const uint32_t sa = tiles + s * S::kStage, sb = sa + kATileBytes;
+          const uint32_t leader_full = map_to_cta(full_bar + 8 * s, 0);
+          if (cta == 0) mbar_expect_tx(full_bar + 8 * s, 2 * S::kStage);  // both CTAs' A rows and B halves
+          tma_load_2d_2cta(sa, &g.mapA[z], leader_full, kb * P::kBK, row_base);  // my 128 rows of the 256-row tile
+          tma_load_2d_2cta(sb, &g.mapB[z], leader_full, kb * P::kBK, col_base);  // my 128 of the 256 B rows
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader only) =====================
+    if (cta == 0) {
+      constexpr uint32_t idesc = make_idesc(P::kFmt, 256, BN, false, false);
+      uint32_t it = 0, j = 0;
+      for (int t = pair; t < total; t += n_pairs, ++j) {
+        const uint32_t a = j & 1;
+        mbar_wait(tempty_bar + 8 * a, ((j >> 1) & 1) ^ 1);  // both CTAs' epilogues have drained this accumulator stage
+        tc_fence_after();
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const uint32_t s = it % k2Stages;
+          mbar_wait(full_bar + 8 * s, (it / k2Stages) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t sa = tiles + s * S::kStage, sb = sa + kATileBytes;
+#pragma unroll
+            for (int k = 0; k < P::kBK / P::kUmmaK; ++k) {
+              const uint64_t da = make_smem_desc(sa + k * 32, 16, 1024);
+              const uint64_t db = make_smem_desc(sb + k * 32, 16, 1024);
+              umma_2cta<PREC>(tmem_base + a * BN, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+          }
+          __syncwarp();
+          if (elect_one()) {
+            umma_commit_2cta(empty_bar + 8 * s, 3);                            // ring slot free in both CTAs
+            if (kb == k_blocks - 1) umma_commit_2cta(tfull_bar + 8 * a, 3);   // accumulator complete in both CTAs
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs: own 128 rows x 256 columns, two slabs per warp) =====================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int c_first = (ew >> 2) * WCOLS;
+    const uint32_t my_slabs = slabs + ew * 2 * kSlabBytes;
+    const uint32_t my_hbar = h_bar + ew * 16;
+    const uint32_t lane_row = lane * kRowBytes, lane_x = lane & 7;
+    auto tile_coords = [&](int t, int& z, int& srow, int& col0) {
+      z = t / per_net;
+      const int r = t - z * per_net;
+      srow = (r / tiles_n) * 256 + (int)cta * 128 + quarter * 32;
+      col0 = (r % tiles_n) * BN + c_first;
+    };
+    auto load_h = [&](int z, int srow, int col, uint32_t buf) {  // lane 0 only
+      mbar_expect_tx(my_hbar + 8 * buf, kSlabBytes);
+      tma_load_2d(my_slabs + buf * kSlabBytes, &g.mapH[z], my_hbar + 8 * buf, col, srow);
+    };
+    uint32_t j = 0;
+    bool h0_issued = false;  // slab 0's H of the tile about to start was already requested at the end of the previous one
+    for (int t = pair; t < total; t += n_pairs, ++j) {
+      int z, srow, col0;
+      tile_coords(t, z, srow, col0);
+      const uint32_t a = j & 1;
+      float* bsm = bias_sm + ew * 64;  // private: no other warp reads or writes it
+      if (MODE == kTcDgrad) {
+        if (lane == 0) {
+          if (!h0_issued) {
+            asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
+            load_h(z, srow, col0, 0);
+          }
+          asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");  // buffer 1: the previous tile's second store
+          load_h(z, srow, col0 + CH, 1);
+        }
+      } else if (WCOLS == 64) {  // fp32: the warp's 64 bias values, once per tile (the previous tile's math is behind us)
+        const float* __restrict__ bp = g.bias[z] + col0;
+        __syncwarp();
+        bsm[lane] = __ldg(bp + lane);
+        bsm[lane + 32] = __ldg(bp + lane + 32);
+        __syncwarp();
+      }
+      if (lane == 0) mbar_wait(tfull_bar + 8 * a, (j >> 1) & 1);
+      __syncwarp();
+      mbar_wait(tfull_bar + 8 * a, (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * BN + c_first;
+#pragma unroll
+      for (int i = 0; i < NSLAB; ++i) {
+        const uint32_t slab = my_slabs + i * kSlabBytes;  // slab i of every tile lives in buffer i
+        uint32_t v[LD][32];
+#pragma unroll
+        for (int l = 0; l < LD; ++l) tmem_ld32(tbase + i * CH + l * 32, v[l]);
+        if (MODE == kTcDgrad) {
+          mbar_wait(my_hbar + 8 * i, j & 1);
+        } else {
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");  // the previous tile's store of slab i
+          if (WCOLS == 128) {  // bf16: 64 bias values per slab
+            const float* __restrict__ bp = g.bias[z] + col0 + i * CH;
+            __syncwarp();
+            bsm[lane] = __ldg(bp + lane);
+            bsm[lane + 32] = __ldg(bp + lane + 32);
+          }
+          __syncwarp();
+        }
+#pragma unroll
+        for (int l = 0; l < LD; ++l) tmem_ld_wait(v[l]);
+        if (i == NSLAB - 1) {  // last TMEM read of this tile: hand the stage back to the leader's MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(map_to_cta(tempty_bar + 8 * a, 0));
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint32_t addr = slab + lane_row + ((q ^ lane_x) << 4);
+          uint4 o;
+          if (PREC == kPrecTf32) {
+            float x[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] = __uint_as_float(v[0][q * 4 + e]);
+            if (MODE == kTcFwd) {
+              const float4 b = *reinterpret_cast<const float4*>(bsm + i * CH + q * 4);
+              x[0] = elu_fast(x[0] + b.x); x[1] = elu_fast(x[1] + b.y); x[2] = elu_fast(x[2] + b.z); x[3] = elu_fast(x[3] + b.w);
+            } else {
+              const uint4 h = ld_shared_v4(addr);
+              x[0] *= elu_grad_from_output(__uint_as_float(h.x)); x[1] *= elu_grad_from_output(__uint_as_float(h.y));
+              x[2] *= elu_grad_from_output(__uint_as_float(h.z)); x[3] *= elu_grad_from_output(__uint_as_float(h.w));
+            }
+            o = make_uint4(__float_as_uint(round_tf32(x[0])), __float_as_uint(round_tf32(x[1])),
+                           __float_as_uint(round_tf32(x[2])), __float_as_uint(round_tf32(x[3])));
+          } else {
+            float x[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[(q >> 2) % LD][(q & 3) * 8 + e]);
+            if (MODE == kTcFwd) {
+              const float4 b0 = *reinterpret_cast<const float4*>(bsm + q * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(bsm + q * 8 + 4);
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) x[e] = elu_fast(x[e] + bb[e]);
+            } else {
+              const uint4 h = ld_shared_v4(addr);
+              const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&h);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                x[2 * e] *= elu_grad_from_output(__low2float(hp[e]));
+                x[2 * e + 1] *= elu_grad_from_output(__high2float(hp[e]));
+              }
+            }
+            o = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+          }
+          st_shared_v4(addr, o);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&g.mapC[z], slab, col0 + i * CH, srow);
+          asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+        }
+      }
+      // dgrad: request slab 0's H of the NEXT tile now (its buffer is free as soon as this tile's first store has been
+      // read; the second one may still be in flight): it travels while this warp waits for the next accumulator
+      h0_issued = false;
+      if (MODE == kTcDgrad && t + n_pairs < total) {
+        if (lane == 0) {
+          int nz, nrow, ncol;
+          tile_coords(t + n_pairs, nz, nrow, ncol);
+          asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
+          load_h(nz, nrow, ncol, 0);
+        }
+        h0_issued = true;
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+    tc_fence_before();
+  }
+  // nobody frees TMEM or leaves (its shared memory is a multicast target) before both CTAs are completely done
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, 512);
+  }
+}
+
 // ---- weight gradient ---------------------------------------------------------------------------------------------
 // Weight-gradient pipeline: a stage holds kWgRows = 64 reduction rows of the 128 dZ features and the BN input features
 // (TMA boxes of one 128-byte feature chunk x 64 rows: 8 KiB per box in tf32 -- with 32-row boxes the 4 KiB requests, six
@@ -771,8 +1051,36 @@ static bool use_tile256(int M, int N) {
   return v == 1 && 2 * ((M + 255) / 256) * (N / bn) >= 96;
 }
 
+// CTA pairs (256 x 256 tiles, cta_group::2) for launches with N a multiple of 256 that give every pair work: opt-in
+// (CATB200_PAIRS=1).  Measured on the B200 (profiles/README.md, round 2): correct, half the operand bytes per flop, but
+// no faster than the 128 x 128 tiles (forward 23 vs 19.5 us, dgrad 25.4 vs 22.7 us per launch at 16384 rows).
+static bool use_pairs(int M, int N) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("CATB200_PAIRS");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1 && N % 256 == 0 && 2 * ((M + 255) / 256) * (N / 256) >= 64;
+}
+
+template <int MODE, int PREC>
+static int launch_gemm_pairs(const TcGemmArgs& g, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    CATB200_CUDA_TRY(cudaFuncSetAttribute(mlp_gemm2cta_kernel<MODE, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2cCfg<PREC>::kTotal));
+    attr = true;
+  }
+  const int total = 2 * ((g.M + 255) / 256) * (g.N / 256);
+  const int pairs = min(total, kNumSMs / 2);
+  // the cluster shape is compiled into the kernel (__cluster_dims__): a plain launch with an even grid
+  mlp_gemm2cta_kernel<MODE, PREC><<<dim3(2 * pairs), dim3(P2cCfg<PREC>::kThreads), (size_t)P2cCfg<PREC>::kTotal, st>>>(g);
+  CATB200_LAUNCH_CHECK();
+  return CATB200_OK;
+}
+
 template <int MODE, int PREC>
 static int launch_gemm_any(const TcGemmArgs& g, cudaStream_t st) {
+  if (use_pairs(g.M, g.N)) return launch_gemm_pairs<MODE, PREC>(g, st);
   if (use_tile256(g.M, g.N)) {
     if (g.N % 256 == 0) return launch_gemm256<MODE, PREC, 256>(g, st);
     return launch_gemm256<MODE, PREC, 128>(g, st);

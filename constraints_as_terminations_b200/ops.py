@@ -279,6 +279,31 @@ def ppo_minibatch_grad(dims, hp, mb_inds, obs_op_all, actions_all, logprobs_all,
     )  # fmt: skip
 
 
+def ppo_minibatch_update(dims, hp, mb_inds, obs_op_all, actions_all, logprobs_all, advantages_all, returns_all, values_all,
+                         norm_stats, params, wc, grads, loss_acc, ws, exp_avg, exp_avg_sq, lr_dev, step_dev, opt_ws,
+                         max_grad_norm=1.0, betas=(0.9, 0.999), eps=1e-5, grad_scale=1.0, grad_norm_out=None) -> None:  # fmt: skip
+    """`ppo_minibatch_grad` + `adam_step` of one minibatch (single GPU) with the fold / norm / clip / Adam tail as one launch."""
+    L.require_cuda(mb_inds, "mb_inds")
+    _check_operand(dims, obs_op_all, "obs_op_all")
+    _check_operand(dims, wc, "wc")
+    if mb_inds.dtype != torch.int64 or not mb_inds.is_contiguous():
+        raise TypeError("mb_inds must be a contiguous int64 tensor")
+    for t, name in ((actions_all, "actions"), (logprobs_all, "logprobs"), (advantages_all, "advantages"), (returns_all, "returns"),
+                    (values_all, "values"), (norm_stats, "norm_stats"), (params, "params"), (grads, "grads"), (loss_acc, "loss_acc"),
+                    (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq"), (lr_dev, "lr")):  # fmt: skip
+        _f32c(t, name)
+    L.check(
+        L.load().catb200_ppo_minibatch_update(
+            dims, hp, mb_inds.numel(), mb_inds.data_ptr(), obs_op_all.data_ptr(), actions_all.data_ptr(),
+            logprobs_all.data_ptr(), advantages_all.data_ptr(), returns_all.data_ptr(), values_all.data_ptr(),
+            norm_stats.data_ptr(), params.data_ptr(), wc.data_ptr(), grads.data_ptr(), loss_acc.data_ptr(),
+            ws.data_ptr(), ws.numel() * 8, exp_avg.data_ptr(), exp_avg_sq.data_ptr(), lr_dev.data_ptr(), step_dev.data_ptr(),
+            max_grad_norm, betas[0], betas[1], eps, grad_scale, L.ptr(grad_norm_out), opt_ws.data_ptr(), L.stream(),
+        ),
+        "ppo_minibatch_update",
+    )  # fmt: skip
+
+
 def adam_step(dims, params, grads, exp_avg, exp_avg_sq, wc, lr_dev, step_dev, opt_ws, max_grad_norm=1.0,
               betas=(0.9, 0.999), eps=1e-5, grad_scale=1.0, grad_norm_out=None) -> None:  # fmt: skip
     for t, name in ((params, "params"), (grads, "grads"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq"), (lr_dev, "lr")):

@@ -300,6 +300,7 @@ class PPOTrainer:
         base_seed = int(seed if seed is not None else getattr(cfg, "seed", 0))
         self.rng_state = ops.make_rng_state(base_seed * 1000003 + 7919 * self.rank + 1, dev)
         self.device_rng = os.environ.get("CATB200_DEVICE_RNG", "1") != "0"
+        self.fused_opt = os.environ.get("CATB200_FUSED_OPT", "1") != "0"
         self.hp = ops.make_hparams(cfg.clip_coef, cfg.ent_coef, cfg.vf_coef, cfg.norm_adv, cfg.clip_vloss)
         self.global_step = 0
         self.iteration = 0
@@ -481,6 +482,17 @@ class PPOTrainer:
             gsum = self.peer.reduce(parity, self.step_dev, self.opt_ws, max_grad_norm=self.cfg.max_grad_norm, grad_norm_out=self.grad_norm)
             ops.adam_apply(a.dims, a.parameters_flat(), gsum, self.exp_avg, self.exp_avg_sq, a._wc, self.lr_dev, self.opt_ws,
                            eps=1e-5, grad_scale=1.0 / self.world)  # fmt: skip
+            return
+        if self.world == 1 and self.fused_opt:
+            # single GPU: gradient + optimizer as one call whose tail (fold, norm, clip, Adam, operand copies) is one launch
+            a, B = self.agent, self.batch_size
+            ops.ppo_minibatch_update(
+                a.dims, self.hp, mb_inds, self.obs_op.view(-1, a.dims.obs_pad), self.actions.view(B, -1),
+                self.logprobs.view(B), self.advantages.view(B), self.returns.view(B), self.values.view(B), self.norm_stats,
+                a.parameters_flat(), a._wc, self.grads, self.loss_acc, self.train_ws, self.exp_avg, self.exp_avg_sq,
+                self.lr_dev, self.step_dev, self.opt_ws, max_grad_norm=self.cfg.max_grad_norm, eps=1e-5,
+                grad_norm_out=self.grad_norm,
+            )  # fmt: skip
             return
         self._minibatch_grad(mb_inds)
         if self.world > 1:  # the one exchange step: sum-allreduce of the flat 1.5 MB gradient over NVLink (NCCL)

@@ -357,6 +357,21 @@ int catb200_adam_step(const catb200_mlp_dims_t* dims, float* params, float* grad
                       float beta1, float beta2, float eps, float grad_scale, float* grad_norm_out, void* opt_ws,
                       void* stream);
 
+/*
+ * catb200_ppo_minibatch_grad + catb200_adam_step of ONE minibatch on one GPU (ppo.py:298-354), with the tail of the two --
+ * fold of the weight-gradient accumulators into `grads`, global gradient norm, clip, Adam, operand-copy refresh -- as a
+ * single launch (one CTA per SM around a grid barrier) instead of three.  Same arguments and results as the two calls
+ * (`grads` zero on entry and on exit; opt_ws: the same 64 bytes of zero-initialised scratch, left clean).
+ */
+int catb200_ppo_minibatch_update(const catb200_mlp_dims_t* dims, const catb200_ppo_hparams_t* hp, int32_t mb_rows,
+                                 const int64_t* mb_inds, const void* obs_op_all, const float* actions_all,
+                                 const float* logprobs_all, const float* advantages_all, const float* returns_all,
+                                 const float* values_all, const float* norm_stats, float* params, void* wc, float* grads,
+                                 float* loss_acc, void* workspace, size_t workspace_bytes, float* exp_avg,
+                                 float* exp_avg_sq, const float* lr_dev, int32_t* step_dev, float max_grad_norm,
+                                 float beta1, float beta2, float eps, float grad_scale, float* grad_norm_out,
+                                 void* opt_ws, void* stream);
+
 /* The Adam + operand-copy-refresh half of catb200_adam_step alone, for callers that obtained the clip coefficient and the
  * bias corrections in opt_ws from catb200_grad_allreduce_norm (multi-GPU). */
 int catb200_adam_apply(const catb200_mlp_dims_t* dims, float* params, float* grads, float* exp_avg, float* exp_avg_sq,

@@ -93,4 +93,15 @@ def run(device: str = "cuda:0") -> None:
     losses = trainer.losses()
     assert all(torch.isfinite(torch.tensor(x)) for x in losses.values()), losses
     assert float((trainer.agent.parameters_flat() - before).abs().max()) > 0.0
+    # the same with CUDA graphs: whole env steps (policy + fused constraint step + append + observation statistics) and
+    # whole epochs (Philox permutation + 6 minibatches) replay as single launches from iteration 2 on
+    env = se.SyntheticSolo12Env(256, device=device, seed=3, pool=2, constraints_cfg=se.solo12_constraints_cfg())
+    env.load_managers()
+    trainer = PPOTrainer(env, solo12_flat_ppo_cfg(logger=None), device=device, use_graphs=True, distributed=False)
+    trainer.start()
+    for _ in range(4):
+        trainer.train_iteration()
+    losses = trainer.losses()
+    assert all(torch.isfinite(torch.tensor(x)) for x in losses.values()), losses
+    assert len(trainer._step_graphs) > 0 and len(trainer._epoch_graphs) > 0
     torch.cuda.synchronize()

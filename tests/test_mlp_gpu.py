@@ -261,9 +261,11 @@ def test_minibatch_gradient_matches_oracle(B, M, prec, margin):
         assert r < T["logstd_mult"] * gtol, f"{name}: log-std gradient relative error {r:.3e}"
 
 
-def test_tile256_kernels_match_the_default_tiles():
-    """The opt-in 256-row-tile GEMM kernels (CATB200_TILE256=1, read once per process -> a subprocess) give the same
-    gradient as the default 128 x 128 tiles on a ragged 16500-row minibatch."""
+@pytest.mark.parametrize("var,prec", [("CATB200_TILE256", "tf32"), ("CATB200_PAIRS", "tf32"), ("CATB200_PAIRS", "bf16")])
+def test_tile_variants_match_each_other(var, prec):
+    """The GEMM tile variants -- CTA pairs (cta_group::2, 256 x 256 tiles; CATB200_PAIRS, opt-in: measured no faster) and the single-CTA 256-row tiles (CATB200_TILE256, opt-in) -- against the plain 128 x 128 tiles: same
+    gradient on a ragged 16500-row minibatch (the last pair tile has one CTA partly and one wholly beyond M).  The
+    switches are read once per process -> subprocesses."""
     import os
     import subprocess
     import sys
@@ -272,20 +274,22 @@ def test_tile256_kernels_match_the_default_tiles():
         "import torch, sys; sys.path.insert(0, %r)\n"
         "from tests import test_mlp_gpu as T\n"
         "from constraints_as_terminations_b200 import ops\n"
-        "agent = T.make_agent(seed=1); dims, layout, params, wc = T.device_agent(agent, 'tf32')\n"
+        "agent = T.make_agent(seed=1); dims, layout, params, wc = T.device_agent(agent, %r)\n"
         "obs, actions, logp, adv, returns, values, ns, idx = T._minibatch(agent, 20000, 16500, seed=5)\n"
         "g = torch.zeros(layout.n_params, device='cuda:0'); la = torch.zeros(8, device='cuda:0')\n"
         "ops.ppo_minibatch_grad(dims, ops.make_hparams(), idx.cuda(), ops.obs_to_operand(dims, obs.cuda()), actions.cuda(), logp.cuda(), adv.cuda(),"
         " returns.cuda(), values.cuda(), ns.cuda(), params, wc, g, la, ops.mlp_workspace(dims, 16500, True, 'cuda:0'))\n"
         "torch.save(g.cpu(), sys.argv[1])\n"
-    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), prec)
     outs = []
     for flag in ("0", "1"):
-        path = f"/tmp/catb200_tile256_{flag}.pt"
-        subprocess.run([sys.executable, "-c", code, path], check=True, env=dict(os.environ, CATB200_TILE256=flag), timeout=300)
+        path = f"/tmp/catb200_{var}_{prec}_{flag}.pt"
+        env = dict(os.environ, CATB200_PAIRS="0", CATB200_TILE256="0")
+        env[var] = flag
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=120)
         outs.append(torch.load(path))
     rel = float((outs[0] - outs[1]).norm() / outs[0].norm())
-    assert rel < 1e-5, rel  # same products, same fp32 accumulation per tile row; only the atomics order of wgrad differs
+    assert rel < 1e-5, rel  # same products, same fp32 accumulation per output element; only the atomics order of wgrad differs
 
 
 @pytest.mark.parametrize("prec", PRECS)
