@@ -313,6 +313,7 @@ def dominant_kernel_roofline(prof, total_us, trainer, peaks):
 def kernel_rooflines(device, num_envs, peaks):
     """Per-kernel achieved bandwidth / throughput, timed alone with CUDA events on the launch stream,
     L2 flushed between timed launches (a 256 MiB write)."""
+    from constraints_as_terminations_b200 import _lib as _L
     from constraints_as_terminations_b200 import ops
     from constraints_as_terminations_b200 import synthetic_env as se
 
@@ -350,8 +351,11 @@ def kernel_rooflines(device, num_envs, peaks):
         mgr = env.load_managers()
         reset = torch.zeros(n, dtype=torch.bool, device=device)
         sec = time_kernel(lambda: mgr.compute_step(env._raw_reward, reset))
+        before = _L.launch_count()
+        mgr.compute_step(env._raw_reward, reset)
+        cat_launches = _L.launch_count() - before  # 1: single-launch kernel (grid barrier, tiles stay in shared memory); 2: eval + apply
         nbytes = 940 * n
-        out[f"cat_step@{n}"] = {"bound": "hbm", "achieved": nbytes / sec / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": nbytes / sec / 1e9 / peaks["hbm_gbs"], "us": sec * 1e6, "bytes": nbytes, "launches": 2}
+        out[f"cat_step@{n}"] = {"bound": "hbm", "achieved": nbytes / sec / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": nbytes / sec / 1e9 / peaks["hbm_gbs"], "us": sec * 1e6, "bytes": nbytes, "launches": cat_launches}
         del env, mgr
     # a6: running observation moments + normalise (+ operand copy) + rollout append: 428 B/env-step
     from constraints_as_terminations_b200 import RunningMeanStd

@@ -376,10 +376,10 @@ class CaT:
             "cat_step",
         )  # fmt: skip
         probs = torch.empty((n, cols), dtype=torch.float32, device=raw.device)
+        rawm = torch.empty((n, cols), dtype=torch.float32, device=raw.device)  # the values as CaT.add casts them (:45-47)
+        L.check(lib.catb200_cat_eval_terms(built.plan, n, rawm.data_ptr(), L.stream()), "cat_eval_terms")
         L.check(
-            lib.catb200_cat_probs(
-                built.plan, params, n, st["running_max"].data_ptr(), probs.data_ptr(), st["ws"].data_ptr(), L.stream()
-            ),
+            lib.catb200_cat_probs(built.plan, params, n, st["running_max"].data_ptr(), probs.data_ptr(), rawm.data_ptr(), L.stream()),
             "cat_probs",
         )
         st.update(raw=raw, probs=probs, max_p=float(max_p), fresh=True)
@@ -798,7 +798,7 @@ class ConstraintManager(ManagerBase):
             L.check(
                 L.load().catb200_cat_probs(
                     self._built.plan, self._params, self.num_envs, self._running_max.data_ptr(), out.data_ptr(),
-                    self._workspace.data_ptr(), L.stream(),
+                    self._raw_matrix().data_ptr(), L.stream(),
                 ),
                 "cat_probs",
             )  # fmt: skip

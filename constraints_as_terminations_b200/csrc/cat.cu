@@ -70,7 +70,7 @@ constexpr int kMaxGroups = 64;
 
 struct CatWorkspace {
   // layout inside the caller's workspace (all 256-byte aligned)
-  unsigned int* ticket;   // 1 + kTicketGroups words (padded)
+  unsigned int* ticket;   // 1 + kTicketGroups words (padded); word 48: generation flag of the single-launch kernel's grid barrier
   uint32_t* colmax;       // [kMaxGroups][CATB200_MAX_COLS] ordered-float column maxima, 0 between launches
   float* c_t;             // [n_tiles][K][32] raw constraints, tile-major
 };
@@ -87,7 +87,15 @@ __host__ __device__ inline CatWorkspace carve(void* base, int num_envs) {
   return w;
 }
 
-enum EvalMode { kEvalStep = 0, kEvalRowMajor = 1 };
+enum EvalMode { kEvalStep = 0, kEvalRowMajor = 1, kEvalFused = 2 };
+
+// what the apply phase reads and writes besides the constraint tile (cat_apply_kernel's arguments; kEvalFused carries them
+// into the single-launch kernel)
+struct ApplyArgs {
+  float* episode_sums; float* mean_values; float* cstr_prob;
+  const float* raw_reward; const uint8_t* reset_buf; float* reward_out; float* dones_out;
+  const int64_t* episode_length; float* reset_out; struct ResetScratch* rsc;
+};
 
 // max over the warp of an fp32 value: one CREDUX.MAX.F32 on sm_100a
 __device__ __forceinline__ float warp_max_f32(float v) {
@@ -142,7 +150,7 @@ struct TermCtx {
 template <int MODE>
 __device__ __forceinline__ void emit(const TermCtx& c, int lc, float v) {
   sts_f32(c.out + lc * (kTile * 4), v);
-  if (MODE == kEvalStep) {
+  if (MODE != kEvalRowMajor) {
     const float m = warp_max_f32(c.live ? v : -INFINITY);
     if (c.lane0) sts_f32(c.colmax + lc * 4, m);  // this tile's column maximum; folded into the CTA's in phase C
   }
@@ -216,6 +224,34 @@ __device__ __forceinline__ void generic_columns(const TermCtx& c, bool is_u8) {
   }
 }
 
+// probability of one column value (constraint_manager.py:64-72)
+__device__ __forceinline__ float violation_prob(float c, float rm, float min_p, float span) {
+  if (!(c > 0.0f)) return 0.0f;
+  float x = __fdiv_rn(c, rm);
+  x = fminf(fmaxf(x, 0.0f), 1.0f);
+  return __fadd_rn(min_p, __fmul_rn(x, span));
+}
+
+struct ResetScratch {  // per slot: double sums + count; zero between launches
+  double v[CATB200_MAX_TERMS], p[CATB200_MAX_TERMS];
+  unsigned long long cnt[CATB200_MAX_TERMS];
+  unsigned int ticket;                       // cat_reset_kernel (small grids)
+  unsigned int tickets[1 + kTicketGroups];   // fused reset inside cat_apply_kernel (grids of up to N / 32 CTAs)
+};
+
+// episode statistics of the envs being reset, from the per-slot accumulators (constraint_manager.py:197-209)
+__device__ __forceinline__ void reset_finalize(ResetScratch* sc, int n_slots, float* out) {
+  for (int s2 = threadIdx.x; s2 < n_slots; s2 += blockDim.x) {
+    const double v = __longlong_as_double(atomicExch((unsigned long long*)&sc->v[s2], 0ull));
+    const double p = __longlong_as_double(atomicExch((unsigned long long*)&sc->p[s2], 0ull));
+    const unsigned long long c = atomicExch(&sc->cnt[s2], 0ull);
+    // empty selection -> mean of nothing = NaN, like torch
+    const float mv = (float)(v / (double)c), mp = (float)(p / (double)c);
+    out[2 * s2] = __fmul_rn(mv, 100.0f);
+    out[2 * s2 + 1] = mp;
+  }
+}
+
 // Persistent CTAs walk the 32-env tiles blockIdx.x, blockIdx.x + gridDim.x, ...; blockDim.x = 32 * G (G = 1, 2, 4
 // or 8 warps share a tile), lane = env.  Two shared-memory images: while tile i is evaluated out of one, the bulk
 // async copies of tile i+1 land in the other and the bulk async store of tile i-1's constraint tile drains.
@@ -223,8 +259,10 @@ template <int MODE>
 __global__ void __launch_bounds__(kEvalMaxWarps * 32)
 cat_eval_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_constant__ catb200_cat_params_t prm,
                 int num_envs, int n_groups, float* __restrict__ running_max, int* __restrict__ rm_init,
-                CatWorkspace ws, float* __restrict__ out_rowmajor) {
-  extern __shared__ __align__(128) uint8_t smem_all[];  // 2 x [source rows | peak table | constraint tile]
+                CatWorkspace ws, float* __restrict__ out_rowmajor, const __grid_constant__ ApplyArgs ap) {
+  // kEvalStep / kEvalRowMajor: 2 x [source rows | peak table | constraint tile];
+  // kEvalFused: 2 x [source rows | peak table], then one constraint tile per tile this CTA walks (they stay here)
+  extern __shared__ __align__(128) uint8_t smem_all[];
   __shared__ float s_colmax[CATB200_MAX_COLS];   // column maxima over all tiles of this CTA
   __shared__ float s_tilemax[CATB200_MAX_COLS];  // column maxima of the tile in flight (plain stores in the column loop)
   __shared__ __align__(8) unsigned long long s_bar[2];
@@ -234,6 +272,8 @@ cat_eval_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_consta
   const int n_tiles = (num_envs + kTile - 1) / kTile;
   const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&s_bar[0]);
   const uint32_t cm_base = launder((uint32_t)__cvta_generic_to_shared(s_tilemax));  // opaque: stays in a register
+  const int image_bytes = MODE == kEvalFused ? plan.smem_ctile_off : plan.smem_bytes;
+  const int ctile_bytes = K * kTile * 4;
 
   // lane s describes source s (n_sources <= 16): a source tile can use the bulk copy engine if it is a full tile,
   // contiguous and 16-byte aligned
@@ -258,7 +298,7 @@ cat_eval_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_consta
       if (bulk_ok(tile)) {
         const uint32_t bytes = kTile * my_len * my_es;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
-        bulk_copy_g2s((uint32_t)__cvta_generic_to_shared(smem_all) + b * plan.smem_bytes + my_off,
+        bulk_copy_g2s((uint32_t)__cvta_generic_to_shared(smem_all) + b * image_bytes + my_off,
                       my_ptr + (size_t)tile * kTile * my_len * my_es, bytes, bar);
       } else {
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
@@ -278,9 +318,12 @@ cat_eval_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_consta
   int it = 0;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
   const int b = it & 1;
-  uint8_t* smem = smem_all + (size_t)b * plan.smem_bytes;
+  uint8_t* smem = smem_all + (size_t)b * image_bytes;
   const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
-  const float* s_c = reinterpret_cast<const float*>(smem + plan.smem_ctile_off);  // [K][32]
+  // this tile's [K][32] constraint tile: inside the image, or (fused) the it-th of the tiles kept behind the two images
+  const uint8_t* ctile_g = MODE == kEvalFused ? smem_all + 2 * (size_t)image_bytes + (size_t)it * ctile_bytes : smem + plan.smem_ctile_off;
+  const float* s_c = reinterpret_cast<const float*>(ctile_g);
+  const uint32_t ctile_s = (uint32_t)__cvta_generic_to_shared(ctile_g);
   const int tile0 = tile * kTile;
   const int rows = min(kTile, num_envs - tile0);
   // prefetch the next tile into the other image: every warp left it behind at the barrier that ended the previous
@@ -370,7 +413,7 @@ cat_eval_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_consta
     c.live = live;
     c.lane0 = lane == 0;
     c.peaks = peaks;
-    c.out = sbase + plan.smem_ctile_off + (t2.col_offset * kTile + lane) * 4;
+    c.out = ctile_s + (t2.col_offset * kTile + lane) * 4;
     c.colmax = cm_base + t2.col_offset * 4;
     const bool u0 = s0.dtype == CATB200_U8;
     c.x0 = ibase + s0.smem_off + row * (s0.row_len * (u0 ? 1 : 4));
@@ -425,12 +468,13 @@ cat_eval_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_consta
   // ---- phase C: the tile leaves as one bulk async store (generic-proxy writes fenced for the async proxy first).
   //      Before that, the store issued two iterations ago out of this same image must have finished reading it --
   //      thread 0 waited for that right after issuing the previous one (at most 1 group pending).
-  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  //      Fused: the tile stays where it is.
+  if (MODE != kEvalFused) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   __syncthreads();  // also: every warp is done with this image's sources before the next iteration's prefetch
-  if (threadIdx.x == 0) {
+  if (MODE != kEvalFused && threadIdx.x == 0) {
     float* dst = ws.c_t + (size_t)tile * K * kTile;
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst),
-                 "r"(sbase + plan.smem_ctile_off), "r"((uint32_t)(K * kTile * 4))
+                 "r"(ctile_s), "r"((uint32_t)ctile_bytes)
                  : "memory");
     asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");  // the other image's constraint tile is free again
@@ -451,8 +495,13 @@ cat_eval_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_consta
     // most CTAs cannot raise the maximum any more: a plain (L2) read first keeps the atomic units idle
     if (key > __ldcg(grow + c)) atomicMax(grow + c, key);
   }
-  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");  // smem read out before exit
-  if (last_block_ticket_grouped(ws.ticket, gridDim.x)) {
+  if (MODE != kEvalFused && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");  // smem read out before exit
+  // fused: the generation of the grid barrier's flag, read BEFORE this CTA counts as arrived (it cannot change earlier)
+  volatile unsigned int* gen_flag = ws.ticket + 48;
+  unsigned int gen0 = 0;
+  if (MODE == kEvalFused && threadIdx.x == 0) gen0 = *gen_flag;
+  const bool last_cta = last_block_ticket_grouped(ws.ticket, gridDim.x);
+  if (last_cta) {
     for (int col = threadIdx.x; col < K; col += n_threads) {
       uint32_t key = 0u;
       int gi = 0;
@@ -475,34 +524,78 @@ cat_eval_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_consta
       running_max[col] = rm;
     }
   }
-}
+  if (MODE != kEvalFused) return;
 
-// probability of one column value (constraint_manager.py:64-72)
-__device__ __forceinline__ float violation_prob(float c, float rm, float min_p, float span) {
-  if (!(c > 0.0f)) return 0.0f;
-  float x = __fdiv_rn(c, rm);
-  x = fminf(fmaxf(x, 0.0f), 1.0f);
-  return __fadd_rn(min_p, __fmul_rn(x, span));
-}
-
-struct ResetScratch {  // per slot: double sums + count; zero between launches
-  double v[CATB200_MAX_TERMS], p[CATB200_MAX_TERMS];
-  unsigned long long cnt[CATB200_MAX_TERMS];
-  unsigned int ticket;                       // cat_reset_kernel (small grids)
-  unsigned int tickets[1 + kTicketGroups];   // fused reset inside cat_apply_kernel (grids of up to N / 32 CTAs)
-};
-
-// episode statistics of the envs being reset, from the per-slot accumulators (constraint_manager.py:197-209)
-__device__ __forceinline__ void reset_finalize(ResetScratch* sc, int n_slots, float* out) {
-  for (int s2 = threadIdx.x; s2 < n_slots; s2 += blockDim.x) {
-    const double v = __longlong_as_double(atomicExch((unsigned long long*)&sc->v[s2], 0ull));
-    const double p = __longlong_as_double(atomicExch((unsigned long long*)&sc->p[s2], 0ull));
-    const unsigned long long c = atomicExch(&sc->cnt[s2], 0ull);
-    // empty selection -> mean of nothing = NaN, like torch
-    const float mv = (float)(v / (double)c), mp = (float)(p / (double)c);
-    out[2 * s2] = __fmul_rn(mv, 100.0f);
-    out[2 * s2 + 1] = mp;
+  // ---- single launch: grid barrier (every CTA is resident: the host sized the grid with the occupancy calculator),
+  //      then the apply phase straight from the constraint tiles in shared memory -- no C_T round trip, no second launch.
+  //      The last CTA has just written running_max; it publishes a new generation of the flag, the others wait for it.
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (last_cta) {
+      __threadfence();
+      atomicExch(const_cast<unsigned int*>(gen_flag), gen0 + 1u);
+    } else {
+      const long long t0 = clock64();
+      while (*gen_flag == gen0) {
+        if (clock64() - t0 > 4000000000ll) __trap();  // a CTA that never became resident: fail the launch, do not hang
+      }
+      __threadfence();
+    }
   }
+  __syncthreads();
+  __shared__ float s_part[kEvalMaxWarps][kTile];
+  for (int c = threadIdx.x; c < K; c += n_threads) s_tilemax[c] = __ldcg(running_max + c);  // reuse: the new running max
+  __syncthreads();
+  const float* s_rm = s_tilemax;
+  const bool fused_reset = ap.episode_length != nullptr;
+  it = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const float* ct = reinterpret_cast<const float*>(smem_all + 2 * (size_t)image_bytes + (size_t)it * ctile_bytes) + lane;
+    const int i = tile * kTile + lane;
+    const bool live = i < num_envs;
+    float overall = -INFINITY;
+    const bool resetting = fused_reset && live && ap.reset_buf[i] != 0;
+    const unsigned reset_lanes = fused_reset ? __ballot_sync(0xffffffffu, resetting) : 0u;
+    const float ep_len = resetting ? (float)ap.episode_length[i] : 1.0f;  // int64 -> float like torch's float / long promotion
+    for (int slot = warp; slot < plan.n_slots; slot += n_warps) {
+      float es2 = 0.0f, mv2 = 0.0f;
+      if (live) {
+        const int c0 = plan.slot_col_begin[slot], c1 = plan.slot_col_begin[slot + 1];
+        const float span = prm.span_dev ? __ldg(prm.span_dev + slot) : prm.span[slot];
+        const size_t k = (size_t)slot * num_envs + i;
+        const float es = ap.episode_sums[k], mv = ap.mean_values[k];
+        float tmax = -INFINITY;
+        for (int col = c0; col < c1; ++col) tmax = fmaxf(tmax, violation_prob(ct[col * kTile], s_rm[col], prm.min_p, span));
+        es2 = __fadd_rn(es, tmax > 0.0f ? 1.0f : 0.0f);  // :226
+        mv2 = __fadd_rn(mv, tmax);                         // :227
+        ap.episode_sums[k] = resetting ? 0.0f : es2;
+        ap.mean_values[k] = resetting ? 0.0f : mv2;
+        overall = fmaxf(overall, tmax);
+      }
+      if (reset_lanes) {  // warp-uniform: some env of this tile resets (every lane of the warp takes part in the sums)
+        const double av = warp_sum(resetting ? (double)__fdiv_rn(es2, ep_len) : 0.0);
+        const double apv = warp_sum(resetting ? (double)__fdiv_rn(mv2, ep_len) : 0.0);
+        if (lane == 0) {
+          atomicAdd(&ap.rsc->v[slot], av);
+          atomicAdd(&ap.rsc->p[slot], apv);
+          atomicAdd(&ap.rsc->cnt[slot], (unsigned long long)__popc(reset_lanes));
+        }
+      }
+    }
+    s_part[warp][lane] = overall;
+    __syncthreads();
+    if (warp == 0 && live) {
+      for (int w = 1; w < n_warps; ++w) overall = fmaxf(overall, s_part[w][lane]);
+      ap.cstr_prob[i] = overall;
+      if (ap.raw_reward != nullptr) {
+        // cat_env.py:102-107: reward = clip(reward * (1 - p), min=0); dones = p; :121 dones[reset] = 1
+        ap.reward_out[i] = fmaxf(__fmul_rn(ap.raw_reward[i], __fsub_rn(1.0f, overall)), 0.0f);
+        ap.dones_out[i] = (ap.reset_buf != nullptr && ap.reset_buf[i]) ? 1.0f : overall;
+      }
+    }
+    __syncthreads();  // s_part is rewritten by the next tile
+  }
+  if (fused_reset && last_block_ticket_grouped(ap.rsc->tickets, gridDim.x)) reset_finalize(ap.rsc, plan.n_slots, ap.reset_out);
 }
 
 // One CTA per 32 envs (lane = env); the warps split the statistics slots (terms) so that the dependent
@@ -583,16 +676,15 @@ cat_apply_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_const
 
 __global__ void __launch_bounds__(kApplyThreads)
 cat_probs_kernel(const __grid_constant__ catb200_plan_t plan, const __grid_constant__ catb200_cat_params_t prm,
-                 int num_envs, const float* __restrict__ running_max, const float* __restrict__ c_t,
+                 int num_envs, const float* __restrict__ running_max, const float* __restrict__ raw,
                  float* __restrict__ probs_out) {
   const int i = blockIdx.x * kApplyThreads + threadIdx.x;
   if (i >= num_envs) return;
   for (int slot = 0; slot < plan.n_slots; ++slot) {
     const int c0 = plan.slot_col_begin[slot], c1 = plan.slot_col_begin[slot + 1];
     for (int col = c0; col < c1; ++col) {
-      const float c = c_t[((size_t)(i / kTile) * plan.n_cols + col) * kTile + (i % kTile)];
-      probs_out[(size_t)i * plan.n_cols + col] =
-          violation_prob(c, running_max[col], prm.min_p, prm.span_dev ? __ldg(prm.span_dev + slot) : prm.span[slot]);
+      const size_t e = (size_t)i * plan.n_cols + col;
+      probs_out[e] = violation_prob(raw[e], running_max[col], prm.min_p, prm.span_dev ? __ldg(prm.span_dev + slot) : prm.span[slot]);
     }
   }
 }
@@ -809,14 +901,49 @@ static int launch_eval(const catb200_plan_t* plan, const catb200_cat_params_t* p
   if (mode == kEvalStep) {
     if (smem > 48 * 1024)
       CATB200_CUDA_TRY(cudaFuncSetAttribute(cat_eval_kernel<kEvalStep>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cat_eval_kernel<kEvalStep><<<grid, threads, smem, stream>>>(*plan, *prm, num_envs, n_groups, running_max, rm_init, ws, nullptr);
+    cat_eval_kernel<kEvalStep><<<grid, threads, smem, stream>>>(*plan, *prm, num_envs, n_groups, running_max, rm_init, ws, nullptr, ApplyArgs{});
   } else {
     if (smem > 48 * 1024)
       CATB200_CUDA_TRY(cudaFuncSetAttribute(cat_eval_kernel<kEvalRowMajor>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cat_eval_kernel<kEvalRowMajor><<<grid, threads, smem, stream>>>(*plan, *prm, num_envs, n_groups, nullptr, nullptr, ws, out_rowmajor);
+    cat_eval_kernel<kEvalRowMajor><<<grid, threads, smem, stream>>>(*plan, *prm, num_envs, n_groups, nullptr, nullptr, ws, out_rowmajor, ApplyArgs{});
   }
   CATB200_LAUNCH_CHECK();
   return CATB200_OK;
+}
+
+// Single-launch step (cat_eval_kernel<kEvalFused>): evaluation, grid barrier, apply phase out of shared memory.  Possible
+// while every CTA of the grid is resident at once AND the constraint tiles of all the tiles a CTA walks fit behind its two
+// staging images: up to ~70 k envs with the Solo12 plan (14 tiles of 10 KiB per CTA).  Returns the grid (0: use the
+// two-launch path) and the dynamic shared memory.  CATB200_CAT_FUSED=0 disables it.
+static int fused_geometry(const catb200_plan_t* plan, int num_envs, int threads, size_t* smem_out) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = std::getenv("CATB200_CAT_FUSED");
+    enabled = (e && e[0] == '0') ? 0 : (e && e[0] == '2') ? 2 : 1;
+  }
+  if (!enabled) return 0;
+  const int n_tiles = (num_envs + kTile - 1) / kTile;
+  const size_t image = (size_t)plan->smem_ctile_off, ctile = (size_t)plan->n_cols * kTile * 4;
+  const size_t budget = 227 * 1024 - 8 * 1024;  // static shared memory (column maxima, partial maxima) + reserve
+  for (int per_sm = min(4, 2048 / threads); per_sm >= 1; --per_sm) {
+    const int grid = min(n_tiles, kNumSMs * per_sm);
+    const int per_cta = (n_tiles + grid - 1) / grid;
+    // Measured on the B200 (profiles/README.md, round 2): with one tile per CTA the single launch matches eval + apply
+    // (19.3 vs 18.9 us inside the step graph at 4096 envs, one launch and the C_T round trip fewer); with several tiles per
+    // CTA the apply phase runs out of 16 warps per SM and loses (95 vs 56 us at 65536 envs).  CATB200_CAT_FUSED=2 forces it.
+    if (per_cta > 1 && enabled != 2) continue;
+    const size_t smem = 2 * image + (size_t)per_cta * ctile;
+    if ((smem + 1024) * per_sm > budget) continue;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(cat_eval_kernel<kEvalFused>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      continue;
+    int resident = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, cat_eval_kernel<kEvalFused>, threads, smem) != cudaSuccess) continue;
+    if (resident * kNumSMs < grid) continue;
+    *smem_out = smem;
+    return grid;
+  }
+  return 0;
 }
 
 static int cat_step_impl(const catb200_plan_t* plan, const catb200_cat_params_t* params, int32_t num_envs,
@@ -832,6 +959,20 @@ static int cat_step_impl(const catb200_plan_t* plan, const catb200_cat_params_t*
   if (workspace_bytes < catb200_cat_workspace_bytes(num_envs, plan->n_cols)) return CATB200_ERR_WORKSPACE_TOO_SMALL;
   cudaStream_t st = as_stream(stream);
   CatWorkspace ws = carve(workspace, num_envs);
+  {
+    const int threads = 32 * eval_warps(plan->n_terms);
+    size_t smem = 0;
+    const int fgrid = fused_geometry(plan, num_envs, threads, &smem);
+    if (fgrid > 0) {
+      int n_groups = 1;
+      while (n_groups < kMaxGroups && n_groups * 256 <= fgrid) n_groups <<= 1;
+      ApplyArgs ap = {episode_sums, mean_values, cstr_prob, raw_reward, reset_buf, reward_out, dones_out, episode_length,
+                      reset_out, static_cast<ResetScratch*>(reset_workspace)};
+      cat_eval_kernel<kEvalFused><<<fgrid, threads, smem, st>>>(*plan, *params, num_envs, n_groups, running_max, rm_init, ws, nullptr, ap);
+      CATB200_LAUNCH_CHECK();
+      return CATB200_OK;
+    }
+  }
   int rc = launch_eval(plan, params, num_envs, running_max, rm_init, ws, nullptr, kEvalStep, st);
   if (rc != CATB200_OK) return rc;
   const int grid = (num_envs + kTile - 1) / kTile;
@@ -870,11 +1011,10 @@ int catb200_cat_eval_terms(const catb200_plan_t* plan, int32_t num_envs, float* 
 }
 
 int catb200_cat_probs(const catb200_plan_t* plan, const catb200_cat_params_t* params, int32_t num_envs,
-                      const float* running_max, float* probs_out, const void* workspace, void* stream) {
-  if (!plan || !params || num_envs <= 0 || !running_max || !probs_out || !workspace) return CATB200_ERR_INVALID_ARGUMENT;
-  CatWorkspace ws = carve(const_cast<void*>(workspace), num_envs);
+                      const float* running_max, float* probs_out, const float* raw, void* stream) {
+  if (!plan || !params || num_envs <= 0 || !running_max || !probs_out || !raw) return CATB200_ERR_INVALID_ARGUMENT;
   const int grid = (num_envs + kApplyThreads - 1) / kApplyThreads;
-  cat_probs_kernel<<<grid, kApplyThreads, 0, as_stream(stream)>>>(*plan, *params, num_envs, running_max, ws.c_t, probs_out);
+  cat_probs_kernel<<<grid, kApplyThreads, 0, as_stream(stream)>>>(*plan, *params, num_envs, running_max, raw, probs_out);
   CATB200_LAUNCH_CHECK();
   return CATB200_OK;
 }

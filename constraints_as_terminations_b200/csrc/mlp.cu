@@ -112,7 +112,16 @@ __device__ __forceinline__ float fold_head_group(const FoldArgs& r, int group, f
   const int warp = threadIdx.x >> 5, ln = threadIdx.x & 31;
   const int e = group * 32 + ln;
   float acc = 0.0f;
-  for (int c = warp; c < r.head_rows; c += 8) acc += r.head_part[(size_t)c * kHeadValues * 32 + e];
+  for (int c0 = warp; c0 < r.head_rows; c0 += 64) {  // eight independent loads in flight per thread
+    float t[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = c0 + 8 * u;
+      t[u] = c < r.head_rows ? r.head_part[(size_t)c * kHeadValues * 32 + e] : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc += t[u];
+  }
   part_s[warp][ln] = acc;
   __syncthreads();
   if (warp != 0) return 0.0f;
@@ -258,6 +267,7 @@ struct HeadArgs {
   catb200_ppo_hparams_t hp;
   // training outputs
   float* head_part;  // [gridDim.x][kHeadValues][32] per-CTA partial sums (training)
+  int reverse;       // walk the samples from the last to the first (row order of the minibatch launches, tc_gemm.cu)
 };
 
 template <int PREC>
@@ -348,7 +358,8 @@ head_kernel(const __grid_constant__ HeadArgs a) {
   float n_hc[F] = {0.f, 0.f, 0.f, 0.f}, n_ha[F] = {0.f, 0.f, 0.f, 0.f};
   float4 n_sc = make_float4(0.f, 0.f, 0.f, 0.f);
   float n_act = 0.0f;
-  auto fetch = [&](int mm) {
+  auto fetch = [&](int mi) {
+    const int mm = a.reverse ? a.M - 1 - mi : mi;
     load_row4<PREC>(a.H3[0], (size_t)mm, a.h3, lane, n_hc);
     load_row4<PREC>(a.H3[1], (size_t)mm, a.h3, lane, n_ha);
     if (TRAIN) {
@@ -357,7 +368,8 @@ head_kernel(const __grid_constant__ HeadArgs a) {
     }
   };
   if (m < a.M) fetch(m);
-  for (; m < a.M; m += m_stride) {
+  for (int mi = m; mi < a.M; mi += m_stride) {
+    m = a.reverse ? a.M - 1 - mi : mi;  // the sample this iteration works on
     // ---- the two 128-wide activation rows (coalesced) + scalars of this sample
     float hc[F], ha[F];
     const float4 sc = n_sc;
@@ -367,7 +379,7 @@ head_kernel(const __grid_constant__ HeadArgs a) {
       hc[f] = n_hc[f];
       ha[f] = n_ha[f];
     }
-    if (m + m_stride < a.M) fetch(m + m_stride);
+    if (mi + m_stride < a.M) fetch(mi + m_stride);
     // ---- heads: value and action mean (fp32), warp all-reduce of the per-lane partial dot products
     float v = 0.0f;
 #pragma unroll
@@ -663,8 +675,8 @@ __global__ void __launch_bounds__(256) adam_cast_kernel(const __grid_constant__ 
 // ---- the whole optimizer step of one minibatch as ONE launch (single GPU) --------------------------------------------
 // fold (padded accumulators + head rows -> flat gradient) | squared norm of the flat gradient  -- grid barrier --
 // clip coefficient, bias corrections | Adam on every element + operand copies.  Replaces fold_grads_kernel +
-// grad_norm_kernel + adam_cast_kernel (11 + 6 + 6 us of three latency-bound launches over 1.5 MB).  One CTA per SM, all
-// co-resident (grid <= kNumSMs, 256 threads, < 6 KiB of shared memory): the barrier is an arrival counter in the
+// grad_norm_kernel + adam_cast_kernel (11 + 6 + 6 us of three latency-bound launches over 1.5 MB).  Up to 4 CTAs per SM, all
+// co-resident (256 threads, 40 registers, < 6 KiB of shared memory; the launch asks the occupancy calculator): the barrier is an arrival counter in the
 // optimizer scratch that only ever grows (arrival ticket / grid = generation), the sum of squares is reset by the last CTA
 // that has read it (ticket), so the scratch is clean for the next launch and for catb200_adam_step.
 struct OptStepArgs {
@@ -868,8 +880,22 @@ static int fill_layout(const catb200_mlp_dims_t* d, catb200_mlp_layout_t* L) {
   return CATB200_OK;
 }
 
+// Launches whose activations outgrow the L2 alternate the direction in which they walk the rows (tc_gemm.cu, "row
+// order"): layer 0 upwards, layer 1 downwards, ... so that every launch starts on the rows the previous one finished with.
+// CATB200_ZIGZAG=0 walks upwards everywhere.
+static bool zigzag_rows(const catb200_mlp_dims_t* d, int rows) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = std::getenv("CATB200_ZIGZAG");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  // both nets' activations and their gradients: 2 * 2 * (h1 + h2 + h3) elements per row
+  const size_t bytes = (size_t)rows * 4 * (d->h1 + d->h2 + d->h3) * (d->prec == kPrecTf32 ? 4 : 2);
+  return enabled == 1 && bytes > (size_t)96 << 20;
+}
+
 static int launch_forward(const catb200_mlp_dims_t* d, const catb200_mlp_layout_t& P, const ActLayout& L, const void* X,
-                          int rows, const float* params, const void* wc, char* ws, cudaStream_t st) {
+                          int rows, const float* params, const void* wc, char* ws, cudaStream_t st, bool zigzag = false) {
   Dims x = make_dims(d);
   const size_t es = esize(d);
   const int ch = ch_elems(d), prec = d->prec;
@@ -885,6 +911,7 @@ static int launch_forward(const catb200_mlp_dims_t* d, const catb200_mlp_layout_
       t.bias[z] = params + P.b[z][l];
     }
     t.M = rows; t.N = x.out[l]; t.K = x.in_pad[l];
+    t.reverse = zigzag && (l & 1);
     int rc = tc_gemm_launch(kTcFwd, prec, t, st);
     if (rc != CATB200_OK) return rc;
   }
@@ -1084,7 +1111,8 @@ static int minibatch_backward(const catb200_mlp_dims_t* dims, const catb200_ppo_
                               reinterpret_cast<float4*>(ws + L.scal_mb), reinterpret_cast<float*>(ws + L.act_mb), mb));
   CATB200_LAUNCH_CHECK();
   // 2. forward through the three hidden layers of both nets
-  int rc = launch_forward(dims, P, L, X, M, params, wc, ws, st);
+  const bool zigzag = zigzag_rows(dims, M);  // up: layers 0 and 2, the weight gradients; down: layer 1, heads, dgrads
+  int rc = launch_forward(dims, P, L, X, M, params, wc, ws, st, zigzag);
   if (rc != CATB200_OK) return rc;
   // 3. heads + loss + dZ3
   {
@@ -1101,6 +1129,7 @@ static int minibatch_backward(const catb200_mlp_dims_t* dims, const catb200_ppo_
     a.act_mb = reinterpret_cast<const float*>(ws + L.act_mb);
     a.norm_stats = norm_stats; a.mb = mb; a.hp = *hp;
     a.head_part = reinterpret_cast<float*>(ws + L.head_part);
+    a.reverse = zigzag;
     rc = launch_head<true>(prec, a, L.head_rows, kHeadSmem, st);
     if (rc != CATB200_OK) return rc;
   }
@@ -1131,6 +1160,7 @@ static int minibatch_backward(const catb200_mlp_dims_t* dims, const catb200_ppo_
         fold.N[seg] = x.out[l]; fold.Kpad[seg] = x.in_pad[l]; fold.Ktrue[seg] = x.in[l];
       }
       t.outs = x.out[l]; t.ins_pad = x.in_pad[l]; t.rows = M; t.m_range = L.m_range[l];
+      t.reverse = 0;
       rc = tc_wgrad_launch(prec, t, L.splits[l], wst);
       if (rc != CATB200_OK) return rc;
     }
@@ -1144,6 +1174,7 @@ static int minibatch_backward(const catb200_mlp_dims_t* dims, const catb200_ppo_
         if (rc != CATB200_OK) return rc;
       }
       t.M = M; t.N = x.in[l]; t.K = x.out[l];
+      t.reverse = zigzag;
       rc = tc_gemm_launch(kTcDgrad, prec, t, st);
       if (rc != CATB200_OK) return rc;
     }
@@ -1212,9 +1243,17 @@ int catb200_ppo_minibatch_update(const catb200_mlp_dims_t* dims, const catb200_p
   o.grad_norm_out = grad_norm_out;
   o.sc = static_cast<OptScratch*>(opt_ws);
   cudaStream_t st = as_stream(stream);
-  // a plain (fully stream-ordered) launch of one CTA per SM: all CTAs are co-resident, which the grid barrier needs
-  if (dims->prec == kPrecTf32) opt_step_kernel<kPrecTf32><<<kNumSMs, 256, 0, st>>>(o);
-  else opt_step_kernel<kPrecBf16><<<kNumSMs, 256, 0, st>>>(o);
+  // a plain (fully stream-ordered) launch of as many CTAs as are co-resident (the grid barrier needs that), at most 4 per
+  // SM: the kernel is a few latency chains over 1.5 MB -- one CTA per SM took 31 us, more than the three launches it replaces
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    int a32 = 0, a16 = 0;
+    CATB200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a32, opt_step_kernel<kPrecTf32>, 256, 0));
+    CATB200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a16, opt_step_kernel<kPrecBf16>, 256, 0));
+    per_sm = max(1, min(4, min(a32, a16)));
+  }
+  if (dims->prec == kPrecTf32) opt_step_kernel<kPrecTf32><<<kNumSMs * per_sm, 256, 0, st>>>(o);
+  else opt_step_kernel<kPrecBf16><<<kNumSMs * per_sm, 256, 0, st>>>(o);
   CATB200_LAUNCH_CHECK();
   return CATB200_OK;
 }

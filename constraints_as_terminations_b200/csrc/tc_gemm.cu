@@ -18,6 +18,14 @@
 // fp32 tile leaves TMEM straight into the gradient accumulators with red.global.add.v4.f32 (no partial-sum buffers,
 // no reduction kernel), and the bias gradient is the same A operand multiplied by a tile of ones (N = 16), so the
 // dgrad epilogue carries no column sums.
+//
+// Row order.  With fp32 activations a 16384-row minibatch moves ~720 MB through HBM (the activations of both nets are
+// 234 MB: twice the L2) and warm-cache ncu counters showed EVERY consumer re-reading from DRAM what the previous launch
+// had just written: producer and consumer both walked the rows upwards, so the rows a consumer wanted first were the ones
+// the L2 had dropped first.  All kernels therefore process rows in one global time order (tile index = row tile first,
+// then net, then column tile; the weight-gradient CTAs sweep interleaved 64-row blocks instead of owning contiguous row
+// ranges) and the launches of a minibatch alternate its direction (`reverse`), so that each one starts on the rows the
+// previous one touched last.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -34,41 +42,72 @@ constexpr int kEpiWarps = kTcThreads / 32 - 2;
 constexpr int kRowBytes = 128;                 // one SWIZZLE_128B row
 constexpr int kATileBytes = 128 * kRowBytes;   // 16 KiB: 128 rows (M or N) x 128 bytes of K
 constexpr int kSlabBytes = 32 * kRowBytes;     // 4 KiB: one epilogue warp's 32 rows x 128 bytes of output
-constexpr int kPStages = 4;
 
-struct PSmem {
-  static constexpr int kStage = 2 * kATileBytes;                  // A tile + B tile (BN = 128)
-  static constexpr int kSlabs = kEpiWarps * 2 * kSlabBytes;       // two slabs per epilogue warp
-  static constexpr int kBars = 8 * (2 * kPStages + 4 + 2 * kEpiWarps);
-  static constexpr int kBias = 2 * kEpiWarps * 64 * 4;            // double-buffered 64 bias values per warp
-  static constexpr int kTotal = kPStages * kStage + kSlabs + ((kBars + 15) & ~15) + 16 + kBias + 1024 /*alignment slack*/;
+// Epilogue geometry.  Measured on the B200 (profiles/README.md, round 2), tf32: 16 epilogue warps (4 per TMEM lane quarter,
+// 32 output columns = one 128-byte slab row each, one slab buffer per warp) make the forward launches 3 % faster than 8
+// -- the 8-warp fp32 epilogue issues ~12 instructions per output element from 2 warps per scheduler at IPC 0.35 -- but the
+// dgrad launches 10 % slower (one buffer per warp: the H slab of the next tile cannot be requested before the store of
+// this one has been read).  So: forward tf32 16 warps, everything else 8 warps with two slab buffers (tf32: the two
+// 32-column halves of a warp's 64 columns; bf16: one 64-column slab, alternating per tile).
+template <int PREC, int MODE, int STAGES>
+struct PCfg {
+  static constexpr int kPStages = STAGES;
+  static constexpr int kEpi = (PREC == kPrecTf32 && MODE == kTcFwd) ? 16 : 8;
+  static constexpr int kThreads = 64 + 32 * kEpi;
+  static constexpr int kWCols = 128 / (kEpi / 4);                  // output columns per epilogue warp: 32 / 64
+  static constexpr int kBufs = kEpi == 16 ? 1 : 2;                 // slab buffers per warp
+  static constexpr int kStage = 2 * kATileBytes;                   // A tile + B tile (BN = 128)
+  static constexpr int kSlabs = kEpi * kBufs * kSlabBytes;
+  static constexpr int kBars = 8 * (2 * kPStages + 4 + 2 * kEpi);
+  static constexpr int kBias = kEpi * kWCols * 4;                  // one private row of bias values per warp
+  // no alignment slack: the kernel has no static shared memory, so the dynamic window starts 1024-byte aligned (checked)
+  static constexpr int kTotal = kPStages * kStage + kSlabs + ((kBars + 15) & ~15) + 16 + kBias;
+  static_assert(kTotal <= 232448, "shared memory budget");
 };
 
-template <int MODE, int PREC>
-__global__ void __launch_bounds__(kTcThreads, 1)
+// cp.async.bulk.wait_group.read with a pending count known after unrolling
+__device__ __forceinline__ void bulk_wait_read(int pending) {
+  if (pending <= 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+  else asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
+}
+
+template <int MODE, int PREC, int STAGES>
+__global__ void __launch_bounds__(PCfg<PREC, MODE, STAGES>::kThreads, 1)
 mlp_gemm_kernel(const __grid_constant__ TcGemmArgs g) {
   using P = PrecT<PREC>;
-  using S = PSmem;
+  using S = PCfg<PREC, MODE, STAGES>;
   constexpr int BN = 128;
+  constexpr int kPStages = STAGES;
+  constexpr int kEpi = S::kEpi, kWCols = S::kWCols, kBufs = S::kBufs;
   constexpr int CH = kRowBytes / (int)sizeof(typename P::T);  // output columns per slab row: 64 bf16 / 32 fp32
-  constexpr int NCHUNK = 64 / CH;                             // slabs per warp and tile: 1 / 2
-  extern __shared__ uint8_t smem_raw[];
+  constexpr int NCHUNK = kWCols / CH;                         // slabs per warp and tile: 1, or 2 (tf32 with 8 warps)
+  constexpr int LD = kWCols / 32;                             // 32-column TMEM loads per warp and tile
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   pdl_launch_dependents();
   const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t tiles = (raw + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
+  if (raw & 1023u) __trap();  // SWIZZLE_128B atoms need 1024-byte alignment
+  const uint32_t tiles = raw;
   const uint32_t slabs = tiles + kPStages * S::kStage;
   const uint32_t bars = slabs + S::kSlabs;
   const uint32_t full_bar = bars, empty_bar = bars + 8 * kPStages;
   const uint32_t tfull_bar = bars + 16 * kPStages, tempty_bar = tfull_bar + 16;
-  const uint32_t h_bar = tempty_bar + 16;  // [kEpiWarps][2]
+  const uint32_t h_bar = tempty_bar + 16;  // [kEpi][2]
   const uint32_t tmem_slot = bars + ((S::kBars + 15) & ~15);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
-  float* bias_sm = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - raw));  // [2][kEpiWarps][64]
+  float* bias_sm = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - raw));  // [kEpi][kWCols]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = g.N / BN, tiles_m = (g.M + 127) / 128;
-  const int per_net = tiles_m * tiles_n, total = 2 * per_net;
+  const int total = 2 * tiles_m * tiles_n;
   const int k_blocks = g.K / P::kBK;
+  // tile t of the launch: row tile first, then net, then column tile -- in time order, or backwards
+  auto tile_coords = [&](int t, int& z, int& row_base, int& col_base) {
+    const int tt = g.reverse ? total - 1 - t : t;
+    const int m = tt / (2 * tiles_n), r = tt - m * 2 * tiles_n;
+    z = r / tiles_n;
+    row_base = m * 128;
+    col_base = (r - z * tiles_n) * BN;
+  };
 
   if (warp == 0 && lane == 0) {
     for (int z = 0; z < 2; ++z) {
@@ -83,9 +122,9 @@ mlp_gemm_kernel(const __grid_constant__ TcGemmArgs g) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar + 8 * a, 1);
-      mbar_init(tempty_bar + 8 * a, kEpiWarps);  // one arrival per epilogue warp
+      mbar_init(tempty_bar + 8 * a, kEpi);  // one arrival per epilogue warp
     }
-    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(h_bar + 8 * i, 1);
+    for (int i = 0; i < 2 * kEpi; ++i) mbar_init(h_bar + 8 * i, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
@@ -102,8 +141,8 @@ mlp_gemm_kernel(const __grid_constant__ TcGemmArgs g) {
     if (elect_one()) {
       uint32_t it = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        const int z = t / per_net, r = t - z * per_net;
-        const int row_base = (r / tiles_n) * 128, col_base = (r % tiles_n) * BN;
+        int z, row_base, col_base;
+        tile_coords(t, z, row_base, col_base);
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {
           const uint32_t s = it % kPStages;
           mbar_wait(empty_bar + 8 * s, ((it / kPStages) & 1) ^ 1);
@@ -145,66 +184,62 @@ mlp_gemm_kernel(const __grid_constant__ TcGemmArgs g) {
       }
     }
   } else {
-    // ===================== epilogue (warps 2..9) =====================
+    // ===================== epilogue (warps 2 .. kEpi + 1) =====================
     const int ew = warp - 2;
-    const int quarter = warp & 3;  // TMEM lanes 32 * quarter .. + 31 are the ones this warp may read
-    const int half = ew >> 2;      // the two warps of a quarter split the BN columns in halves
-    const int c_first = half * 64;
-    const uint32_t my_slabs = slabs + ew * 2 * kSlabBytes;
+    const int quarter = warp & 3;        // TMEM lanes 32 * quarter .. + 31 are the ones this warp may read
+    const int c_first = (ew >> 2) * kWCols;  // the warps of a quarter split the BN columns
+    const uint32_t my_slabs = slabs + ew * kBufs * kSlabBytes;
     const uint32_t my_hbar = h_bar + ew * 16;
     const uint32_t lane_row = lane * kRowBytes, lane_x = lane & 7;
     uint32_t j = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
-      const int z = t / per_net, r = t - z * per_net;
-      const int row_base = (r / tiles_n) * 128, col_base = (r % tiles_n) * BN;
+      int z, row_base, col_base;
+      tile_coords(t, z, row_base, col_base);
       const uint32_t a = j & 1;
-      // slab buffer of chunk c: fp32 has two 32-column chunks per tile (buffer c, used once per tile); bf16 has one
-      // 64-column chunk (buffer j & 1, used every other tile).  Before a buffer is refilled, the TMA store that last
-      // read it must have finished reading: bulk groups complete in order, so "at most n pending" is enough.
-      float* bsm = bias_sm + ((j & 1) * kEpiWarps + ew) * 64;
+      // Slab n = j * NCHUNK + c of this warp lives in buffer n % kBufs.  Before a buffer is refilled, the TMA store that
+      // last read it (slab n - kBufs) must have finished reading; bulk groups complete in order, so it is enough to bound
+      // the number of stores still pending.
+      float* bsm = bias_sm + ew * kWCols;  // private to this warp: rewritten only after the previous tile's math
       if (MODE == kTcDgrad) {
-        // H values of this warp's slabs arrive by TMA while the MMAs still run
+        // the H values of this warp's slabs arrive by TMA while the MMAs still run
         if (lane == 0) {
 #pragma unroll
           for (int c = 0; c < NCHUNK; ++c) {
-            const uint32_t buf = NCHUNK == 2 ? (uint32_t)c : (j & 1);
-            if (NCHUNK == 2 && c == 1) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
-            else asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
+            const uint32_t n = j * NCHUNK + c, buf = n % kBufs;
+            bulk_wait_read(kBufs - 1 - c);  // stores issued so far: up to slab j * NCHUNK - 1
             mbar_expect_tx(my_hbar + 8 * buf, kSlabBytes);
             tma_load_2d(my_slabs + buf * kSlabBytes, &g.mapH[z], my_hbar + 8 * buf, col_base + c_first + c * CH, row_base + quarter * 32);
           }
         }
       } else {
-        // this warp's 64 bias values, fetched coalesced into its own scratch row; the math reads them as broadcasts
+        // this warp's bias values, fetched coalesced into its own scratch row; the math reads them as broadcasts
         const float* __restrict__ bp = g.bias[z] + col_base + c_first;
-        bsm[lane] = __ldg(bp + lane);
-        bsm[32 + lane] = __ldg(bp + 32 + lane);
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < kWCols; c += 32) bsm[c + lane] = __ldg(bp + c + lane);
       }
       if (lane == 0) mbar_wait(tfull_bar + 8 * a, (j >> 1) & 1);  // one sleeping lane per warp
       __syncwarp();
       mbar_wait(tfull_bar + 8 * a, (j >> 1) & 1);                 // already complete: a single acquire per thread
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * BN + c_first;
-      uint32_t v[2][32];
-      tmem_ld32(taddr, v[0]);
-      tmem_ld32(taddr + 32, v[1]);
-      tmem_ld_wait(v[0]);
-      tmem_ld_wait(v[1]);
+      uint32_t v[LD][32];
+#pragma unroll
+      for (int l = 0; l < LD; ++l) tmem_ld32(taddr + l * 32, v[l]);
+#pragma unroll
+      for (int l = 0; l < LD; ++l) tmem_ld_wait(v[l]);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar + 8 * a);  // the MMA warp may overwrite this stage (tile j + 2)
 
 #pragma unroll
       for (int c = 0; c < NCHUNK; ++c) {
-        const uint32_t buf = NCHUNK == 2 ? (uint32_t)c : (j & 1);
+        const uint32_t n = j * NCHUNK + c, buf = n % kBufs;
         const uint32_t slab = my_slabs + buf * kSlabBytes;
         if (MODE == kTcDgrad) {
-          mbar_wait(my_hbar + 8 * buf, NCHUNK == 2 ? (j & 1) : ((j >> 1) & 1));
+          mbar_wait(my_hbar + 8 * buf, (n / kBufs) & 1);
         } else {
-          if (lane == 0) {
-            if (NCHUNK == 2 && c == 1) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
-            else asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
-          }
+          if (lane == 0) bulk_wait_read(kBufs - 1);  // stores issued so far: up to slab n - 1
           __syncwarp();
         }
 #pragma unroll
@@ -228,7 +263,7 @@ mlp_gemm_kernel(const __grid_constant__ TcGemmArgs g) {
           } else {
             float x[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[q >> 2][(q & 3) * 8 + e]);
+            for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[(q >> 2) % LD][(q & 3) * 8 + e]);
             if (MODE == kTcFwd) {
               const float4 b0 = *reinterpret_cast<const float4*>(bsm + q * 8);
               const float4 b1 = *reinterpret_cast<const float4*>(bsm + q * 8 + 4);
@@ -834,9 +869,10 @@ mlp_wgrad_kernel(const __grid_constant__ TcWgradArgs g) {
   const int row_base = (blockIdx.x / n_tiles) * 128;  // dW rows = output features of the layer
   const int col_base = (blockIdx.x % n_tiles) * BN;   // dW columns = input features
   const bool with_bias = col_base == 0;                // one column tile per row tile also produces db
-  const int k_begin = blockIdx.y * g.m_range;
-  const int k_end = min(g.rows, k_begin + g.m_range);
-  const int k_blocks = max(0, (k_end - k_begin + kWgRows - 1) / kWgRows);
+  // the splits sweep the minibatch together: split y takes the 64-row blocks y, y + splits, y + 2 splits, ... (from the
+  // far end when `reverse`), so the launch as a whole walks the rows in one direction
+  const int blocks_total = (g.rows + kWgRows - 1) / kWgRows;
+  const int k_blocks = max(0, (blocks_total - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(&g.mapA[z]));
@@ -869,7 +905,8 @@ mlp_wgrad_kernel(const __grid_constant__ TcWgradArgs g) {
         mbar_wait(empty_bar + 8 * s, ((kb / kWgStages) & 1) ^ 1);
         const uint32_t sa = tiles + s * S::kStage, sb = sa + kABytes;
         mbar_expect_tx(full_bar + 8 * s, S::kStage);
-        const int k0 = k_begin + kb * kWgRows;
+        const int rb = kb * (int)gridDim.y + (int)blockIdx.y;
+        const int k0 = (g.reverse ? blocks_total - 1 - rb : rb) * kWgRows;
         // MN-major operands: boxes of CH contiguous features x 64 reduction rows; rows beyond the matrix are zero-filled
         for (int h = 0; h < 128 / CH; ++h) tma_load_2d(sa + h * kBoxBytes, &g.mapA[z], full_bar + 8 * s, row_base + h * CH, k0);
         for (int h = 0; h < BN / CH; ++h) tma_load_2d(sb + h * kBoxBytes, &g.mapB[z], full_bar + 8 * s, col_base + h * CH, k0);
@@ -1009,17 +1046,32 @@ int make_tmap(CUtensorMap* map, int prec, const void* ptr, uint64_t inner, uint6
   return rc;
 }
 
-template <int MODE, int PREC>
-static int launch_gemm(const TcGemmArgs& g, cudaStream_t st) {
+template <int MODE, int PREC, int STAGES>
+static int launch_gemm_st(const TcGemmArgs& g, cudaStream_t st) {
+  using S = PCfg<PREC, MODE, STAGES>;
   static bool attr = false;
   if (!attr) {
-    CATB200_CUDA_TRY(cudaFuncSetAttribute(mlp_gemm_kernel<MODE, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, PSmem::kTotal));
+    CATB200_CUDA_TRY(cudaFuncSetAttribute(mlp_gemm_kernel<MODE, PREC, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     attr = true;
   }
   const int total = 2 * ((g.M + 127) / 128) * (g.N / 128);
-  CATB200_CUDA_TRY(launch_pdl(mlp_gemm_kernel<MODE, PREC>, dim3(min(total, kNumSMs)), dim3(kTcThreads), (size_t)PSmem::kTotal, st, g));
+  CATB200_CUDA_TRY(launch_pdl(mlp_gemm_kernel<MODE, PREC, STAGES>, dim3(min(total, kNumSMs)), dim3(S::kThreads), (size_t)S::kTotal, st, g));
   CATB200_LAUNCH_CHECK();
   return CATB200_OK;
+}
+
+// ring depth: CATB200_GEMM_STAGES = 3, 4 (default) or 5 -- 32 KiB of operands per stage
+template <int MODE, int PREC>
+static int launch_gemm(const TcGemmArgs& g, cudaStream_t st) {
+  static int stages = 0;
+  if (stages == 0) {
+    const char* e = std::getenv("CATB200_GEMM_STAGES");
+    stages = e ? atoi(e) : 4;
+    if (stages < 3 || stages > 5) stages = 4;
+  }
+  if (stages == 3) return launch_gemm_st<MODE, PREC, 3>(g, st);
+  if (stages == 5) return launch_gemm_st<MODE, PREC, 5>(g, st);
+  return launch_gemm_st<MODE, PREC, 4>(g, st);
 }
 
 template <int MODE, int PREC, int BN>

@@ -19,6 +19,7 @@ struct TcGemmArgs {
   CUtensorMap mapH[2];   // dgrad: forward activation H [M, N] whose ELU' scales the result, same boxes as mapC
   const float* bias[2];  // fwd: [N]
   int M, N, K;           // rows, output features, reduction length
+  int reverse;           // mlp_gemm_kernel: walk the row tiles from the last to the first (see "row order" in tc_gemm.cu)
 };
 
 // weight gradient dW[outs, ins] += dZ[rows, outs]^T Hin[rows, ins] over a range of minibatch rows, and
@@ -29,7 +30,8 @@ struct TcWgradArgs {
   float* gw[2];         // fp32 accumulators [outs, ins_pad] (16-byte aligned rows): red.global.add.v4.f32
   float* gb[2];         // bias gradient [outs]
   int outs, ins_pad, rows;
-  int m_range;          // minibatch rows per split (multiple of kBK)
+  int m_range;          // minibatch rows per split (multiple of kBK): sizes the split count only
+  int reverse;          // sweep the minibatch rows from the last block to the first
 };
 
 // 2-D tensor map over a row-major [outer, inner] matrix of bf16 (prec 0) or fp32 (prec 1) elements with leading

@@ -172,10 +172,10 @@ int catb200_cat_step_reset(const catb200_plan_t* plan, const catb200_cat_params_
  * raw_constraints, constraint_manager.py:52; also backs the stand-alone term functions). */
 int catb200_cat_eval_terms(const catb200_plan_t* plan, int32_t num_envs, float* out, void* stream);
 
-/* Per-column probabilities [num_envs, n_cols] of the most recent catb200_cat_step, rebuilt from the
- * constraint values kept in `workspace` (what CaT keeps as `probs`, constraint_manager.py:74). */
+/* Per-column probabilities [num_envs, n_cols] (what CaT keeps as `probs`, constraint_manager.py:64-74) of the raw
+ * constraint values `raw` (row-major [num_envs, n_cols], from catb200_cat_eval_terms) under `running_max`. */
 int catb200_cat_probs(const catb200_plan_t* plan, const catb200_cat_params_t* params, int32_t num_envs,
-                      const float* running_max, float* probs_out, const void* workspace, void* stream);
+                      const float* running_max, float* probs_out, const float* raw, void* stream);
 
 /*
  * ConstraintManager.reset (U/cat/constraint_manager.py:190-211): for each statistics row s,

@@ -332,3 +332,50 @@ def test_adam_step_matches_torch(prec):
     ops.adam_step(dims, params, (grad * 4).clone(), m, v, w16, lr, step, opt_ws, grad_scale=0.25)
     ops.adam_step(dims, p2, grad.clone(), m2, v2, w16, lr, step2, opt_ws, grad_scale=1.0)
     torch.testing.assert_close(params, p2, rtol=1e-6, atol=1e-8)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_fused_minibatch_update_matches_grad_then_adam(prec):
+    """catb200_ppo_minibatch_update (gradient + ONE fold / norm / clip / Adam / operand-copy launch) against the two
+    separate calls it replaces, three optimizer steps: same parameters, moments, operand copies, step counter, gradient
+    norm; gradient and scratch left clean.  Only the atomics order of the weight-gradient sums differs between two runs of
+    either path; the two states are re-synchronised after every step so that a flipped operand rounding (one bf16 / tf32
+    ulp of a weight) cannot compound."""
+    agent = make_agent(seed=4)
+    obs, actions, logp, adv, returns, values, ns, idx = _minibatch(agent, 9000, 5000, seed=11)
+    hp = ops.make_hparams()
+    states = []
+    for _ in range(2):
+        dims, layout, params, wc = device_agent(agent, prec)
+        n = layout.n_params
+        states.append(dict(
+            dims=dims, params=params, wc=wc, grads=torch.zeros(n, device=DEV), m=torch.zeros(n, device=DEV), v=torch.zeros(n, device=DEV),
+            la=torch.zeros(8, device=DEV), lr=torch.tensor(3e-4, device=DEV), step=torch.zeros(1, dtype=torch.int32, device=DEV),
+            opt_ws=torch.zeros(8, dtype=torch.int64, device=DEV), norm=torch.zeros(1, device=DEV), ws=ops.mlp_workspace(dims, 5000, True, DEV),
+        ))  # fmt: skip
+    obs_op = ops.obs_to_operand(states[0]["dims"], obs.to(DEV))
+    data = [t.to(DEV) for t in (actions, logp, adv, returns, values, ns)]
+    A, B = states
+    for k in range(3):
+        mb = idx.to(DEV).roll(37 * k)
+        ops.ppo_minibatch_grad(A["dims"], hp, mb, obs_op, *data, A["params"], A["wc"], A["grads"], A["la"], A["ws"])
+        ops.adam_step(A["dims"], A["params"], A["grads"], A["m"], A["v"], A["wc"], A["lr"], A["step"], A["opt_ws"],
+                      max_grad_norm=1.0, eps=1e-5, grad_norm_out=A["norm"])
+        ops.ppo_minibatch_update(B["dims"], hp, mb, obs_op, *data, B["params"], B["wc"], B["grads"], B["la"], B["ws"], B["m"], B["v"],
+                                 B["lr"], B["step"], B["opt_ws"], max_grad_norm=1.0, eps=1e-5, grad_norm_out=B["norm"])
+        torch.cuda.synchronize()
+        for S in (A, B):
+            assert float(S["grads"].abs().sum()) == 0.0
+            assert int(S["step"]) == k + 1
+            assert int(S["opt_ws"].view(torch.int32)[0]) == 0  # ticket back at zero
+            assert float(S["opt_ws"].view(torch.float64)[4]) == 0.0  # sum of squares reset
+        assert float(B["norm"]) == pytest.approx(float(A["norm"]), rel=1e-5)
+        torch.testing.assert_close(B["la"], A["la"], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(B["m"], A["m"], rtol=1e-4, atol=1e-7)
+        torch.testing.assert_close(B["v"], A["v"], rtol=1e-4, atol=1e-12)
+        # Adam's first steps move every weight by ~lr whatever the gradient's size: parameters are compared to a
+        # fraction of one step, operand copies to one unit in the last place of their precision
+        assert float((B["params"] - A["params"]).abs().max()) < 0.05 * 3e-4
+        assert float((B["wc"].float() - A["wc"].float()).abs().max()) < (2e-2 if prec == "bf16" else 2e-3)
+        for key in ("params", "m", "v", "wc"):
+            B[key].copy_(A[key])
