@@ -852,7 +852,7 @@ mlp_wgrad_kernel(const __grid_constant__ TcWgradArgs g) {
   constexpr int CH = kRowBytes / (int)sizeof(T);   // features per 128-byte row: 64 / 32
   constexpr int kBoxBytes = kWgRows * kRowBytes;   // one TMA box: CH features x 64 rows (8 KiB)
   constexpr int kABytes = (128 / CH) * kBoxBytes;  // the 128 dZ features of a stage
-  constexpr int kTmemCols = BN == 128 ? 256 : 128; // BN accumulator columns + 16 for the bias MMA, power of two
+  constexpr int kTmemCols = BN == 256 ? 512 : BN == 128 ? 256 : 128;  // BN accumulator columns + 16 for the bias MMA, power of two
   extern __shared__ uint8_t smem_raw[];
   pdl_launch_dependents();
   const uint32_t raw = smem_u32(smem_raw);
@@ -955,18 +955,22 @@ mlp_wgrad_kernel(const __grid_constant__ TcWgradArgs g) {
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    uint32_t v[NCH][32];
-#pragma unroll
-    for (int i = 0; i < NCH; ++i) tmem_ld32(taddr + c_first + i * 32, v[i]);
-#pragma unroll
-    for (int i = 0; i < NCH; ++i) tmem_ld_wait(v[i]);
     float* __restrict__ grow = g.gw[z] + (size_t)row * g.ins_pad + col_base + c_first;
+    constexpr int G = NCH >= 2 ? 2 : 1;  // 32-column chunks read from TMEM at a time
 #pragma unroll
-    for (int i = 0; i < NCH; ++i)
+    for (int i0 = 0; i0 < NCH; i0 += G) {
+      uint32_t v[G][32];
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        red_add_v4(grow + i * 32 + q * 4, __uint_as_float(v[i][q * 4]), __uint_as_float(v[i][q * 4 + 1]),
-                   __uint_as_float(v[i][q * 4 + 2]), __uint_as_float(v[i][q * 4 + 3]));
+      for (int i = 0; i < G; ++i) tmem_ld32(taddr + c_first + (i0 + i) * 32, v[i]);
+#pragma unroll
+      for (int i = 0; i < G; ++i) tmem_ld_wait(v[i]);
+#pragma unroll
+      for (int i = 0; i < G; ++i)
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          red_add_v4(grow + (i0 + i) * 32 + q * 4, __uint_as_float(v[i][q * 4]), __uint_as_float(v[i][q * 4 + 1]),
+                     __uint_as_float(v[i][q * 4 + 2]), __uint_as_float(v[i][q * 4 + 3]));
+    }
     if (with_bias && half == 0) {
       uint32_t b[8];
       tmem_ld8(taddr + BN, b);
@@ -1088,19 +1092,21 @@ static int launch_gemm256(const TcGemmArgs& g, cudaStream_t st) {
   return CATB200_OK;
 }
 
-// 256-row tiles: opt-in (CATB200_TILE256=1) for launches that still fill most of the machine with them.  Measured on
-// the B200 (profiles/README.md, round 2): half the operand bytes, but no faster than the 128 x 128 tiles -- 22.2 vs
-// 19.5 us per forward launch, 25.8 vs 22.7 us per dgrad launch at 16384 rows: with BN = 256 the single accumulator stage
-// serialises load -> MMA -> epilogue per tile, and 256 tiles on 148 SMs quantise to two waves.  The 128 x 128 kernel runs
-// at ~13 TB/s of L2 -> SM operand traffic, the chip's L2 cap; halving the bytes WITH overlap needs cta_group::2 pairs.
-static bool use_tile256(int M, int N) {
+// 256-row tiles (half the operand bytes per flop).  Measured per launch inside the step graph at 16384 rows (B200,
+// profiles/README.md, round 2; 128 x 128 tiles -> 256-row tiles): forward 512 -> 256: 30.3 -> 25.0 us, forward 256 -> 128:
+// 12.4 -> 11.4 us, forward 45 -> 512: 15.2 -> 19.4 us, dgrads 14.7 -> 15.8 and 34.1 -> 35.9 us.  The launches with a long
+// reduction are bound by L2 -> SM operand traffic (~10 TB/s) and gain; where the epilogue dominates (K = 64, the dgrads'
+// H loads) the single accumulator stage of BN = 256 loses.  Default: forward launches with K >= 256 that fill most of
+// the machine.  CATB200_TILE256=1 uses them everywhere, =0 nowhere.
+static bool use_tile256(int mode, int prec, int M, int N, int K) {
   static int v = -1;
   if (v < 0) {
     const char* e = std::getenv("CATB200_TILE256");
-    v = (e && e[0] == '1') ? 1 : 0;
+    v = (e && e[0] == '1') ? 1 : (e && e[0] == '0') ? 0 : 2;
   }
   const int bn = N % 256 == 0 ? 256 : 128;
-  return v == 1 && 2 * ((M + 255) / 256) * (N / bn) >= 96;
+  if (v == 0 || 2 * ((M + 255) / 256) * (N / bn) < 96) return false;
+  return v == 1 || (mode == kTcFwd && prec == kPrecTf32 && K >= 256);  // (not measured with bf16 operands)
 }
 
 // CTA pairs (256 x 256 tiles, cta_group::2) for launches with N a multiple of 256 that give every pair work: opt-in
@@ -1133,7 +1139,7 @@ static int launch_gemm_pairs(const TcGemmArgs& g, cudaStream_t st) {
 template <int MODE, int PREC>
 static int launch_gemm_any(const TcGemmArgs& g, cudaStream_t st) {
   if (use_pairs(g.M, g.N)) return launch_gemm_pairs<MODE, PREC>(g, st);
-  if (use_tile256(g.M, g.N)) {
+  if (use_tile256(MODE, PREC, g.M, g.N, g.K)) {
     if (g.N % 256 == 0) return launch_gemm256<MODE, PREC, 256>(g, st);
     return launch_gemm256<MODE, PREC, 128>(g, st);
   }
@@ -1161,8 +1167,23 @@ static int launch_wgrad(const TcWgradArgs& g, int splits, cudaStream_t st) {
   return CATB200_OK;
 }
 
+// Column tile of the weight gradient.  256 input features per CTA (a CTA streams its 128 dZ features once per 256 instead
+// of once per 128 input features) is opt-in, CATB200_WGRAD256=1: measured slower on the B200 (profiles/README.md, round 2:
+// 17.0 vs 12.5 us and 30.7 vs 29.4 us per launch) -- its 96 KiB stages leave a two-deep ring.
+int tc_wgrad_bn(int prec, int ins_pad) {
+  static int wide = -1;
+  if (wide < 0) {
+    const char* e = std::getenv("CATB200_WGRAD256");
+    wide = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (wide && prec == kPrecTf32 && ins_pad % 256 == 0) return 256;
+  return ins_pad % 128 == 0 ? 128 : 64;
+}
+
 int tc_wgrad_launch(int prec, const TcWgradArgs& g, int splits, cudaStream_t st) {
   if (g.outs % 128 || splits <= 0) return CATB200_ERR_UNSUPPORTED;
+  const int bn = tc_wgrad_bn(prec, g.ins_pad);
+  if (bn == 256) return launch_wgrad<kPrecTf32, 256>(g, splits, st);
   if (g.ins_pad % 128 == 0)
     return prec == kPrecTf32 ? launch_wgrad<kPrecTf32, 128>(g, splits, st) : launch_wgrad<kPrecBf16, 128>(g, splits, st);
   if (g.ins_pad % 64 == 0)

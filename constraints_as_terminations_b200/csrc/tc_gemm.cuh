@@ -41,5 +41,6 @@ int make_tmap(CUtensorMap* map, int prec, const void* ptr, uint64_t inner, uint6
               uint32_t box_outer, int swz32 = 0);
 int tc_gemm_launch(int mode, int prec, const TcGemmArgs& g, cudaStream_t st);
 int tc_wgrad_launch(int prec, const TcWgradArgs& g, int splits, cudaStream_t st);
+int tc_wgrad_bn(int prec, int ins_pad);  // input features per weight-gradient CTA: 256, 128 or 64
 
 }  // namespace catb200
