@@ -265,26 +265,39 @@ def _traffic():
     return json.load(open(path)) if os.path.isfile(path) else {}
 
 
+def _gemm_kernel_name(mode, p, rows, n_out, k_pad):
+    """Kernel a forward (mode 0) / dgrad (mode 1) launch is dispatched to -- the default rules of csrc/tc_gemm.cu
+    (`launch_gemm_any` / `use_tile256`), spelled the way CUPTI prints the instantiation."""
+    bn = 256 if n_out % 256 == 0 else 128
+    ctas256 = 2 * ((rows + 255) // 256) * (n_out // bn)
+    tile256 = os.environ.get("CATB200_TILE256", "")
+    if tile256 != "0" and ctas256 >= 96 and (tile256 == "1" or (mode == 0 and p == 1 and k_pad >= 256)):
+        return f"mlp_gemm256_kernel<{mode}, {p}, {bn}>"
+    stages = os.environ.get("CATB200_GEMM_STAGES", "4")
+    return f"mlp_gemm_kernel<{mode}, {p}, {stages if stages in ('3', '5') else '4'}>"
+
+
 def _gemm_flops_by_kernel(trainer):
-    """ALGORITHMIC tensor-core flops per iteration attributed to each tcgen05 kernel name (csrc/tc_gemm.cu): layer 0
-    counted at K = 45 (SURVEY.md §8d: 0.7508 MFLOP/sample forward), not at the K = 64 the padded operand rows carry;
-    both nets (critic + actor) run in every launch.  mlp_gemm_kernel<0, P> = forward, <1, P> = dgrad,
-    mlp_wgrad_kernel<P, BN> = weight gradients (BN = 64 for the 45 -> 512 layer, 128 otherwise)."""
+    """ALGORITHMIC tensor-core flops per iteration attributed to each tcgen05 kernel instantiation (csrc/tc_gemm.cu):
+    layer 0 counted at K = 45 (0.7508 MFLOP/sample forward), not at the K = 64 the padded operand rows
+    carry; both nets (critic + actor) run in every launch.  mlp_gemm_kernel<0, P, S> / mlp_gemm256_kernel<0, P, BN> =
+    forward, <1, ...> = dgrad, mlp_wgrad_kernel<P, BN> = weight gradients (BN = 64 for the 45 -> 512 layer)."""
     n, T = trainer.num_envs, trainer.T
-    opt_rows = trainer.batch_size * int(trainer.cfg.updates_epochs)  # minibatch rows per iteration
+    mb, n_opt = trainer.minibatch_size, (trainer.batch_size // trainer.minibatch_size) * int(trainer.cfg.updates_epochs)
     p = 1 if trainer.agent.precision == "tf32" else 0
-    layers = [(45, 512), (512, 256), (256, 128)]  # (K, N) of the hidden layers
+    layers = [(45, 64, 512), (512, 512, 256), (256, 256, 128)]  # (K, K padded, N) of the hidden layers
     flops = {}
 
-    def add(name, total_rows, k, n_out):
-        flops[name] = flops.get(name, 0.0) + 2.0 * 2 * k * n_out * total_rows
+    def add(name, rows, launches, k, n_out):
+        flops[name] = flops.get(name, 0.0) + 2.0 * 2 * k * n_out * rows * launches
 
-    for k, n_out in layers:
-        add(f"mlp_gemm_kernel<0, {p}>", opt_rows + n * (T + 1), k, n_out)   # update forward + rollout policy + bootstrap
-    for k, n_out in layers[1:]:
-        add(f"mlp_gemm_kernel<1, {p}>", opt_rows, n_out, k)                # dgrad: dZ_l [M, N_l] x W_l -> [M, K_l]
-    for k, n_out in layers:
-        add(f"mlp_wgrad_kernel<{p}, {64 if k < 128 else 128}>", opt_rows, k, n_out)
+    for k, k_pad, n_out in layers:
+        add(_gemm_kernel_name(0, p, mb, n_out, k_pad), mb, n_opt, k, n_out)   # update forward
+        add(_gemm_kernel_name(0, p, n, n_out, k_pad), n, T + 1, k, n_out)     # rollout policy + bootstrap value
+    for k, k_pad, n_out in layers[1:]:
+        add(_gemm_kernel_name(1, p, mb, k, n_out), mb, n_opt, n_out, k)       # dgrad: dZ_l [M, N_l] x W_l -> [M, K_l]
+    for k, k_pad, n_out in layers:
+        add(f"mlp_wgrad_kernel<{p}, {64 if k_pad < 128 else 128}>", mb, n_opt, k, n_out)
     return flops
 
 
@@ -450,6 +463,7 @@ def run_ours(args):
     precision = trainer.agent.precision
     prof, prof_total = kernel_profile(trainer, record=(rank == 0))
     dominant = dominant_kernel_roofline(prof, prof_total, trainer, peaks) if rank == 0 else None
+    gemm_flops = _gemm_flops_by_kernel(trainer)
     del env, trainer
     torch.cuda.empty_cache()
 
@@ -520,7 +534,8 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": main,
         "rooflines": roof,
-        "kernel_shares": {k: {"share": round(v["share"], 4), "us_per_step": round(v["us"], 1), "launches_per_step": v["launches"]} for k, v in list(prof.items())[:18]},
+        "kernel_shares": {k: {"share": round(v["share"], 4), "us_per_step": round(v["us"], 1), "launches_per_step": v["launches"],
+                              **({"tflops": round(gemm_flops[k] / v["us"] / 1e6, 1)} if k in gemm_flops else {})} for k, v in list(prof.items())[:18]},
         "sweep": sweep,
         "other_precision": other,
         "cpu_baseline": cpu,

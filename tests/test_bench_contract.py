@@ -58,9 +58,13 @@ def test_gemm_flops_attribution_adds_up():
     opt_rows, roll_rows = 5 * 4096 * 24, 4096 * 25
     mac_fwd = 2 * (45 * 512 + 512 * 256 + 256 * 128)   # both nets, layer 0 at its true K = 45
     mac_dgrad = 2 * (256 * 128 + 512 * 256)
-    assert set(flops) == {"mlp_gemm_kernel<0, 1>", "mlp_gemm_kernel<1, 1>", "mlp_wgrad_kernel<1, 64>", "mlp_wgrad_kernel<1, 128>"}
-    assert flops["mlp_gemm_kernel<0, 1>"] == 2.0 * mac_fwd * (opt_rows + roll_rows)
-    assert flops["mlp_gemm_kernel<1, 1>"] == 2.0 * mac_dgrad * opt_rows
+    # the names are the instantiations CUPTI reports (csrc/tc_gemm.cu dispatch): 128 x 128 persistent tiles, 256-row tiles for
+    # the minibatch-sized forward launches with K >= 256, weight gradients by column-tile width
+    fwd = {"mlp_gemm_kernel<0, 1, 4>", "mlp_gemm256_kernel<0, 1, 256>", "mlp_gemm256_kernel<0, 1, 128>"}
+    assert set(flops) == fwd | {"mlp_gemm_kernel<1, 1, 4>", "mlp_wgrad_kernel<1, 64>", "mlp_wgrad_kernel<1, 128>"}
+    assert sum(flops[k] for k in fwd) == 2.0 * mac_fwd * (opt_rows + roll_rows)
+    assert flops["mlp_gemm256_kernel<0, 1, 256>"] == 2.0 * 2 * 512 * 256 * opt_rows   # rollout-sized launches stay on 128-row tiles
+    assert flops["mlp_gemm_kernel<1, 1, 4>"] == 2.0 * mac_dgrad * opt_rows
     assert flops["mlp_wgrad_kernel<1, 64>"] + flops["mlp_wgrad_kernel<1, 128>"] == 2.0 * mac_fwd * opt_rows
     # 750 848 FLOP/sample forward = the hidden layers on the tensor cores + the fp32 heads (128 -> 12, 128 -> 1)
     assert 2.0 * mac_fwd + 2 * (128 * 12 + 128) == 750848
