@@ -262,7 +262,9 @@ def _traffic():
     CURRENT kernels (profiles/r2_traffic.json names the ncu CSV each value came from).  ncu flushes the caches before
     every replay, so these are cold-cache figures: an upper bound on what the same launch moves inside the step."""
     path = os.path.join(ROOT, "profiles", "r2_traffic.json")
-    return json.load(open(path)) if os.path.isfile(path) else {}
+    if not os.path.isfile(path):
+        return {}
+    return {k: v for k, v in json.load(open(path)).items() if isinstance(v, dict)}
 
 
 def _gemm_kernel_name(mode, p, rows, n_out, k_pad):
@@ -301,9 +303,38 @@ def _gemm_flops_by_kernel(trainer):
     return flops
 
 
+def _gemm_bytes_by_kernel(trainer):
+    """ALGORITHMIC HBM bytes per iteration of the same kernels: every activation tensor a launch consumes
+    is read once and every one it produces is written once, both nets, at the operand size of the precision (fp32 storage
+    for tf32 operands, 2 bytes for bf16); the weights (1.5 MB, L2 resident) are left out.  forward l: read H_{l-1} (X once
+    for both nets), write H_l; dgrad l: read dZ_l and H_{l-1}, write dZ_{l-1}; wgrad l: read dZ_l and H_{l-1}."""
+    n, T = trainer.num_envs, trainer.T
+    mb, n_opt = trainer.minibatch_size, (trainer.batch_size // trainer.minibatch_size) * int(trainer.cfg.updates_epochs)
+    tf32 = trainer.agent.precision == "tf32"
+    p, es = (1, 4) if tf32 else (0, 2)
+    layers = [(45, 64, 512), (512, 512, 256), (256, 256, 128)]
+    nbytes = {}
+
+    def add(name, v):
+        nbytes[name] = nbytes.get(name, 0.0) + v
+
+    for li, (k, k_pad, n_out) in enumerate(layers):
+        a_in = k_pad * (1 if li == 0 else 2)  # the observation rows are shared by the two nets
+        for rows, launches in ((mb, n_opt), (n, T + 1)):
+            add(_gemm_kernel_name(0, p, rows, n_out, k_pad), es * rows * launches * (a_in + 2 * n_out))
+    for k, k_pad, n_out in layers[1:]:
+        add(_gemm_kernel_name(1, p, mb, k, n_out), es * mb * n_opt * 2 * (n_out + k + k))
+    for li, (k, k_pad, n_out) in enumerate(layers):
+        add(f"mlp_wgrad_kernel<{p}, {64 if k_pad < 128 else 128}>", es * mb * n_opt * (2 * n_out + k_pad * (1 if li == 0 else 2)))
+    return nbytes
+
+
 def dominant_kernel_roofline(prof, total_us, trainer, peaks):
-    """Roofline entry of the kernel with the largest share of the iteration."""
+    """Roofline entry of the kernel with the largest share of the iteration.  A GEMM launch has two roofs: the tensor
+    pipe (algorithmic flops / peak) and HBM (algorithmic bytes of its activation operands / measured copy bandwidth);
+    `bound` names the one that leaves less headroom, both fractions are printed."""
     flops = _gemm_flops_by_kernel(trainer)
+    nbytes = _gemm_bytes_by_kernel(trainer)
     if not prof:  # no CUPTI records (e.g. the process itself runs under ncu, which owns the profiling interface)
         return {"kernel": None, "note": "kernel shares unavailable: CUPTI produced no records in this process"}
     name, row = next(iter(prof.items()))
@@ -313,13 +344,22 @@ def dominant_kernel_roofline(prof, total_us, trainer, peaks):
         tf32 = trainer.agent.precision == "tf32"
         # kind::tf32 issues half the MACs per tcgen05.mma of kind::f16 (K = 8 vs 16 per instruction at the same
         # dispatch rate; nominal 1.1 vs 2.25 PFLOP/s dense, B200_PROFILING.md): peak = half the MEASURED bf16 rate
-        peak = bf16_peak * (0.5 if tf32 else 1.0)
-        ach = flops[name] / (row["us"] * 1e-6) / 1e12
-        out.update({"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                    "frac_of_measured_bf16_peak": ach / bf16_peak,
-                    "flops_per_step": flops[name], "traffic": (_traffic().get(name) or {}).get("bytes_per_launch"),
+        t_peak = bf16_peak * (0.5 if tf32 else 1.0)
+        t_ach = flops[name] / (row["us"] * 1e-6) / 1e12
+        h_ach = nbytes[name] / (row["us"] * 1e-6) / 1e9
+        tensor = {"achieved": t_ach, "peak": t_peak, "unit": "TFLOP/s", "frac": t_ach / t_peak, "flops_per_step": flops[name],
+                  "peak_source": peaks["source"] + (" (sustained bf16 cuBLAS rate x 0.5: tf32 operands; the kernel runs inside a long step)" if tf32 else " (sustained bf16: the kernel runs inside a long step)")}
+        hbm = {"achieved": h_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": h_ach / peaks["hbm_gbs"], "bytes_per_step": nbytes[name],
+               "peak_source": peaks["source"] + " (copy bandwidth)"}
+        bound = "hbm" if hbm["frac"] >= tensor["frac"] else "tensor"
+        pick = hbm if bound == "hbm" else tensor
+        out.update({"bound": bound, "achieved": pick["achieved"], "peak": pick["peak"], "unit": pick["unit"], "frac": pick["frac"],
+                    "tensor_roof": tensor, "hbm_roof": hbm,
+                    "frac_of_measured_bf16_peak": t_ach / bf16_peak,
+                    "traffic": (_traffic().get(name) or {}).get("bytes_per_launch"),
                     "traffic_source": (_traffic().get(name) or {}).get("source"),
-                    "peak_source": peaks["source"] + (" (sustained bf16 cuBLAS rate x 0.5: tf32 operands; the kernel runs inside a long step)" if tf32 else " (sustained bf16: the kernel runs inside a long step)")})
+                    "algorithmic_bytes_per_launch": nbytes[name] / max(row["launches"], 1.0),
+                    "peak_source": pick["peak_source"]})
     return out
 
 
@@ -403,8 +443,21 @@ def kernel_rooflines(device, num_envs, peaks):
     flops = 2.2525e6 * mb
     tf32 = tr.agent.precision == "tf32"
     peak = peaks["bf16_tflops"] * (0.5 if tf32 else 1.0)
-    out[f"ppo_minibatch_step@{mb}"] = {"bound": "tensor", "achieved": flops / sec / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": flops / sec / 1e12 / peak, "us": sec * 1e6, "flops": flops, "launches": launches,
-                                       "peak_source": "measured burst bf16 cuBLAS rate" + (" x 0.5 (tf32 operands)" if tf32 else "")}
+    # the same step against HBM: every activation tensor read / written once per consuming / producing launch
+    es = 4 if tf32 else 2
+    per_row = (2 * 64                                                     # gather: operand rows in + out
+               + (64 + 2 * 512) + (2 * 512 + 2 * 256) + (2 * 256 + 2 * 128)  # forward
+               + 4 * 128                                                   # heads: H3 in, dZ3 out (both nets)
+               + 2 * (128 + 256 + 256) + 2 * (256 + 512 + 512)             # dgrad
+               + (2 * 128 + 2 * 256) + (2 * 256 + 2 * 512) + (2 * 512 + 64))  # wgrad
+    hbytes = float(es * per_row * mb)
+    t_frac, h_frac = flops / sec / 1e12 / peak, hbytes / sec / 1e9 / peaks["hbm_gbs"]
+    entry = {"bound": "hbm" if h_frac >= t_frac else "tensor", "us": sec * 1e6, "flops": flops, "bytes": hbytes, "launches": launches,
+             "tensor_roof": {"achieved": flops / sec / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": t_frac,
+                             "peak_source": "measured burst bf16 cuBLAS rate" + (" x 0.5 (tf32 operands)" if tf32 else "")},
+             "hbm_roof": {"achieved": hbytes / sec / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": h_frac}}
+    entry.update({k: entry[entry["bound"] + "_roof"][k] for k in ("achieved", "peak", "unit", "frac")})
+    out[f"ppo_minibatch_step@{mb}"] = entry
     del env, tr
     out.update(roof_a6)
     # DRAM traffic per launch from the committed `ncu --set full` captures of the current kernels, where available
@@ -463,7 +516,7 @@ def run_ours(args):
     precision = trainer.agent.precision
     prof, prof_total = kernel_profile(trainer, record=(rank == 0))
     dominant = dominant_kernel_roofline(prof, prof_total, trainer, peaks) if rank == 0 else None
-    gemm_flops = _gemm_flops_by_kernel(trainer)
+    gemm_flops, gemm_bytes = _gemm_flops_by_kernel(trainer), _gemm_bytes_by_kernel(trainer)
     del env, trainer
     torch.cuda.empty_cache()
 
@@ -535,7 +588,7 @@ def run_ours(args):
         "roofline": main,
         "rooflines": roof,
         "kernel_shares": {k: {"share": round(v["share"], 4), "us_per_step": round(v["us"], 1), "launches_per_step": v["launches"],
-                              **({"tflops": round(gemm_flops[k] / v["us"] / 1e6, 1)} if k in gemm_flops else {})} for k, v in list(prof.items())[:18]},
+                              **({"tflops": round(gemm_flops[k] / v["us"] / 1e6, 1), "algorithmic_gbs": round(gemm_bytes[k] / v["us"] / 1e3, 1)} if k in gemm_flops else {})} for k, v in list(prof.items())[:18]},
         "sweep": sweep,
         "other_precision": other,
         "cpu_baseline": cpu,
