@@ -297,6 +297,11 @@ SIGNATURES = {
     "catb200_peer_close": (C.c_int, [_P]),
     "catb200_peer_free": (C.c_int, [_P]),
     "catb200_grad_allreduce_norm": (C.c_int, [_P, _I32, _I32, _I64, _I32, _P, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P]),
+    "catb200_ppo_minibatch_update_peer": (
+        C.c_int,
+        [C.POINTER(MlpDims), C.POINTER(PpoHparams), _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ,
+         _P, _P, _P, _P, _F, _F, _F, _F, _P, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P],
+    ),
     "catb200_philox4x32_10": (C.c_int, [_P, _P, _P]),
     "catb200_random_permutation_host": (C.c_int, [_I64, C.c_uint64, C.c_uint64, _P]),
     "catb200_random_permutation": (C.c_int, [_I64, _P, _P, _P]),

@@ -534,6 +534,415 @@ head_kernel(const __grid_constant__ HeadArgs a) {
   }
 }
 
+// ---- heads + loss on warp-level tensor cores (training) ------------------------------------------------
+// head_kernel<true> above gives every sample a whole warp: 594 warp instructions per sample, two warps per scheduler,
+// issue bound (ncu: 22 us for 16384 samples).  head_mma_kernel gives a warp 16 samples at a time and runs the three
+// small matrix products of the heads as mma.sync.m16n8k8 tf32 fragments out of a shared-memory copy of the tile:
+//   mean[16, A]   = Ha[16, 128] W4a^T      forward: the weights are split hi + lo (two tf32 terms), the activations
+//   value[16]     = Hc[16, 128] w4c^T      are tf32-exact already -> fp32-grade head outputs, as in head_kernel
+//   dHa[16, 128]  = dmean[16, A] W4a       (tf32 operands, like every other backward GEMM of the step)
+//   gW4a[A, 128] += dmean^T[A, 16] Ha[16, 128]
+// The accumulator fragment of one product is the A fragment of the next: mma.sync leaves C[row g][cols 2t, 2t+1] in
+// thread (g = lane / 4, t = lane % 4) and wants A[row g][k-slots t, t + 4]; the reduction index of the consumer is
+// free to be permuted, so slot t is bound to column 2t and slot t + 4 to column 2t + 1 and the B fragments are fetched
+// through the same permutation -- no shuffles, no shared-memory round trip (only gW4a needs dmean transposed).
+// Loss arithmetic per sample is head_kernel's, executed redundantly by the four threads that share a row.
+// Output format (per-CTA partial rows for fold_grads / opt_step) is head_kernel's.
+constexpr int kHmWarps = 8;
+constexpr int kHmStride = 132;                       // floats per tile row: conflict-free fragment loads (132 % 32 == 4)
+constexpr int kHmTile = 16 * kHmStride;              // floats per 16 x 128 tile
+constexpr int kHmTrans = 16 * 17;                    // dmean^T staging, per warp
+constexpr int kHmWeights = 2 * kHmTile + 3 * 128;    // W4a hi, lo; w4c hi, lo, full
+constexpr int kHmPerWarp = 2 * kHmTile + kHmTrans;   // Ha, Hc, dmean^T
+constexpr int kHmSmem = (kHmWeights + kHmWarps * kHmPerWarp) * 4;
+constexpr int kHmPark = 33;                          // row stride of the parked per-warp values: conflict-free scatter
+static_assert(kHmWarps * kHmPerWarp >= kHmWarps * kHeadValues * kHmPark, "the final per-warp rows alias the tiles");
+
+__device__ __forceinline__ void mma_tf32_1688(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int PREC>
+__device__ __forceinline__ void store_pair(void* base, size_t row, int h3, int col, float x, float y) {
+  if (PREC == kPrecBf16) {
+    *reinterpret_cast<uint32_t*>(static_cast<bf16*>(base) + row * h3 + col) = pack_bf16x2(x, y);
+  } else {  // tensor-core operand of dgrad / wgrad: stored rounded to tf32
+    *reinterpret_cast<float2*>(static_cast<float*>(base) + row * h3 + col) = make_float2(round_tf32(x), round_tf32(y));
+  }
+}
+
+template <int PREC>
+__global__ void __launch_bounds__(kHmWarps * 32, 1)
+head_mma_kernel(const __grid_constant__ HeadArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ __align__(16) float hm[];
+  float* wa_hi = hm;
+  float* wa_lo = hm + kHmTile;
+  float* wc_hi = hm + 2 * kHmTile;
+  float* wc_lo = wc_hi + 128;
+  float* wc_full = wc_lo + 128;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  float* tiles = hm + kHmWeights + warp * kHmPerWarp;
+  float* sHa = tiles;
+  float* sHc = tiles + kHmTile;
+  float* sT = tiles + 2 * kHmTile;
+  const int A = a.A, M = a.M;
+
+  // The activation tiles of a pass travel global -> shared memory: with fp32 storage as 16-byte cp.async copies (no
+  // registers, one wait for all 32 of a lane; rows beyond M are zero-filled), with bf16 storage through registers.
+  const int passes = (M + 15) / 16;
+  const int pass_stride = gridDim.x * kHmWarps;
+  auto issue_tiles = [&](int pi) {
+    const int row0 = (a.reverse ? passes - 1 - pi : pi) * 16;
+    if (PREC == kPrecTf32) {
+      const float* ga = static_cast<const float*>(a.H3[1]);
+      const float* gc = static_cast<const float*>(a.H3[0]);
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const int row = row0 + r;
+        const bool ok = row < M;
+        const size_t off = (size_t)(ok ? row : 0) * 128 + lane * 4;
+        cp_async16(smem_u32(sHa + r * kHmStride + lane * 4), ga + off, ok);
+        cp_async16(smem_u32(sHc + r * kHmStride + lane * 4), gc + off, ok);
+      }
+      cp_async_commit();
+    } else {
+#pragma unroll
+      for (int r0 = 0; r0 < 16; r0 += 4) {
+        float ha[4][4], hc[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int row = row0 + r0 + r;
+          if (row < M) {
+            load_row4<PREC>(a.H3[1], (size_t)row, 128, lane, ha[r]);
+            load_row4<PREC>(a.H3[0], (size_t)row, 128, lane, hc[r]);
+          } else {
+#pragma unroll
+            for (int f = 0; f < 4; ++f) ha[r][f] = hc[r][f] = 0.0f;
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          *reinterpret_cast<float4*>(sHa + (r0 + r) * kHmStride + lane * 4) = make_float4(ha[r][0], ha[r][1], ha[r][2], ha[r][3]);
+          *reinterpret_cast<float4*>(sHc + (r0 + r) * kHmStride + lane * 4) = make_float4(hc[r][0], hc[r][1], hc[r][2], hc[r][3]);
+        }
+      }
+    }
+  };
+  const int first_pass = blockIdx.x + gridDim.x * warp;
+  if (first_pass < passes) issue_tiles(first_pass);  // in flight while the weights are split below
+
+  // this thread's four action slots: js[n][e] = 8n + 2t + e (the C-fragment columns of n-tile n); the scalar loads are
+  // issued here so that they are in flight, like the tiles, while the weights are split
+  float s_b4a[2][2], s_logstd[2][2], s_inv_var[2][2];
+  bool s_ok[2][2];
+#pragma unroll
+  for (int n = 0; n < 2; ++n)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int j = 8 * n + 2 * t + e;
+      s_ok[n][e] = j < A;
+      s_b4a[n][e] = s_ok[n][e] ? __ldg(a.b4a + j) : 0.0f;
+      s_logstd[n][e] = s_ok[n][e] ? __ldg(a.logstd + j) : 0.0f;
+    }
+  const float b4c = __ldg(a.b4c);
+  const float adv_mean = a.mb->adv_mean, adv_std = a.mb->adv_std;
+  const float m1 = a.norm_stats[0], v1 = a.norm_stats[1], m2 = a.norm_stats[2], v2 = a.norm_stats[3];
+
+  // head weights -> shared memory, split into two tf32 terms (rows beyond A are zero)
+  for (int i = threadIdx.x; i < 16 * 128; i += blockDim.x) {
+    const int j = i >> 7, f = i & 127;
+    const float w = j < A ? __ldg(a.W4a + j * 128 + f) : 0.0f;
+    const float hi = round_tf32(w);
+    wa_hi[j * kHmStride + f] = hi;
+    wa_lo[j * kHmStride + f] = round_tf32(w - hi);
+  }
+  for (int f = threadIdx.x; f < 128; f += blockDim.x) {
+    const float w = __ldg(a.W4c + f);
+    const float hi = round_tf32(w);
+    wc_full[f] = w;
+    wc_hi[f] = hi;
+    wc_lo[f] = round_tf32(w - hi);
+  }
+  __syncthreads();
+
+#pragma unroll
+  for (int n = 0; n < 2; ++n)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float sd = expf(s_logstd[n][e]);
+      s_inv_var[n][e] = 1.0f / (sd * sd);
+    }
+  const float inv_sd1 = 1.0f / sqrtf(v1 + 1e-8f), inv_sd2 = 1.0f / sqrtf(v2 + 1e-8f);
+  const float inv_M = 1.0f / (float)M;
+
+  float gwa[16][4];  // gW4a fragments: [n-tile of 8 features][(action g, 2t) (g, 2t+1) (g+8, 2t) (g+8, 2t+1)]
+  float gwc[16][2];  // gW4c partial over this thread's two rows: features 8nn + 2t + e
+#pragma unroll
+  for (int nn = 0; nn < 16; ++nn) {
+    gwa[nn][0] = gwa[nn][1] = gwa[nn][2] = gwa[nn][3] = 0.0f;
+    gwc[nn][0] = gwc[nn][1] = 0.0f;
+  }
+  float g_b4a[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, g_logstd[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  float g_b4c = 0.0f, l_pg = 0.0f, l_v = 0.0f, l_kl = 0.0f, l_clip = 0.0f, l_oldkl = 0.0f;
+
+  for (int pi = first_pass; pi < passes; pi += pass_stride) {
+    const int p = a.reverse ? passes - 1 - pi : pi;
+    const int row0 = p * 16;
+    if (pi != first_pass) {
+      __syncwarp();  // every lane is done reading the previous pass's tiles
+      issue_tiles(pi);
+    }
+    // per-sample scalars of this thread's two rows (the four threads of a quad read the same values)
+    const int rowA = row0 + g, rowB = row0 + g + 8;
+    const bool okA = rowA < M, okB = rowB < M;
+    const float4 scA = okA ? __ldg(a.scal_mb + rowA) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 scB = okB ? __ldg(a.scal_mb + rowB) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float act[2][2][2];  // [row A / B][n][e]
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = 8 * n + 2 * t + e;
+        act[0][n][e] = (okA && s_ok[n][e]) ? __ldg(a.act_mb + (size_t)rowA * A + j) : 0.0f;
+        act[1][n][e] = (okB && s_ok[n][e]) ? __ldg(a.act_mb + (size_t)rowB * A + j) : 0.0f;
+      }
+    if (PREC == kPrecTf32) cp_async_wait<0>();
+    __syncwarp();
+
+    // ---- forward: action means (two n-tiles of 8 actions) and the value (column 0 of a third n-tile)
+    float cm[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, cv[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int k = 0; k < 16; ++k) {
+      const int c0 = 8 * k + t;
+      uint32_t fa[4], fc[4];
+      fa[0] = __float_as_uint(sHa[g * kHmStride + c0]);
+      fa[1] = __float_as_uint(sHa[(g + 8) * kHmStride + c0]);
+      fa[2] = __float_as_uint(sHa[g * kHmStride + c0 + 4]);
+      fa[3] = __float_as_uint(sHa[(g + 8) * kHmStride + c0 + 4]);
+      fc[0] = __float_as_uint(sHc[g * kHmStride + c0]);
+      fc[1] = __float_as_uint(sHc[(g + 8) * kHmStride + c0]);
+      fc[2] = __float_as_uint(sHc[g * kHmStride + c0 + 4]);
+      fc[3] = __float_as_uint(sHc[(g + 8) * kHmStride + c0 + 4]);
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        const float* wh = wa_hi + (8 * n + g) * kHmStride + c0;
+        const float* wl = wa_lo + (8 * n + g) * kHmStride + c0;
+        mma_tf32_1688(cm[n], fa, __float_as_uint(wh[0]), __float_as_uint(wh[4]));
+        mma_tf32_1688(cm[n], fa, __float_as_uint(wl[0]), __float_as_uint(wl[4]));
+      }
+      const uint32_t vh0 = g == 0 ? __float_as_uint(wc_hi[c0]) : 0u, vh1 = g == 0 ? __float_as_uint(wc_hi[c0 + 4]) : 0u;
+      const uint32_t vl0 = g == 0 ? __float_as_uint(wc_lo[c0]) : 0u, vl1 = g == 0 ? __float_as_uint(wc_lo[c0 + 4]) : 0u;
+      mma_tf32_1688(cv, fc, vh0, vh1);
+      mma_tf32_1688(cv, fc, vl0, vl1);
+    }
+    // value of row g / g + 8 sits in column 0 = thread t == 0 of the quad
+    const float valA = __shfl_sync(0xffffffffu, cv[0], lane & ~3) + b4c;
+    const float valB = __shfl_sync(0xffffffffu, cv[2], lane & ~3) + b4c;
+
+    // ---- PPO-clip loss and its gradient (ppo.py:300-344), rows A and B
+    float dm[2][4];  // dL / d mean in C-fragment layout: [n][(row A, 2t) (row A, 2t+1) (row B, 2t) (row B, 2t+1)]
+    float dvv[2];    // dL / d value of rows A, B
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const bool ok = rr ? okB : okA;
+      const float4 sc = rr ? scB : scA;
+      const float v = rr ? valB : valA;
+      float lp = 0.0f, dmu[2][2], dls[2][2];
+#pragma unroll
+      for (int n = 0; n < 2; ++n)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float mean_j = cm[n][2 * rr + e] + s_b4a[n][e];
+          const float d = act[rr][n][e] - mean_j;
+          const float term = -(d * d) * 0.5f * s_inv_var[n][e] - s_logstd[n][e] - kLogSqrt2Pi;
+          lp += s_ok[n][e] ? term : 0.0f;
+          dmu[n][e] = s_ok[n][e] ? d * s_inv_var[n][e] : 0.0f;
+          dls[n][e] = s_ok[n][e] ? d * d * s_inv_var[n][e] - 1.0f : 0.0f;
+        }
+      lp += __shfl_xor_sync(0xffffffffu, lp, 1);
+      lp += __shfl_xor_sync(0xffffffffu, lp, 2);
+      const float logratio = lp - sc.x;
+      const float ratio = expf(logratio);
+      float adv = sc.y;
+      if (a.hp.norm_adv) adv = (adv - adv_mean) / (adv_std + 1e-8f);
+      const float clipped = fminf(fmaxf(ratio, 1.0f - a.hp.clip_coef), 1.0f + a.hp.clip_coef);
+      const float pg1 = -adv * ratio, pg2 = -adv * clipped;
+      const float pg = fmaxf(pg1, pg2);
+      float dpg_dratio;
+      if (pg1 > pg2) dpg_dratio = -adv;
+      else if (pg1 < pg2) dpg_dratio = (clipped == ratio) ? -adv : 0.0f;
+      else dpg_dratio = (clipped == ratio) ? -adv : -0.5f * adv;
+      const float dL_dlogp = ok ? dpg_dratio * ratio * inv_M : 0.0f;
+      const float nv = (v - m2) * inv_sd2;
+      const float ret_n = (sc.z - m2) * inv_sd2;
+      const float val_n = (sc.w - m1) * inv_sd1;
+      float vl, dvl_dnv;
+      const float e_u = nv - ret_n;
+      if (a.hp.clip_vloss) {
+        const float diff = nv - val_n;
+        const float dclip = fminf(fmaxf(diff, -a.hp.clip_coef), a.hp.clip_coef);
+        const float e_c = val_n + dclip - ret_n;
+        const float lu = e_u * e_u, lc = e_c * e_c;
+        const float pass = (dclip == diff) ? 1.0f : 0.0f;
+        if (lu > lc) { vl = lu; dvl_dnv = 2.0f * e_u; }
+        else if (lu < lc) { vl = lc; dvl_dnv = 2.0f * e_c * pass; }
+        else { vl = lu; dvl_dnv = e_u + e_c * pass; }
+      } else {
+        vl = e_u * e_u;
+        dvl_dnv = 2.0f * e_u;
+      }
+      const float dL_dv = ok ? a.hp.vf_coef * 0.5f * dvl_dnv * inv_sd2 * inv_M : 0.0f;
+      dvv[rr] = dL_dv;
+      if (ok && t == 0) {  // one thread of the quad keeps the per-sample scalars
+        l_pg += pg; l_v += 0.5f * vl; l_kl += (ratio - 1.0f) - logratio; l_oldkl += -logratio;
+        l_clip += fabsf(ratio - 1.0f) > a.hp.clip_coef ? 1.0f : 0.0f;
+        g_b4c += dL_dv;
+      }
+#pragma unroll
+      for (int n = 0; n < 2; ++n)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float dmean = dL_dlogp * dmu[n][e];
+          dm[n][2 * rr + e] = round_tf32(dmean);
+          g_b4a[n][e] += dmean;
+          g_logstd[n][e] += dL_dlogp * dls[n][e];
+        }
+    }
+    // dmean^T for the weight-gradient product: T[sample][action]
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        sT[g * 17 + 8 * n + 2 * t + e] = dm[n][e];
+        sT[(g + 8) * 17 + 8 * n + 2 * t + e] = dm[n][2 + e];
+      }
+    __syncwarp();
+
+    // ---- backward through the heads, 8 features (one n-tile) at a time
+    // A fragments of dHa = dmean W4a: k-step s covers actions 8s .. 8s+7, slot t = action 8s + 2t, slot t + 4 = 8s + 2t + 1
+    uint32_t fdm[2][4];
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2) {
+      fdm[s2][0] = __float_as_uint(dm[s2][0]);
+      fdm[s2][1] = __float_as_uint(dm[s2][2]);
+      fdm[s2][2] = __float_as_uint(dm[s2][1]);
+      fdm[s2][3] = __float_as_uint(dm[s2][3]);
+    }
+    // A fragments of gW4a = dmean^T Ha: rows = actions, k-step s covers samples 8s .. 8s+7 under the same slot permutation
+    uint32_t fdt[2][4];
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2) {
+      fdt[s2][0] = __float_as_uint(sT[(8 * s2 + 2 * t) * 17 + g]);
+      fdt[s2][1] = __float_as_uint(sT[(8 * s2 + 2 * t) * 17 + g + 8]);
+      fdt[s2][2] = __float_as_uint(sT[(8 * s2 + 2 * t + 1) * 17 + g]);
+      fdt[s2][3] = __float_as_uint(sT[(8 * s2 + 2 * t + 1) * 17 + g + 8]);
+    }
+#pragma unroll
+    for (int nn = 0; nn < 16; ++nn) {
+      const int fcol = 8 * nn + 2 * t;  // this thread's two output features of the n-tile
+      float dh[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2) {
+        const float* w = wa_hi + (8 * s2 + 2 * t) * kHmStride + 8 * nn + g;
+        mma_tf32_1688(dh, fdm[s2], __float_as_uint(w[0]), __float_as_uint(w[kHmStride]));
+        const float* h = sHa + (8 * s2 + 2 * t) * kHmStride + 8 * nn + g;
+        mma_tf32_1688(gwa[nn], fdt[s2], __float_as_uint(h[0]), __float_as_uint(h[kHmStride]));
+      }
+      const float2 haA = *reinterpret_cast<const float2*>(sHa + g * kHmStride + fcol);
+      const float2 haB = *reinterpret_cast<const float2*>(sHa + (g + 8) * kHmStride + fcol);
+      const float2 hcA = *reinterpret_cast<const float2*>(sHc + g * kHmStride + fcol);
+      const float2 hcB = *reinterpret_cast<const float2*>(sHc + (g + 8) * kHmStride + fcol);
+      const float2 wc = *reinterpret_cast<const float2*>(wc_full + fcol);
+      if (okA) {
+        store_pair<PREC>(a.dZ3[1], (size_t)rowA, 128, fcol, dh[0] * elu_grad_from_output(haA.x), dh[1] * elu_grad_from_output(haA.y));
+        store_pair<PREC>(a.dZ3[0], (size_t)rowA, 128, fcol, dvv[0] * wc.x * elu_grad_from_output(hcA.x), dvv[0] * wc.y * elu_grad_from_output(hcA.y));
+      }
+      if (okB) {
+        store_pair<PREC>(a.dZ3[1], (size_t)rowB, 128, fcol, dh[2] * elu_grad_from_output(haB.x), dh[3] * elu_grad_from_output(haB.y));
+        store_pair<PREC>(a.dZ3[0], (size_t)rowB, 128, fcol, dvv[1] * wc.x * elu_grad_from_output(hcB.x), dvv[1] * wc.y * elu_grad_from_output(hcB.y));
+      }
+      gwc[nn][0] = fmaf(dvv[0], hcA.x, fmaf(dvv[1], hcB.x, gwc[nn][0]));
+      gwc[nn][1] = fmaf(dvv[0], hcA.y, fmaf(dvv[1], hcB.y, gwc[nn][1]));
+    }
+  }
+
+  // ---- CTA-level reduction in head_kernel's format: every warp parks its values in a [kHeadValues][32] row set (aliasing
+  //      the tiles), the CTA sums over its warps in a fixed order and writes ONE partial row per CTA
+  // sums over the 8 row groups (lanes with the same t): gW4c, bias / log-std gradients, scalars
+#pragma unroll
+  for (int o = 4; o <= 16; o <<= 1) {
+#pragma unroll
+    for (int nn = 0; nn < 16; ++nn) {
+      gwc[nn][0] += __shfl_xor_sync(0xffffffffu, gwc[nn][0], o);
+      gwc[nn][1] += __shfl_xor_sync(0xffffffffu, gwc[nn][1], o);
+    }
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        g_b4a[n][e] += __shfl_xor_sync(0xffffffffu, g_b4a[n][e], o);
+        g_logstd[n][e] += __shfl_xor_sync(0xffffffffu, g_logstd[n][e], o);
+      }
+    g_b4c += __shfl_xor_sync(0xffffffffu, g_b4c, o);
+    l_pg += __shfl_xor_sync(0xffffffffu, l_pg, o);
+    l_v += __shfl_xor_sync(0xffffffffu, l_v, o);
+    l_kl += __shfl_xor_sync(0xffffffffu, l_kl, o);
+    l_clip += __shfl_xor_sync(0xffffffffu, l_clip, o);
+    l_oldkl += __shfl_xor_sync(0xffffffffu, l_oldkl, o);
+  }
+  __syncthreads();  // every warp is done with its tiles
+  float* rows_all = hm + kHmWeights;
+  float* mine = rows_all + (size_t)warp * kHeadValues * kHmPark;  // [value][lane'] rows of 33 floats (scatter below: 32 banks)
+  for (int o = lane; o < (kHeadValues - kHvB4a) * kHmPark; o += 32) mine[kHvB4a * kHmPark + o] = 0.0f;  // sparse rows: zero first
+  __syncwarp();
+#pragma unroll
+  for (int nn = 0; nn < 16; ++nn)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int j = g + 8 * (c >> 1), f = 8 * nn + 2 * t + (c & 1);
+      mine[(j * 4 + (f & 3)) * kHmPark + (f >> 2)] = gwa[nn][c];  // value j*4 + f%4, lane f/4 (head_kernel's lane owns 4 features)
+    }
+  if (g == 0) {
+#pragma unroll
+    for (int nn = 0; nn < 16; ++nn)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int f = 8 * nn + 2 * t + e;
+        mine[(kHvW4c + (f & 3)) * kHmPark + (f >> 2)] = gwc[nn][e];
+      }
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = 8 * n + 2 * t + e;
+        if (j < A) {  // per-action scalars live in the even lane of pair (2j, 2j+1)
+          mine[kHvB4a * kHmPark + 2 * j] = g_b4a[n][e];
+          mine[kHvLogstd * kHmPark + 2 * j] = g_logstd[n][e];
+        }
+      }
+    if (t == 0) {
+      const float scal[6] = {g_b4c, l_pg, l_v, l_kl, l_clip, l_oldkl};
+#pragma unroll
+      for (int k = 0; k < 6; ++k) mine[(kHvScalars + k) * kHmPark] = scal[k];
+    }
+  }
+  __syncthreads();
+  float* __restrict__ row = a.head_part + (size_t)blockIdx.x * kHeadValues * 32;
+  for (int o = threadIdx.x; o < kHeadValues * 32; o += blockDim.x) {
+    const int po = (o >> 5) * kHmPark + (o & 31);
+    float tsum = 0.0f;
+#pragma unroll
+    for (int w = 0; w < kHmWarps; ++w) tsum += rows_all[(size_t)w * kHeadValues * kHmPark + po];
+    row[o] = tsum;
+  }
+}
+
 // ---- small utility kernels ------------------------------------------------------------------------------
 template <int PREC>
 __global__ void obs_to_operand_kernel(const float* __restrict__ obs, long long rows, int dim, int pad,
@@ -784,6 +1193,158 @@ __global__ void __launch_bounds__(256) opt_step_kernel(const __grid_constant__ O
   }
 }
 
+// ---- the optimizer step of one minibatch on several GPUs as ONE launch --------------------------------------------------
+// opt_step_kernel with the gradient exchange of peer.cu in the middle (catb200_ppo_minibatch_update_peer):
+//   A  fold the padded accumulators + head rows into this rank's peer-visible arena of the minibatch's parity
+//      -- local grid barrier; its last arriver announces the arena to every peer (st.release.sys into their flag rows) --
+//      every CTA waits until all peers have announced theirs (bounded)
+//   B  rank-ordered sum of the `world` arenas over NVLink -> private gradient + squared norm; the OTHER arena is zeroed
+//      -- local grid barrier: clip coefficient, bias corrections --
+//   C  Adam + operand copies from the private sum.
+// Replaces fold_grads_kernel + grad_allreduce_norm_kernel + adam_cast_kernel (10 + 17 + 7 us per optimizer step at 2 GPUs).
+struct OptStepPeerArgs {
+  OptStepArgs o;                  // o.f.grad[] point into this rank's arena, o.c.a.grads is the private sum
+  const float* arena[kPeerMax];   // arena of this minibatch's parity on every rank (index = rank)
+  uint32_t* flags[kPeerMax];      // flag row of every rank
+  float* zero_arena;              // this rank's other arena
+  float* out;                     // private summed gradient [n]
+  long long n;
+  int rank, world;
+  unsigned int* epoch;            // device-local count of completed exchanges
+  int* err;                       // device-local error flag (1: a peer did not arrive, 2: parity out of step)
+  unsigned int parity;
+};
+
+template <int PREC>
+__global__ void __launch_bounds__(256) opt_step_peer_kernel(const __grid_constant__ OptStepPeerArgs p) {
+  const OptStepArgs& r = p.o;
+  __shared__ float part_s[8][32];
+  __shared__ float tile[32][33];
+  __shared__ double red_s[8];
+  __shared__ float coef_s[3];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gtid = blockIdx.x * 256 + tid, gthreads = gridDim.x * 256;
+  const float gscale = r.c.a.grad_scale;
+  OptScratch* sc = r.sc;
+  const int step0 = *r.step;               // CTA 0 advances it only after the second barrier
+  const unsigned int e = *p.epoch + 1u;    // likewise
+  unsigned int* bar = reinterpret_cast<unsigned int*>(&sc->pad[0]);
+  auto grid_barrier = [&](bool announce) {  // thread 0 only; arrival counter that only ever grows (ticket / grid = generation)
+    const unsigned int ticket = atomicAdd(bar, 1u);
+    const unsigned int target = (ticket / gridDim.x + 1u) * gridDim.x;
+    if (announce && ticket == target - 1u) {
+      // last arriver: every CTA fenced its arena writes (system scope) before its arrival, which this thread has observed
+      __threadfence_system();
+      for (int q = 0; q < p.world; ++q)
+        if (q != p.rank) st_release_sys(p.flags[q] + p.rank, e);
+    }
+    const long long t0 = clock64();
+    while ((int)(*reinterpret_cast<volatile unsigned int*>(bar) - target) < 0) {
+      if (clock64() - t0 > 4000000000ll) __trap();  // a CTA that never arrived (not co-resident): fail, do not hang
+    }
+    __threadfence();
+  };
+
+  // ---- phase A: fold into the arena
+  const int total_quads = r.quad_prefix[r.f.n_segments];
+  for (int q = gtid; q < total_quads; q += gthreads) {
+    int seg = 0;
+    while (q >= r.quad_prefix[seg + 1]) ++seg;
+    fold_weight_quad(r.f, seg, q - r.quad_prefix[seg]);
+  }
+  if ((int)blockIdx.x < kHeadValues) fold_head_group(r.f, blockIdx.x, part_s);
+  __syncthreads();
+  if (tid == 0) {
+    if (((*p.epoch) & 1u) != p.parity) atomicExch(p.err, 2);
+    __threadfence_system();
+    grid_barrier(true);
+  }
+  __syncthreads();
+  if (tid < p.world && tid != p.rank) {  // every peer's arena of this parity is complete
+    const uint32_t* mine = p.flags[p.rank] + tid;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(mine) < e) {
+      if (clock64() - t0 > 4000000000ll) {  // ~2 s: give up loudly, do not hang the GPU
+        atomicExch(p.err, 1);
+        break;
+      }
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+
+  // ---- phase B: rank-ordered sum (identical on every rank), squared norm, zero the other arena
+  double ss = 0.0;
+  const long long n4 = p.n / 4;
+  for (long long i = gtid; i < n4; i += gthreads) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int q = 0; q < p.world; ++q) {
+      const float4 v = __ldcv(reinterpret_cast<const float4*>(p.arena[q]) + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    reinterpret_cast<float4*>(p.out)[i] = acc;
+    reinterpret_cast<float4*>(p.zero_arena)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const double x = (double)(acc.x * gscale), y = (double)(acc.y * gscale), z = (double)(acc.z * gscale), w = (double)(acc.w * gscale);
+    ss += x * x + y * y + z * z + w * w;
+  }
+  for (long long i = n4 * 4 + gtid; i < p.n; i += gthreads) {  // scalar tail
+    float acc = 0.f;
+    for (int q = 0; q < p.world; ++q) acc += __ldcv(p.arena[q] + i);
+    p.out[i] = acc;
+    p.zero_arena[i] = 0.f;
+    const double x = (double)(acc * gscale);
+    ss += x * x;
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) red_s[warp] = ss;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red_s[w];
+    atomicAdd(&sc->sumsq, t);
+    __threadfence();
+    grid_barrier(false);
+    const double tot = *reinterpret_cast<volatile double*>(&sc->sumsq);
+    const float norm = (float)sqrt(tot);
+    const float clip_coef = fminf(r.max_norm / (norm + 1e-6f), 1.0f);  // torch.nn.utils.clip_grad_norm_
+    const int t1 = step0 + 1;
+    const double bc1 = 1.0 - pow((double)r.c.a.beta1, (double)t1), bc2 = 1.0 - pow((double)r.c.a.beta2, (double)t1);
+    coef_s[0] = clip_coef * gscale;
+    coef_s[1] = __ldg(r.c.a.lr) * (float)(1.0 / bc1);
+    coef_s[2] = (float)sqrt(bc2);
+    if (blockIdx.x == 0) {
+      sc->clip_coef = clip_coef;
+      sc->total_norm = norm;
+      sc->step_size_scale = (float)(1.0 / bc1);
+      sc->bc2_sqrt = (float)sqrt(bc2);
+      *r.step = t1;
+      *p.epoch = e;
+      if (r.grad_norm_out) *r.grad_norm_out = norm;
+    }
+    __threadfence();
+    if (atomicAdd(&sc->ticket, 1u) == gridDim.x - 1) {  // the last CTA to have read the sum resets it
+      sc->ticket = 0u;
+      sc->sumsq = 0.0;
+    }
+  }
+  __syncthreads();
+  const float clip = coef_s[0], step_size = coef_s[1], bc2_sqrt = coef_s[2];
+
+  // ---- phase C: Adam + operand copies from the private sum
+  const int n_tiles = r.tile_prefix[6], n_items = n_tiles + (r.n_rest + 255) / 256;
+  for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+    if (w < n_tiles) {
+      int seg = 0;
+      while (w >= r.tile_prefix[seg + 1]) ++seg;
+      __syncthreads();  // the previous tile's transpose reads are done
+      adam_cast_tile<PREC>(r.c, seg, w - r.tile_prefix[seg], lane, warp, clip, step_size, bc2_sqrt, tile);
+    } else {
+      adam_rest(r.c, (w - n_tiles) * 256 + tid, clip, step_size, bc2_sqrt);
+    }
+  }
+}
+
 // advances the device-side Philox offset after a sampling launch (keeps the launch graph-capturable)
 __global__ void rng_bump_kernel(unsigned long long* rng_state, unsigned long long n) { rng_state[1] += n; }
 
@@ -992,6 +1553,29 @@ int launch_adam_cast(const catb200_mlp_dims_t* dims, const AdamState& a, void* w
   return CATB200_OK;
 }
 
+// training heads: warp-level tensor-core kernel (default) or the warp-per-sample kernel (CATB200_HEAD=warp)
+static bool head_use_mma(const catb200_mlp_dims_t* d) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("CATB200_HEAD");
+    v = (e && e[0] == 'w') ? 0 : 1;
+  }
+  return v == 1 && d->h3 == 128 && d->act_dim <= 16;
+}
+
+static int launch_head_mma(int prec, const HeadArgs& a, int grid, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    CATB200_CUDA_TRY(cudaFuncSetAttribute(head_mma_kernel<kPrecTf32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHmSmem));
+    CATB200_CUDA_TRY(cudaFuncSetAttribute(head_mma_kernel<kPrecBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHmSmem));
+    attr = true;
+  }
+  if (prec == kPrecTf32) CATB200_CUDA_TRY(launch_pdl(head_mma_kernel<kPrecTf32>, dim3(grid), dim3(kHmWarps * 32), (size_t)kHmSmem, st, a));
+  else CATB200_CUDA_TRY(launch_pdl(head_mma_kernel<kPrecBf16>, dim3(grid), dim3(kHmWarps * 32), (size_t)kHmSmem, st, a));
+  CATB200_LAUNCH_CHECK();
+  return CATB200_OK;
+}
+
 template <bool TRAIN>
 static int launch_head(int prec, const HeadArgs& a, int grid, size_t smem, cudaStream_t st) {
   static bool attr = false;
@@ -1130,7 +1714,7 @@ static int minibatch_backward(const catb200_mlp_dims_t* dims, const catb200_ppo_
     a.norm_stats = norm_stats; a.mb = mb; a.hp = *hp;
     a.head_part = reinterpret_cast<float*>(ws + L.head_part);
     a.reverse = zigzag;
-    rc = launch_head<true>(prec, a, L.head_rows, kHeadSmem, st);
+    rc = head_use_mma(dims) ? launch_head_mma(prec, a, L.head_rows, st) : launch_head<true>(prec, a, L.head_rows, kHeadSmem, st);
     if (rc != CATB200_OK) return rc;
   }
   // 4. backward through the hidden layers
@@ -1202,6 +1786,37 @@ static int minibatch_backward(const catb200_mlp_dims_t* dims, const catb200_ppo_
   return CATB200_OK;
 }
 
+// the optimizer-step arguments shared by the single-GPU and the peer kernel: fold description `o.f` already filled
+static void fill_opt_step(const catb200_mlp_dims_t* dims, const AdamState& a, void* wcv, float max_grad_norm, int32_t* step_dev,
+                          float* grad_norm_out, void* opt_ws, OptStepArgs& o) {
+  catb200_mlp_layout_t P;
+  fill_layout(dims, &P);
+  Dims x = make_dims(dims);
+  fill_adam_cast_args(dims, a, wcv, &o.c);
+  for (int s = 0; s < o.f.n_segments; ++s) o.quad_prefix[s + 1] = o.quad_prefix[s] + o.f.N[s] * o.f.Kpad[s] / 4;
+  for (int s = 0; s < 6; ++s) o.tile_prefix[s + 1] = o.tile_prefix[s] + (o.c.seg[s].rows / 32) * ((o.c.seg[s].cols_pad + 31) / 32);
+  for (int z = 0; z < 2; ++z)
+    for (int l = 0; l < 3; ++l) {
+      o.bias_begin[z * 3 + l] = P.b[z][l];
+      o.bias_len[z * 3 + l] = x.out[l];
+    }
+  for (int i = 0; i < o.c.n_rest_ranges; ++i) o.n_rest += o.c.rest_len[i];
+  o.max_norm = max_grad_norm;
+  o.step = step_dev;
+  o.grad_norm_out = grad_norm_out;
+  o.sc = static_cast<OptScratch*>(opt_ws);
+}
+
+// co-resident CTAs per SM for the grid-barrier kernels, at most 4: they are a few latency chains over 1.5 MB -- one CTA per
+// SM took 31 us, more than the three launches it replaces
+template <typename K>
+static int coresident_per_sm(K k32, K k16) {
+  int a32 = 0, a16 = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a32, k32, 256, 0) != cudaSuccess) return 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a16, k16, 256, 0) != cudaSuccess) return 1;
+  return max(1, min(4, min(a32, a16)));
+}
+
 extern "C" {
 
 int catb200_ppo_minibatch_grad(const catb200_mlp_dims_t* dims, const catb200_ppo_hparams_t* hp, int32_t mb_rows,
@@ -1225,35 +1840,55 @@ int catb200_ppo_minibatch_update(const catb200_mlp_dims_t* dims, const catb200_p
   int rc = minibatch_backward(dims, hp, mb_rows, mb_inds, obs_op_all, actions_all, logprobs_all, advantages_all, returns_all,
                               values_all, norm_stats, params, wcv, grads, loss_acc, workspace, workspace_bytes, stream, &o.f);
   if (rc != CATB200_OK) return rc;
-  catb200_mlp_layout_t P;
-  fill_layout(dims, &P);
-  Dims x = make_dims(dims);
   AdamState a = {params, grads, exp_avg, exp_avg_sq, lr_dev, static_cast<OptScratch*>(opt_ws), beta1, beta2, eps, grad_scale};
-  fill_adam_cast_args(dims, a, wcv, &o.c);
-  for (int s = 0; s < o.f.n_segments; ++s) o.quad_prefix[s + 1] = o.quad_prefix[s] + o.f.N[s] * o.f.Kpad[s] / 4;
-  for (int s = 0; s < 6; ++s) o.tile_prefix[s + 1] = o.tile_prefix[s] + (o.c.seg[s].rows / 32) * ((o.c.seg[s].cols_pad + 31) / 32);
-  for (int z = 0; z < 2; ++z)
-    for (int l = 0; l < 3; ++l) {
-      o.bias_begin[z * 3 + l] = P.b[z][l];
-      o.bias_len[z * 3 + l] = x.out[l];
-    }
-  for (int i = 0; i < o.c.n_rest_ranges; ++i) o.n_rest += o.c.rest_len[i];
-  o.max_norm = max_grad_norm;
-  o.step = step_dev;
-  o.grad_norm_out = grad_norm_out;
-  o.sc = static_cast<OptScratch*>(opt_ws);
+  fill_opt_step(dims, a, wcv, max_grad_norm, step_dev, grad_norm_out, opt_ws, o);
   cudaStream_t st = as_stream(stream);
-  // a plain (fully stream-ordered) launch of as many CTAs as are co-resident (the grid barrier needs that), at most 4 per
-  // SM: the kernel is a few latency chains over 1.5 MB -- one CTA per SM took 31 us, more than the three launches it replaces
+  // a plain (fully stream-ordered) launch of as many CTAs as are co-resident (the grid barrier needs that)
   static int per_sm = 0;
-  if (per_sm == 0) {
-    int a32 = 0, a16 = 0;
-    CATB200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a32, opt_step_kernel<kPrecTf32>, 256, 0));
-    CATB200_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a16, opt_step_kernel<kPrecBf16>, 256, 0));
-    per_sm = max(1, min(4, min(a32, a16)));
-  }
+  if (per_sm == 0) per_sm = coresident_per_sm(opt_step_kernel<kPrecTf32>, opt_step_kernel<kPrecBf16>);
   if (dims->prec == kPrecTf32) opt_step_kernel<kPrecTf32><<<kNumSMs * per_sm, 256, 0, st>>>(o);
   else opt_step_kernel<kPrecBf16><<<kNumSMs * per_sm, 256, 0, st>>>(o);
+  CATB200_LAUNCH_CHECK();
+  return CATB200_OK;
+}
+
+int catb200_ppo_minibatch_update_peer(const catb200_mlp_dims_t* dims, const catb200_ppo_hparams_t* hp, int32_t mb_rows,
+                                      const int64_t* mb_inds, const void* obs_op_all, const float* actions_all,
+                                      const float* logprobs_all, const float* advantages_all, const float* returns_all,
+                                      const float* values_all, const float* norm_stats, float* params, void* wcv,
+                                      float* loss_acc, void* workspace, size_t workspace_bytes, float* exp_avg,
+                                      float* exp_avg_sq, const float* lr_dev, int32_t* step_dev, float max_grad_norm,
+                                      float beta1, float beta2, float eps, float* grad_norm_out, void* opt_ws,
+                                      void* const* peer_bases, int32_t rank, int32_t world, int32_t parity, float* grad_sum,
+                                      uint32_t* epoch_dev, int32_t* err_dev, void* stream) {
+  if (!exp_avg || !exp_avg_sq || !lr_dev || !step_dev || !opt_ws || !peer_bases || world < 1 || world > kPeerMax || rank < 0 ||
+      rank >= world || !grad_sum || !epoch_dev || !err_dev || (parity != 0 && parity != 1) || !dims_ok(dims))
+    return CATB200_ERR_INVALID_ARGUMENT;
+  catb200_mlp_layout_t P;
+  fill_layout(dims, &P);
+  const size_t n_pad = peer_n_pad(P.n_params);
+  OptStepPeerArgs pa = {};
+  for (int q = 0; q < world; ++q) {
+    if (!peer_bases[q]) return CATB200_ERR_INVALID_ARGUMENT;
+    char* base = static_cast<char*>(peer_bases[q]);
+    pa.flags[q] = reinterpret_cast<uint32_t*>(base);
+    pa.arena[q] = reinterpret_cast<const float*>(base + kFlagWords * 4) + (size_t)parity * n_pad;
+  }
+  float* own = reinterpret_cast<float*>(static_cast<char*>(peer_bases[rank]) + kFlagWords * 4);
+  float* arena = own + (size_t)parity * n_pad;  // this minibatch's gradient accumulates here
+  int rc = minibatch_backward(dims, hp, mb_rows, mb_inds, obs_op_all, actions_all, logprobs_all, advantages_all, returns_all,
+                              values_all, norm_stats, params, wcv, arena, loss_acc, workspace, workspace_bytes, stream, &pa.o.f);
+  if (rc != CATB200_OK) return rc;
+  AdamState a = {params, grad_sum, exp_avg, exp_avg_sq, lr_dev, static_cast<OptScratch*>(opt_ws), beta1, beta2, eps, 1.0f / (float)world};
+  fill_opt_step(dims, a, wcv, max_grad_norm, step_dev, grad_norm_out, opt_ws, pa.o);
+  pa.zero_arena = own + (size_t)(parity ^ 1) * n_pad;
+  pa.out = grad_sum; pa.n = P.n_params; pa.rank = rank; pa.world = world;
+  pa.epoch = epoch_dev; pa.err = err_dev; pa.parity = (unsigned int)parity;
+  cudaStream_t st = as_stream(stream);
+  static int per_sm = 0;
+  if (per_sm == 0) per_sm = coresident_per_sm(opt_step_peer_kernel<kPrecTf32>, opt_step_peer_kernel<kPrecBf16>);
+  if (dims->prec == kPrecTf32) opt_step_peer_kernel<kPrecTf32><<<kNumSMs * per_sm, 256, 0, st>>>(pa);
+  else opt_step_peer_kernel<kPrecBf16><<<kNumSMs * per_sm, 256, 0, st>>>(pa);
   CATB200_LAUNCH_CHECK();
   return CATB200_OK;
 }

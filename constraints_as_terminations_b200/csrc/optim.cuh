@@ -30,6 +30,20 @@ struct AdamState {
   float beta1, beta2, eps, grad_scale;
 };
 
+// ---- peer-visible gradient block of the multi-GPU exchange (peer.cu, mlp.cu): [flags: kFlagWords x u32][arena 0][arena 1]
+constexpr int kPeerMax = 8;
+constexpr int kFlagWords = 64;
+__host__ __device__ inline size_t peer_n_pad(long long n_params) { return ((size_t)n_params + 63) / 64 * 64; }
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // mlp.cu: Adam over the whole flat parameter vector AND the operand-precision compute copies (W, W^T) of the six
 // hidden matrices in one launch -- the tiled cast kernel with the update applied to every element on its way through.
 int launch_adam_cast(const catb200_mlp_dims_t* dims, const AdamState& a, void* wc, cudaStream_t st);

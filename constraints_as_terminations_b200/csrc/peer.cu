@@ -20,18 +20,6 @@
 
 namespace catb200 {
 
-constexpr int kPeerMax = 8;
-constexpr int kFlagWords = 64;
-
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
 struct PeerArgs {
   const float* arena[kPeerMax];  // gradient arena of this epoch's parity on every rank (index = rank)
   uint32_t* flags[kPeerMax];     // flag row of every rank

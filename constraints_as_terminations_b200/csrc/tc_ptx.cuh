@@ -238,9 +238,11 @@ __device__ __forceinline__ void umma_2cta(uint32_t tmem_d, uint64_t adesc, uint6
 // round-to-nearest fp32 -> tf32 (low 13 mantissa bits cleared); operands are rounded where they are stored so that
 // the tensor core's own truncation of the fp32 bit pattern never discards anything
 __device__ __forceinline__ float round_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  // cvt.rna.tf32.f32 (round the magnitude to a 10-bit mantissa, ties away from zero) as two integer instructions: half an
+  // ulp of the kept mantissa is added to the sign-magnitude bits and the dropped bits are masked.  ptxas expands the cvt
+  // to the same add + mask behind an |x| < inf test; infinities survive this form unchanged as well (0x7f800000 + 0x1000
+  // masks back to 0x7f800000), so the test buys nothing on the epilogue paths, where every output element is rounded.
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {

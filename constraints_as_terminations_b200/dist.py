@@ -123,6 +123,24 @@ class PeerGradExchange:
         )  # fmt: skip
         return self.grad_sum
 
+    def minibatch_update(self, parity: int, dims, hp, mb_inds, obs_op_all, actions_all, logprobs_all, advantages_all, returns_all,
+                         values_all, norm_stats, params, wc, loss_acc, ws, exp_avg, exp_avg_sq, lr_dev, step_dev, opt_ws,
+                         max_grad_norm=1.0, betas=(0.9, 0.999), eps=1e-5, grad_norm_out=None) -> None:  # fmt: skip
+        """Forward + backward of one minibatch into arena `parity`, then fold + exchange + norm + clip + Adam + operand
+        refresh as ONE launch (catb200_ppo_minibatch_update_peer): `reduce` and the two launches around it in one."""
+        L = self.L
+        L.check(
+            self.lib.catb200_ppo_minibatch_update_peer(
+                dims, hp, mb_inds.numel(), mb_inds.data_ptr(), obs_op_all.data_ptr(), actions_all.data_ptr(),
+                logprobs_all.data_ptr(), advantages_all.data_ptr(), returns_all.data_ptr(), values_all.data_ptr(),
+                norm_stats.data_ptr(), params.data_ptr(), wc.data_ptr(), loss_acc.data_ptr(), ws.data_ptr(), ws.numel() * 8,
+                exp_avg.data_ptr(), exp_avg_sq.data_ptr(), lr_dev.data_ptr(), step_dev.data_ptr(), max_grad_norm, betas[0],
+                betas[1], eps, L.ptr(grad_norm_out), opt_ws.data_ptr(), self._bases, self.rank, self.world, int(parity),
+                self.grad_sum.data_ptr(), self.epoch.data_ptr(), self.err.data_ptr(), L.stream(),
+            ),
+            "ppo_minibatch_update_peer",
+        )  # fmt: skip
+
     def check(self) -> None:
         """Raise if a handshake timed out or the arena parity went out of step (one device->host read)."""
         code = int(self.err.item())

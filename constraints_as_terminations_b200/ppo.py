@@ -477,7 +477,15 @@ class PPOTrainer:
         if self.peer is not None:
             # gradient into the peer-visible arena of this minibatch's parity; ONE kernel exchanges it with every rank over
             # NVLink, sums in rank order and produces the clip coefficient; Adam then consumes the private sum
-            a, parity = self.agent, index & 1
+            a, parity, B = self.agent, index & 1, self.batch_size
+            if self.fused_opt:  # ... and the fold / exchange / norm / clip / Adam / operand refresh tail is ONE launch
+                self.peer.minibatch_update(
+                    parity, a.dims, self.hp, mb_inds, self.obs_op.view(-1, a.dims.obs_pad), self.actions.view(B, -1),
+                    self.logprobs.view(B), self.advantages.view(B), self.returns.view(B), self.values.view(B), self.norm_stats,
+                    a.parameters_flat(), a._wc, self.loss_acc, self.train_ws, self.exp_avg, self.exp_avg_sq, self.lr_dev,
+                    self.step_dev, self.opt_ws, max_grad_norm=self.cfg.max_grad_norm, eps=1e-5, grad_norm_out=self.grad_norm,
+                )  # fmt: skip
+                return
             self._minibatch_grad(mb_inds, grads=self.peer.arena[parity])
             gsum = self.peer.reduce(parity, self.step_dev, self.opt_ws, max_grad_norm=self.cfg.max_grad_norm, grad_norm_out=self.grad_norm)
             ops.adam_apply(a.dims, a.parameters_flat(), gsum, self.exp_avg, self.exp_avg_sq, a._wc, self.lr_dev, self.opt_ws,

@@ -408,6 +408,24 @@ int catb200_grad_allreduce_norm(void* const* peer_bases, int32_t rank, int32_t w
                                 int32_t* step_dev, float* grad_norm_out, void* opt_ws, uint32_t* epoch_dev,
                                 int32_t* err_dev, void* stream);
 
+/*
+ * catb200_ppo_minibatch_update on several GPUs: forward + backward of one minibatch (gradient accumulated straight into
+ * this rank's arena `parity`) and then ONE launch for the rest of the optimizer step -- fold of the accumulators into the
+ * arena, flag handshake with every peer, rank-ordered sum of the world arenas into the private `grad_sum`, squared norm,
+ * clip, Adam (grad_scale = 1 / world) and the operand-copy refresh -- around two local grid barriers.  Replaces
+ * catb200_ppo_minibatch_grad + catb200_grad_allreduce_norm + catb200_adam_apply (reference: the optimizer step of
+ * U/cleanrl/ppo.py:351-354 after the gradient all-reduce its multi-process front-ends do); peer arguments as above.
+ */
+int catb200_ppo_minibatch_update_peer(const catb200_mlp_dims_t* dims, const catb200_ppo_hparams_t* hp, int32_t mb_rows,
+                                      const int64_t* mb_inds, const void* obs_op_all, const float* actions_all,
+                                      const float* logprobs_all, const float* advantages_all, const float* returns_all,
+                                      const float* values_all, const float* norm_stats, float* params, void* wc,
+                                      float* loss_acc, void* workspace, size_t workspace_bytes, float* exp_avg,
+                                      float* exp_avg_sq, const float* lr_dev, int32_t* step_dev, float max_grad_norm,
+                                      float beta1, float beta2, float eps, float* grad_norm_out, void* opt_ws,
+                                      void* const* peer_bases, int32_t rank, int32_t world, int32_t parity, float* grad_sum,
+                                      uint32_t* epoch_dev, int32_t* err_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Device-side random draws (Philox4x32-10; csrc/philox.cuh, CPU restatement oracle/philox_oracle.py)
  *

@@ -44,6 +44,18 @@ def flat_grads(agent, layout) -> torch.Tensor:
     return flat
 
 
+def flat_slices(layout) -> dict:
+    """name -> (begin, end) of every parameter tensor inside the flat vector."""
+    offs = sorted([*layout.w[0], *layout.b[0], *layout.w[1], *layout.b[1], layout.logstd, layout.n_params])
+    out = {}
+    for z in range(2):
+        for l in range(4):
+            for kind, off in (("w", layout.w[z][l]), ("b", layout.b[z][l])):
+                out[f"net{z}.layer{l}.{kind}"] = (off, next(o for o in offs if o > off))
+    out["logstd"] = (layout.logstd, layout.logstd + ACT)
+    return out
+
+
 def test_layout_follows_reference_parameter_order():
     agent = ppo_oracle.AgentOracle(OBS, ACT)
     layout = ops.mlp_layout(ops.make_dims(OBS, ACT))
@@ -291,6 +303,44 @@ def test_tile_variants_match_each_other(var, prec):
         outs.append(torch.load(path))
     rel = float((outs[0] - outs[1]).norm() / outs[0].norm())
     assert rel < 1e-5, rel  # same products, same fp32 accumulation per output element; only the atomics order of wgrad differs
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("B,M", [(20000, 16500), (700, 333)])
+def test_head_kernels_match_each_other(B, M, prec):
+    """head_mma_kernel (mma.sync tf32 fragments, 16 samples per warp, the default) against head_kernel<true> (one warp per
+    sample, fp32 FMAs; CATB200_HEAD=warp): same losses and the same gradient on ragged minibatches.  The forward products
+    of the mma kernel use hi + lo tf32 weight terms (fp32-grade), its backward products plain tf32 operands: the head
+    weight gradients and everything downstream of dZ3 agree to tf32 rounding of dL/dmean (2^-11 relative per term).
+    The switch is read once per process -> subprocesses."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import torch, sys; sys.path.insert(0, %r)\n"
+        "from tests import test_mlp_gpu as T\n"
+        "from constraints_as_terminations_b200 import ops\n"
+        "agent = T.make_agent(seed=3); dims, layout, params, wc = T.device_agent(agent, %r)\n"
+        "obs, actions, logp, adv, returns, values, ns, idx = T._minibatch(agent, %d, %d, seed=7)\n"
+        "g = torch.zeros(layout.n_params, device='cuda:0'); la = torch.zeros(8, device='cuda:0')\n"
+        "ops.ppo_minibatch_grad(dims, ops.make_hparams(), idx.cuda(), ops.obs_to_operand(dims, obs.cuda()), actions.cuda(), logp.cuda(), adv.cuda(),"
+        " returns.cuda(), values.cuda(), ns.cuda(), params, wc, g, la, ops.mlp_workspace(dims, %d, True, 'cuda:0'))\n"
+        "torch.save((g.cpu(), la.cpu()), sys.argv[1])\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), prec, B, M, M)
+    outs = []
+    for variant in ("warp", "mma"):
+        path = f"/tmp/catb200_head_{variant}_{prec}_{M}.pt"
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=dict(os.environ, CATB200_HEAD=variant), timeout=120)
+        outs.append(torch.load(path))
+    (g0, la0), (g1, la1) = outs
+    assert torch.allclose(la0, la1, rtol=2e-5, atol=1e-6), (la0, la1)   # losses, KL, clip fraction: fp32-grade forward
+    layout = device_agent(make_agent(seed=3), prec)[1]
+    for name, (lo, hi) in flat_slices(layout).items():
+        a, b = g0[lo:hi], g1[lo:hi]
+        rel = float((a - b).norm() / a.norm().clamp_min(1e-20))
+        # bf16: dZ3 is stored with an 8-bit mantissa, so a 2^-11 difference in dL/dmean flips roundings of 2^-9
+        assert rel < (2e-3 if prec == "tf32" else 1.5e-2), f"{name}: {rel:.3e}"
 
 
 @pytest.mark.parametrize("prec", PRECS)

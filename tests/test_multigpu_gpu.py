@@ -122,8 +122,9 @@ def test_rank_summed_gradient_equals_single_gpu_gradient_of_the_concatenated_min
     assert max(out.values()) < 2e-5, dict(out)
 
 
-def _trainer_worker(rank, world, port, peer, out):
+def _trainer_worker(rank, world, port, peer, out, fused=True):
     os.environ["CATB200_PEER_ALLREDUCE"] = "1" if peer else "0"
+    os.environ["CATB200_FUSED_OPT"] = "1" if fused else "0"
     _init(rank, world, port)
     from constraints_as_terminations_b200 import PPOTrainer, solo12_flat_ppo_cfg
     from constraints_as_terminations_b200 import synthetic_env as se
@@ -140,8 +141,9 @@ def _trainer_worker(rank, world, port, peer, out):
         tr.train_iteration()
         tr.losses()
     torch.cuda.synchronize()
-    out[(peer, rank)] = tr.agent.parameters_flat().detach().cpu()
+    out[(peer, rank) if fused else (peer, rank, "split")] = tr.agent.parameters_flat().detach().cpu()
     if tr.peer is not None:
+        tr.peer.check()
         tr.peer.close()
     torch.distributed.destroy_process_group()
 
@@ -154,3 +156,18 @@ def test_two_rank_trainer_peer_exchange_matches_nccl_and_keeps_ranks_identical()
     assert torch.equal(out[(True, 0)], out[(True, 1)])  # rank-ordered sums: every rank takes bit-identical steps
     assert torch.equal(out[(False, 0)], out[(False, 1)])
     torch.testing.assert_close(out[(True, 0)], out[(False, 0)], rtol=1e-3, atol=3e-4)  # vs NCCL: summation order only
+
+
+@needs_two
+def test_single_launch_peer_optimizer_step_equals_the_three_launch_one():
+    """catb200_ppo_minibatch_update_peer (fold + handshake + rank-ordered sum + norm + clip + Adam + operand refresh in ONE
+    launch around two local grid barriers) against fold_grads + grad_allreduce_norm + adam_cast: same per-element
+    arithmetic.  Two runs of either path already differ in the last bits of the weight gradients (red.global.add order of
+    mlp_wgrad_kernel) and Adam's first steps normalise every gradient element by its own magnitude, so near-zero elements
+    may move by up to 2 lr per step in either direction: same tolerance as the comparison with NCCL above."""
+    out = mp.Manager().dict()
+    for fused, port in zip((True, False), _free_ports(2)):
+        mp.spawn(_trainer_worker, args=(2, port, True, out, fused), nprocs=2, join=True)
+    assert torch.equal(out[(True, 0)], out[(True, 1)])
+    assert torch.equal(out[(True, 0, "split")], out[(True, 1, "split")])
+    torch.testing.assert_close(out[(True, 0)], out[(True, 0, "split")], rtol=1e-3, atol=3e-4)
