@@ -55,6 +55,27 @@ def allreduce_grads(flat_grads: torch.Tensor) -> float:
     return 1.0 / w
 
 
+def pooled_moments(mean: torch.Tensor, var: torch.Tensor, count: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Statistics of the union of every rank's samples from the per-rank running (mean, population variance, count):
+    the parallel-moments merge `RunningMeanStd.update_from_moments` itself uses (reference U/cleanrl/ppo.py:41-62), applied
+    across ranks in rank order, in float64.  Collective (all ranks must call it); the inputs are not modified.  Used when
+    a checkpoint is written: training keeps the normalisers rank-local, as the reference's multi-process front-ends do,
+    but the saved policy should carry the statistics of all env shards, not rank 0's."""
+    if world_size() == 1:
+        return mean.clone(), var.clone(), count.clone()
+    packed = torch.cat([mean.reshape(-1), var.reshape(-1), count.reshape(-1)]).to(torch.float64)
+    gathered = [torch.empty_like(packed) for _ in range(world_size())]
+    dist.all_gather(gathered, packed)
+    d = mean.numel()
+    m, v, n = gathered[0][:d].clone(), gathered[0][d : 2 * d].clone(), gathered[0][2 * d].clone()
+    for g in gathered[1:]:
+        mb, vb, nb = g[:d], g[d : 2 * d], g[2 * d]
+        delta, tot = mb - m, n + nb
+        m2 = v * n + vb * nb + delta * delta * n * nb / tot
+        m, v, n = m + delta * nb / tot, m2 / tot, tot
+    return m.to(mean.dtype).view_as(mean), v.to(var.dtype).view_as(var), n.to(count.dtype).view_as(count)
+
+
 def shard_seed(base_seed: int) -> int:
     """Per-rank seed, like the reference's distributed front-ends (`scripts/skrl/train.py:116-117`)."""
     return base_seed + rank()

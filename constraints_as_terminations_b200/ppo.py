@@ -619,9 +619,43 @@ class PPOTrainer:
         self._validate = False
         return ep_infos
 
+    def checkpoint_state(self) -> dict:
+        """`agent.state_dict()` (the reference's keys, ppo.py:357) for a checkpoint.  With several ranks the observation /
+        value normalisers in it are the pooled statistics of all env shards (dist.pooled_moments; every rank must call
+        this), while the live ones stay rank-local."""
+        state = {k: v.detach().clone() for k, v in self.agent.state_dict().items()}
+        if self.world > 1:
+            for name in ("obs_rms", "value_rms"):
+                rms = getattr(self.agent, name)
+                m, v, n = cdist.pooled_moments(rms.running_mean, rms.running_var, rms.count)
+                state[f"{name}.running_mean"], state[f"{name}.running_var"], state[f"{name}.count"] = m, v, n
+        return state
+
+    def losses_async(self):
+        """Enqueue the device->host copy of the last update's loss accumulators (into pinned memory, behind the work
+        submitted so far) and return a handle for `read_losses`.  A logger that reads the handle of iteration i while
+        iteration i + 1 is being submitted never drains the GPU queue, which a blocking `losses()` per iteration does."""
+        ring = getattr(self, "_loss_ring", None)
+        if ring is None:
+            ring = self._loss_ring = [(torch.empty(8, dtype=torch.float32).pin_memory(), torch.cuda.Event()) for _ in range(4)]
+            self._loss_seq = 0
+        buf, ev = ring[self._loss_seq % len(ring)]
+        self._loss_seq += 1
+        buf.copy_(self.loss_acc, non_blocking=True)
+        ev.record()
+        return buf, ev
+
+    def read_losses(self, handle) -> dict:
+        """Wait for the copy `losses_async` enqueued (not for anything submitted after it) and return the mean losses."""
+        buf, ev = handle
+        ev.synchronize()
+        return self._loss_dict(buf.clone())
+
     def losses(self) -> dict:
-        """Mean losses over the minibatches of the last update (one device->host read)."""
-        acc = self.loss_acc.cpu()
+        """Mean losses over the minibatches of the last update (one blocking device->host read)."""
+        return self._loss_dict(self.loss_acc.cpu())
+
+    def _loss_dict(self, acc) -> dict:
         if self.peer is not None:
             self.peer.check()
         n = max(float(acc[7]), 1.0)
@@ -680,9 +714,11 @@ def PPO(envs, ppo_cfg, run_path):
             for name in ("mean_pg_loss", "mean_entropy_loss", "mean_v_loss", "mean_surrogate_loss"):
                 writer.add_scalar("Loss/" + name, losses[name], iteration)
             writer.add_scalar("Loss/learning_rate", float(trainer.lr_dev), iteration)
-        if (iteration + 1) % ppo_cfg.save_interval == 0 and trainer.rank == 0:
-            torch.save(trainer.agent.state_dict(), f"{run_path}/model_{iteration}.pt")
-            print("Saved model")
+        if (iteration + 1) % ppo_cfg.save_interval == 0:
+            state = trainer.checkpoint_state()  # collective with several ranks: pooled normaliser statistics
+            if trainer.rank == 0:
+                torch.save(state, f"{run_path}/model_{iteration}.pt")
+                print("Saved model")
     torch.cuda.synchronize()
     elapsed = time.time() - start_time
     print(f"Trained {trainer.global_step} env steps in {elapsed:.1f} s")

@@ -91,3 +91,34 @@ def test_single_process_helpers_are_noops():
     assert cdist.world_size() == 1 and cdist.rank() == 0
     cdist.broadcast_params(t)
     assert cdist.allreduce_grads(t) == 1.0 and torch.equal(t, torch.arange(4.0))
+
+
+def _moments_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.set_num_threads(1)
+    cdist.init_from_env("gloo")
+    g = torch.Generator().manual_seed(11)
+    data = torch.randn(1000, 5, generator=g) * torch.tensor([1.0, 3.0, 0.1, 10.0, 2.0]) + torch.tensor([0.0, 5.0, -2.0, 100.0, 1e-3])
+    shard = data[:300] if rank == 0 else data[300:]  # uneven shards
+    mean, var, count = shard.mean(0), shard.var(0, unbiased=False), torch.tensor(float(len(shard)))
+    keep = (mean.clone(), var.clone(), count.clone())
+    m, v, n = cdist.pooled_moments(mean, var, count)
+    assert all(torch.equal(a, b) for a, b in zip(keep, (mean, var, count)))  # inputs untouched
+    out[rank] = (m, v, n, data.mean(0), data.var(0, unbiased=False))
+    torch.distributed.destroy_process_group()
+
+
+def test_pooled_moments_are_the_statistics_of_the_union_of_the_shards():
+    """dist.pooled_moments (used for the normaliser entries of multi-rank checkpoints): the rank-ordered parallel-moments
+    merge of per-rank (mean, population variance, count) equals the moments of all samples, identically on every rank."""
+    out = mp.Manager().dict()
+    mp.spawn(_moments_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    for r in (0, 1):
+        m, v, n, want_m, want_v = out[r]
+        assert float(n) == 1000.0
+        torch.testing.assert_close(m, want_m, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(v, want_v, rtol=1e-5, atol=1e-6)
+    assert all(torch.equal(a, b) for a, b in zip(out[0][:3], out[1][:3]))
+    # single process: a copy
+    m, v, n = cdist.pooled_moments(torch.ones(3), torch.full((3,), 2.0), torch.tensor(5.0))
+    assert torch.equal(m, torch.ones(3)) and torch.equal(v, torch.full((3,), 2.0)) and float(n) == 5.0

@@ -106,7 +106,9 @@ def test_trainer_end_to_end_on_synthetic_env():
     for _ in range(3):
         infos = tr.train_iteration()
         assert len(infos) > 0  # resets happened (episode_length 20) and carried the constraint statistics
+        handle = tr.losses_async()  # the non-blocking read-back a logger would use ...
         losses = tr.losses()
+        assert tr.read_losses(handle) == losses  # ... returns what the blocking read returns
         assert all(torch.isfinite(torch.tensor(v)) for v in losses.values()), losses
     torch.cuda.synchronize()
     assert float(tr.agent.obs_rms.count) == 1 + n * (1 + 3 * T)
