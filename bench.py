@@ -506,8 +506,13 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    numa_cpus = []
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=device)
+        from constraints_as_terminations_b200 import dist as cdist
+
+        # one rank per GPU: keep this rank's host threads and its pinned staging buffers on the GPU's own NUMA node
+        numa_cpus = cdist.bind_to_gpu_numa_node(local_rank)
     import __graft_entry__
 
     if rank == 0:
@@ -593,6 +598,7 @@ def run_ours(args):
         "config": workload_config(N, world),
         "precision": precision,
         "cuda_graphs": not args.no_graphs,
+        "host_binding": (f"rank 0 bound to {len(numa_cpus)} CPUs of its GPU's NUMA node" if numa_cpus else "none"),
         "e2e": e2e,
         "gpu_launches": launches,
         "clocks": clocks,

@@ -217,6 +217,10 @@ gather_kernel(const int64_t* __restrict__ mb_inds, int M, const uint4* __restric
     s += a;
     q += a * a;
   }
+  // Only the CTAs that own a sample in the loop above have anything to add; the others (15 of 16 at M = 16384) skip the
+  // reduction and the ticket: ~3000 fewer same-address atomics queueing in the L2 per launch.
+  const int stat_ctas = min((M + (int)blockDim.x - 1) / (int)blockDim.x, (int)gridDim.x);
+  if ((int)blockIdx.x >= stat_ctas) return;
   s = warp_sum(s);
   q = warp_sum(q);
   __shared__ double sh_s[8], sh_q[8];
@@ -234,7 +238,7 @@ gather_kernel(const int64_t* __restrict__ mb_inds, int M, const uint4* __restric
     atomicAdd(&st->sum, ts);
     atomicAdd(&st->sumsq, tq);
   }
-  if (last_block_ticket(&st->ticket, gridDim.x)) {
+  if (last_block_ticket(&st->ticket, stat_ctas)) {
     if (threadIdx.x == 0) {
       const double ts = __longlong_as_double(atomicExch((unsigned long long*)&st->sum, 0ull));
       const double tq = __longlong_as_double(atomicExch((unsigned long long*)&st->sumsq, 0ull));
@@ -1169,7 +1173,7 @@ __global__ void __launch_bounds__(256) opt_step_kernel(const __grid_constant__ O
       *r.step = t1;
       if (r.grad_norm_out) *r.grad_norm_out = norm;
     }
-    // the last CTA to have read the sum resets it
+    // the last CTA to have read the sum resets it (measured: behind phase C instead, the launch takes 19.0 instead of 17.8 us)
     __threadfence();
     if (atomicAdd(&sc->ticket, 1u) == gridDim.x - 1) {
       sc->ticket = 0u;
@@ -1213,6 +1217,11 @@ struct OptStepPeerArgs {
   unsigned int* epoch;            // device-local count of completed exchanges
   int* err;                       // device-local error flag (1: a peer did not arrive, 2: parity out of step)
   unsigned int parity;
+  // reduce-scatter / all-gather variant (world > 2): every rank sums ONE slice of the vector over all arenas and writes it
+  // into every rank's summed-gradient region, so a rank moves 2 (W-1)/W of the vector over NVLink instead of pulling W-1
+  // whole arenas (10.5 MB per step at 8 ranks: 48 us); costs a second handshake, which also carries the partial norms
+  int rs;
+  float* gsum[kPeerMax];          // summed-gradient region of every rank's peer block (index = rank)
 };
 
 template <int PREC>
@@ -1260,52 +1269,21 @@ __global__ void __launch_bounds__(256) opt_step_peer_kernel(const __grid_constan
     grid_barrier(true);
   }
   __syncthreads();
-  if (tid < p.world && tid != p.rank) {  // every peer's arena of this parity is complete
-    const uint32_t* mine = p.flags[p.rank] + tid;
-    const long long t0 = clock64();
-    while (ld_acquire_sys(mine) < e) {
-      if (clock64() - t0 > 4000000000ll) {  // ~2 s: give up loudly, do not hang the GPU
-        atomicExch(p.err, 1);
-        break;
+  auto wait_flags = [&](int word0, bool with_self) {  // threads < world: every rank's epoch-e flag has arrived in this rank's row
+    if (tid < p.world && (with_self || tid != p.rank)) {
+      const uint32_t* mine = p.flags[p.rank] + word0 + tid;
+      const long long t0 = clock64();
+      while (ld_acquire_sys(mine) < e) {
+        if (clock64() - t0 > 4000000000ll) {  // ~2 s: give up loudly, do not hang the GPU
+          atomicExch(p.err, 1);
+          break;
+        }
+        __nanosleep(200);
       }
-      __nanosleep(200);
     }
-  }
-  __syncthreads();
-
-  // ---- phase B: rank-ordered sum (identical on every rank), squared norm, zero the other arena
-  double ss = 0.0;
-  const long long n4 = p.n / 4;
-  for (long long i = gtid; i < n4; i += gthreads) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-    for (int q = 0; q < p.world; ++q) {
-      const float4 v = __ldcv(reinterpret_cast<const float4*>(p.arena[q]) + i);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-    }
-    reinterpret_cast<float4*>(p.out)[i] = acc;
-    reinterpret_cast<float4*>(p.zero_arena)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const double x = (double)(acc.x * gscale), y = (double)(acc.y * gscale), z = (double)(acc.z * gscale), w = (double)(acc.w * gscale);
-    ss += x * x + y * y + z * z + w * w;
-  }
-  for (long long i = n4 * 4 + gtid; i < p.n; i += gthreads) {  // scalar tail
-    float acc = 0.f;
-    for (int q = 0; q < p.world; ++q) acc += __ldcv(p.arena[q] + i);
-    p.out[i] = acc;
-    p.zero_arena[i] = 0.f;
-    const double x = (double)(acc * gscale);
-    ss += x * x;
-  }
-  ss = warp_sum(ss);
-  if (lane == 0) red_s[warp] = ss;
-  __syncthreads();
-  if (tid == 0) {
-    double t = 0.0;
-    for (int w = 0; w < 8; ++w) t += red_s[w];
-    atomicAdd(&sc->sumsq, t);
-    __threadfence();
-    grid_barrier(false);
-    const double tot = *reinterpret_cast<volatile double*>(&sc->sumsq);
+    __syncthreads();
+  };
+  auto publish_coefficients = [&](double tot) {  // thread 0: clip coefficient + Adam bias corrections from the squared norm
     const float norm = (float)sqrt(tot);
     const float clip_coef = fminf(r.max_norm / (norm + 1e-6f), 1.0f);  // torch.nn.utils.clip_grad_norm_
     const int t1 = step0 + 1;
@@ -1322,10 +1300,97 @@ __global__ void __launch_bounds__(256) opt_step_peer_kernel(const __grid_constan
       *p.epoch = e;
       if (r.grad_norm_out) *r.grad_norm_out = norm;
     }
-    __threadfence();
-    if (atomicAdd(&sc->ticket, 1u) == gridDim.x - 1) {  // the last CTA to have read the sum resets it
-      sc->ticket = 0u;
-      sc->sumsq = 0.0;
+  };
+
+  wait_flags(0, false);  // every peer's arena of this parity is complete
+
+  double ss = 0.0;
+  if (p.rs) {
+    // ---- phase B (reduce-scatter / all-gather): this rank's slice of the vector, summed over the arenas in rank order
+    //      (so the slice is bit-identical wherever it lands), goes to every rank's summed-gradient region
+    const long long n4 = (long long)(peer_n_pad(p.n) / 4);  // whole 16-byte quads; the padding stays zero
+    const long long per = (n4 + p.world - 1) / p.world;
+    const long long lo = per * p.rank, hi = min(n4, lo + per);
+    for (long long i = lo + gtid; i < hi; i += gthreads) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+      for (int q = 0; q < p.world; ++q) {
+        const float4 v = __ldcv(reinterpret_cast<const float4*>(p.arena[q]) + i);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+#pragma unroll 8
+      for (int q = 0; q < p.world; ++q) reinterpret_cast<float4*>(p.gsum[q])[i] = acc;
+      const double x = (double)(acc.x * gscale), y = (double)(acc.y * gscale), z = (double)(acc.z * gscale), w = (double)(acc.w * gscale);
+      ss += x * x + y * y + z * z + w * w;
+    }
+    for (long long i = gtid; i < n4; i += gthreads) reinterpret_cast<float4*>(p.zero_arena)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ss = warp_sum(ss);
+    if (lane == 0) red_s[warp] = ss;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += red_s[w];
+      atomicAdd(&sc->sumsq, t);
+      __threadfence_system();  // this CTA's slice stores (remote ones included) are ordered before its arrival
+      const unsigned int ticket = atomicAdd(bar, 1u);
+      const unsigned int target = (ticket / gridDim.x + 1u) * gridDim.x;
+      if (ticket == target - 1u) {
+        // last arriver: the slice is complete everywhere.  Its squared norm goes into slot `rank` of every rank's row (own
+        // one included), then the second flag.  Nobody waits on the arrival counter itself: every CTA waits for the flags.
+        __threadfence();
+        const double part = *reinterpret_cast<volatile double*>(&sc->sumsq);
+        sc->sumsq = 0.0;
+        for (int q = 0; q < p.world; ++q)
+          reinterpret_cast<double*>(reinterpret_cast<char*>(p.flags[q]) + kNormByte)[p.rank] = part;
+        __threadfence_system();
+        for (int q = 0; q < p.world; ++q) st_release_sys(p.flags[q] + kFlag2Word + p.rank, e);
+      }
+    }
+    wait_flags(kFlag2Word, true);  // every rank's slice and partial norm have landed here
+    if (tid == 0) {
+      double tot = 0.0;
+      const volatile double* parts = reinterpret_cast<const volatile double*>(reinterpret_cast<char*>(p.flags[p.rank]) + kNormByte);
+      for (int q = 0; q < p.world; ++q) tot += parts[q];  // rank order: the same total on every rank
+      publish_coefficients(tot);
+    }
+  } else {
+    // ---- phase B (pull): rank-ordered sum of the whole arenas (identical on every rank), squared norm, zero the other arena
+    const long long n4 = p.n / 4;
+    for (long long i = gtid; i < n4; i += gthreads) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+      for (int q = 0; q < p.world; ++q) {
+        const float4 v = __ldcv(reinterpret_cast<const float4*>(p.arena[q]) + i);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      reinterpret_cast<float4*>(p.out)[i] = acc;
+      reinterpret_cast<float4*>(p.zero_arena)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const double x = (double)(acc.x * gscale), y = (double)(acc.y * gscale), z = (double)(acc.z * gscale), w = (double)(acc.w * gscale);
+      ss += x * x + y * y + z * z + w * w;
+    }
+    for (long long i = n4 * 4 + gtid; i < p.n; i += gthreads) {  // scalar tail
+      float acc = 0.f;
+      for (int q = 0; q < p.world; ++q) acc += __ldcv(p.arena[q] + i);
+      p.out[i] = acc;
+      p.zero_arena[i] = 0.f;
+      const double x = (double)(acc * gscale);
+      ss += x * x;
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) red_s[warp] = ss;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += red_s[w];
+      atomicAdd(&sc->sumsq, t);
+      __threadfence();
+      grid_barrier(false);
+      publish_coefficients(*reinterpret_cast<volatile double*>(&sc->sumsq));
+      __threadfence();
+      if (atomicAdd(&sc->ticket, 1u) == gridDim.x - 1) {  // the last CTA to have read the sum resets it
+        sc->ticket = 0u;
+        sc->sumsq = 0.0;
+      }
     }
   }
   __syncthreads();
@@ -1879,7 +1944,18 @@ int catb200_ppo_minibatch_update_peer(const catb200_mlp_dims_t* dims, const catb
   int rc = minibatch_backward(dims, hp, mb_rows, mb_inds, obs_op_all, actions_all, logprobs_all, advantages_all, returns_all,
                               values_all, norm_stats, params, wcv, arena, loss_acc, workspace, workspace_bytes, stream, &pa.o.f);
   if (rc != CATB200_OK) return rc;
-  AdamState a = {params, grad_sum, exp_avg, exp_avg_sq, lr_dev, static_cast<OptScratch*>(opt_ws), beta1, beta2, eps, 1.0f / (float)world};
+  // exchange pattern: pull whole arenas (one handshake) for two ranks, reduce-scatter / all-gather (two handshakes, 1 / world
+  // of the traffic per peer) beyond; CATB200_PEER_RS=1 / 0 forces either
+  static int rs_mode = -1;
+  if (rs_mode < 0) {
+    const char* e = std::getenv("CATB200_PEER_RS");
+    rs_mode = (e && e[0] == '1') ? 1 : (e && e[0] == '0') ? 0 : 2;
+  }
+  pa.rs = rs_mode == 1 || (rs_mode == 2 && world > 2);
+  for (int q = 0; q < world; ++q)
+    pa.gsum[q] = reinterpret_cast<float*>(static_cast<char*>(peer_bases[q]) + kFlagWords * 4) + 2 * n_pad;
+  float* summed = pa.rs ? pa.gsum[rank] : grad_sum;  // what Adam consumes
+  AdamState a = {params, summed, exp_avg, exp_avg_sq, lr_dev, static_cast<OptScratch*>(opt_ws), beta1, beta2, eps, 1.0f / (float)world};
   fill_opt_step(dims, a, wcv, max_grad_norm, step_dev, grad_norm_out, opt_ws, pa.o);
   pa.zero_arena = own + (size_t)(parity ^ 1) * n_pad;
   pa.out = grad_sum; pa.n = P.n_params; pa.rank = rank; pa.world = world;

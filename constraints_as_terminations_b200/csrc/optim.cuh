@@ -31,8 +31,13 @@ struct AdamState {
 };
 
 // ---- peer-visible gradient block of the multi-GPU exchange (peer.cu, mlp.cu): [flags: kFlagWords x u32][arena 0][arena 1]
+// flag row of rank r (64 words): [0, 8) "arena ready" epoch written by rank q into word q, [8, 16) "slice + partial norm
+// delivered" epoch of the reduce-scatter path, bytes [64, 128) one double per rank: its partial squared norm.  Behind the
+// two arenas sits a third region of n_pad floats: the summed gradient the reduce-scatter path assembles from the peers' slices.
 constexpr int kPeerMax = 8;
 constexpr int kFlagWords = 64;
+constexpr int kFlag2Word = 8;
+constexpr int kNormByte = 64;
 __host__ __device__ inline size_t peer_n_pad(long long n_params) { return ((size_t)n_params + 63) / 64 * 64; }
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {

@@ -118,7 +118,7 @@ extern "C" {
 
 size_t catb200_peer_arena_bytes(int64_t n_params) {
   const size_t n_pad = ((size_t)n_params + 63) / 64 * 64;
-  return kFlagWords * 4 + 2 * n_pad * 4;
+  return kFlagWords * 4 + 3 * n_pad * 4;  // flags, two arenas, the summed gradient of the reduce-scatter path
 }
 
 int catb200_peer_alloc(size_t bytes, void** ptr, uint8_t* ipc_handle64) {

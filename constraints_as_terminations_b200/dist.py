@@ -33,6 +33,37 @@ def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
     return rank, world, local_rank
 
 
+def bind_to_gpu_numa_node(device_index: int) -> list[int]:
+    """Pin the calling thread to the CPUs of the NUMA node the GPU hangs off, so that pinned host buffers allocated and
+    first touched afterwards are node-local (8 ranks feeding 118 MB per iteration each through the wrong socket's memory
+    controller is what limited the end-to-end scaling).  NVML's own affinity helper when available, sysfs otherwise; returns
+    the CPU list (empty: nothing was changed -- no NVML, no sysfs, or a container without the right to set affinity)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return sorted(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    try:
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(device_index), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(device_index), "pci_device_id", 0)
+        node = int(open(f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node").read())
+        if node < 0:
+            return []
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.extend(range(int(lo), int(hi or lo) + 1))
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return []
+
+
 def world_size() -> int:
     return dist.get_world_size() if dist.is_initialized() else 1
 
@@ -91,7 +122,7 @@ class _RawCuda:
 class PeerGradExchange:
     """One-shot gradient all-reduce over NVLink peer memory, fused with the gradient norm (csrc/peer.cu).
 
-    Every rank cudaMallocs one peer-visible block ([flags][arena 0][arena 1]); the 64-byte IPC handles travel once
+    Every rank cudaMallocs one peer-visible block ([flags][arena 0][arena 1][summed gradient of the reduce-scatter path]); the 64-byte IPC handles travel once
     through `torch.distributed.all_gather_object` (host plumbing) and every rank maps its peers' blocks.  After that the
     exchange is ONE kernel per optimizer step and rank (`reduce`), with no library collective and no host
     synchronisation, so a whole epoch of minibatches replays as a single CUDA graph on every rank."""

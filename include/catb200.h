@@ -382,7 +382,8 @@ int catb200_adam_apply(const catb200_mlp_dims_t* dims, float* params, float* gra
  * Multi-GPU gradient exchange over NVLink peer memory  (one exchange step per optimizer step)
  *
  * Each rank owns one peer-visible allocation of catb200_peer_arena_bytes(n_params) bytes:
- *   [flags: 64 x uint32][gradient arena 0: n_pad floats][gradient arena 1: n_pad floats],  n_pad = n_params rounded up to 64.
+ *   [flags: 64 x uint32][gradient arena 0: n_pad floats][gradient arena 1: n_pad floats][summed gradient: n_pad floats],
+ *   n_pad = n_params rounded up to 64.
  * Minibatch k accumulates its flat gradient into arena k & 1 (`grads` of catb200_ppo_minibatch_grad points there).
  * catb200_grad_allreduce_norm is then ONE kernel per rank: flag handshake with every peer over NVLink, rank-ordered sum
  * of the world arenas of that parity into the private `grad_sum` (bit-identical on every rank), squared norm -> clip
@@ -415,6 +416,10 @@ int catb200_grad_allreduce_norm(void* const* peer_bases, int32_t rank, int32_t w
  * clip, Adam (grad_scale = 1 / world) and the operand-copy refresh -- around two local grid barriers.  Replaces
  * catb200_ppo_minibatch_grad + catb200_grad_allreduce_norm + catb200_adam_apply (reference: the optimizer step of
  * U/cleanrl/ppo.py:351-354 after the gradient all-reduce its multi-process front-ends do); peer arguments as above.
+ * Two ranks exchange by pulling the peer's whole arena (one handshake); more ranks reduce-scatter / all-gather: every rank
+ * sums one slice of the vector over all arenas and writes it into every rank's summed-gradient region (the third n_pad
+ * floats of the peer block; `grad_sum` is then unused), the partial squared norms travel with the second handshake.
+ * CATB200_PEER_RS=1 / 0 forces either pattern.
  */
 int catb200_ppo_minibatch_update_peer(const catb200_mlp_dims_t* dims, const catb200_ppo_hparams_t* hp, int32_t mb_rows,
                                       const int64_t* mb_inds, const void* obs_op_all, const float* actions_all,

@@ -123,8 +123,10 @@ def test_rank_summed_gradient_equals_single_gpu_gradient_of_the_concatenated_min
 
 
 def _trainer_worker(rank, world, port, peer, out, fused=True):
+    # fused: True (one launch, default exchange pattern), False (three launches), "rs" (one launch, reduce-scatter / all-gather)
     os.environ["CATB200_PEER_ALLREDUCE"] = "1" if peer else "0"
     os.environ["CATB200_FUSED_OPT"] = "1" if fused else "0"
+    os.environ["CATB200_PEER_RS"] = "1" if fused == "rs" else "0"
     _init(rank, world, port)
     from constraints_as_terminations_b200 import PPOTrainer, solo12_flat_ppo_cfg
     from constraints_as_terminations_b200 import synthetic_env as se
@@ -141,7 +143,7 @@ def _trainer_worker(rank, world, port, peer, out, fused=True):
         tr.train_iteration()
         tr.losses()
     torch.cuda.synchronize()
-    out[(peer, rank) if fused else (peer, rank, "split")] = tr.agent.parameters_flat().detach().cpu()
+    out[(peer, rank) if fused is True else (peer, rank, "split" if not fused else fused)] = tr.agent.parameters_flat().detach().cpu()
     if tr.peer is not None:
         tr.peer.check()
         tr.peer.close()
@@ -166,8 +168,12 @@ def test_single_launch_peer_optimizer_step_equals_the_three_launch_one():
     mlp_wgrad_kernel) and Adam's first steps normalise every gradient element by its own magnitude, so near-zero elements
     may move by up to 2 lr per step in either direction: same tolerance as the comparison with NCCL above."""
     out = mp.Manager().dict()
-    for fused, port in zip((True, False), _free_ports(2)):
+    for fused, port in zip((True, False, "rs"), _free_ports(3)):
         mp.spawn(_trainer_worker, args=(2, port, True, out, fused), nprocs=2, join=True)
     assert torch.equal(out[(True, 0)], out[(True, 1)])
     assert torch.equal(out[(True, 0, "split")], out[(True, 1, "split")])
     torch.testing.assert_close(out[(True, 0)], out[(True, 0, "split")], rtol=1e-3, atol=3e-4)
+    # the reduce-scatter / all-gather pattern (default beyond two ranks, forced here): every slice is summed once, in rank
+    # order, and copied -> still bit-identical on every rank
+    assert torch.equal(out[(True, 0, "rs")], out[(True, 1, "rs")])
+    torch.testing.assert_close(out[(True, 0, "rs")], out[(True, 0, "split")], rtol=1e-3, atol=3e-4)
