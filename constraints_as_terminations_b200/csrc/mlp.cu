@@ -1243,9 +1243,9 @@ __global__ void __launch_bounds__(256) opt_step_peer_kernel(const __grid_constan
     const unsigned int target = (ticket / gridDim.x + 1u) * gridDim.x;
     if (announce && ticket == target - 1u) {
       // last arriver: every CTA fenced its arena writes (system scope) before its arrival, which this thread has observed
-      __threadfence_system();
+      __threadfence_system();  // one release fence for all the flag stores (a st.release per peer would serialise W - 1 fences)
       for (int q = 0; q < p.world; ++q)
-        if (q != p.rank) st_release_sys(p.flags[q] + p.rank, e);
+        if (q != p.rank) st_relaxed_sys(p.flags[q] + p.rank, e);
     }
     const long long t0 = clock64();
     while ((int)(*reinterpret_cast<volatile unsigned int*>(bar) - target) < 0) {
@@ -1273,13 +1273,14 @@ __global__ void __launch_bounds__(256) opt_step_peer_kernel(const __grid_constan
     if (tid < p.world && (with_self || tid != p.rank)) {
       const uint32_t* mine = p.flags[p.rank] + word0 + tid;
       const long long t0 = clock64();
-      while (ld_acquire_sys(mine) < e) {
+      while (ld_relaxed_sys(mine) < e) {  // relaxed polls, ONE acquire fence behind the loop
         if (clock64() - t0 > 4000000000ll) {  // ~2 s: give up loudly, do not hang the GPU
           atomicExch(p.err, 1);
           break;
         }
-        __nanosleep(200);
+        __nanosleep(100);
       }
+      __threadfence_system();
     }
     __syncthreads();
   };
@@ -1343,7 +1344,7 @@ __global__ void __launch_bounds__(256) opt_step_peer_kernel(const __grid_constan
         for (int q = 0; q < p.world; ++q)
           reinterpret_cast<double*>(reinterpret_cast<char*>(p.flags[q]) + kNormByte)[p.rank] = part;
         __threadfence_system();
-        for (int q = 0; q < p.world; ++q) st_release_sys(p.flags[q] + kFlag2Word + p.rank, e);
+        for (int q = 0; q < p.world; ++q) st_relaxed_sys(p.flags[q] + kFlag2Word + p.rank, e);
       }
     }
     wait_flags(kFlag2Word, true);  // every rank's slice and partial norm have landed here
@@ -1520,6 +1521,17 @@ static bool zigzag_rows(const catb200_mlp_dims_t* d, int rows) {
   return enabled == 1 && bytes > (size_t)96 << 20;
 }
 
+// L2 eviction-priority hints on the TMA traffic of the minibatch-sized launches (tc_ptx.cuh): what the next launch re-reads
+// is kept (evict_last), what is dead after this read goes first.  CATB200_L2_HINTS=0 disables them.
+static bool l2_hints(int rows) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("CATB200_L2_HINTS");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1 && rows >= 8192;  // rollout-sized launches fit the L2 anyway
+}
+
 static int launch_forward(const catb200_mlp_dims_t* d, const catb200_mlp_layout_t& P, const ActLayout& L, const void* X,
                           int rows, const float* params, const void* wc, char* ws, cudaStream_t st, bool zigzag = false) {
   Dims x = make_dims(d);
@@ -1538,6 +1550,9 @@ static int launch_forward(const catb200_mlp_dims_t* d, const catb200_mlp_layout_
     }
     t.M = rows; t.N = x.out[l]; t.K = x.in_pad[l];
     t.reverse = zigzag && (l & 1);
+    if (l2_hints(rows)) {  // H_{l-1} is not needed again before the backward pass; H_l is the next launch's operand
+      t.hintA = kL2EvictFirst; t.hintB = kL2EvictLast; t.hintC = kL2EvictLast;
+    }
     int rc = tc_gemm_launch(kTcFwd, prec, t, st);
     if (rc != CATB200_OK) return rc;
   }
@@ -1810,6 +1825,17 @@ static int minibatch_backward(const catb200_mlp_dims_t* dims, const catb200_ppo_
       }
       t.outs = x.out[l]; t.ins_pad = x.in_pad[l]; t.rows = M; t.m_range = L.m_range[l];
       t.reverse = 0;
+      if (l2_hints(M)) {
+        // dgrad_l re-reads both operands next (dZ_l as A, H_{l-1} for ELU'); layer 0 has no dgrad.  CATB200_L2_HINTS=2: keep
+        // only dZ_l (H_{l-1} of the 512-wide layer alone is half the L2)
+        static int keep_h = -1;
+        if (keep_h < 0) {
+          const char* e = std::getenv("CATB200_L2_HINTS");
+          keep_h = (e && e[0] == '2') ? 0 : 1;
+        }
+        t.hintA = l > 0 ? kL2EvictLast : kL2EvictFirst;
+        t.hintB = l > 0 ? (keep_h ? kL2EvictLast : kL2EvictNormal) : kL2EvictFirst;
+      }
       rc = tc_wgrad_launch(prec, t, L.splits[l], wst);
       if (rc != CATB200_OK) return rc;
     }
@@ -1824,6 +1850,9 @@ static int minibatch_backward(const catb200_mlp_dims_t* dims, const catb200_ppo_
       }
       t.M = M; t.N = x.in[l]; t.K = x.out[l];
       t.reverse = zigzag;
+      if (l2_hints(M)) {  // last reads of dZ_l and H_{l-1}; dZ_{l-1} feeds the next two launches
+        t.hintA = kL2EvictFirst; t.hintH = kL2EvictFirst; t.hintB = kL2EvictLast; t.hintC = kL2EvictLast;
+      }
       rc = tc_gemm_launch(kTcDgrad, prec, t, st);
       if (rc != CATB200_OK) return rc;
     }

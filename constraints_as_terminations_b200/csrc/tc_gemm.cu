@@ -84,6 +84,9 @@ mlp_gemm_kernel(const __grid_constant__ TcGemmArgs g) {
   constexpr int LD = kWCols / 32;                             // 32-column TMEM loads per warp and tile
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   pdl_launch_dependents();
+  const unsigned long long hA = g.hintA ? g.hintA : kL2EvictNormal, hB = g.hintB ? g.hintB : kL2EvictNormal;
+  const unsigned long long hC = g.hintC ? g.hintC : kL2EvictNormal, hH = g.hintH ? g.hintH : kL2EvictNormal;
+  (void)hH;
   const uint32_t raw = smem_u32(smem_raw);
   if (raw & 1023u) __trap();  // SWIZZLE_128B atoms need 1024-byte alignment
   const uint32_t tiles = raw;
@@ -148,8 +151,8 @@ mlp_gemm_kernel(const __grid_constant__ TcGemmArgs g) {
           mbar_wait(empty_bar + 8 * s, ((it / kPStages) & 1) ^ 1);
           const uint32_t sa = tiles + s * S::kStage, sb = sa + kATileBytes;
           mbar_expect_tx(full_bar + 8 * s, S::kStage);
-          tma_load_2d(sa, &g.mapA[z], full_bar + 8 * s, kb * P::kBK, row_base);  // 128 bytes of K x 128 rows
-          tma_load_2d(sb, &g.mapB[z], full_bar + 8 * s, kb * P::kBK, col_base);
+          tma_load_2d(sa, &g.mapA[z], full_bar + 8 * s, kb * P::kBK, row_base, hA);  // 128 bytes of K x 128 rows
+          tma_load_2d(sb, &g.mapB[z], full_bar + 8 * s, kb * P::kBK, col_base, hB);
         }
       }
     }
@@ -208,7 +211,7 @@ mlp_gemm_kernel(const __grid_constant__ TcGemmArgs g) {
             const uint32_t n = j * NCHUNK + c, buf = n % kBufs;
             bulk_wait_read(kBufs - 1 - c);  // stores issued so far: up to slab j * NCHUNK - 1
             mbar_expect_tx(my_hbar + 8 * buf, kSlabBytes);
-            tma_load_2d(my_slabs + buf * kSlabBytes, &g.mapH[z], my_hbar + 8 * buf, col_base + c_first + c * CH, row_base + quarter * 32);
+            tma_load_2d(my_slabs + buf * kSlabBytes, &g.mapH[z], my_hbar + 8 * buf, col_base + c_first + c * CH, row_base + quarter * 32, hH);
           }
         }
       } else {
@@ -287,7 +290,7 @@ mlp_gemm_kernel(const __grid_constant__ TcGemmArgs g) {
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&g.mapC[z], slab, col_base + c_first + c * CH, row_base + quarter * 32);
+          tma_store_2d(&g.mapC[z], slab, col_base + c_first + c * CH, row_base + quarter * 32, hC);
           asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
         }
       }
@@ -333,6 +336,9 @@ mlp_gemm256_kernel(const __grid_constant__ TcGemmArgs g) {
   constexpr int NSLAB = 2 * (BN / 2) / CH;                    // slabs per warp and tile (both accumulators)
   extern __shared__ uint8_t smem_raw[];
   pdl_launch_dependents();
+  const unsigned long long hA = g.hintA ? g.hintA : kL2EvictNormal, hB = g.hintB ? g.hintB : kL2EvictNormal;
+  const unsigned long long hC = g.hintC ? g.hintC : kL2EvictNormal, hH = g.hintH ? g.hintH : kL2EvictNormal;
+  (void)hH;
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t tiles = (raw + 1023u) & ~1023u;
   const uint32_t slabs = tiles + kStages * S::kStage;
@@ -386,10 +392,10 @@ mlp_gemm256_kernel(const __grid_constant__ TcGemmArgs g) {
           mbar_wait(empty_bar + 8 * s, ((it / kStages) & 1) ^ 1);
           const uint32_t sa = tiles + s * S::kStage, sb = sa + 2 * kATileBytes;
           mbar_expect_tx(full_bar + 8 * s, S::kStage);
-          tma_load_2d(sa, &g.mapA[z], full_bar + 8 * s, kb * P::kBK, row_base);                     // rows   0..127 of the tile
-          tma_load_2d(sa + kATileBytes, &g.mapA[z], full_bar + 8 * s, kb * P::kBK, row_base + 128);  // rows 128..255 (zero-filled beyond M)
+          tma_load_2d(sa, &g.mapA[z], full_bar + 8 * s, kb * P::kBK, row_base, hA);                     // rows   0..127 of the tile
+          tma_load_2d(sa + kATileBytes, &g.mapA[z], full_bar + 8 * s, kb * P::kBK, row_base + 128, hA);  // rows 128..255 (zero-filled beyond M)
 #pragma unroll
-          for (int h = 0; h < BN / 128; ++h) tma_load_2d(sb + h * kATileBytes, &g.mapB[z], full_bar + 8 * s, kb * P::kBK, col_base + h * 128);
+          for (int h = 0; h < BN / 128; ++h) tma_load_2d(sb + h * kATileBytes, &g.mapB[z], full_bar + 8 * s, kb * P::kBK, col_base + h * 128, hB);
         }
       }
     }
@@ -448,7 +454,7 @@ mlp_gemm256_kernel(const __grid_constant__ TcGemmArgs g) {
           asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
           const uint32_t buf = n_slab & 1;
           mbar_expect_tx(my_hbar + 8 * buf, kSlabBytes);
-          tma_load_2d(my_slabs + buf * kSlabBytes, &g.mapH[z], my_hbar + 8 * buf, slab_col(0), slab_row(0));
+          tma_load_2d(my_slabs + buf * kSlabBytes, &g.mapH[z], my_hbar + 8 * buf, slab_col(0), slab_row(0), hH);
         }
       } else {
         const float* __restrict__ bp = g.bias[z] + col_base + c_first;
@@ -473,7 +479,7 @@ mlp_gemm256_kernel(const __grid_constant__ TcGemmArgs g) {
             asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
             const uint32_t nb = buf ^ 1;
             mbar_expect_tx(my_hbar + 8 * nb, kSlabBytes);
-            tma_load_2d(my_slabs + nb * kSlabBytes, &g.mapH[z], my_hbar + 8 * nb, slab_col(i + 1), slab_row(i + 1));
+            tma_load_2d(my_slabs + nb * kSlabBytes, &g.mapH[z], my_hbar + 8 * nb, slab_col(i + 1), slab_row(i + 1), hH);
           }
           mbar_wait(my_hbar + 8 * buf, (n_slab >> 1) & 1);
         } else {
@@ -531,7 +537,7 @@ mlp_gemm256_kernel(const __grid_constant__ TcGemmArgs g) {
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&g.mapC[z], slab, slab_col(i), slab_row(i));
+          tma_store_2d(&g.mapC[z], slab, slab_col(i), slab_row(i), hC);
           asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
         }
       }
@@ -855,6 +861,7 @@ mlp_wgrad_kernel(const __grid_constant__ TcWgradArgs g) {
   constexpr int kTmemCols = BN == 256 ? 512 : BN == 128 ? 256 : 128;  // BN accumulator columns + 16 for the bias MMA, power of two
   extern __shared__ uint8_t smem_raw[];
   pdl_launch_dependents();
+  const unsigned long long hA = g.hintA ? g.hintA : kL2EvictNormal, hB = g.hintB ? g.hintB : kL2EvictNormal;
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t tiles = (raw + 1023u) & ~1023u;
   const uint32_t ones = tiles + kWgStages * S::kStage;
@@ -908,8 +915,8 @@ mlp_wgrad_kernel(const __grid_constant__ TcWgradArgs g) {
         const int rb = kb * (int)gridDim.y + (int)blockIdx.y;
         const int k0 = (g.reverse ? blocks_total - 1 - rb : rb) * kWgRows;
         // MN-major operands: boxes of CH contiguous features x 64 reduction rows; rows beyond the matrix are zero-filled
-        for (int h = 0; h < 128 / CH; ++h) tma_load_2d(sa + h * kBoxBytes, &g.mapA[z], full_bar + 8 * s, row_base + h * CH, k0);
-        for (int h = 0; h < BN / CH; ++h) tma_load_2d(sb + h * kBoxBytes, &g.mapB[z], full_bar + 8 * s, col_base + h * CH, k0);
+        for (int h = 0; h < 128 / CH; ++h) tma_load_2d(sa + h * kBoxBytes, &g.mapA[z], full_bar + 8 * s, row_base + h * CH, k0, hA);
+        for (int h = 0; h < BN / CH; ++h) tma_load_2d(sb + h * kBoxBytes, &g.mapB[z], full_bar + 8 * s, col_base + h * CH, k0, hB);
       }
     }
   } else if (warp == 1) {

@@ -20,6 +20,7 @@ struct TcGemmArgs {
   const float* bias[2];  // fwd: [N]
   int M, N, K;           // rows, output features, reduction length
   int reverse;           // mlp_gemm_kernel: walk the row tiles from the last to the first (see "row order" in tc_gemm.cu)
+  unsigned long long hintA, hintB, hintC, hintH;  // L2 eviction-priority hints of the TMA loads / stores (tc_ptx.cuh); 0 = normal
 };
 
 // weight gradient dW[outs, ins] += dZ[rows, outs]^T Hin[rows, ins] over a range of minibatch rows, and
@@ -32,6 +33,7 @@ struct TcWgradArgs {
   int outs, ins_pad, rows;
   int m_range;          // minibatch rows per split (multiple of kBK): sizes the split count only
   int reverse;          // sweep the minibatch rows from the last block to the first
+  unsigned long long hintA, hintB;  // L2 eviction-priority hints of the operand loads; 0 = normal
 };
 
 // 2-D tensor map over a row-major [outer, inner] matrix of bf16 (prec 0) or fp32 (prec 1) elements with leading

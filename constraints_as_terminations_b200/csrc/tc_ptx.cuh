@@ -51,6 +51,24 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// The same with an L2 eviction-priority hint (createpolicy descriptors as constants: the encodings CUTLASS' TMA::CacheHintSm90
+// uses).  The activations of a minibatch (2 x 235 MB in tf32) do not fit the 126 MB L2; the hints say which of them the NEXT
+// launch re-reads (evict_last: the tensor a kernel has just produced, the weights) and which are dead after this read
+// (evict_first), so that the former are not pushed out by the latter.
+constexpr unsigned long long kL2EvictNormal = 0x1000000000000000ull;
+constexpr unsigned long long kL2EvictFirst = 0x12F0000000000000ull;
+constexpr unsigned long long kL2EvictLast = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, unsigned long long hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;\n" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1, unsigned long long hint) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;\n" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1), "l"(hint)
+               : "memory");
+}
 // shared -> global tensor store of one box (coordinates {c0 = column, c1 = row}); completion tracked by bulk groups
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(map), "r"(src), "r"(c0),

@@ -273,10 +273,11 @@ def test_minibatch_gradient_matches_oracle(B, M, prec, margin):
         assert r < T["logstd_mult"] * gtol, f"{name}: log-std gradient relative error {r:.3e}"
 
 
-@pytest.mark.parametrize("var,prec", [("CATB200_TILE256", "tf32"), ("CATB200_PAIRS", "tf32"), ("CATB200_PAIRS", "bf16"), ("CATB200_WGRAD256", "tf32"), ("CATB200_ZIGZAG", "tf32")])
+@pytest.mark.parametrize("var,prec", [("CATB200_TILE256", "tf32"), ("CATB200_PAIRS", "tf32"), ("CATB200_PAIRS", "bf16"), ("CATB200_WGRAD256", "tf32"), ("CATB200_ZIGZAG", "tf32"), ("CATB200_L2_HINTS", "tf32"), ("CATB200_L2_HINTS", "bf16")])
 def test_tile_variants_match_each_other(var, prec):
     """The GEMM tile variants -- CTA pairs (cta_group::2, 256 x 256 tiles; CATB200_PAIRS, opt-in: measured no faster) the single-CTA 256-row tiles (CATB200_TILE256; default: long-K forward launches only), the 256-column weight-gradient tiles
-    (CATB200_WGRAD256, opt-in) and the alternating row order (CATB200_ZIGZAG, opt-in) -- against the plain 128 x 128 tiles: same
+    (CATB200_WGRAD256, opt-in), the alternating row order (CATB200_ZIGZAG, opt-in) and the L2 eviction-priority hints on the TMA
+    traffic (CATB200_L2_HINTS) -- against the plain 128 x 128 tiles: same
     gradient on a ragged 16500-row minibatch (the last pair tile has one CTA partly and one wholly beyond M).  The
     switches are read once per process -> subprocesses."""
     import os
@@ -297,7 +298,7 @@ def test_tile_variants_match_each_other(var, prec):
     outs = []
     for flag in ("0", "1"):
         path = f"/tmp/catb200_{var}_{prec}_{flag}.pt"
-        env = dict(os.environ, CATB200_PAIRS="0", CATB200_TILE256="0", CATB200_WGRAD256="0", CATB200_ZIGZAG="0")
+        env = dict(os.environ, CATB200_PAIRS="0", CATB200_TILE256="0", CATB200_WGRAD256="0", CATB200_ZIGZAG="0", CATB200_L2_HINTS="0")
         env[var] = flag
         subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=120)
         outs.append(torch.load(path))
