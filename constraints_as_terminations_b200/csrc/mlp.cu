@@ -1273,14 +1273,13 @@ __global__ void __launch_bounds__(256) opt_step_peer_kernel(const __grid_constan
     if (tid < p.world && (with_self || tid != p.rank)) {
       const uint32_t* mine = p.flags[p.rank] + word0 + tid;
       const long long t0 = clock64();
-      while (ld_relaxed_sys(mine) < e) {  // relaxed polls, ONE acquire fence behind the loop
+      while (ld_acquire_sys(mine) < e) {  // (relaxed polls + one fence.sys behind the loop measured slower: 38.6 vs 33.9 us at 2 ranks)
         if (clock64() - t0 > 4000000000ll) {  // ~2 s: give up loudly, do not hang the GPU
           atomicExch(p.err, 1);
           break;
         }
-        __nanosleep(100);
+        __nanosleep(200);
       }
-      __threadfence_system();
     }
     __syncthreads();
   };
@@ -1973,14 +1972,16 @@ int catb200_ppo_minibatch_update_peer(const catb200_mlp_dims_t* dims, const catb
   int rc = minibatch_backward(dims, hp, mb_rows, mb_inds, obs_op_all, actions_all, logprobs_all, advantages_all, returns_all,
                               values_all, norm_stats, params, wcv, arena, loss_acc, workspace, workspace_bytes, stream, &pa.o.f);
   if (rc != CATB200_OK) return rc;
-  // exchange pattern: pull whole arenas (one handshake) for two ranks, reduce-scatter / all-gather (two handshakes, 1 / world
-  // of the traffic per peer) beyond; CATB200_PEER_RS=1 / 0 forces either
+  // exchange pattern: pull whole arenas (one handshake; default) or reduce-scatter / all-gather (two handshakes, 1 / world of
+  // the traffic per peer; CATB200_PEER_RS=1).  Measured per optimizer step on B200s (profiles/README.md, round 2): 4 ranks
+  // 38.8 us pull vs 43.6 us reduce-scatter, 8 ranks 65.7 vs 68.2 us -- at 1.5 MB the second handshake costs more than the
+  // saved NVLink traffic.
   static int rs_mode = -1;
   if (rs_mode < 0) {
     const char* e = std::getenv("CATB200_PEER_RS");
-    rs_mode = (e && e[0] == '1') ? 1 : (e && e[0] == '0') ? 0 : 2;
+    rs_mode = (e && e[0] == '1') ? 1 : 0;
   }
-  pa.rs = rs_mode == 1 || (rs_mode == 2 && world > 2);
+  pa.rs = rs_mode == 1;
   for (int q = 0; q < world; ++q)
     pa.gsum[q] = reinterpret_cast<float*>(static_cast<char*>(peer_bases[q]) + kFlagWords * 4) + 2 * n_pad;
   float* summed = pa.rs ? pa.gsum[rank] : grad_sum;  // what Adam consumes
