@@ -1,6 +1,7 @@
 // Per-step CaT path on sm_100a: constraint terms -> termination probabilities.
 //
-// Replaces, in two launches, the ~250-300 eager kernels + 13 host syncs of the reference's
+// Replaces, in one launch (up to ~9.5 k envs: kEvalFused -- evaluation, grid barrier, apply phase straight out of the
+// shared-memory tiles) or two (beyond), the ~250-300 eager kernels + 13 host syncs of the reference's
 // ConstraintManager.compute() (U/cat/constraint_manager.py:213-229 driving constraints.py:23-235 and
 // CaT.add/get_probs :39-82) and the reward/dones lines of CaTEnv.step (U/cat/cat_env.py:102-121).
 //

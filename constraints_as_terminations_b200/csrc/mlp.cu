@@ -5,12 +5,17 @@
 // Structure of one minibatch (M rows, both nets batched into every launch: 0 = critic, 1 = actor):
 //   gather_kernel        : X[M, obs_pad] <- padded operand rows of the rollout at mb_inds + advantage mean / unbiased std
 //   mlp_gemm<fwd> (x3)   : H_l = ELU(H_{l-1} W_l^T + b_l) on tcgen05 (tc_gemm.cu), activations kept for the backward pass
-//   head_kernel<train>   : fp32 heads (h3 -> act_dim / 1), Normal log-prob, PPO-clip + clipped value loss + entropy,
-//                          their gradients w.r.t. the head weights / biases / log-std (per-CTA partial rows) and
-//                          dZ3 = dH3 * ELU'(H3) for both nets
+//   head_mma_kernel      : heads (h3 -> act_dim / 1) as mma.sync tf32 fragments, 16 samples per warp (fp32-grade forward:
+//                          hi + lo weight terms), Normal log-prob, PPO-clip + clipped value loss + entropy, their
+//                          gradients w.r.t. the head weights / biases / log-std (per-CTA partial rows) and
+//                          dZ3 = dH3 * ELU'(H3) for both nets.  head_kernel<train> (one warp per sample, fp32 FMAs) is the
+//                          older variant (CATB200_HEAD=warp); head_kernel<rollout> serves the rollout policy
 //   mlp_wgrad (x3)       : dW_l += dZ_l^T H_{l-1}, db_l += dZ_l^T 1 on tcgen05, red.global.add into padded accumulators
 //   mlp_gemm<dgrad> (x2) : dZ_{l-1} = (dZ_l W_l) * ELU'(H_{l-1})
-//   fold_grads_kernel    : padded weight-gradient accumulators + head partial rows -> flat gradient (reference order)
+//   opt_step_kernel      : padded weight-gradient accumulators + head partial rows -> flat gradient (reference order),
+//                          squared norm -- grid barrier -- clip, Adam, operand copies W / W^T: the optimizer step as ONE
+//                          launch (opt_step_peer_kernel: the same with the NVLink gradient exchange in the middle;
+//                          fold_grads_kernel + optim.cu's grad_norm_kernel + adam_cast_kernel: the separate launches)
 // Operand precision (dims->prec): tf32 = fp32 storage rounded to tf32, the reference's GPU numerics
 // (scripts/clean_rl/train.py:86-87); bf16 = half the operand bytes.  Heads, loss and optimizer math are fp32 either way.
 #include <cstdlib>

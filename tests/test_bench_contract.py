@@ -68,3 +68,29 @@ def test_gemm_flops_attribution_adds_up():
     assert flops["mlp_wgrad_kernel<1, 64>"] + flops["mlp_wgrad_kernel<1, 128>"] == 2.0 * mac_fwd * opt_rows
     # 750 848 FLOP/sample forward = the hidden layers on the tensor cores + the fp32 heads (128 -> 12, 128 -> 1)
     assert 2.0 * mac_fwd + 2 * (128 * 12 + 128) == 750848
+
+
+def test_dominant_kernel_roofline_reports_both_roofs_and_names_the_binding_one():
+    """A GEMM launch has a tensor roof (algorithmic flops) and an HBM roof (algorithmic activation bytes): bench.py prints
+    both and `bound` is the one that leaves less headroom.  Numbers of the round-2 line: the tf32 dgrad kernel, 60 launches
+    in 1413 us -> 0.33 of the tensor roof, 0.82 of the HBM roof."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    tr = SimpleNamespace(num_envs=4096, T=24, batch_size=4096 * 24, minibatch_size=16384, cfg=SimpleNamespace(updates_epochs=5),
+                         agent=SimpleNamespace(precision="tf32"))
+    peaks = {"hbm_gbs": 6547.2, "bf16_tflops": 1682.4, "bf16_tflops_sustained": 1396.2, "source": "measured"}
+    prof = {"mlp_gemm_kernel<1, 1, 4>": {"us": 1413.0, "launches": 60.0, "share": 0.18}}
+    r = bench.dominant_kernel_roofline(prof, 7880.0, tr, peaks)
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["peak"] == 6547.2
+    # dZ_l + H_{l-1} in, dZ_{l-1} out, both nets, fp32, for the 256- and the 512-wide layer, 30 minibatches of 16384 rows
+    assert r["hbm_roof"]["bytes_per_step"] == 4 * 16384 * 30 * 2 * ((128 + 256 + 256) + (256 + 512 + 512))
+    assert abs(r["hbm_roof"]["frac"] - 0.816) < 2e-3 and abs(r["tensor_roof"]["frac"] - 0.3266) < 2e-3
+    assert r["frac"] == r["hbm_roof"]["frac"] and r["tensor_roof"]["peak"] == 1396.2 / 2
+    # bf16 operands: half the bytes, twice the tensor peak
+    tr.agent.precision = "bf16"
+    r16 = bench.dominant_kernel_roofline({"mlp_gemm_kernel<1, 0, 4>": {"us": 900.0, "launches": 60.0, "share": 0.2}}, 6000.0, tr, peaks)
+    assert r16["hbm_roof"]["bytes_per_step"] * 2 == r["hbm_roof"]["bytes_per_step"] and r16["tensor_roof"]["peak"] == 1396.2
+    # a kernel without a flops attribution (e.g. the CaT step) keeps its share but claims no roof
+    other = bench.dominant_kernel_roofline({"cat_eval_kernel<2>": {"us": 500.0, "launches": 24.0, "share": 0.3}}, 1600.0, tr, peaks)
+    assert "frac" not in other and other["kernel"] == "cat_eval_kernel<2>"
