@@ -1,6 +1,7 @@
 """Per-kernel counts of the SASS mnemonics that prove a Blackwell-native kernel (B200_PROFILING.md): tcgen05.mma ->
 UTC*MMA, tcgen05.ld/st -> LDTM/STTM, TMA -> UTMALDG/UTMASTG/UBLKCP, vector reductions -> REDG...F32x4, CREDUX, and the
-legacy HMMA (must be absent).   python tools/sass_summary.py > profiles/r2_sass_summary.txt   (no GPU needed)"""
+warp-level HMMA (expected ONLY in head_mma_kernel: the 12- / 1-wide head products are mma.sync tf32 fragments, DESIGN.md §4;
+the hidden-layer GEMMs must show none).   python tools/sass_summary.py > profiles/r2_sass_summary.txt   (no GPU needed)"""
 import collections, os, re, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
